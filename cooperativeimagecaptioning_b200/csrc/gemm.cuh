@@ -1,0 +1,345 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = sum_k A[m,k] * B[n,k]        (fp32 accumulation in TMEM)
+//
+// * operands: bf16 (kind::f16) or fp32 read as tf32 (kind::tf32); each operand either K-major
+//   (row-major [rows, K]) or MN-major (row-major [K, rows]) so that forward (X W^T), dgrad (dY W)
+//   and wgrad (dY^T X) all run on the same kernel without transposed copies.
+// * TMA (128-byte swizzle) -> smem ring -> one elected thread issues tcgen05.mma -> fp32
+//   accumulators double-buffered in TMEM -> 4 epilogue warps read them back with tcgen05.ld
+//   (one thread per output row) and run a fused epilogue functor.
+// * warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace coopcap {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_STAGE_BUDGET = 196608;  // 192 KB of operand stages
+constexpr int GEMM_SMEM_EXTRA = 2048;           // barriers + alignment slack
+
+template <int KIND, int BN>
+struct GemmCfg {
+  static constexpr int EB = (KIND == 0) ? 2 : 4;   // element bytes
+  static constexpr int BK = 128 / EB;              // elements per 128-byte swizzle row
+  static constexpr int UK = 32 / EB;               // K per tcgen05.mma
+  static constexpr int MN_ATOM = 128 / EB;         // elements along MN per MN-major atom
+  static constexpr int A_BYTES = GEMM_BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = GEMM_SMEM_STAGE_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                   : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_SMEM_EXTRA + 1024;
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32,256]");
+};
+
+// ------------------------------------------------------------------------------------------
+// Generic store epilogue: v = alpha*acc (+bias[col]) (+relu) ; row-major fp32 and/or bf16 output,
+// optional transposed bf16 output; store / read-add-write / atomicAdd.
+// ------------------------------------------------------------------------------------------
+struct EpiStoreParams {
+  float* C;              // [M, ldc] fp32 or null
+  __nv_bfloat16* C16;    // [M, ldc16] bf16 or null
+  __nv_bfloat16* Ct16;   // transposed [N, ldct] bf16 or null
+  const float* bias;     // [N] or null
+  const float* row_scale;  // [M] or null: v *= row_scale[row] (applied after relu)
+  int64_t ldc, ldc16, ldct;
+  float alpha;
+  int relu;
+  int mode;              // 0 store, 1 C += v (plain RMW), 2 atomicAdd (split-K)
+};
+
+struct EpiStore {
+  using Params = EpiStoreParams;
+  __device__ __forceinline__ void begin(const Params&, int, int, int, int, int) {}
+  __device__ __forceinline__ void end(const Params&, int, int, int, int, int) {}
+  __device__ __forceinline__ void chunk(const Params& p, int row, int col0, float (&v)[32], int M,
+                                        int N) {
+    if (row >= M) return;
+    const int ncols = min(32, N - col0);
+    if (ncols <= 0) return;
+    const float rs = p.row_scale ? p.row_scale[row] : 1.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = v[j] * p.alpha;
+      if (p.bias && j < ncols) x += __ldg(p.bias + col0 + j);
+      if (p.relu) x = fmaxf(x, 0.f);
+      v[j] = x * rs;
+    }
+    if (p.C) {
+      float* dst = p.C + int64_t(row) * p.ldc + col0;
+      if (p.mode == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) atomicAdd(dst + j, v[j]);
+      } else {
+        const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        if (vec) {
+          float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (p.mode == 1) {
+              float4 old = d4[j];
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            d4[j] = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) dst[j] = (p.mode == 1) ? dst[j] + v[j] : v[j];
+        }
+      }
+    }
+    if (p.C16) {
+      __nv_bfloat16* dst = p.C16 + int64_t(row) * p.ldc16 + col0;
+      const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+      if (vec) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+          __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+          __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+          __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+          uint4 o;
+          o.x = *reinterpret_cast<uint32_t*>(&a);
+          o.y = *reinterpret_cast<uint32_t*>(&b);
+          o.z = *reinterpret_cast<uint32_t*>(&c);
+          o.w = *reinterpret_cast<uint32_t*>(&d);
+          d4[j] = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+    if (p.Ct16) {
+      // for a fixed column the 32 lanes of a warp hold 32 consecutive rows -> coalesced
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) p.Ct16[int64_t(col0 + j) * p.ldct + row] = __float2bfloat16_rn(v[j]);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+template <int KIND, int BN, int AMAJ, int BMAJ, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               int M, int N, int K, int split_k, typename Epi::Params ep) {
+  using Cfg = GemmCfg<KIND, BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int nkb = (K + Cfg::BK - 1) / Cfg::BK;
+  const int kb_per_split = (nkb + split_k - 1) / split_k;
+  const int num_tiles = num_m * num_n * split_k;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t % num_m;
+        const int rest = t / num_m;
+        const int n_blk = rest % num_n;
+        const int ks = rest / num_n;
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = min(nkb, kb0 + kb_per_split);
+        const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          mbar_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
+          uint8_t* a_dst = sA + st * Cfg::A_BYTES;
+          uint8_t* b_dst = sB + st * Cfg::B_BYTES;
+          const int k0 = kb * Cfg::BK;
+          if constexpr (AMAJ == 0) {
+            tma_load_2d(a_dst, &tmA, &full_bar[st], k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < GEMM_BM / Cfg::MN_ATOM; ++j)
+              tma_load_2d(a_dst + j * (Cfg::BK * 128), &tmA, &full_bar[st],
+                          m0 + j * Cfg::MN_ATOM, k0);
+          }
+          if constexpr (BMAJ == 0) {
+            tma_load_2d(b_dst, &tmB, &full_bar[st], k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / Cfg::MN_ATOM; ++j)
+              tma_load_2d(b_dst + j * (Cfg::BK * 128), &tmB, &full_bar[st],
+                          n0 + j * Cfg::MN_ATOM, k0);
+          }
+          if (++st == STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<KIND>(GEMM_BM, BN, AMAJ, BMAJ);
+      int st = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int ks = (t / num_m) / num_n;
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = min(nkb, kb0 + kb_per_split);
+        if (kb0 >= kb1) continue;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[st], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + st * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + st * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
+            const uint64_t da = (AMAJ == 0)
+                                    ? make_smem_desc(a_addr + k * 32, 16, 1024)
+                                    : make_smem_desc(a_addr + k * Cfg::UK * 128, Cfg::BK * 128, 1024);
+            const uint64_t db = (BMAJ == 0)
+                                    ? make_smem_desc(b_addr + k * 32, 16, 1024)
+                                    : make_smem_desc(b_addr + k * Cfg::UK * 128, Cfg::BK * 128, 1024);
+            umma_ss<KIND>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[st]);
+          if (++st == STAGES) { st = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    Epi epi;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t % num_m;
+      const int rest = t / num_m;
+      const int n_blk = rest % num_n;
+      const int ks = rest / num_n;
+      const int kb0 = ks * kb_per_split;
+      const int kb1 = min(nkb, kb0 + kb_per_split);
+      if (kb0 >= kb1) continue;
+      const int row = m_blk * GEMM_BM + q * 32 + lane;
+      const int n0 = n_blk * BN;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      epi.begin(ep, row, n0, M, N, ks);
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(t_addr + c * 32, v);
+        tmem_ld_wait();
+        epi.chunk(ep, row, n0 + c * 32, v, M, N);
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      epi.end(ep, row, n0, M, N, n_blk);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+// Encode a 2D row-major [rows, cols] matrix (leading dimension ld elements) as a TMA tensor map
+// with a [box_rows, box_cols] box and 128B swizzle. elem_bytes 2 -> bf16, 4 -> fp32.
+int encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, int64_t rows, int64_t cols,
+                   int64_t ld, int box_rows, int box_cols);
+
+template <int KIND, int BN, int AMAJ, int BMAJ, class Epi>
+int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
+                   int split_k, const typename Epi::Params& ep, cudaStream_t stream,
+                   int max_ctas = 0) {
+  using Cfg = GemmCfg<KIND, BN>;
+  CC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  CC_REQUIRE(split_k >= 1, "gemm: split_k must be >= 1");
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (AMAJ == 0)
+    rc = encode_tmap_2d(&tmA, A, Cfg::EB, M, K, lda, GEMM_BM, Cfg::BK);
+  else
+    rc = encode_tmap_2d(&tmA, A, Cfg::EB, K, M, lda, Cfg::BK, Cfg::MN_ATOM);
+  if (rc) return rc;
+  if (BMAJ == 0)
+    rc = encode_tmap_2d(&tmB, B, Cfg::EB, N, K, ldb, BN, Cfg::BK);
+  else
+    rc = encode_tmap_2d(&tmB, B, Cfg::EB, K, N, ldb, Cfg::BK, Cfg::MN_ATOM);
+  if (rc) return rc;
+
+  auto kern = gemm_tc_kernel<KIND, BN, AMAJ, BMAJ, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_m = (M + GEMM_BM - 1) / GEMM_BM, num_n = (N + BN - 1) / BN;
+  const int nkb = (K + Cfg::BK - 1) / Cfg::BK;
+  if (split_k > nkb) split_k = nkb;
+  const int tiles = num_m * num_n * split_k;
+  int grid = num_sms();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (tiles < grid) grid = tiles;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, split_k, ep);
+  CC_LAUNCH_CHECK();
+  return CC_OK;
+}
+
+}  // namespace coopcap

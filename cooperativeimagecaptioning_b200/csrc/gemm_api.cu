@@ -1,0 +1,167 @@
+// C ABI for the dense contraction engine: dispatch over operand kind / majors / tile width, the
+// SIMT cross-check kernel, and the fp32->bf16 cast.
+#include "../../include/coopcap.h"
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace coopcap {
+
+// ------------------------------------------------------------------------------------------
+// SIMT cross-check kernel (tests only): one thread per output element, fp32 math.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) {
+  return *p;
+}
+
+template <typename T>
+__global__ void gemm_simt_kernel(const T* __restrict__ A, int64_t lda, int a_major,
+                                 const T* __restrict__ B, int64_t ldb, int b_major, int M, int N,
+                                 int K, EpiStoreParams p) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y * blockDim.y + threadIdx.y;
+  if (m >= M || n >= N) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float a = a_major == 0 ? ld_as_float(A + int64_t(m) * lda + k)
+                                 : ld_as_float(A + int64_t(k) * lda + m);
+    const float b = b_major == 0 ? ld_as_float(B + int64_t(n) * ldb + k)
+                                 : ld_as_float(B + int64_t(k) * ldb + n);
+    acc = fmaf(a, b, acc);
+  }
+  float x = acc * p.alpha;
+  if (p.bias) x += p.bias[n];
+  if (p.relu) x = fmaxf(x, 0.f);
+  if (p.row_scale) x *= p.row_scale[m];
+  if (p.C) {
+    float* d = p.C + int64_t(m) * p.ldc + n;
+    if (p.mode == 0) *d = x;
+    else if (p.mode == 1) *d += x;
+    else atomicAdd(d, x);
+  }
+  if (p.C16) p.C16[int64_t(m) * p.ldc16 + n] = __float2bfloat16_rn(x);
+  if (p.Ct16) p.Ct16[int64_t(n) * p.ldct + m] = __float2bfloat16_rn(x);
+}
+
+template <int KIND, int BN>
+static int dispatch_major(const coopcap_gemm_args* a, const EpiStoreParams& ep, cudaStream_t s) {
+  if (a->a_major == 0 && a->b_major == 0)
+    return launch_gemm_tc<KIND, BN, 0, 0, EpiStore>(a->A, a->lda, a->B, a->ldb, a->M, a->N, a->K,
+                                                    a->split_k, ep, s);
+  if (a->a_major == 0 && a->b_major == 1)
+    return launch_gemm_tc<KIND, BN, 0, 1, EpiStore>(a->A, a->lda, a->B, a->ldb, a->M, a->N, a->K,
+                                                    a->split_k, ep, s);
+  if (a->a_major == 1 && a->b_major == 1)
+    return launch_gemm_tc<KIND, BN, 1, 1, EpiStore>(a->A, a->lda, a->B, a->ldb, a->M, a->N, a->K,
+                                                    a->split_k, ep, s);
+  if (a->a_major == 1 && a->b_major == 0)
+    return launch_gemm_tc<KIND, BN, 1, 0, EpiStore>(a->A, a->lda, a->B, a->ldb, a->M, a->N, a->K,
+                                                    a->split_k, ep, s);
+  set_last_error("gemm: bad majors %d/%d", a->a_major, a->b_major);
+  return CC_ERR_ARG;
+}
+
+int pick_tile_n(int M, int N, int requested) {
+  if (requested == 64 || requested == 128 || requested == 256) return requested;
+  const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int sms = num_sms();
+  // prefer the widest tile that still fills ~one wave of SMs
+  if (num_m * ((N + 255) / 256) >= sms) return 256;
+  if (num_m * ((N + 127) / 128) >= (sms * 3) / 4) return 128;
+  if (N <= 64) return 64;
+  return num_m * ((N + 127) / 128) >= sms / 3 ? 128 : 64;
+}
+
+int gemm_store(const coopcap_gemm_args* a, cudaStream_t s) {
+  CC_REQUIRE(a != nullptr, "gemm: null args");
+  CC_REQUIRE(a->kind == 0 || a->kind == 1, "gemm: kind %d", a->kind);
+  CC_REQUIRE(a->split_k <= 1 || (a->mode == 2 && a->C16 == nullptr && a->Ct16 == nullptr),
+             "gemm: split_k > 1 needs mode 2 (atomicAdd) and fp32 output only");
+  EpiStoreParams ep;
+  ep.C = a->C;
+  ep.C16 = reinterpret_cast<__nv_bfloat16*>(a->C16);
+  ep.Ct16 = reinterpret_cast<__nv_bfloat16*>(a->Ct16);
+  ep.bias = a->bias;
+  ep.row_scale = a->row_scale;
+  ep.ldc = a->ldc;
+  ep.ldc16 = a->ldc16;
+  ep.ldct = a->ldct;
+  ep.alpha = a->alpha;
+  ep.relu = a->relu;
+  ep.mode = a->mode;
+  if (a->backend == 1) {
+    dim3 blk(32, 8), grd((a->N + 31) / 32, (a->M + 7) / 8);
+    if (a->kind == 0)
+      gemm_simt_kernel<__nv_bfloat16><<<grd, blk, 0, s>>>(
+          reinterpret_cast<const __nv_bfloat16*>(a->A), a->lda, a->a_major,
+          reinterpret_cast<const __nv_bfloat16*>(a->B), a->ldb, a->b_major, a->M, a->N, a->K, ep);
+    else
+      gemm_simt_kernel<float><<<grd, blk, 0, s>>>(reinterpret_cast<const float*>(a->A), a->lda,
+                                                  a->a_major, reinterpret_cast<const float*>(a->B),
+                                                  a->ldb, a->b_major, a->M, a->N, a->K, ep);
+    CC_LAUNCH_CHECK();
+    return CC_OK;
+  }
+  const int bn = pick_tile_n(a->M, a->N, a->tile_n);
+  if (a->kind == 0) {
+    if (bn == 256) return dispatch_major<0, 256>(a, ep, s);
+    if (bn == 128) return dispatch_major<0, 128>(a, ep, s);
+    return dispatch_major<0, 64>(a, ep, s);
+  } else {
+    if (bn == 256) return dispatch_major<1, 256>(a, ep, s);
+    if (bn == 128) return dispatch_major<1, 128>(a, ep, s);
+    return dispatch_major<1, 64>(a, ep, s);
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, int64_t rows, int64_t cols,
+                                 int64_t ld_src, __nv_bfloat16* __restrict__ dst, int64_t ld_dst,
+                                 __nv_bfloat16* __restrict__ dst_t, int64_t ld_dst_t) {
+  // 32x32 tiles through shared memory so both the straight and the transposed store coalesce
+  __shared__ float tile[32][33];
+  const int64_t c0 = int64_t(blockIdx.x) * 32, r0 = int64_t(blockIdx.y) * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = src[r * ld_src + c];
+      if (dst) dst[r * ld_dst + c] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  if (!dst_t) return;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst_t[c * ld_dst_t + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+}  // namespace coopcap
+
+extern "C" {
+
+int coopcap_gemm(const coopcap_gemm_args* args, coopcap_stream_t stream) {
+  return coopcap::gemm_store(args, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int coopcap_cast_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* dst,
+                      int64_t ld_dst, void* dst_t, int64_t ld_dst_t, coopcap_stream_t stream) {
+  using namespace coopcap;
+  if (rows <= 0 || cols <= 0) return CC_OK;
+  dim3 blk(32, 8), grd((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  CC_REQUIRE(grd.y <= 65535, "cast_bf16: too many rows for one launch (%lld)", (long long)rows);
+  cast_bf16_kernel<<<grd, blk, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, rows, cols, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst,
+      reinterpret_cast<__nv_bfloat16*>(dst_t), ld_dst_t);
+  CC_LAUNCH_CHECK();
+  return CC_OK;
+}
+
+}  // extern "C"
