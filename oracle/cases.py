@@ -1,0 +1,91 @@
+"""TEST INFRASTRUCTURE ONLY.  Rebuild a golden case from its metadata and run the oracle on it.
+
+Shared by tests/test_oracle_golden.py (oracle vs. stored reference outputs, CPU) and the GPU
+parity tests (CUDA path vs. oracle on the same seeded tensors).
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict
+
+import numpy as np
+import torch
+
+from . import joint as OJ
+from . import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                          "tests", "golden")
+
+
+def load_golden(name: str):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    return meta, z
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+
+
+def build_case(meta: Dict):
+    dims = synth.Dims(**meta["dims"])
+    seed, mode = meta["seed"], meta["mode"]
+    rows, regions = meta["rows"], meta["regions"]
+    Ps = synth.speaker_params(dims, seed=seed, eos_bias=meta["eos_bias"])
+    Pl = synth.listener_params(dims, seed=seed + 1)
+    batch = synth.make_batch(dims, rows, regions, seed=seed + 2, varlen=meta["varlen"],
+                             min_regions=2)
+    noise = synth.make_noise(
+        dims, rows, regions, seed + 3, dropout=meta["dropout"],
+        gumbel=mode in ("gumbel", "gumbel_softmax"),
+        multinomial=mode in ("multinomial", "multinomial_soft", "reinforce"),
+        partial=mode in ("gumbel_softmax", "multinomial_soft"))
+    noise2 = synth.make_noise(dims, rows, regions, seed + 4, dropout=meta["dropout"])
+    kind = meta["kind"]
+    cfg = OJ.JointCfg(
+        vocab_size=dims.vocab_size, seq_length=dims.seq_length,
+        drop_p=0.5 if meta["dropout"] else 0.0, retrieval_reward=mode, gumbel_temp=meta["tau"],
+        multinomial_temp=meta["tau"], prob_gumbel_softmax=meta["prob"],
+        prob_multinomial_soft=meta["prob"], retrieval_reward_weight=meta["weight"],
+        reinforce_baseline_type=meta["baseline"],
+        vse_loss_weight=1.0 if kind == "listener_turn" else 0.0,
+        caption_loss_weight=1.0 if kind == "mle" else 0.0)
+    return dims, Ps, Pl, batch, noise, noise2, cfg
+
+
+def run_oracle(meta: Dict, forced_tokens=None, keep_all_steps=False):
+    """Returns dict(loss, seq, logprobs, ..., grads={name: tensor})."""
+    dims, Ps, Pl, batch, noise, noise2, cfg = build_case(meta)
+    Pso = {k: v.clone().requires_grad_(True) for k, v in Ps.items()}
+    Plo = {k: v.clone().requires_grad_(True) for k, v in Pl.items()}
+    kind, mode = meta["kind"], meta["mode"]
+    out = {}
+    if kind == "mle":
+        loss = OJ.mle_loss(Pso, batch.att_feats, batch.att_masks, batch.labels, batch.masks,
+                           noise, cfg)
+    elif kind == "listener_turn":
+        loss, res, _ = OJ.listener_turn_loss(Pso, Plo, batch.fc_feats, batch.att_feats,
+                                             batch.att_masks, noise, cfg, forced_tokens,
+                                             keep_all_steps)
+        out.update(seq=res.seq, logprobs=res.logprobs.detach())
+    elif mode == "reinforce":
+        loss, res, r, b = OJ.reinforce_speaker_loss(
+            Pso, Plo, batch.fc_feats, batch.att_feats, batch.att_masks, batch.labels, batch.masks,
+            noise, cfg, noise_greedy=noise2, forced_tokens=forced_tokens,
+            keep_all_steps=keep_all_steps)
+        out.update(seq=res.seq, logprobs=res.logprobs.detach(), reward=r, baseline=b)
+    else:
+        loss, res, masks, loss_vse = OJ.st_joint_loss(Pso, Plo, batch.fc_feats, batch.att_feats,
+                                                      batch.att_masks, noise, cfg, forced_tokens,
+                                                      keep_all_steps)
+        out.update(seq=res.seq, logprobs=res.logprobs.detach(), loss_vse=loss_vse.detach(),
+                   sample=res)
+    out["loss"] = loss.detach()
+    names = ["caption_generator." + k for k in Pso] + ["vse." + k for k in Plo]
+    tensors = list(Pso.values()) + list(Plo.values())
+    gs = torch.autograd.grad(loss, tensors, allow_unused=True)
+    out["grads"] = {n: (torch.zeros_like(t) if g is None else g)
+                    for n, t, g in zip(names, tensors, gs)}
+    return out

@@ -1,0 +1,103 @@
+"""TEST INFRASTRUCTURE ONLY (checker, never the product path).
+
+CPU fp32 restatement of the reference listener (VSEFCModel): image encoder, GRU caption encoder
+over index or one-hot captions, cosine score matrix and the max-violation hinge loss.  Parameters
+are a plain dict keyed by the reference's state-dict names.  Pinned against
+the real reference by tests/golden/make_golden.py.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+Params = Dict[str, torch.Tensor]
+
+
+def l2norm(X):
+    """X / (||X||_2 + 1e-7), eps outside the sqrt                       (VSEFCModel.py:12-17)"""
+    return X / (torch.norm(X, dim=1, keepdim=True) + 1e-7)
+
+
+def img_enc(P: Params, fc_feats, no_imgnorm=False, use_abs=False):
+    """EncoderImage.forward                                             (VSEFCModel.py:40-54)"""
+    f = torch.nn.functional.linear(fc_feats, P["img_enc.fc.weight"], P["img_enc.fc.bias"])
+    if not no_imgnorm:
+        f = l2norm(f)
+    if use_abs:
+        f = f.abs()
+    return f
+
+
+def gru_step(P: Params, x, h):
+    """One step of nn.GRU (gate order r, z, n; torch semantics)        (VSEFCModel.py:74-76)"""
+    H = h.size(1)
+    gi = torch.nn.functional.linear(x, P["txt_enc.rnn.weight_ih_l0"], P["txt_enc.rnn.bias_ih_l0"])
+    gh = torch.nn.functional.linear(h, P["txt_enc.rnn.weight_hh_l0"], P["txt_enc.rnn.bias_hh_l0"])
+    r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+    z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+    n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+    return (1 - z) * n + z * h
+
+
+def txt_enc(P: Params, seqs, masks, pool_type="last", use_abs=False):
+    """EncoderText.forward                                              (VSEFCModel.py:83-140)
+    lengths = sum(mask > 0) (:84); embedding by lookup or dense one-hot matmul (:102-106);
+    a packed GRU only advances rows with t < len (:108-112) -- restated as a masked update, which
+    also removes the sort / unsort (:85-93,:134) since rows are independent; pooling :115-127."""
+    lens = (masks > 0).long().sum(1)
+    W = P["txt_enc.embed.weight"]
+    emb = torch.matmul(seqs, W) if seqs.dim() > 2 else W[seqs]
+    B, S = emb.shape[:2]
+    H = P["txt_enc.rnn.weight_hh_l0"].size(1)
+    h = emb.new_zeros(B, H)
+    outs = []
+    tmax = int(lens.max())
+    for t in range(tmax):
+        hn = gru_step(P, emb[:, t], h)
+        act = (t < lens)[:, None]
+        h = torch.where(act, hn, h)
+        outs.append(torch.where(act, hn, torch.zeros_like(hn)))   # pad_packed zero-fills
+    if pool_type == "mean":
+        m = masks[:, :tmax].float()
+        out = (torch.stack(outs, 1) * m[:, :, None]).sum(1) / masks.float().sum(1, keepdim=True)
+    elif pool_type == "max":
+        m = masks[:, :tmax].float()
+        out = (torch.stack(outs, 1) * m[:, :, None] + (m == 0)[:, :, None].float() * -1e10).max(1)[0]
+    else:
+        out = h                                                        # gather at len-1 (:128)
+    out = l2norm(out)
+    if use_abs:
+        out = out.abs()
+    return out
+
+
+def contrastive_loss(im, s, margin=0.2, max_violation=True, whole_batch=False,
+                     only_one_retrieval="off"):
+    """ContrastiveLoss.forward                                          (VSEFCModel.py:167-207)"""
+    scores = im @ s.t()                                                # cosine_sim, :143-146
+    diag = scores.diag().view(-1, 1)
+    cost_s = (margin + scores - diag).clamp(min=0)                     # :176 caption retrieval
+    cost_im = (margin + scores - diag.t()).clamp(min=0)                # :179 image retrieval
+    eye = torch.eye(scores.size(0), dtype=torch.bool)
+    cost_s = cost_s.masked_fill(eye, 0)                                # :182-188
+    cost_im = cost_im.masked_fill(eye, 0)
+    if max_violation:
+        cost_s = cost_s.max(1)[0]                                      # :191-193
+        cost_im = cost_im.max(0)[0]
+    else:
+        cost_s = cost_s.mean(1)
+        cost_im = cost_im.mean(0)
+    fn = (lambda x: x) if whole_batch else (lambda x: x.sum())         # :197-200
+    if only_one_retrieval == "image":
+        return fn(cost_im)
+    if only_one_retrieval == "caption":
+        return fn(cost_s)
+    return fn(cost_s) + fn(cost_im)
+
+
+def vse_forward(P: Params, fc_feats, seq, masks, whole_batch=False, only_one_retrieval="off",
+                margin=0.2, max_violation=True, pool_type="last"):
+    """VSEFCModel.forward                                               (VSEFCModel.py:230-241)"""
+    return contrastive_loss(img_enc(P, fc_feats), txt_enc(P, seq, masks, pool_type), margin,
+                            max_violation, whole_batch, only_one_retrieval)

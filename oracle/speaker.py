@@ -1,0 +1,321 @@
+"""TEST INFRASTRUCTURE ONLY (checker, never the product path).
+
+CPU fp32 restatement of the reference speaker (Att2in2): prologue, attention, maxout-LSTM core,
+vocabulary logits, the samplers, the `sample` decode loop and the teacher-forced XE `forward`.
+Written functionally over a plain dict of parameters that uses the reference's state-dict names
+(SURVEY.md Appendix B).  All randomness (Gumbel uniforms, multinomial exponentials, dropout
+keep-masks, partial-sampling uniforms) is INJECTED so that the CUDA path and the real reference
+can be driven with identical noise.
+
+Pinned against the real reference (imported through oracle/ref_loader.py) by
+tests/golden/make_golden.py; the resulting vectors live in tests/golden/*.npz and are re-checked
+by tests/test_oracle_golden.py on every CPU run.
+
+Each function cites the reference lines (relative to the reference root) it follows.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+Params = Dict[str, torch.Tensor]
+
+GUMBEL_EPS = 1e-20  # models/gumbel.py:6
+
+
+@dataclass
+class SpeakerNoise:
+    """Injected randomness for one speaker pass.
+
+    drop_att   keep-mask {0,1} for att_embed's dropout, padded layout [B, L, R]    (AttModel.py:82-85)
+    drop_embed keep-masks [steps, B, E] for `embed`'s dropout, one per decode step (AttModel.py:74-76)
+    drop_core  keep-masks [steps, B, R] for Att2in2Core.dropout                    (AttModel.py:529)
+    U          uniforms [T, B, V+1] turned into Gumbel noise                       (gumbel.py:6-11)
+    E          Exp(1) draws [T, B, V+1]; torch.multinomial(p,1) == argmax(p / E)   (multinomial.py:17)
+    part_u     uniforms [T, B] for the partial-sampling variants                   (gumbel_softmax.py:31)
+    Any entry may be None -> that source of randomness is off (dropout) or unused.
+    """
+    drop_att: Optional[torch.Tensor] = None
+    drop_embed: Optional[torch.Tensor] = None
+    drop_core: Optional[torch.Tensor] = None
+    U: Optional[torch.Tensor] = None
+    E: Optional[torch.Tensor] = None
+    part_u: Optional[torch.Tensor] = None
+
+
+def _dropout(x, keep, p):
+    """nn.Dropout in training mode with an injected keep-mask (scale 1/(1-p))."""
+    if keep is None or p <= 0.0:
+        return x
+    return x * keep.to(x.dtype) * (1.0 / (1.0 - p))
+
+
+def _linear(x, P, name):
+    return F.linear(x, P[name + ".weight"], P[name + ".bias"])
+
+
+# --------------------------------------------------------------------------------------------
+# prologue: att_embed through pack_wrapper, ctx2att                      (AttModel.py:31-51,110-114)
+# --------------------------------------------------------------------------------------------
+def prologue(P: Params, att_feats, att_masks, noise: SpeakerNoise, drop_p: float):
+    """att_e = dropout(relu(att W^T + b)) on valid regions, exactly 0 on padded regions, width
+    clipped to the longest row (pack_wrapper, AttModel.py:44-51); p_att = ctx2att(att_e)
+    (AttModel.py:114) -- so padded positions of p_att hold ctx2att's bias."""
+    x = torch.relu(_linear(att_feats, P, "att_embed.0"))
+    x = _dropout(x, noise.drop_att, drop_p)
+    if att_masks is not None:
+        lens = att_masks.long().sum(1)                    # AttModel.py:47
+        lmax = int(lens.max())
+        valid = (torch.arange(att_feats.size(1))[None, :] < lens[:, None]).to(x.dtype)
+        x = (x * valid[:, :, None])[:, :lmax]             # pad_packed_sequence zero-fills
+    p_att = _linear(x, P, "ctx2att")
+    return x, p_att
+
+
+# --------------------------------------------------------------------------------------------
+# Attention.forward                                                        (AttModel.py:465-489)
+# --------------------------------------------------------------------------------------------
+def attention(P: Params, h, att_e, p_att, att_masks):
+    att_h = _linear(h, P, "core.attention.h2att")                       # :470
+    dot = torch.tanh(p_att + att_h[:, None, :])                         # :473-474
+    e = F.linear(dot, P["core.attention.alpha_net.weight"],
+                 P["core.attention.alpha_net.bias"]).squeeze(-1)        # :477-478
+    w = torch.softmax(e, dim=1)                                         # :480 (padded width)
+    if att_masks is not None:
+        m = att_masks[:, : att_e.size(1)].to(w.dtype)                   # :482
+        w = w * m
+        w = w / w.sum(1, keepdim=True)                                  # :483
+    return torch.bmm(w[:, None, :], att_e).squeeze(1), w                # :487
+
+
+# --------------------------------------------------------------------------------------------
+# Att2in2Core.forward                                                      (AttModel.py:510-531)
+# --------------------------------------------------------------------------------------------
+def core_step(P: Params, xt, h, c, att_e, p_att, att_masks, keep_core, drop_p):
+    R = h.size(1)
+    att_res, w = attention(P, h, att_e, p_att, att_masks)               # :511
+    s = _linear(xt, P, "core.i2h") + _linear(h, P, "core.h2h")          # :514
+    sig = torch.sigmoid(s[:, : 3 * R])                                  # :515-516
+    i, f, o = sig[:, :R], sig[:, R:2 * R], sig[:, 2 * R:3 * R]          # :517-519
+    u = s[:, 3 * R:] + _linear(att_res, P, "core.a2c")                  # :521-522
+    g = torch.max(u[:, :R], u[:, R:])                                   # :523-525 (maxout)
+    c2 = f * c + i * g                                                  # :526
+    h2 = o * torch.tanh(c2)                                             # :527
+    out = _dropout(h2, keep_core, drop_p)                               # :529
+    return out, h2, c2, w
+
+
+def embed_tokens(P: Params, it, keep, drop_p):
+    """self.embed = Embedding -> ReLU -> Dropout                          (AttModel.py:74-76)"""
+    return _dropout(torch.relu(P["embed.0.weight"][it]), keep, drop_p)
+
+
+def logits_of(P: Params, out):
+    return _linear(out, P, "logit")                                     # AttModel.py:87,140,444
+
+
+# --------------------------------------------------------------------------------------------
+# samplers
+# --------------------------------------------------------------------------------------------
+def gumbel_from_uniform(U):
+    """sample_gumbel: -log(-log(U + eps) + eps)                           (gumbel.py:6-11)"""
+    return -torch.log(-torch.log(U + GUMBEL_EPS) + GUMBEL_EPS)
+
+
+def _hard(y, ind):
+    y_hard = torch.zeros_like(y)
+    y_hard.scatter_(1, ind.view(-1, 1), 1.0)
+    return y_hard
+
+
+def st_gumbel(logprobs, tau, U):
+    """gumbel_softmax: y = softmax((lp+G)/tau); ind = argmax y; STE one-hot  (gumbel.py:13-30)"""
+    y = torch.softmax((logprobs + gumbel_from_uniform(U)) / tau, dim=-1)
+    ind = y.max(dim=-1)[1]
+    return (_hard(y, ind) - y).detach() + y, ind, y
+
+
+def st_multinomial(logprobs, tau, E):
+    """multinomial: y = softmax(lp/tau); ind ~ Multinomial(y); STE one-hot   (multinomial.py:4-27)
+    torch.multinomial(y, 1) draws q ~ Exp(1) elementwise and returns argmax(y / q)."""
+    y = torch.softmax(logprobs if tau == 1 else logprobs / tau, dim=1)
+    ind = (y / E).max(dim=1)[1]
+    return (_hard(y, ind) - y).detach() + y, ind, y
+
+
+def _ps_out(y, ind, part_u, prob):
+    if prob > 0.0:
+        sel = (part_u < prob).to(y.dtype)[:, None]
+        return (sel * _hard(y, ind) - sel * y).detach() + y
+    return y
+
+
+def ps_gumbel(logprobs, tau, U, part_u, prob):
+    """gumbel_soft: rows with part_u < prob output the hard one-hot value, the others stay soft;
+    all rows back-propagate through y                              (gumbel_softmax.py:17-42)"""
+    y = torch.softmax((logprobs + gumbel_from_uniform(U)) / tau, dim=-1)
+    ind = y.max(dim=-1)[1]
+    return _ps_out(y, ind, part_u, prob), ind, y
+
+
+def ps_multinomial(logprobs, tau, E, part_u, prob):
+    """multinomial_soft: y = exp(lp/tau) (unnormalised when tau != 1)  (multinomial_soft.py:5-35)"""
+    y = torch.exp(logprobs if tau == 1 else logprobs / tau)
+    ind = (y / E).max(dim=1)[1]
+    return _ps_out(y, ind, part_u, prob), ind, y
+
+
+# --------------------------------------------------------------------------------------------
+# AttModel.sample                                                          (AttModel.py:291-452)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class SampleResult:
+    seq: torch.Tensor                      # [B, n] int64 (word_index)
+    logprobs: torch.Tensor                 # [B, n] sampleLogprobs
+    one_hots: Optional[torch.Tensor]       # [B, n, V+2] (ST / PS modes with use_one_hot)
+    n_steps: int                           # number of core evaluations executed
+    step_logprobs: List[torch.Tensor] = field(default_factory=list)   # log_softmax(logit) per step
+    tokens_raw: List[torch.Tensor] = field(default_factory=list)      # sampled ids before masking
+    perturbed: List[torch.Tensor] = field(default_factory=list)       # the score whose argmax is the sample
+
+
+def sample(P: Params, att_feats, att_masks, *, mode: str, seq_length: int, vocab_size: int,
+           noise: SpeakerNoise, drop_p: float = 0.0, sample_max: int = 1, use_one_hot: int = 0,
+           temperature: float = 1.0, gumbel_temp: float = 1.0, multinomial_temp: float = 1.0,
+           prob_gumbel_softmax: float = 1.0, prob_multinomial_soft: float = 1.0,
+           forced_tokens: Optional[torch.Tensor] = None, keep_all_steps: bool = False
+           ) -> SampleResult:
+    """mode = retrieval_reward in {'reinforce','gumbel','multinomial','gumbel_softmax',
+    'multinomial_soft'}.  `forced_tokens` [B, T] (optional, test aid) replaces the sampled id at
+    each step so that a near-tie flip in one implementation cannot cascade; the id the oracle
+    would have drawn is still recorded in `tokens_raw`.  `keep_all_steps` disables the early
+    `break` (the CUDA path always runs all steps and slices afterwards)."""
+    B = att_feats.size(0)
+    V1 = vocab_size + 1
+    att_e, p_att = prologue(P, att_feats, att_masks, noise, drop_p)           # :315-319
+    h = att_feats.new_zeros(B, P["core.h2h.weight"].size(1))
+    c = torch.zeros_like(h)
+    eos_one_hot = torch.zeros(1, V1 + 1)
+    eos_one_hot[0, 0] = 1.0                                                   # :297-304
+    idx_mode = bool(sample_max) or (mode == "reinforce") or (not use_one_hot)
+    ps_mode = (not idx_mode) and mode in ("gumbel_softmax", "multinomial_soft")
+    word_index, seq, seq_lp = [], [], []
+    res = SampleResult(None, None, None, 0)
+    logprobs = None
+    unfinished = None
+    for t in range(seq_length + 1):                                           # :323
+        keep_e = None if noise.drop_embed is None else noise.drop_embed[t]
+        keep_c = None if noise.drop_core is None else noise.drop_core[t]
+        vec = None   # one_hot (ST modes) or soft_vec (PS modes), width V+1
+        if t == 0:
+            it = torch.full((B,), vocab_size + 1, dtype=torch.long)           # :324-326
+        else:
+            y = None
+            if sample_max:
+                score = logprobs
+                it = torch.max(logprobs, 1)[1]                                # :327-329
+            elif idx_mode:
+                prob_prev = torch.exp(logprobs if temperature == 1.0 else logprobs / temperature)
+                score = prob_prev / noise.E[t - 1]
+                it = score.max(dim=1)[1]                                      # :332-343
+            elif mode == "gumbel":
+                vec, it, y = st_gumbel(logprobs, gumbel_temp, noise.U[t - 1])  # :345-354
+                score = y
+            elif mode == "multinomial":
+                vec, it, y = st_multinomial(logprobs, multinomial_temp, noise.E[t - 1])  # :356-365
+                score = y / noise.E[t - 1]
+            elif mode == "gumbel_softmax":
+                vec, it, y = ps_gumbel(logprobs, gumbel_temp, noise.U[t - 1],
+                                       noise.part_u[t - 1], prob_gumbel_softmax)   # :367-378
+                score = y
+            elif mode == "multinomial_soft":
+                vec, it, y = ps_multinomial(logprobs, multinomial_temp, noise.E[t - 1],
+                                            noise.part_u[t - 1], prob_multinomial_soft)  # :381-392
+                score = y / noise.E[t - 1]
+            else:
+                raise ValueError(mode)
+            res.tokens_raw.append(it.clone())
+            res.perturbed.append(score.detach())
+            if forced_tokens is not None:
+                it = forced_tokens[:, t - 1].clone()
+                if vec is not None and not ps_mode:
+                    vec = (_hard(y, it) - y).detach() + y
+                elif vec is not None:
+                    prob = prob_gumbel_softmax if mode == "gumbel_softmax" else prob_multinomial_soft
+                    vec = _ps_out(y, it, noise.part_u[t - 1], prob)
+            sample_lp = logprobs.gather(1, it[:, None]).squeeze(1)   # :328,:341,:347,:358,:370,:384
+            if vec is not None:
+                vec = torch.cat([vec, vec.new_zeros(B, 1)], 1)        # :348-354,:373-378
+        # next input                                                          # :395-399
+        if ps_mode and t >= 1:
+            xt = _dropout(torch.relu(vec @ P["embed.0.weight"]), keep_e, drop_p)
+        else:
+            xt = embed_tokens(P, it, keep_e, drop_p)
+        if t >= 1:
+            unfinished = (it > 0) if t == 1 else unfinished * (it > 0)        # :403-406
+            if not keep_all_steps and unfinished.sum() == 0:                  # :407-408
+                break
+            it = it * unfinished.type_as(it)                                  # :409
+            if idx_mode:
+                seq.append(it)                                                # :411-413
+            else:
+                word_index.append(it)                                         # :415,:427
+                vec = vec * unfinished[:, None].to(vec.dtype)                 # :416-417,:428-429
+                if bool((unfinished == 0).any()):
+                    vec = torch.where(unfinished[:, None], vec, eos_one_hot)  # :419-420,:431-432
+                seq.append(vec)
+            seq_lp.append(sample_lp)                                          # :413,:423,:434
+        out, h, c, _ = core_step(P, xt, h, c, att_e, p_att, att_masks, keep_c, drop_p)  # :436
+        logprobs = F.log_softmax(logits_of(P, out), dim=1)                    # :444
+        res.step_logprobs.append(logprobs)
+        res.n_steps += 1
+    if len(seq) == 0:
+        # the reference crashes on torch.cat([]) here; return width 0
+        res.seq = torch.zeros(B, 0, dtype=torch.long)
+        res.logprobs = torch.zeros(B, 0)
+        return res
+    if idx_mode:
+        res.seq = torch.stack(seq, 1)                                         # :445-447
+        res.logprobs = torch.stack(seq_lp, 1)
+    else:
+        res.seq = torch.stack(word_index, 1)                                  # :448-452
+        res.one_hots = torch.stack(seq, 1)
+        res.logprobs = torch.stack(seq_lp, 1)
+    return res
+
+
+# --------------------------------------------------------------------------------------------
+# AttModel.forward (teacher-forced XE)                 (AttModel.py:103-148, misc/utils.py:49-58)
+# --------------------------------------------------------------------------------------------
+def language_model_criterion(logp, target, mask):
+    """LanguageModelCriterion.forward                                     (misc/utils.py:49-58)"""
+    target = target[:, : logp.size(1)]
+    mask = mask[:, : logp.size(1)]
+    out = -logp.gather(2, target[:, :, None]).squeeze(2) * mask
+    return out.sum() / mask.sum()
+
+
+def forward_xe(P: Params, att_feats, att_masks, seq, masks, *, noise: SpeakerNoise,
+               drop_p: float = 0.0, return_logprobs: bool = False):
+    """ss_prob = 0 path of AttModel.forward: step i feeds seq[:, i]; stops at the first i >= 1
+    whose whole column is 0 (:133); loss over seq[:,1:], masks[:,1:] (:144)."""
+    B = att_feats.size(0)
+    att_e, p_att = prologue(P, att_feats, att_masks, noise, drop_p)
+    h = att_feats.new_zeros(B, P["core.h2h.weight"].size(1))
+    c = torch.zeros_like(h)
+    outputs = []
+    for i in range(seq.size(1) - 1):                                          # :116
+        it = seq[:, i]
+        if i >= 1 and int(seq[:, i].sum()) == 0:                              # :133
+            break
+        keep_e = None if noise.drop_embed is None else noise.drop_embed[i]
+        keep_c = None if noise.drop_core is None else noise.drop_core[i]
+        xt = embed_tokens(P, it, keep_e, drop_p)                              # :136
+        out, h, c, _ = core_step(P, xt, h, c, att_e, p_att, att_masks, keep_c, drop_p)  # :138
+        outputs.append(F.log_softmax(logits_of(P, out), dim=1))               # :140
+    logp = torch.stack(outputs, 1)                                            # :143
+    loss = language_model_criterion(logp, seq[:, 1:], masks[:, 1:])           # :144
+    return (loss, logp) if return_logprobs else loss
