@@ -50,6 +50,15 @@ struct EpiStoreParams {
   float alpha;
   int relu;
   int mode;              // 0 store, 1 C += v (plain RMW), 2 atomicAdd (split-K)
+  // optional segment mask: row r is zeroed unless (r % seg_L) < seg_lens[r / seg_L]
+  const int* seg_lens;
+  int seg_L;
+  // optional dropout after relu: injected keep bytes [M, ld_keep] or Philox(seed, stream, r*N+c)
+  const uint8_t* keep;
+  int64_t ld_keep;
+  int philox_dropout;
+  float drop_p;
+  uint64_t seed, stream;
 };
 
 struct EpiStore {
@@ -61,13 +70,32 @@ struct EpiStore {
     if (row >= M) return;
     const int ncols = min(32, N - col0);
     if (ncols <= 0) return;
-    const float rs = p.row_scale ? p.row_scale[row] : 1.f;
+    float rs = p.row_scale ? p.row_scale[row] : 1.f;
+    if (p.seg_lens && (row % p.seg_L) >= p.seg_lens[row / p.seg_L]) rs = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float x = v[j] * p.alpha;
       if (p.bias && j < ncols) x += __ldg(p.bias + col0 + j);
       if (p.relu) x = fmaxf(x, 0.f);
       v[j] = x * rs;
+    }
+    if (p.keep) {
+      const float sc = 1.f / (1.f - p.drop_p);
+      const uint8_t* k = p.keep + int64_t(row) * p.ld_keep + col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] = k[j] ? v[j] * sc : 0.f;
+    } else if (p.philox_dropout) {
+      const float sc = 1.f / (1.f - p.drop_p);
+      const uint64_t base = (uint64_t(row) * uint64_t(N) + uint64_t(col0)) >> 2;  // N % 4 == 0
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const uint4 r = Philox::gen(p.seed, p.stream, base + j4);
+        v[4 * j4 + 0] = Philox::u01(r.x) >= p.drop_p ? v[4 * j4 + 0] * sc : 0.f;
+        v[4 * j4 + 1] = Philox::u01(r.y) >= p.drop_p ? v[4 * j4 + 1] * sc : 0.f;
+        v[4 * j4 + 2] = Philox::u01(r.z) >= p.drop_p ? v[4 * j4 + 2] * sc : 0.f;
+        v[4 * j4 + 3] = Philox::u01(r.w) >= p.drop_p ? v[4 * j4 + 3] * sc : 0.f;
+      }
     }
     if (p.C) {
       float* dst = p.C + int64_t(row) * p.ldc + col0;
@@ -341,5 +369,10 @@ int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int M
   CC_LAUNCH_CHECK();
   return CC_OK;
 }
+
+// Runtime-dispatched GEMM with the generic store epilogue (defined in gemm_api.cu).
+int gemm_run(int kind, int a_major, int b_major, const void* A, int64_t lda, const void* B,
+             int64_t ldb, int M, int N, int K, int split_k, int tile_n, const EpiStoreParams& ep,
+             cudaStream_t s);
 
 }  // namespace coopcap

@@ -78,12 +78,33 @@ int pick_tile_n(int M, int N, int requested) {
   return num_m * ((N + 127) / 128) >= sms / 3 ? 128 : 64;
 }
 
+// internal entry used by the orchestration code (speaker.cu, listener.cu)
+int gemm_run(int kind, int a_major, int b_major, const void* A, int64_t lda, const void* B,
+             int64_t ldb, int M, int N, int K, int split_k, int tile_n, const EpiStoreParams& ep,
+             cudaStream_t s) {
+  coopcap_gemm_args a = {};
+  a.kind = kind; a.a_major = a_major; a.b_major = b_major;
+  a.A = A; a.lda = lda; a.B = B; a.ldb = ldb;
+  a.M = M; a.N = N; a.K = K; a.split_k = split_k < 1 ? 1 : split_k;
+  CC_REQUIRE(kind == 0 || (a_major == 0 && b_major == 0),
+             "gemm: tf32 operands must be K-major (MN-major tf32 needs the 32B-atom swizzle)");
+  CC_REQUIRE(a.split_k <= 1 || (ep.mode == 2 && ep.C16 == nullptr && ep.Ct16 == nullptr),
+             "gemm: split_k > 1 needs mode 2 (atomicAdd) and fp32 output only");
+  const int bn = pick_tile_n(M, N, tile_n);
+  if (kind == 0) {
+    if (bn == 256) return dispatch_major<0, 256>(&a, ep, s);
+    if (bn == 128) return dispatch_major<0, 128>(&a, ep, s);
+    return dispatch_major<0, 64>(&a, ep, s);
+  }
+  if (bn == 256) return launch_gemm_tc<1, 256, 0, 0, EpiStore>(A, lda, B, ldb, M, N, K, a.split_k, ep, s);
+  if (bn == 128) return launch_gemm_tc<1, 128, 0, 0, EpiStore>(A, lda, B, ldb, M, N, K, a.split_k, ep, s);
+  return launch_gemm_tc<1, 64, 0, 0, EpiStore>(A, lda, B, ldb, M, N, K, a.split_k, ep, s);
+}
+
 int gemm_store(const coopcap_gemm_args* a, cudaStream_t s) {
   CC_REQUIRE(a != nullptr, "gemm: null args");
   CC_REQUIRE(a->kind == 0 || a->kind == 1, "gemm: kind %d", a->kind);
-  CC_REQUIRE(a->split_k <= 1 || (a->mode == 2 && a->C16 == nullptr && a->Ct16 == nullptr),
-             "gemm: split_k > 1 needs mode 2 (atomicAdd) and fp32 output only");
-  EpiStoreParams ep;
+  EpiStoreParams ep = {};
   ep.C = a->C;
   ep.C16 = reinterpret_cast<__nv_bfloat16*>(a->C16);
   ep.Ct16 = reinterpret_cast<__nv_bfloat16*>(a->Ct16);
@@ -108,16 +129,8 @@ int gemm_store(const coopcap_gemm_args* a, cudaStream_t s) {
     CC_LAUNCH_CHECK();
     return CC_OK;
   }
-  const int bn = pick_tile_n(a->M, a->N, a->tile_n);
-  if (a->kind == 0) {
-    if (bn == 256) return dispatch_major<0, 256>(a, ep, s);
-    if (bn == 128) return dispatch_major<0, 128>(a, ep, s);
-    return dispatch_major<0, 64>(a, ep, s);
-  } else {
-    if (bn == 256) return dispatch_major<1, 256>(a, ep, s);
-    if (bn == 128) return dispatch_major<1, 128>(a, ep, s);
-    return dispatch_major<1, 64>(a, ep, s);
-  }
+  return gemm_run(a->kind, a->a_major, a->b_major, a->A, a->lda, a->B, a->ldb, a->M, a->N, a->K,
+                  a->split_k, a->tile_n, ep, s);
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, int64_t rows, int64_t cols,

@@ -1,0 +1,78 @@
+// Speaker (Att2in2) kernels other than the dense contractions: additive attention forward /
+// backward, LSTM (maxout) pointwise forward / backward, sampling + next-input gather, the
+// straight-through and log-prob logit gradients, and small reductions.
+//
+// HBM-bound kernels: bf16 storage for the region tensors (att_e, p_att), 16-byte vector loads,
+// one CTA per batch row for attention (warp per region, online softmax), warp-shuffle reductions.
+#pragma once
+#include "common.cuh"
+
+namespace coopcap {
+
+// RNG site ids (Philox "stream" = site base + step)
+enum : uint64_t {
+  SITE_DROP_ATT = 1ull << 32,
+  SITE_DROP_EMBED = 2ull << 32,
+  SITE_DROP_CORE = 3ull << 32,
+  SITE_NOISE = 4ull << 32,
+};
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 float8_to_bf16x8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// 4 dropout keep decisions for elements [4*g, 4*g+3] of a site
+__device__ __forceinline__ void keep4(const uint8_t* inj, int64_t idx4, uint64_t seed,
+                                      uint64_t stream, float p, bool (&k)[4]) {
+  if (inj) {
+    const uchar4 b = *reinterpret_cast<const uchar4*>(inj + idx4 * 4);
+    k[0] = b.x; k[1] = b.y; k[2] = b.z; k[3] = b.w;
+  } else {
+    const uint4 r = Philox::gen(seed, stream, static_cast<uint64_t>(idx4));
+    k[0] = Philox::u01(r.x) >= p; k[1] = Philox::u01(r.y) >= p;
+    k[2] = Philox::u01(r.z) >= p; k[3] = Philox::u01(r.w) >= p;
+  }
+}
+
+// block-wide reductions for 256-thread CTAs (8 warps)
+__device__ __forceinline__ float block_sum_256(float v, float* sm /*[8]*/) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += sm[i];
+  return t;
+}
+__device__ __forceinline__ float block_max_256(float v, float* sm /*[8]*/) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = sm[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) t = fmaxf(t, sm[i]);
+  return t;
+}
+
+}  // namespace coopcap

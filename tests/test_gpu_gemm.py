@@ -29,8 +29,8 @@ CASES = [
     (torch.bfloat16, 1, 1, 512, 2048, 4000, 128, 4),
     (torch.bfloat16, 1, 0, 256, 192, 320, 64, 1),
     (torch.float32, 0, 0, 130, 1024, 2048, 0, 1),
-    (torch.float32, 0, 1, 96, 200, 300, 128, 1),
-    (torch.float32, 1, 1, 512, 2048, 777, 0, 2),
+    (torch.float32, 0, 0, 96, 200, 300, 128, 1),
+    (torch.float32, 0, 0, 512, 2048, 776, 0, 2),
 ]
 
 
