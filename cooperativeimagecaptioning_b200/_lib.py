@@ -1,41 +1,105 @@
-"""ctypes binding of libcoopcap.so (see include/coopcap.h).
+"""ctypes binding of libcoopcap.so, generated from include/coopcap.h.
 
-There is no CPU fallback and no alternative backend: if the library is missing or a call fails
-the error is raised to the caller.
+The struct layouts and function prototypes are parsed out of the header at import time, so the
+Python side cannot drift from the C ABI; `load()` additionally checks every struct size against
+`coopcap_sizeof`.  There is no CPU fallback and no alternative backend: if the library is missing
+or a call fails the error is raised to the caller.
 """
 from __future__ import annotations
 
 import ctypes as C
 import os
+import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcoopcap.so")
-
-c_void_p = C.c_void_p
-c_int = C.c_int
-c_i64 = C.c_int64
-c_float = C.c_float
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "coopcap.h")
 
 
 class CoopcapError(RuntimeError):
     pass
 
 
-class GemmArgs(C.Structure):
-    _fields_ = [
-        ("kind", c_int), ("a_major", c_int), ("b_major", c_int),
-        ("A", c_void_p), ("lda", c_i64),
-        ("B", c_void_p), ("ldb", c_i64),
-        ("M", c_int), ("N", c_int), ("K", c_int),
-        ("alpha", c_float),
-        ("bias", c_void_p), ("row_scale", c_void_p),
-        ("relu", c_int), ("mode", c_int),
-        ("C", c_void_p), ("ldc", c_i64),
-        ("C16", c_void_p), ("ldc16", c_i64),
-        ("Ct16", c_void_p), ("ldct", c_i64),
-        ("split_k", c_int), ("tile_n", c_int), ("backend", c_int),
-    ]
+_SCALARS = {
+    "int": C.c_int, "float": C.c_float, "int64_t": C.c_int64, "uint64_t": C.c_uint64,
+    "coopcap_stream_t": C.c_void_p,
+}
 
+
+def _ctype_of(decl_type: str, structs):
+    t = decl_type.replace("const", "").strip()
+    if t.endswith("*"):
+        base = t[:-1].strip()
+        if base in structs:
+            return C.POINTER(structs[base])
+        if base == "int" and False:
+            return C.POINTER(C.c_int)
+        return C.c_void_p
+    if t in _SCALARS:
+        return _SCALARS[t]
+    raise CoopcapError(f"coopcap.h: unsupported type {decl_type!r}")
+
+
+def _parse_header(path):
+    with open(path, "r") as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    structs, order = {}, []
+    for m in re.finditer(r"typedef\s+struct\s+(\w+)\s*\{(.*?)\}\s*(\w+)\s*;", src, flags=re.S):
+        name, body = m.group(3), m.group(2)
+        fields = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            mm = re.match(r"^(.*?)([\w\s,\*]+)$", decl)
+            # split "type a, b, c": the type is everything up to the first declarator
+            parts = decl.split(",")
+            first = parts[0].strip()
+            fm = re.match(r"^(.*?[\s\*])(\w+)$", first)
+            if not fm:
+                raise CoopcapError(f"coopcap.h: cannot parse field {decl!r} of {name}")
+            ftype = fm.group(1).strip()
+            names = [fm.group(2)] + [p.strip() for p in parts[1:]]
+            for n in names:
+                t = ftype
+                while n.startswith("*"):
+                    t, n = t + "*", n[1:].strip()
+                fields.append((n, _ctype_of(t, structs)))
+        cls = type(name, (C.Structure,), {"_fields_": fields})
+        structs[name] = cls
+        order.append(name)
+    funcs = {}
+    body = re.sub(r"typedef\s+struct\s+\w+\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
+    for m in re.finditer(r"\b(int|const char\s*\*)\s+(coopcap_\w+)\s*\(([^)]*)\)\s*;", body):
+        ret, fname, args = m.group(1), m.group(2), m.group(3).strip()
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                am = re.match(r"^(.*?[\s\*])(\w+)$", a)
+                argtypes.append(_ctype_of(am.group(1).strip(), structs))
+        funcs[fname] = (C.c_char_p if "char" in ret else C.c_int, argtypes)
+    return structs, order, funcs
+
+
+STRUCTS, STRUCT_ORDER, FUNCTIONS = _parse_header(HEADER_PATH)
+
+GemmArgs = STRUCTS["coopcap_gemm_args"]
+SpeakerPack = STRUCTS["coopcap_speaker_pack"]
+Speaker = STRUCTS["coopcap_speaker"]
+SpeakerGrads = STRUCTS["coopcap_speaker_grads"]
+ListenerPack = STRUCTS["coopcap_listener_pack"]
+Listener = STRUCTS["coopcap_listener"]
+ListenerGrads = STRUCTS["coopcap_listener_grads"]
+
+_SIZEOF_IDS = {"coopcap_gemm_args": 0, "coopcap_speaker_pack": 1, "coopcap_speaker": 2,
+               "coopcap_speaker_grads": 3, "coopcap_listener_pack": 4, "coopcap_listener": 5,
+               "coopcap_listener_grads": 6}
+
+# kept for tests: name -> argtypes
+SIGNATURES = {k: v[1] for k, v in FUNCTIONS.items()}
 
 _lib = None
 
@@ -50,9 +114,17 @@ def load() -> C.CDLL:
             f"{LIB_PATH} not found: build it with `python -m cooperativeimagecaptioning_b200.build` "
             "(or __graft_entry__.build()). There is no fallback path.")
     lib = C.CDLL(LIB_PATH)
-    lib.coopcap_last_error.restype = C.c_char_p
-    lib.coopcap_version.restype = c_int
-    _declare(lib)
+    for name, (restype, argtypes) in FUNCTIONS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise CoopcapError(f"libcoopcap.so does not export {name} (stale build?)") from e
+        fn.restype = restype
+        fn.argtypes = argtypes
+    for sname, sid in _SIZEOF_IDS.items():
+        got, want = C.sizeof(STRUCTS[sname]), lib.coopcap_sizeof(sid)
+        if got != want:
+            raise CoopcapError(f"struct {sname}: ctypes size {got} != C size {want}")
     _lib = lib
     return lib
 
@@ -61,24 +133,3 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = load().coopcap_last_error().decode("utf-8", "replace")
         raise CoopcapError(f"libcoopcap call failed (code {rc}): {msg}")
-
-
-# name -> argtypes; every function returns int.  Kept in one table so tests can verify that the
-# library exports exactly what include/coopcap.h declares.
-SIGNATURES = {}
-
-
-def _sig(name, *argtypes):
-    SIGNATURES[name] = list(argtypes)
-
-
-_sig("coopcap_device_info", C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int))
-_sig("coopcap_gemm", C.POINTER(GemmArgs), c_void_p)
-_sig("coopcap_cast_bf16", c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p)
-
-
-def _declare(lib):
-    for name, argtypes in SIGNATURES.items():
-        fn = getattr(lib, name)
-        fn.argtypes = argtypes
-        fn.restype = c_int

@@ -82,6 +82,19 @@ const char* coopcap_last_error(void) { return coopcap::g_last_error; }
 
 int coopcap_version(void) { return COOPCAP_VERSION; }
 
+int coopcap_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(coopcap_gemm_args);
+    case 1: return (int)sizeof(coopcap_speaker_pack);
+    case 2: return (int)sizeof(coopcap_speaker);
+    case 3: return (int)sizeof(coopcap_speaker_grads);
+    case 4: return (int)sizeof(coopcap_listener_pack);
+    case 5: return (int)sizeof(coopcap_listener);
+    case 6: return (int)sizeof(coopcap_listener_grads);
+    default: return -1;
+  }
+}
+
 int coopcap_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
   CC_CHECK_CUDA(cudaGetDevice(&dev));

@@ -1,0 +1,582 @@
+// Speaker (Att2in2) forward: weight packing, prologue (att_embed / ctx2att over packed regions),
+// and the decode loop (gate GEMM -> additive attention -> a2c GEMM -> maxout-LSTM pointwise ->
+// logit GEMM -> sampling + next-input gather).  See include/coopcap.h for the buffer layout and
+// the reference lines each piece replaces.
+#include "../../include/coopcap.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "speaker_kernels.cuh"
+
+namespace coopcap {
+
+using bf16 = __nv_bfloat16;
+
+// ------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------
+// fp32 [rows, cols] -> bf16 block of a wider matrix (ld_dst), 4 elements per thread
+__global__ void cast_block_kernel(const float* __restrict__ src, int64_t rows, int cols,
+                                  bf16* __restrict__ dst, int64_t ld_dst) {
+  const int64_t n4 = rows * (cols / 4);
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / (cols / 4);
+    const int c = int(i % (cols / 4)) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + r * cols + c);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst + r * ld_dst + c) = o;
+  }
+}
+
+int cast_block(const float* src, int64_t rows, int cols, void* dst, int64_t ld_dst,
+               cudaStream_t s) {
+  CC_REQUIRE(cols % 4 == 0 && ld_dst % 4 == 0, "cast_block: cols %d / ld %lld not multiple of 4",
+             cols, (long long)ld_dst);
+  if (rows <= 0) return CC_OK;
+  const int64_t n4 = rows * (cols / 4);
+  int64_t want = (n4 + 255) / 256, cap_blocks = int64_t(num_sms()) * 16;
+  int grid = int(want < cap_blocks ? want : cap_blocks);
+  cast_block_kernel<<<grid, 256, 0, s>>>(src, rows, cols, reinterpret_cast<bf16*>(dst), ld_dst);
+  CC_LAUNCH_CHECK();
+  return CC_OK;
+}
+
+__global__ void bias_cat_kernel(const float* __restrict__ b_i2h, const float* __restrict__ b_h2h,
+                                const float* __restrict__ b_h2att, int n5r, int A,
+                                float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n5r) out[i] = b_i2h[i] + b_h2h[i];
+  else if (i < n5r + A) out[i] = b_h2att[i - n5r];
+}
+
+// ------------------------------------------------------------------------------------------
+// prologue: cast + pack valid regions
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_row(const int* __restrict__ off, int B, int r) {
+  // largest b with off[b] <= r
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= r) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void pack_att_kernel(const float* __restrict__ att, const int* __restrict__ off, int B,
+                                int L, int D, bf16* __restrict__ out) {
+  const int r = blockIdx.x;
+  int64_t src_row;
+  if (off) {
+    const int b = find_row(off, B, r);
+    src_row = int64_t(b) * L + (r - off[b]);
+  } else {
+    src_row = r;
+  }
+  const float4* src = reinterpret_cast<const float4*>(att + src_row * D);
+  uint2* dst = reinterpret_cast<uint2*>(out + int64_t(r) * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    const float4 v = __ldcs(src + i);  // streamed once
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b2 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b2);
+    dst[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// embedding of the fed token: x = dropout(relu(embed[tok]))            (AttModel.py:74-76)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void embed_row(const float* __restrict__ embed, int64_t tok, int E,
+                                          const uint8_t* keep_row, uint64_t seed, uint64_t stream,
+                                          int64_t elem_base, float drop_p, bf16* __restrict__ dst) {
+  const float sc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const float4* src = reinterpret_cast<const float4*>(embed + tok * E);
+  for (int i = threadIdx.x; i < E / 4; i += blockDim.x) {
+    float4 v = __ldg(src + i);
+    float x[4] = {fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)};
+    if (drop_p > 0.f) {
+      bool k[4];
+      keep4(keep_row, keep_row ? i : (elem_base >> 2) + i, seed, stream, drop_p, k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = k[j] ? x[j] * sc : 0.f;
+    }
+    __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b2 = __floats2bfloat162_rn(x[2], x[3]);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b2);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+}
+
+// step 0: feed the start token, zero h_{-1} and c_{-1}
+__global__ void start_step_kernel(const float* __restrict__ embed, int64_t start, int B, int E, int R,
+                                  const uint8_t* __restrict__ keep_embed, uint64_t seed,
+                                  float drop_p, bf16* __restrict__ xh0, float* __restrict__ c0,
+                                  int64_t* __restrict__ tok_fed0) {
+  const int b = blockIdx.x;
+  bf16* row = xh0 + int64_t(b) * (E + R);
+  embed_row(embed, start, E, keep_embed ? keep_embed + int64_t(b) * E : nullptr, seed,
+            SITE_DROP_EMBED, int64_t(b) * E, drop_p, row);
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    row[E + i] = __float2bfloat16_rn(0.f);
+    c0[int64_t(b) * R + i] = 0.f;
+  }
+  if (threadIdx.x == 0) tok_fed0[b] = start;
+}
+
+// ------------------------------------------------------------------------------------------
+// additive attention forward                                           (AttModel.py:465-489)
+//   e_l = sum_j alpha_j tanh(p_att[l,j] + att_h[j]);  w = softmax_l(e) over the valid regions
+//   att_res[j] = sum_l w_l att_e[l,j]
+// one CTA per batch row; HBM-bound: reads p_att[b] and att_e[b] once (bf16, 16-byte loads).
+// ------------------------------------------------------------------------------------------
+constexpr int ATT_THREADS = 256;
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_fwd_kernel(const bf16* __restrict__ p_att16, const bf16* __restrict__ att_e16,
+                     const int* __restrict__ off, int Lfix, const float* __restrict__ s_row0,
+                     int64_t lds, int att_h_col, const float* __restrict__ w_alpha,
+                     bf16* __restrict__ att_res16, float* __restrict__ att_w, int A, int R) {
+  extern __shared__ float sm[];
+  float* s_ah = sm;              // [A]
+  float* s_al = sm + A;          // [A]
+  float* s_red = sm + 2 * A;     // [8]
+  float* s_e = sm + 2 * A + 8;   // [Lb]
+  const int b = blockIdx.x;
+  const int r0 = off ? off[b] : b * Lfix;
+  const int Lb = off ? off[b + 1] - r0 : Lfix;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* att_h = s_row0 + int64_t(b) * lds + att_h_col;
+  for (int i = threadIdx.x; i < A; i += ATT_THREADS) {
+    s_ah[i] = att_h[i];
+    s_al[i] = w_alpha[i];
+  }
+  __syncthreads();
+  // phase 1: scores, one warp per region
+  for (int l = warp; l < Lb; l += ATT_THREADS / 32) {
+    const uint4* prow = reinterpret_cast<const uint4*>(p_att16 + int64_t(r0 + l) * A);
+    float acc = 0.f;
+    for (int c = lane; c < A / 8; c += 32) {
+      const uint4 u = __ldg(prow + c);
+      float f[8];
+      bf16x8_to_float(u, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += s_al[c * 8 + j] * tanh_fast(f[j] + s_ah[c * 8 + j]);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_e[l] = acc;
+  }
+  __syncthreads();
+  // phase 2: softmax over the valid regions
+  float m = -INFINITY;
+  for (int l = threadIdx.x; l < Lb; l += ATT_THREADS) m = fmaxf(m, s_e[l]);
+  m = block_max_256(m, s_red);
+  float sum = 0.f;
+  for (int l = threadIdx.x; l < Lb; l += ATT_THREADS) {
+    const float e = __expf(s_e[l] - m);
+    s_e[l] = e;
+    sum += e;
+  }
+  sum = block_sum_256(sum, s_red);
+  const float inv = 1.f / sum;
+  __syncthreads();
+  for (int l = threadIdx.x; l < Lb; l += ATT_THREADS) {
+    const float w = s_e[l] * inv;
+    s_e[l] = w;
+    att_w[r0 + l] = w;
+  }
+  __syncthreads();
+  // phase 3: weighted sum; thread owns 8 columns, thread groups stride over the regions
+  const int tpr = R / 8;               // threads per region row
+  const int groups = ATT_THREADS / tpr;
+  const int g = threadIdx.x / tpr, c = threadIdx.x % tpr;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (g < groups) {
+    for (int l = g; l < Lb; l += groups) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(att_e16 + int64_t(r0 + l) * R) + c);
+      float f[8];
+      bf16x8_to_float(u, f);
+      const float w = s_e[l];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += w * f[j];
+    }
+  }
+  __syncthreads();
+  // cross-group reduction through shared memory (reuses s_ah/s_al: 2A >= groups*R is not
+  // guaranteed, so use a dedicated region after s_e)
+  float* s_acc = s_e + ((Lb + 3) & ~3);  // [groups][R]
+  if (g < groups) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_acc[g * R + c * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < R; j += ATT_THREADS) {
+    float t = 0.f;
+    for (int gg = 0; gg < groups; ++gg) t += s_acc[gg * R + j];
+    att_res16[int64_t(b) * R + j] = __float2bfloat16_rn(t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// maxout-LSTM pointwise forward                                         (AttModel.py:515-530)
+// ------------------------------------------------------------------------------------------
+__global__ void lstm_fwd_kernel(const float* __restrict__ s, int64_t lds, const float* __restrict__ u,
+                                const float* __restrict__ c_prev, float* __restrict__ c_next,
+                                bf16* __restrict__ h_dst, int64_t ld_h, bf16* __restrict__ out16,
+                                const uint8_t* __restrict__ keep, uint64_t seed, uint64_t stream,
+                                float drop_p, int B, int R) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // 4 units per thread
+  const int per_row = R / 4;
+  if (idx >= B * per_row) return;
+  const int b = idx / per_row, j = (idx % per_row) * 4;
+  const float* sr = s + int64_t(b) * lds;
+  const float4 si = *reinterpret_cast<const float4*>(sr + j);
+  const float4 sf = *reinterpret_cast<const float4*>(sr + R + j);
+  const float4 so = *reinterpret_cast<const float4*>(sr + 2 * R + j);
+  const float4 s1 = *reinterpret_cast<const float4*>(sr + 3 * R + j);
+  const float4 s2 = *reinterpret_cast<const float4*>(sr + 4 * R + j);
+  const float4 u1 = *reinterpret_cast<const float4*>(u + int64_t(b) * 2 * R + j);
+  const float4 u2 = *reinterpret_cast<const float4*>(u + int64_t(b) * 2 * R + R + j);
+  const float4 cp = *reinterpret_cast<const float4*>(c_prev + int64_t(b) * R + j);
+  const float ai[4] = {si.x, si.y, si.z, si.w}, af[4] = {sf.x, sf.y, sf.z, sf.w};
+  const float ao[4] = {so.x, so.y, so.z, so.w};
+  const float a1[4] = {s1.x + u1.x, s1.y + u1.y, s1.z + u1.z, s1.w + u1.w};
+  const float a2[4] = {s2.x + u2.x, s2.y + u2.y, s2.z + u2.z, s2.w + u2.w};
+  const float ac[4] = {cp.x, cp.y, cp.z, cp.w};
+  float cn[4], h[4], o[4];
+  bool k[4] = {true, true, true, true};
+  const float sc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  if (drop_p > 0.f)
+    keep4(keep, (int64_t(b) * R + j) >> 2, seed, stream, drop_p, k);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float ig = 1.f / (1.f + expf(-ai[q]));
+    const float fg = 1.f / (1.f + expf(-af[q]));
+    const float og = 1.f / (1.f + expf(-ao[q]));
+    const float g = fmaxf(a1[q], a2[q]);
+    cn[q] = fg * ac[q] + ig * g;
+    h[q] = og * tanhf(cn[q]);
+    o[q] = k[q] ? h[q] * sc : 0.f;
+  }
+  *reinterpret_cast<float4*>(c_next + int64_t(b) * R + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+  {
+    __nv_bfloat162 a = __floats2bfloat162_rn(h[0], h[1]), b2 = __floats2bfloat162_rn(h[2], h[3]);
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&a);
+    w.y = *reinterpret_cast<uint32_t*>(&b2);
+    *reinterpret_cast<uint2*>(h_dst + int64_t(b) * ld_h + j) = w;
+  }
+  {
+    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b2 = __floats2bfloat162_rn(o[2], o[3]);
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&a);
+    w.y = *reinterpret_cast<uint32_t*>(&b2);
+    *reinterpret_cast<uint2*>(out16 + int64_t(b) * R + j) = w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// sampling: one CTA per row, one pass over the logits (online log-sum-exp), then the fed token's
+// embedding is written as the next step's input.
+//   greedy        : id = argmax z                                        (AttModel.py:327-329)
+//   multinomial   : id = argmax exp(lp/T)/E == argmax (z/T - log E)       (:332-343)
+//   ST gumbel     : id = argmax (z+G), y = softmax((z+G)/tau)              (gumbel.py:6-30)
+//   ST multinomial: id = argmax (z/tau - log E), y = softmax(z/tau)        (multinomial.py:4-27)
+// ------------------------------------------------------------------------------------------
+struct OnlineLse {
+  float m, s;
+  __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
+  __device__ __forceinline__ void add(float x) {
+    if (x > m) { s = s * __expf(m - x) + 1.f; m = x; }
+    else s += __expf(x - m);
+  }
+  __device__ __forceinline__ void merge(float m2, float s2) {
+    if (m2 == -INFINITY) return;
+    if (m2 > m) { s = s * __expf(m - m2) + s2; m = m2; }
+    else s += s2 * __expf(m2 - m);
+  }
+};
+
+__device__ __forceinline__ float gumbel_of(float u) {
+  return -logf(-logf(u + 1e-20f) + 1e-20f);   // gumbel.py:6-11
+}
+
+// 4 noise values for elements [4*v4, 4*v4+3] of a row: injected (fp32 row) or Philox uniforms
+__device__ __forceinline__ void noise4(const float* inj_row, int v4, uint64_t seed, uint64_t stream,
+                                       uint64_t ctr, float (&u)[4]) {
+  if (inj_row) {
+    const float4 t = *reinterpret_cast<const float4*>(inj_row + 4 * v4);
+    u[0] = t.x; u[1] = t.y; u[2] = t.z; u[3] = t.w;
+  } else {
+    const uint4 r = Philox::gen(seed, stream, ctr);
+    u[0] = Philox::u01(r.x); u[1] = Philox::u01(r.y); u[2] = Philox::u01(r.z); u[3] = Philox::u01(r.w);
+  }
+}
+__device__ __forceinline__ float exp1_of_u(float u) { return -logf(1.f - u); }  // Exp(1) from U[0,1)
+
+constexpr int SAMPLE_THREADS = 256;
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
+              const float* __restrict__ noise, uint64_t seed, uint64_t nstream,
+              const int64_t* __restrict__ forced, const uint8_t* __restrict__ unf_prev,
+              int64_t* __restrict__ tok_raw, int64_t* __restrict__ tok_out,
+              int64_t* __restrict__ tok_fed_next, float* __restrict__ logp, float* __restrict__ lse_o,
+              float* __restrict__ ymax_o, float* __restrict__ ysum_o, uint8_t* __restrict__ unf,
+              // next-step input
+              const float* __restrict__ embed, int E, const uint8_t* __restrict__ keep_embed_next,
+              uint64_t estream, float drop_p, bf16* __restrict__ xh_next, int64_t ld_xh) {
+  __shared__ float s_m1[8], s_s1[8], s_m2[8], s_s2[8], s_bv[8];
+  __shared__ int s_bi[8];
+  __shared__ int64_t s_fed;
+  const int b = blockIdx.x;
+  const float* zr = z + int64_t(b) * V1;
+  const float* nr = noise ? noise + int64_t(b) * V1 : nullptr;
+  OnlineLse l1, l2;
+  l1.init();
+  l2.init();
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  const bool need_y = (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL);
+  const bool use_noise = (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_MULTINOMIAL ||
+                          mode == COOPCAP_SAMPLE_ST_MULTINOMIAL);
+  for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += SAMPLE_THREADS) {
+    const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
+    const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
+    float u4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (use_noise) noise4(nr, v4, seed, nstream, uint64_t(b) * (V1 / 4) + v4, u4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float x = x4[q];
+      l1.add(x);
+      float score = x;
+      if (mode == COOPCAP_SAMPLE_ST_GUMBEL) {
+        score = (x + gumbel_of(u4[q])) * inv_tau;
+        l2.add(score);
+      } else if (mode == COOPCAP_SAMPLE_MULTINOMIAL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL) {
+        const float e = nr ? u4[q] : exp1_of_u(u4[q]);
+        score = x * inv_tau - logf(e);
+        if (need_y) l2.add(x * inv_tau);
+      }
+      if (mode != COOPCAP_SAMPLE_NONE && (score > bv)) { bv = score; bi = 4 * v4 + q; }
+    }
+  }
+  // warp then block merge
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m1 = __shfl_xor_sync(0xffffffffu, l1.m, o), s1 = __shfl_xor_sync(0xffffffffu, l1.s, o);
+    l1.merge(m1, s1);
+    const float m2 = __shfl_xor_sync(0xffffffffu, l2.m, o), s2 = __shfl_xor_sync(0xffffffffu, l2.s, o);
+    l2.merge(m2, s2);
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_m1[warp] = l1.m; s_s1[warp] = l1.s; s_m2[warp] = l2.m; s_s2[warp] = l2.s;
+    s_bv[warp] = bv; s_bi[warp] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < SAMPLE_THREADS / 32; ++w) {
+      l1.merge(s_m1[w], s_s1[w]);
+      l2.merge(s_m2[w], s_s2[w]);
+      if (s_bv[w] > bv || (s_bv[w] == bv && s_bi[w] < bi)) { bv = s_bv[w]; bi = s_bi[w]; }
+    }
+    const float lse = l1.m + logf(l1.s);
+    const int64_t raw = (mode == COOPCAP_SAMPLE_NONE) ? 0 : int64_t(bi);
+    const int64_t fed = forced ? forced[b] : raw;
+    const bool up = unf_prev ? (unf_prev[b] != 0) : true;
+    const bool un = up && (fed > 0);                 // AttModel.py:403-406
+    tok_raw[b] = raw;
+    tok_out[b] = un ? fed : 0;                       // :409
+    tok_fed_next[b] = fed;
+    logp[b] = zr[fed] - lse;
+    lse_o[b] = lse;
+    ymax_o[b] = l2.m;
+    ysum_o[b] = l2.s;
+    unf[b] = un ? 1 : 0;
+    s_fed = fed;
+  }
+  __syncthreads();
+  if (xh_next) {
+    embed_row(embed, s_fed, E, keep_embed_next ? keep_embed_next + int64_t(b) * E : nullptr, seed,
+              estream, int64_t(b) * E, drop_p, xh_next + int64_t(b) * ld_xh);
+  }
+}
+
+// caption summary after the last step: k_b = number of leading non-zero ids, n = max_b k_b,
+// cap_len[b] = min(k_b + 2, n + 1)                    (AlternatingJointModel.py:353-355)
+__global__ void caption_summary_kernel(const int64_t* __restrict__ tok_out, int B, int n_steps,
+                                       int* __restrict__ n_out, int* __restrict__ cap_len) {
+  __shared__ int s_max;
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int k = 0;
+    while (k < n_steps && tok_out[int64_t(k) * B + b] > 0) ++k;
+    cap_len[b] = k;
+    atomicMax(&s_max, k);
+  }
+  __syncthreads();
+  const int n = s_max;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) cap_len[b] = min(cap_len[b] + 2, n + 1);
+  if (threadIdx.x == 0) n_out[0] = n;
+}
+
+// ------------------------------------------------------------------------------------------
+// orchestration
+// ------------------------------------------------------------------------------------------
+static int check_dims(const coopcap_speaker* c) {
+  CC_REQUIRE(c != nullptr, "speaker: null context");
+  CC_REQUIRE(c->B > 0 && c->L > 0 && c->NL > 0, "speaker: empty batch B=%d L=%d NL=%d", c->B, c->L,
+             c->NL);
+  CC_REQUIRE(c->D % 8 == 0 && c->R % 8 == 0 && c->E % 8 == 0 && c->A % 8 == 0 && c->V1 % 4 == 0,
+             "speaker: D,R,E,A must be multiples of 8 and V1 of 4");
+  CC_REQUIRE(ATT_THREADS % (c->R / 8) == 0 && c->R / 8 <= ATT_THREADS,
+             "speaker: R/8 must divide %d", ATT_THREADS);
+  CC_REQUIRE(c->n_steps >= 0 && c->n_steps <= c->cap, "speaker: n_steps %d > cap %d", c->n_steps,
+             c->cap);
+  CC_REQUIRE(c->drop_p >= 0.f && c->drop_p < 1.f, "speaker: drop_p %f", c->drop_p);
+  return CC_OK;
+}
+
+size_t attention_smem_bytes(int A, int R, int L) {
+  const int groups = ATT_THREADS / (R / 8);
+  return sizeof(float) * (2 * A + 8 + ((L + 3) & ~3) + groups * R);
+}
+
+int speaker_prologue_fwd(const coopcap_speaker* c, cudaStream_t s) {
+  int rc = check_dims(c);
+  if (rc) return rc;
+  pack_att_kernel<<<c->NL, 256, 0, s>>>(c->att_feats, c->att_off, c->B, c->L, c->D,
+                                        reinterpret_cast<bf16*>(c->att16));
+  CC_LAUNCH_CHECK();
+  EpiStoreParams ep = {};
+  ep.alpha = 1.f;
+  ep.bias = c->b_att_embed;
+  ep.relu = 1;
+  ep.C16 = reinterpret_cast<bf16*>(c->att_e16);
+  ep.ldc16 = c->R;
+  if (c->drop_p > 0.f) {
+    ep.drop_p = c->drop_p;
+    if (c->keep_att) { ep.keep = c->keep_att; ep.ld_keep = c->R; }
+    else { ep.philox_dropout = 1; ep.seed = c->seed; ep.stream = SITE_DROP_ATT; }
+  }
+  rc = gemm_run(0, 0, 0, c->att16, c->D, c->w_att_embed16, c->D, c->NL, c->R, c->D, 1, 0, ep, s);
+  if (rc) return rc;
+  EpiStoreParams e2 = {};
+  e2.alpha = 1.f;
+  e2.bias = c->b_ctx2att;
+  e2.C16 = reinterpret_cast<bf16*>(c->p_att16);
+  e2.ldc16 = c->A;
+  return gemm_run(0, 0, 0, c->att_e16, c->R, c->w_ctx2att16, c->R, c->NL, c->A, c->R, 1, 0, e2, s);
+}
+
+int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
+  int rc = check_dims(c);
+  if (rc) return rc;
+  const int B = c->B, R = c->R, E = c->E, A = c->A, V1 = c->V1;
+  const int NS = 5 * R + A, XH = E + R;
+  bf16* xh16 = reinterpret_cast<bf16*>(c->xh16);
+  bf16* att_res16 = reinterpret_cast<bf16*>(c->att_res16);
+  bf16* out16 = reinterpret_cast<bf16*>(c->out16);
+  const size_t att_smem = attention_smem_bytes(A, R, c->L);
+  static size_t att_smem_set = 0;
+  if (att_smem > 48 * 1024 && att_smem > att_smem_set) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(att_smem)));
+    att_smem_set = att_smem;
+  }
+  start_step_kernel<<<B, 128, 0, s>>>(c->embed, c->start_token, B, E, R, c->keep_embed, c->seed,
+                                      c->drop_p, xh16, c->c_all, c->tok_fed);
+  CC_LAUNCH_CHECK();
+  for (int t = 0; t < c->n_steps; ++t) {
+    float* s_t = c->s_all + int64_t(t) * B * NS;
+    float* u_t = c->u_all + int64_t(t) * B * 2 * R;
+    // gates + att_h:  [x_t | h_{t-1}] . w_cat^T + b_cat
+    EpiStoreParams e1 = {};
+    e1.alpha = 1.f; e1.bias = c->b_cat; e1.C = s_t; e1.ldc = NS;
+    rc = gemm_run(0, 0, 0, xh16 + int64_t(t) * B * XH, XH, c->w_cat16, XH, B, NS, XH, 1, 0, e1, s);
+    if (rc) return rc;
+    attention_fwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
+        reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
+        c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, att_res16 + int64_t(t) * B * R,
+        c->att_w + int64_t(t) * c->NL, A, R);
+    CC_LAUNCH_CHECK();
+    EpiStoreParams e2 = {};
+    e2.alpha = 1.f; e2.bias = c->b_a2c; e2.C = u_t; e2.ldc = 2 * R;
+    rc = gemm_run(0, 0, 0, att_res16 + int64_t(t) * B * R, R, c->w_a2c16, R, B, 2 * R, R, 1, 0, e2, s);
+    if (rc) return rc;
+    {
+      const int n = B * (R / 4);
+      lstm_fwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(
+          s_t, NS, u_t, c->c_all + int64_t(t) * B * R, c->c_all + int64_t(t + 1) * B * R,
+          xh16 + int64_t(t + 1) * B * XH + E, XH, out16 + int64_t(t) * B * R,
+          c->keep_core ? c->keep_core + int64_t(t) * B * R : nullptr, c->seed, SITE_DROP_CORE + t,
+          c->drop_p, B, R);
+      CC_LAUNCH_CHECK();
+    }
+    float* z_t = c->z_all + int64_t(t) * B * V1;
+    EpiStoreParams e3 = {};
+    e3.alpha = 1.f; e3.bias = c->b_logit; e3.C = z_t; e3.ldc = V1;
+    rc = gemm_run(0, 0, 0, out16 + int64_t(t) * B * R, R, c->w_logit16, R, B, V1, R, 1, 0, e3, s);
+    if (rc) return rc;
+    sample_kernel<<<B, SAMPLE_THREADS, 0, s>>>(
+        z_t, V1, c->mode, c->inv_tau, c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed,
+        SITE_NOISE + t, c->forced ? c->forced + int64_t(t) * B : nullptr,
+        t > 0 ? c->unfinished + int64_t(t - 1) * B : nullptr, c->tok_raw + int64_t(t) * B,
+        c->tok_out + int64_t(t) * B, c->tok_fed + int64_t(t + 1) * B, c->logp + int64_t(t) * B,
+        c->lse + int64_t(t) * B, c->y_max + int64_t(t) * B, c->y_sum + int64_t(t) * B,
+        c->unfinished + int64_t(t) * B, c->embed, E,
+        c->keep_embed ? c->keep_embed + int64_t(t + 1) * B * E : nullptr, SITE_DROP_EMBED + t + 1,
+        c->drop_p, xh16 + int64_t(t + 1) * B * XH, XH);
+    CC_LAUNCH_CHECK();
+  }
+  if (c->n_out && c->cap_len) {
+    caption_summary_kernel<<<1, 256, 0, s>>>(c->tok_out, B, c->n_steps, c->n_out, c->cap_len);
+    CC_LAUNCH_CHECK();
+  }
+  return CC_OK;
+}
+
+}  // namespace coopcap
+
+extern "C" {
+
+int coopcap_speaker_pack_weights(const coopcap_speaker_pack* p, coopcap_stream_t stream) {
+  using namespace coopcap;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  CC_REQUIRE(p != nullptr, "speaker_pack: null");
+  const int R = p->R, E = p->E, A = p->A, D = p->D, XH = E + R;
+  bf16* wc = reinterpret_cast<bf16*>(p->w_cat16);
+  int rc;
+  if ((rc = cast_block(p->w_att_embed, R, D, p->w_att_embed16, D, s))) return rc;
+  if ((rc = cast_block(p->w_ctx2att, A, R, p->w_ctx2att16, R, s))) return rc;
+  if ((rc = cast_block(p->w_i2h, 5 * R, E, wc, XH, s))) return rc;
+  if ((rc = cast_block(p->w_h2h, 5 * R, R, wc + E, XH, s))) return rc;
+  CC_CHECK_CUDA(cudaMemset2DAsync(wc + int64_t(5 * R) * XH, XH * sizeof(bf16), 0, E * sizeof(bf16),
+                                  A, s));
+  if ((rc = cast_block(p->w_h2att, A, R, wc + int64_t(5 * R) * XH + E, XH, s))) return rc;
+  if ((rc = cast_block(p->w_a2c, 2 * R, R, p->w_a2c16, R, s))) return rc;
+  if ((rc = cast_block(p->w_logit, p->V1, R, p->w_logit16, R, s))) return rc;
+  const int n = 5 * R + A;
+  bias_cat_kernel<<<(n + 255) / 256, 256, 0, s>>>(p->b_i2h, p->b_h2h, p->b_h2att, 5 * R, A, p->b_cat);
+  CC_LAUNCH_CHECK();
+  return CC_OK;
+}
+
+int coopcap_speaker_prologue_fwd(const coopcap_speaker* ctx, coopcap_stream_t stream) {
+  return coopcap::speaker_prologue_fwd(ctx, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int coopcap_speaker_decode_fwd(const coopcap_speaker* ctx, coopcap_stream_t stream) {
+  return coopcap::speaker_decode_fwd(ctx, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -85,63 +85,102 @@ int coopcap_cast_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_s
 
 
 /* ---- speaker (Att2in2) -----------------------------------------------------------------------
- * One context struct describes a whole speaker pass over B rows: dimensions, inputs, parameters
- * (fp32 masters + packed bf16 operand copies), RNG configuration, and every activation that the
- * backward pass needs.  All buffers are caller-allocated; the library only launches kernels.
+ * One context struct describes a whole speaker pass over B rows: dimensions, inputs, packed
+ * parameters, RNG configuration, and every activation the backward pass needs.  All buffers are
+ * caller-allocated; the library only launches kernels (no allocation, no synchronisation).
  *
- * Layout in HBM (row-major, sizes in elements):
- *   att16      bf16 [B*L, D]            cast of att_feats (operand of att_embed fwd and wgrad)
- *   att_e16    bf16 [B*L, R]            dropout(relu(att_embed(att))) with zeros on padded regions
- *   p_att16    bf16 [B*L, A]            ctx2att(att_e)
+ * Region tensors are PACKED: only valid regions are stored, row b owning packed rows
+ * att_off[b] .. att_off[b+1]-1 (att_off == NULL: every row has L regions).  This is the varlen
+ * restatement of pack_wrapper (AttModel.py:31-51) + the mask-renormalised softmax (:480-483).
+ *
+ * Layout in HBM (row-major, sizes in elements; NL = number of valid regions in the batch):
+ *   att16      bf16 [NL, D]             cast + pack of att_feats (operand of att_embed fwd / wgrad)
+ *   att_e16    bf16 [NL, R]             dropout(relu(att_embed(att)))
+ *   p_att16    bf16 [NL, A]             ctx2att(att_e)
  *   xh16       bf16 [cap+1, B, E+R]     per step: [ x_t | h_{t-1} ]  (operand of the gate GEMM)
  *   s_all      fp32 [cap, B, 5R+A]      per step: i2h(x)+h2h(h) pre-activations | h2att(h)
  *   u_all      fp32 [cap, B, 2R]        per step: a2c(att_res) (+bias)
  *   c_all      fp32 [cap+1, B, R]       cell state, c_all[0] = 0
  *   att_res16  bf16 [cap, B, R]         attention output per step
- *   att_w      fp32 [cap, B, L]         attention weights per step (0 on padded regions)
+ *   att_w      fp32 [cap, NL]           attention weights per step (packed like the regions)
  *   out16      bf16 [cap, B, R]         dropout(h_t) (operand of the logit GEMM)
  *   z_all      fp32 [cap, B, V1]        vocabulary logits per step
- *   tok_raw / tok_out int64 [cap, B]    sampled id before / after finished-row masking
+ *   tok_raw    int64 [cap, B]           id drawn from z_t (before forcing / finished-row masking)
+ *   tok_out    int64 [cap, B]           id after forcing and finished-row masking (AttModel.py:409)
+ *   tok_fed    int64 [cap+1, B]         id embedded as the input of step t (tok_fed[0] = start)
  *   logp, lse, y_max, y_sum fp32 [cap, B]; unfinished uint8 [cap, B]
- * w_cat16 rows 0..5R-1 = [W_i2h | W_h2h], rows 5R..5R+A-1 = [0 | W_h2att]  (so that one GEMM on
- * [x_t | h_{t-1}] yields the gate pre-activations and att_h).
+ * w_cat16 rows 0..5R-1 = [W_i2h | W_h2h], rows 5R..5R+A-1 = [0 | W_h2att]  (one GEMM on
+ * [x_t | h_{t-1}] yields the gate pre-activations and att_h);  b_cat = [b_i2h+b_h2h | b_h2att].
  *
  * Replaces: AttModel.py:44-51,110-114 (prologue), :465-489 (Attention), :510-531 (Att2in2Core),
  * :74-76 (embed), :87,140,444 (logit + log_softmax), :323-444 (the decode loop of `sample`),
  * :116-141 (the loop of `forward`), gumbel.py:6-30, multinomial.py:4-27.
  */
-#define COOPCAP_SAMPLE_GREEDY 0      /* AttModel.py:327-329 */
-#define COOPCAP_SAMPLE_MULTINOMIAL 1 /* AttModel.py:332-343: ids only */
-#define COOPCAP_SAMPLE_ST_GUMBEL 2   /* gumbel.py:17-30 */
+#define COOPCAP_SAMPLE_GREEDY 0         /* AttModel.py:327-329 */
+#define COOPCAP_SAMPLE_MULTINOMIAL 1    /* AttModel.py:332-343: ids only */
+#define COOPCAP_SAMPLE_ST_GUMBEL 2      /* gumbel.py:17-30 */
 #define COOPCAP_SAMPLE_ST_MULTINOMIAL 3 /* multinomial.py:4-27 */
+#define COOPCAP_SAMPLE_NONE 4           /* teacher forcing: only lse / logp of the forced id */
+
+/* fp32 master parameters -> packed bf16 operand copies (run after every optimizer step). */
+typedef struct coopcap_speaker_pack {
+  int D;
+  int R;
+  int E;
+  int A;
+  int V1;
+  const float* w_att_embed; /* [R, D]   att_embed.0.weight */
+  const float* w_ctx2att;   /* [A, R]   ctx2att.weight */
+  const float* w_i2h;       /* [5R, E]  core.i2h.weight */
+  const float* w_h2h;       /* [5R, R]  core.h2h.weight */
+  const float* w_h2att;     /* [A, R]   core.attention.h2att.weight */
+  const float* w_a2c;       /* [2R, R]  core.a2c.weight */
+  const float* w_logit;     /* [V1, R]  logit.weight */
+  const float* b_i2h;
+  const float* b_h2h;
+  const float* b_h2att;
+  void* w_att_embed16;
+  void* w_ctx2att16;
+  void* w_cat16;            /* [5R+A, E+R] */
+  void* w_a2c16;
+  void* w_logit16;
+  float* b_cat;             /* [5R+A] */
+} coopcap_speaker_pack;
+
+int coopcap_speaker_pack_weights(const coopcap_speaker_pack* p, coopcap_stream_t stream);
 
 typedef struct coopcap_speaker {
   /* dimensions */
-  int B, L, D, R, E, A, V1;
+  int B;
+  int L;        /* padded region width of att_feats */
+  int D;
+  int R;
+  int E;
+  int A;
+  int V1;
+  int NL;       /* total valid regions (== B*L when att_off is NULL) */
   int cap;      /* allocated step capacity of the per-step buffers */
   int n_steps;  /* steps to run (<= cap) */
   /* inputs */
   const float* att_feats; /* [B, L, D] */
-  const int* att_lens;    /* [B] valid regions per row, or NULL (all L valid) */
+  const int* att_off;     /* [B+1] packed-row offsets, or NULL */
   /* parameters */
   const float* embed;     /* [V+2, E] fp32 */
   const float* b_att_embed;
   const float* b_ctx2att;
-  const float* b_i2h;
-  const float* b_h2h;
-  const float* b_h2att;
+  const float* b_cat;
   const float* b_a2c;
   const float* b_logit;
-  const float* w_alpha;   /* [A] */
-  const void* w_att_embed16; /* [R, D] */
-  const void* w_ctx2att16;   /* [A, R] */
-  const void* w_cat16;       /* [5R+A, E+R] */
-  const void* w_a2c16;       /* [2R, R] */
-  const void* w_logit16;     /* [V1, R] */
+  const float* w_alpha;   /* [A] alpha_net.weight (its bias cancels in the softmax) */
+  const void* w_att_embed16;
+  const void* w_ctx2att16;
+  const void* w_cat16;
+  const void* w_a2c16;
+  const void* w_logit16;
   /* randomness: Philox(seed, site stream, element) unless an injected tensor is given */
   uint64_t seed;
   float drop_p;
-  const uint8_t* keep_att;   /* [B, L, R] or NULL */
+  const uint8_t* keep_att;   /* [NL, R] packed, or NULL */
   const uint8_t* keep_embed; /* [cap+1, B, E] or NULL */
   const uint8_t* keep_core;  /* [cap, B, R] or NULL */
   const float* noise;        /* [cap, B, V1] uniforms (gumbel) / Exp(1) draws (multinomial) or NULL */
@@ -164,11 +203,17 @@ typedef struct coopcap_speaker {
   float* z_all;
   int64_t* tok_raw;
   int64_t* tok_out;
+  int64_t* tok_fed;
   float* logp;
   float* lse;
   float* y_max;
   float* y_sum;
   uint8_t* unfinished;
+  /* caption summary written by coopcap_speaker_decode_fwd after the last step:
+   * n_out[0] = n = output width of `sample` (AttModel.py:407-408), cap_len[b] = number of valid
+   * positions of [BOS, w_1..w_n] under _masks = [1,1,(w_1>0),..] (AlternatingJointModel.py:353-355) */
+  int* n_out;                /* [1] */
+  int* cap_len;              /* [B] */
 } coopcap_speaker;
 
 /* att16, att_e16, p_att16 from att_feats (AttModel.py:110-114 / :315-319). */
@@ -177,45 +222,175 @@ int coopcap_speaker_prologue_fwd(const coopcap_speaker* ctx, coopcap_stream_t st
  * logit GEMM -> sampling (+ next-input gather).  No host synchronisation. */
 int coopcap_speaker_decode_fwd(const coopcap_speaker* ctx, coopcap_stream_t stream);
 
-/* d(loss)/d(logits) of the straight-through samplers:
+/* d(loss)/d(logits) of the straight-through samplers for all n_steps:
+ *   g  = demb[t+1] . W_emb^T                  (listener-embedding dgrad, VSEFCModel.py:104)
  *   dz = inv_tau * y * (g - <y, g>) on unfinished rows, 0 elsewhere, y = softmax((z+G)*inv_tau)
- * g: [n_steps*B, V1] fp32 (ld ldg) = d(loss)/d(one_hot[:, :V1]); dz16: bf16 [n_steps*B, V1]. */
-int coopcap_st_backward(const coopcap_speaker* ctx, const float* g, int64_t ldg, void* dz16,
-                        coopcap_stream_t stream);
-/* d(loss)/d(logits) of sum_rows coef[row] * log_softmax(z)[row, tok[row]]
- * (REINFORCE: AlternatingJointModel.py:305-309,324; XE: misc/utils.py:49-58 with coef = -mask/sum). */
+ * demb16: bf16 [n_steps*B, E] gradient w.r.t. the listener's word embedding at caption positions
+ * 1..n_steps; w_emb16: bf16 [>=V1, E]; g_ws: fp32 [B, V1] workspace; dz16: bf16 [n_steps*B, V1]. */
+int coopcap_st_backward(const coopcap_speaker* ctx, const void* demb16, const void* w_emb16,
+                        float* g_ws, void* dz16, coopcap_stream_t stream);
+/* d(loss)/d(logits) of sum_{t,b} coef[t,b] * log_softmax(z[t,b])[tok[t,b]]
+ * (REINFORCE: AlternatingJointModel.py:305-309,324; XE: misc/utils.py:49-58 with coef = -mask/sum).
+ * tok: int64 [n_steps, B]; coef: fp32 [n_steps, B]. */
 int coopcap_logp_backward(const coopcap_speaker* ctx, const int64_t* tok, const float* coef,
                           void* dz16, coopcap_stream_t stream);
 
 typedef struct coopcap_speaker_grads {
-  /* inputs */
+  /* input */
   const void* dz16;     /* bf16 [n_steps*B, V1] */
   /* workspaces */
-  float* d_out;         /* [cap*B, R] */
+  float* d_out;         /* [cap*B, R]  d(loss)/d(dropout(h_t)) from the logit layer */
   void* dscat16;        /* bf16 [cap*B, 5R+A] : d(gate pre-acts) | d(att_h) */
   float* d_att_res;     /* [cap*B, R] */
-  void* d_att_res16;    /* unused placeholder (must be NULL) */
-  float* de;            /* [cap*B, L] d(attention scores) */
-  float* dh;            /* [2, B, R] ping-pong */
+  float* de;            /* [cap, NL] d(attention scores) */
+  float* d_xh;          /* [cap*B, E+R] : d(x_t) | d(h_{t-1}) */
   float* dc;            /* [2, B, R] ping-pong */
-  float* d_x;           /* [cap*B, E] */
-  float* d_att_e;       /* [B*L, R] */
-  void* d_p_att16;      /* bf16 [B*L, A] */
-  void* d_pre16;        /* bf16 [B*L, R] */
-  /* outputs: gradients, fp32, same shapes as the reference parameters; written (not accumulated) */
-  float* g_embed;       /* [V+2, E]  (must be zero on entry: scatter-add target) */
-  float* g_w_att_embed; float* g_b_att_embed;
-  float* g_w_ctx2att;   float* g_b_ctx2att;
-  float* g_w_cat;       /* [5R+A, E+R] packed like w_cat16 */
-  float* g_b_cat;       /* [5R+A]: d b_i2h = d b_h2h = g_b_cat[:5R]; d b_h2att = g_b_cat[5R:] */
-  float* g_w_a2c;       float* g_b_a2c;
-  float* g_w_logit;     float* g_b_logit;
-  float* g_w_alpha;     /* [A] (must be zero on entry) */
+  float* d_att_e;       /* [NL, R] */
+  void* d_p_att16;      /* bf16 [NL, A] */
+  void* d_pre16;        /* bf16 [NL, R] */
+  /* outputs: gradients, fp32, reference parameter shapes; written (overwritten), except g_embed
+   * and g_w_alpha which are accumulated into (the caller zeroes them) */
+  float* g_embed;       /* [V+2, E] */
+  float* g_w_att_embed;
+  float* g_b_att_embed;
+  float* g_w_ctx2att;
+  float* g_b_ctx2att;
+  float* g_w_i2h;
+  float* g_w_h2h;
+  float* g_b_gates;     /* [5R]: d b_i2h = d b_h2h */
+  float* g_w_h2att;
+  float* g_b_h2att;
+  float* g_w_a2c;
+  float* g_b_a2c;
+  float* g_w_logit;
+  float* g_b_logit;
+  float* g_w_alpha;     /* [A] */
 } coopcap_speaker_grads;
 
 /* BPTT through the decode loop and the prologue given d(loss)/d(logits). */
 int coopcap_speaker_decode_bwd(const coopcap_speaker* ctx, const coopcap_speaker_grads* gr,
                                coopcap_stream_t stream);
+
+/* ---- listener (VSEFC) ------------------------------------------------------------------------
+ * Image encoder, GRU caption encoder over index captions, cosine score matrix and max-violation
+ * hinge loss, forward and backward.  Captions are time-major ids tok [S, B] with per-row valid
+ * lengths len [B] (= sum(mask > 0), VSEFCModel.py:84); the packed GRU (:108-112) is restated as a
+ * masked update so no sort / unsort is needed.
+ *
+ * Layout in HBM:
+ *   fc16     bf16 [B, F]           cast of fc_feats
+ *   img_pre  fp32 [B, M]           fc W^T + b              (VSEFCModel.py:44)
+ *   im       fp32 [B, M]           l2norm(img_pre)         (:12-17,47-48)
+ *   emb16    bf16 [S, B, E]        Embedding[tok]          (:102-106)
+ *   gi_all   fp32 [S, B, 3M]       x W_ih^T + b_ih for all positions
+ *   gh       fp32 [B, 3M]          h W_hh^T + b_hh (per-step scratch)
+ *   gates    fp32 [S, B, 4M]       r | z | n | (W_hn h + b_hn) per step (saved for backward)
+ *   h32      fp32 [S+1, B, M]      hidden state, h32[0] = 0
+ *   h16      bf16 [S+1, B, M]
+ *   cap_pre  == h32[S]             state after len steps (pool 'last', :128)
+ *   cap      fp32 [B, M]           l2norm(cap_pre)
+ *   scores   fp32 [B, B]           im . cap^T              (:143-146)
+ *   cost_s, cost_im fp32 [B]; arg_s, arg_im int32 [B]   max-violation terms (:176-193)
+ *   loss_rows fp32 [B] (whole_batch vector, :197-207); loss fp32 [1] (their sum)
+ */
+typedef struct coopcap_listener_pack {
+  int F;
+  int M;
+  int E;
+  int V2;
+  const float* w_img;   /* [M, F]  img_enc.fc.weight */
+  const float* w_ih;    /* [3M, E] txt_enc.rnn.weight_ih_l0 */
+  const float* w_hh;    /* [3M, M] txt_enc.rnn.weight_hh_l0 */
+  const float* w_emb;   /* [V2, E] txt_enc.embed.weight */
+  void* w_img16;
+  void* w_ih16;
+  void* w_hh16;
+  void* w_emb16;
+} coopcap_listener_pack;
+
+int coopcap_listener_pack_weights(const coopcap_listener_pack* p, coopcap_stream_t stream);
+
+typedef struct coopcap_listener {
+  int B;
+  int S;       /* caption positions (incl. BOS) */
+  int F;
+  int M;
+  int E;
+  int V2;
+  float margin;
+  int only_one_retrieval; /* 0 off, 1 image, 2 caption (VSEFCModel.py:202-207) */
+  int no_imgnorm;
+  /* inputs */
+  const float* fc_feats;  /* [B, F] */
+  const int64_t* tok;     /* [S, B] time-major ids */
+  const int* len;         /* [B] valid positions per row */
+  /* parameters */
+  const float* w_emb;     /* [V2, E] fp32 */
+  const float* b_img;
+  const float* b_ih;
+  const float* b_hh;
+  const void* w_img16;
+  const void* w_ih16;
+  const void* w_hh16;
+  /* saved activations / outputs */
+  void* fc16;
+  float* img_pre;
+  float* im;
+  void* emb16;
+  float* gi_all;
+  float* gh;
+  float* gates;
+  float* h32;
+  void* h16;
+  float* cap;
+  float* scores;
+  float* cost_s;
+  float* cost_im;
+  int* arg_s;
+  int* arg_im;
+  float* loss_rows;
+  float* loss;
+} coopcap_listener;
+
+int coopcap_listener_fwd(const coopcap_listener* ctx, coopcap_stream_t stream);
+
+typedef struct coopcap_listener_grads {
+  /* upstream gradient: d(total)/d(loss) scalar (device, [1]) or per-row vector [B]; exactly one */
+  const float* g_loss;
+  const float* g_rows;
+  int need_param_grads;  /* 0: only demb16 (speaker turn with a frozen listener) */
+  /* workspaces */
+  float* d_im;          /* [B, M] */
+  float* d_cap;         /* [B, M] */
+  float* dh;            /* [B, M] running d(h) */
+  void* d_img_pre16;    /* bf16 [B, M] */
+  void* d_gi16;         /* bf16 [S, B, 3M] */
+  void* d_gh16;         /* bf16 [S, B, 3M] */
+  /* outputs */
+  void* demb16;         /* bf16 [S, B, E]  d(loss)/d(word embedding input) */
+  float* g_w_img;
+  float* g_b_img;
+  float* g_w_emb;       /* [V2, E]  accumulated into (caller zeroes) */
+  float* g_w_ih;
+  float* g_w_hh;
+  float* g_b_ih;
+  float* g_b_hh;
+} coopcap_listener_grads;
+
+int coopcap_listener_bwd(const coopcap_listener* ctx, const coopcap_listener_grads* gr,
+                         coopcap_stream_t stream);
+
+/* ---- optimizer (optimizer.py:233-242 + misc/utils.py:65-69 + torch.optim.Adam) ---------------
+ * One pass over a flat fp32 bucket: g *= grad_scale (1/world_size after the all-reduce);
+ * g = clamp(g, -clip, clip); Adam(lr, beta1, beta2, eps, weight_decay) with bias correction for
+ * `step` (1-based).  clip <= 0 disables clamping. */
+int coopcap_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       int64_t n, float grad_scale, float clip, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int step, coopcap_stream_t stream);
+
+/* sizeof() of the structs above, for binding self-checks: which = 0 gemm_args, 1 speaker_pack,
+ * 2 speaker, 3 speaker_grads, 4 listener_pack, 5 listener, 6 listener_grads. */
+int coopcap_sizeof(int which);
 
 #ifdef __cplusplus
 }
