@@ -1,0 +1,427 @@
+// Listener (VSEFC): image encoder, GRU caption encoder over index captions, cosine score matrix,
+// max-violation hinge loss -- forward and backward.  See include/coopcap.h for the buffer layout
+// and the reference lines each piece replaces (models/VSEFCModel.py).
+#include "../../include/coopcap.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "speaker_kernels.cuh"
+
+namespace coopcap {
+
+using bf16 = __nv_bfloat16;
+
+int cast_block(const float* src, int64_t rows, int cols, void* dst, int64_t ld_dst, cudaStream_t s);
+int colsum_bf16(const void* src, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t s);
+int wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, float* C,
+          int64_t ldc, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------
+// forward kernels
+// ------------------------------------------------------------------------------------------
+// emb16[s, b, :] = bf16(W_emb[tok[s, b], :])                           (VSEFCModel.py:102-106)
+__global__ void gather_embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ w_emb,
+                                    int E, bf16* __restrict__ emb16) {
+  const int64_t row = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(w_emb + tok[row] * E);
+  uint2* dst = reinterpret_cast<uint2*>(emb16 + row * E);
+  for (int i = threadIdx.x; i < E / 4; i += blockDim.x) {
+    const float4 v = __ldg(src + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    dst[i] = o;
+  }
+}
+
+// one GRU step (torch gate order r, z, n), masked update for rows with t >= len
+//   r = sig(gi_r + gh_r); z = sig(gi_z + gh_z); n = tanh(gi_n + r * gh_n); h' = (1-z) n + z h
+__global__ void gru_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+                               const float* __restrict__ h_prev, const int* __restrict__ len, int t,
+                               float* __restrict__ gates, float* __restrict__ h_next,
+                               bf16* __restrict__ h_next16, int B, int M) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = M / 4;
+  if (idx >= B * per_row) return;
+  const int b = idx / per_row, j = (idx % per_row) * 4;
+  const float* gib = gi + int64_t(b) * 3 * M;
+  const float* ghb = gh + int64_t(b) * 3 * M;
+  const float4 ir = *reinterpret_cast<const float4*>(gib + j);
+  const float4 iz = *reinterpret_cast<const float4*>(gib + M + j);
+  const float4 in = *reinterpret_cast<const float4*>(gib + 2 * M + j);
+  const float4 hr = *reinterpret_cast<const float4*>(ghb + j);
+  const float4 hz = *reinterpret_cast<const float4*>(ghb + M + j);
+  const float4 hn = *reinterpret_cast<const float4*>(ghb + 2 * M + j);
+  const float4 hp = *reinterpret_cast<const float4*>(h_prev + int64_t(b) * M + j);
+  const float a_ir[4] = {ir.x, ir.y, ir.z, ir.w}, a_iz[4] = {iz.x, iz.y, iz.z, iz.w};
+  const float a_in[4] = {in.x, in.y, in.z, in.w}, a_hr[4] = {hr.x, hr.y, hr.z, hr.w};
+  const float a_hz[4] = {hz.x, hz.y, hz.z, hz.w}, a_hn[4] = {hn.x, hn.y, hn.z, hn.w};
+  const float a_hp[4] = {hp.x, hp.y, hp.z, hp.w};
+  const bool active = t < len[b];
+  float r[4], z[4], n[4], h[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    r[q] = 1.f / (1.f + expf(-(a_ir[q] + a_hr[q])));
+    z[q] = 1.f / (1.f + expf(-(a_iz[q] + a_hz[q])));
+    n[q] = tanhf(a_in[q] + r[q] * a_hn[q]);
+    h[q] = active ? (1.f - z[q]) * n[q] + z[q] * a_hp[q] : a_hp[q];
+  }
+  float* g = gates + int64_t(b) * 4 * M;
+  *reinterpret_cast<float4*>(g + j) = make_float4(r[0], r[1], r[2], r[3]);
+  *reinterpret_cast<float4*>(g + M + j) = make_float4(z[0], z[1], z[2], z[3]);
+  *reinterpret_cast<float4*>(g + 2 * M + j) = make_float4(n[0], n[1], n[2], n[3]);
+  *reinterpret_cast<float4*>(g + 3 * M + j) = hn;
+  *reinterpret_cast<float4*>(h_next + int64_t(b) * M + j) = make_float4(h[0], h[1], h[2], h[3]);
+  __nv_bfloat162 a = __floats2bfloat162_rn(h[0], h[1]), c = __floats2bfloat162_rn(h[2], h[3]);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a);
+  o.y = *reinterpret_cast<uint32_t*>(&c);
+  *reinterpret_cast<uint2*>(h_next16 + int64_t(b) * M + j) = o;
+}
+
+// y = x / (||x||_2 + 1e-7), one CTA (256 threads) per row          (VSEFCModel.py:12-17)
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int M,
+                                  int passthrough) {
+  __shared__ float red[8];
+  const float* xr = x + int64_t(blockIdx.x) * M;
+  float* yr = y + int64_t(blockIdx.x) * M;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < M; i += 256) ss += xr[i] * xr[i];
+  ss = block_sum_256(ss, red);
+  const float inv = passthrough ? 1.f : 1.f / (sqrtf(ss) + 1e-7f);
+  for (int i = threadIdx.x; i < M; i += 256) yr[i] = xr[i] * inv;
+}
+
+// dx = dy / (n + eps) - x (dy . x) / (n (n + eps)^2); optional fp32 and bf16 outputs
+__global__ void l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                  float* __restrict__ dx, bf16* __restrict__ dx16, int M,
+                                  int passthrough) {
+  __shared__ float red[8];
+  const float* xr = x + int64_t(blockIdx.x) * M;
+  const float* dr = dy + int64_t(blockIdx.x) * M;
+  float ss = 0.f, dot = 0.f;
+  for (int i = threadIdx.x; i < M; i += 256) {
+    ss += xr[i] * xr[i];
+    dot += xr[i] * dr[i];
+  }
+  ss = block_sum_256(ss, red);
+  dot = block_sum_256(dot, red);
+  const float n = sqrtf(ss), ne = n + 1e-7f;
+  const float a = passthrough ? 1.f : 1.f / ne;
+  const float c = (passthrough || n == 0.f) ? 0.f : dot / (n * ne * ne);
+  for (int i = threadIdx.x; i < M; i += 256) {
+    const float v = dr[i] * a - xr[i] * c;
+    if (dx) dx[int64_t(blockIdx.x) * M + i] = v;
+    if (dx16) dx16[int64_t(blockIdx.x) * M + i] = __float2bfloat16_rn(v);
+  }
+}
+
+// max-violation hinge terms                                         (VSEFCModel.py:167-193)
+//   cost_s[i]  = relu(margin + max_{j != i} S_ij - S_ii)   (caption retrieval, row max)
+//   cost_im[j] = relu(margin + max_{i != j} S_ij - S_jj)   (image retrieval, column max)
+__global__ void hinge_rows_kernel(const float* __restrict__ S, int B, float margin,
+                                  float* __restrict__ cost_s, int* __restrict__ arg_s) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int i = blockIdx.x;
+  const float* row = S + int64_t(i) * B;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = threadIdx.x; j < B; j += 256) {
+    if (j == i) continue;
+    const float v = row[j];
+    if (v > bv) { bv = v; bi = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+    const float c = (bi == 0x7fffffff) ? 0.f : fmaxf(margin + bv - row[i], 0.f);
+    cost_s[i] = c;
+    arg_s[i] = (bi == 0x7fffffff) ? i : bi;
+  }
+}
+
+__global__ void hinge_cols_kernel(const float* __restrict__ S, int B, float margin,
+                                  float* __restrict__ cost_im, int* __restrict__ arg_im) {
+  __shared__ float sv[8][33];
+  __shared__ int si[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  if (j < B) {
+    for (int i = threadIdx.y; i < B; i += 8) {
+      if (i == j) continue;
+      const float v = S[int64_t(i) * B + j];
+      if (v > bv) { bv = v; bi = i; }
+    }
+  }
+  sv[threadIdx.y][threadIdx.x] = bv;
+  si[threadIdx.y][threadIdx.x] = bi;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < B) {
+    for (int w = 1; w < 8; ++w) {
+      const float ov = sv[w][threadIdx.x];
+      const int oi = si[w][threadIdx.x];
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    const float c = (bi == 0x7fffffff) ? 0.f : fmaxf(margin + bv - S[int64_t(j) * B + j], 0.f);
+    cost_im[j] = c;
+    arg_im[j] = (bi == 0x7fffffff) ? j : bi;
+  }
+}
+
+// loss_rows = cost_s (+) cost_im according to only_one_retrieval; loss = sum (deterministic order)
+__global__ void hinge_finish_kernel(const float* __restrict__ cost_s, const float* __restrict__ cost_im,
+                                    int B, int only, float* __restrict__ loss_rows,
+                                    float* __restrict__ loss) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B; i += 256) {
+    const float v = (only == 1 ? 0.f : cost_s[i]) + (only == 2 ? 0.f : cost_im[i]);
+    loss_rows[i] = v;
+    acc += v;
+  }
+  acc = block_sum_256(acc, red);
+  if (threadIdx.x == 0) loss[0] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward kernels
+// ------------------------------------------------------------------------------------------
+// sparse backward of the max-violation hinge: one off-diagonal entry + the diagonal per row and
+// per column.  d_im / d_cap are zeroed by the caller; contributions are atomically added.
+__global__ void hinge_bwd_kernel(const float* __restrict__ im, const float* __restrict__ cap,
+                                 const float* __restrict__ cost_s, const float* __restrict__ cost_im,
+                                 const int* __restrict__ arg_s, const int* __restrict__ arg_im,
+                                 const float* __restrict__ g_loss, const float* __restrict__ g_rows,
+                                 int only, int M, float* __restrict__ d_im, float* __restrict__ d_cap) {
+  const int i = blockIdx.x;
+  const float g = g_loss ? g_loss[0] : g_rows[i];
+  const bool do_s = (only != 1) && cost_s[i] > 0.f && g != 0.f;
+  const bool do_i = (only != 2) && cost_im[i] > 0.f && g != 0.f;
+  if (do_s) {
+    const int j = arg_s[i];   // d cost_s[i] = g * (dS[i,j] - dS[i,i]),  S[i,j] = im[i] . cap[j]
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+      const float imi = im[int64_t(i) * M + k];
+      atomicAdd(d_im + int64_t(i) * M + k, g * (cap[int64_t(j) * M + k] - cap[int64_t(i) * M + k]));
+      atomicAdd(d_cap + int64_t(j) * M + k, g * imi);
+      atomicAdd(d_cap + int64_t(i) * M + k, -g * imi);
+    }
+  }
+  if (do_i) {
+    const int r = arg_im[i];  // column i: d cost_im[i] = g * (dS[r,i] - dS[i,i])
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+      const float ci = cap[int64_t(i) * M + k];
+      atomicAdd(d_cap + int64_t(i) * M + k, g * (im[int64_t(r) * M + k] - im[int64_t(i) * M + k]));
+      atomicAdd(d_im + int64_t(r) * M + k, g * ci);
+      atomicAdd(d_im + int64_t(i) * M + k, -g * ci);
+    }
+  }
+}
+
+// one reverse GRU step.  dh (in/out): on entry d(loss)/d(h_t); on exit the direct part of
+// d(loss)/d(h_{t-1}) (the recurrent part, d_gh . W_hh, is accumulated by the following GEMM).
+__global__ void gru_bwd_kernel(float* __restrict__ dh, const float* __restrict__ gates,
+                               const float* __restrict__ h_prev, const int* __restrict__ len, int t,
+                               bf16* __restrict__ d_gi16, bf16* __restrict__ d_gh16, int B, int M) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * M) return;
+  const int b = idx / M, j = idx % M;
+  const bool active = t < len[b];
+  bf16* gi = d_gi16 + int64_t(b) * 3 * M;
+  bf16* gh = d_gh16 + int64_t(b) * 3 * M;
+  if (!active) {
+    const bf16 zero = __float2bfloat16_rn(0.f);
+    gi[j] = zero; gi[M + j] = zero; gi[2 * M + j] = zero;
+    gh[j] = zero; gh[M + j] = zero; gh[2 * M + j] = zero;
+    return;  // dh passes through unchanged
+  }
+  const float* g = gates + int64_t(b) * 4 * M;
+  const float r = g[j], z = g[M + j], n = g[2 * M + j], ghn = g[3 * M + j];
+  const float hp = h_prev[idx];
+  const float d = dh[idx];
+  const float dn = d * (1.f - z);
+  const float dz = d * (hp - n);
+  const float dnp = dn * (1.f - n * n);
+  const float dzp = dz * z * (1.f - z);
+  const float drp = dnp * ghn * r * (1.f - r);
+  gi[j] = __float2bfloat16_rn(drp);
+  gi[M + j] = __float2bfloat16_rn(dzp);
+  gi[2 * M + j] = __float2bfloat16_rn(dnp);
+  gh[j] = __float2bfloat16_rn(drp);
+  gh[M + j] = __float2bfloat16_rn(dzp);
+  gh[2 * M + j] = __float2bfloat16_rn(dnp * r);
+  dh[idx] = d * z;
+}
+
+// g_w_emb[tok[s,b], :] += demb[s, b, :] for s < len[b]            (sparse embedding wgrad)
+__global__ void embed_scatter_kernel(const int64_t* __restrict__ tok, const int* __restrict__ len,
+                                     const bf16* __restrict__ demb16, int B, int E,
+                                     float* __restrict__ g_w_emb) {
+  const int64_t row = blockIdx.x;
+  const int s = int(row / B), b = int(row % B);
+  if (s >= len[b]) return;
+  float* dst = g_w_emb + tok[row] * E;
+  for (int i = threadIdx.x; i < E; i += blockDim.x)
+    atomicAdd(dst + i, __bfloat162float(demb16[row * E + i]));
+}
+
+// ------------------------------------------------------------------------------------------
+// orchestration
+// ------------------------------------------------------------------------------------------
+static int check_dims(const coopcap_listener* c) {
+  CC_REQUIRE(c != nullptr, "listener: null context");
+  CC_REQUIRE(c->B > 0 && c->S > 0, "listener: empty batch B=%d S=%d", c->B, c->S);
+  CC_REQUIRE(c->F % 8 == 0 && c->M % 8 == 0 && c->E % 8 == 0, "listener: F,M,E must be multiples of 8");
+  return CC_OK;
+}
+
+int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
+  int rc = check_dims(c);
+  if (rc) return rc;
+  const int B = c->B, S = c->S, M = c->M, E = c->E, F = c->F;
+  bf16* h16 = reinterpret_cast<bf16*>(c->h16);
+  // image branch                                                      (VSEFCModel.py:40-54)
+  if ((rc = cast_block(c->fc_feats, B, F, c->fc16, F, s))) return rc;
+  {
+    EpiStoreParams e = {};
+    e.alpha = 1.f; e.bias = c->b_img; e.C = c->img_pre; e.ldc = M;
+    if ((rc = gemm_run(0, 0, 0, c->fc16, F, c->w_img16, F, B, M, F, 1, 0, e, s))) return rc;
+  }
+  l2norm_fwd_kernel<<<B, 256, 0, s>>>(c->img_pre, c->im, M, c->no_imgnorm);
+  CC_LAUNCH_CHECK();
+  // caption branch                                                    (VSEFCModel.py:83-140)
+  gather_embed_kernel<<<S * B, 128, 0, s>>>(c->tok, c->w_emb, E, reinterpret_cast<bf16*>(c->emb16));
+  CC_LAUNCH_CHECK();
+  {
+    EpiStoreParams e = {};
+    e.alpha = 1.f; e.bias = c->b_ih; e.C = c->gi_all; e.ldc = 3 * M;
+    if ((rc = gemm_run(0, 0, 0, c->emb16, E, c->w_ih16, E, S * B, 3 * M, E, 1, 0, e, s))) return rc;
+  }
+  CC_CHECK_CUDA(cudaMemsetAsync(c->h32, 0, sizeof(float) * B * M, s));
+  CC_CHECK_CUDA(cudaMemsetAsync(h16, 0, sizeof(bf16) * B * M, s));
+  for (int t = 0; t < S; ++t) {
+    EpiStoreParams e = {};
+    e.alpha = 1.f; e.bias = c->b_hh; e.C = c->gh; e.ldc = 3 * M;
+    if ((rc = gemm_run(0, 0, 0, h16 + int64_t(t) * B * M, M, c->w_hh16, M, B, 3 * M, M, 1, 0, e, s)))
+      return rc;
+    const int n = B * (M / 4);
+    gru_fwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(
+        c->gi_all + int64_t(t) * B * 3 * M, c->gh, c->h32 + int64_t(t) * B * M, c->len, t,
+        c->gates + int64_t(t) * B * 4 * M, c->h32 + int64_t(t + 1) * B * M,
+        h16 + int64_t(t + 1) * B * M, B, M);
+    CC_LAUNCH_CHECK();
+  }
+  l2norm_fwd_kernel<<<B, 256, 0, s>>>(c->h32 + int64_t(S) * B * M, c->cap, M, 0);
+  CC_LAUNCH_CHECK();
+  // scores (tf32 operands: the hinge compares score differences against a 0.2 margin)
+  {
+    EpiStoreParams e = {};
+    e.alpha = 1.f; e.C = c->scores; e.ldc = B;
+    if ((rc = gemm_run(1, 0, 0, c->im, M, c->cap, M, B, B, M, 1, 0, e, s))) return rc;
+  }
+  hinge_rows_kernel<<<B, 256, 0, s>>>(c->scores, B, c->margin, c->cost_s, c->arg_s);
+  CC_LAUNCH_CHECK();
+  hinge_cols_kernel<<<(B + 31) / 32, dim3(32, 8), 0, s>>>(c->scores, B, c->margin, c->cost_im,
+                                                           c->arg_im);
+  CC_LAUNCH_CHECK();
+  hinge_finish_kernel<<<1, 256, 0, s>>>(c->cost_s, c->cost_im, B, c->only_one_retrieval,
+                                        c->loss_rows, c->loss);
+  CC_LAUNCH_CHECK();
+  return CC_OK;
+}
+
+int listener_bwd(const coopcap_listener* c, const coopcap_listener_grads* g, cudaStream_t s) {
+  int rc = check_dims(c);
+  if (rc) return rc;
+  CC_REQUIRE(g != nullptr, "listener_bwd: null grads");
+  CC_REQUIRE((g->g_loss != nullptr) != (g->g_rows != nullptr),
+             "listener_bwd: exactly one of g_loss / g_rows must be given");
+  const int B = c->B, S = c->S, M = c->M, E = c->E, F = c->F;
+  bf16* h16 = reinterpret_cast<bf16*>(c->h16);
+  bf16* d_gi16 = reinterpret_cast<bf16*>(g->d_gi16);
+  bf16* d_gh16 = reinterpret_cast<bf16*>(g->d_gh16);
+  CC_CHECK_CUDA(cudaMemsetAsync(g->d_im, 0, sizeof(float) * B * M, s));
+  CC_CHECK_CUDA(cudaMemsetAsync(g->d_cap, 0, sizeof(float) * B * M, s));
+  hinge_bwd_kernel<<<B, 256, 0, s>>>(c->im, c->cap, c->cost_s, c->cost_im, c->arg_s, c->arg_im,
+                                     g->g_loss, g->g_rows, c->only_one_retrieval, M, g->d_im,
+                                     g->d_cap);
+  CC_LAUNCH_CHECK();
+  if (g->need_param_grads) {
+    l2norm_bwd_kernel<<<B, 256, 0, s>>>(c->img_pre, g->d_im, nullptr,
+                                        reinterpret_cast<bf16*>(g->d_img_pre16), M, c->no_imgnorm);
+    CC_LAUNCH_CHECK();
+    if ((rc = wgrad(g->d_img_pre16, M, c->fc16, F, M, F, B, g->g_w_img, F, s))) return rc;
+    if ((rc = colsum_bf16(g->d_img_pre16, B, M, M, g->g_b_img, s))) return rc;
+  }
+  l2norm_bwd_kernel<<<B, 256, 0, s>>>(c->h32 + int64_t(S) * B * M, g->d_cap, g->dh, nullptr, M, 0);
+  CC_LAUNCH_CHECK();
+  for (int t = S - 1; t >= 0; --t) {
+    const int n = B * M;
+    gru_bwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(
+        g->dh, c->gates + int64_t(t) * B * 4 * M, c->h32 + int64_t(t) * B * M, c->len, t,
+        d_gi16 + int64_t(t) * B * 3 * M, d_gh16 + int64_t(t) * B * 3 * M, B, M);
+    CC_LAUNCH_CHECK();
+    if (t > 0) {
+      // dh += d_gh . W_hh        ([B,3M] x [3M,M]; W_hh stored [K, N])
+      EpiStoreParams e = {};
+      e.alpha = 1.f; e.C = g->dh; e.ldc = M; e.mode = 1;
+      if ((rc = gemm_run(0, 0, 1, d_gh16 + int64_t(t) * B * 3 * M, 3 * M, c->w_hh16, M, B, M, 3 * M,
+                         1, 0, e, s)))
+        return rc;
+    }
+  }
+  // d(word embedding input) = d_gi . W_ih   ([S*B,3M] x [3M,E])
+  {
+    EpiStoreParams e = {};
+    e.alpha = 1.f; e.C16 = reinterpret_cast<bf16*>(g->demb16); e.ldc16 = E;
+    if ((rc = gemm_run(0, 0, 1, d_gi16, 3 * M, c->w_ih16, E, S * B, E, 3 * M, 1, 0, e, s))) return rc;
+  }
+  if (g->need_param_grads) {
+    const int K = S * B;
+    if ((rc = wgrad(d_gi16, 3 * M, c->emb16, E, 3 * M, E, K, g->g_w_ih, E, s))) return rc;
+    if ((rc = wgrad(d_gh16, 3 * M, h16, M, 3 * M, M, K, g->g_w_hh, M, s))) return rc;
+    if ((rc = colsum_bf16(d_gi16, K, 3 * M, 3 * M, g->g_b_ih, s))) return rc;
+    if ((rc = colsum_bf16(d_gh16, K, 3 * M, 3 * M, g->g_b_hh, s))) return rc;
+    embed_scatter_kernel<<<S * B, 128, 0, s>>>(c->tok, c->len,
+                                               reinterpret_cast<const bf16*>(g->demb16), B, E,
+                                               g->g_w_emb);
+    CC_LAUNCH_CHECK();
+  }
+  return CC_OK;
+}
+
+}  // namespace coopcap
+
+extern "C" {
+
+int coopcap_listener_pack_weights(const coopcap_listener_pack* p, coopcap_stream_t stream) {
+  using namespace coopcap;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  CC_REQUIRE(p != nullptr, "listener_pack: null");
+  int rc;
+  if ((rc = cast_block(p->w_img, p->M, p->F, p->w_img16, p->F, s))) return rc;
+  if ((rc = cast_block(p->w_ih, 3 * p->M, p->E, p->w_ih16, p->E, s))) return rc;
+  if ((rc = cast_block(p->w_hh, 3 * p->M, p->M, p->w_hh16, p->M, s))) return rc;
+  if (p->w_emb16 && (rc = cast_block(p->w_emb, p->V2, p->E, p->w_emb16, p->E, s))) return rc;
+  return CC_OK;
+}
+
+int coopcap_listener_fwd(const coopcap_listener* ctx, coopcap_stream_t stream) {
+  return coopcap::listener_fwd(ctx, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int coopcap_listener_bwd(const coopcap_listener* ctx, const coopcap_listener_grads* gr,
+                         coopcap_stream_t stream) {
+  return coopcap::listener_bwd(ctx, gr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,684 @@
+// Speaker (Att2in2) backward: logit gradients of the straight-through samplers and of log-prob
+// losses, BPTT through the decode loop, deferred accumulation of the region-tensor gradients and
+// all weight gradients.  Maths: SURVEY.md Appendix A.2/A.3/A.5; buffers: include/coopcap.h.
+#include "../../include/coopcap.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "speaker_kernels.cuh"
+
+namespace coopcap {
+
+using bf16 = __nv_bfloat16;
+
+size_t attention_smem_bytes(int A, int R, int L);
+
+// ------------------------------------------------------------------------------------------
+// small shared helpers
+// ------------------------------------------------------------------------------------------
+// out[c] = sum_r src[r, c]   (bf16 or fp32 source); out is overwritten.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ src, int64_t rows, int cols, int64_t ld,
+                              float* __restrict__ out, int64_t rows_per_block) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = int64_t(blockIdx.y) * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc = 0.f;
+  if (c < cols) {
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      if constexpr (sizeof(T) == 2) acc += __bfloat162float(src[r * ld + c]);
+      else acc += src[r * ld + c];
+    }
+  }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+template <typename T>
+static int colsum_impl(const T* src, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t s) {
+  CC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
+  if (rows <= 0) return CC_OK;
+  const int col_blocks = (cols + 31) / 32;
+  int64_t row_blocks = (int64_t(num_sms()) * 4 + col_blocks - 1) / col_blocks;
+  if (row_blocks > (rows + 63) / 64) row_blocks = (rows + 63) / 64;
+  if (row_blocks < 1) row_blocks = 1;
+  const int64_t rpb = (rows + row_blocks - 1) / row_blocks;
+  colsum_kernel<T><<<dim3(col_blocks, (unsigned)row_blocks), dim3(32, 8), 0, s>>>(src, rows, cols,
+                                                                                  ld, out, rpb);
+  CC_LAUNCH_CHECK();
+  return CC_OK;
+}
+int colsum_bf16(const void* src, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t s) {
+  return colsum_impl(reinterpret_cast<const bf16*>(src), rows, cols, ld, out, s);
+}
+int colsum_f32(const float* src, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t s) {
+  return colsum_impl(src, rows, cols, ld, out, s);
+}
+
+// weight-gradient contraction C[M,N] = A^T B with A stored [K, M], B stored [K, N] (bf16),
+// split along K so that the grid fills the machine; C is overwritten.
+int wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
+                 float* C, int64_t ldc, cudaStream_t s) {
+  const int bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
+  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  int split = num_sms() / tiles;
+  const int max_split = (K + 255) / 256;
+  if (split > max_split) split = max_split;
+  if (split < 1) split = 1;
+  EpiStoreParams e = {};
+  e.alpha = 1.f; e.C = C; e.ldc = ldc;
+  if (split > 1) {
+    e.mode = 2;
+    CC_CHECK_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, N * sizeof(float), M, s));
+  }
+  return gemm_run(0, 1, 1, A, lda, B, ldb, M, N, K, split, bn, e, s);
+}
+
+__device__ __forceinline__ float gumbel_of(float u) { return -logf(-logf(u + 1e-20f) + 1e-20f); }
+__device__ __forceinline__ void noise4(const float* inj_row, int v4, uint64_t seed, uint64_t stream,
+                                       uint64_t ctr, float (&u)[4]) {
+  if (inj_row) {
+    const float4 t = *reinterpret_cast<const float4*>(inj_row + 4 * v4);
+    u[0] = t.x; u[1] = t.y; u[2] = t.z; u[3] = t.w;
+  } else {
+    const uint4 r = Philox::gen(seed, stream, ctr);
+    u[0] = Philox::u01(r.x); u[1] = Philox::u01(r.y); u[2] = Philox::u01(r.z); u[3] = Philox::u01(r.w);
+  }
+}
+
+__device__ __forceinline__ void store_bf16x4(bf16* dst, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&lo);
+  o.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = o;
+}
+
+// ------------------------------------------------------------------------------------------
+// d(loss)/d(logits) of the straight-through samplers, one CTA per row:
+//   y = softmax(score), score = (z+G)/tau (gumbel) or z/tau (multinomial), rebuilt from the saved
+//   (max, sum) and the regenerated / injected noise;  dz = y (g - <y,g>) / tau on unfinished rows.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t ldg, int V1, int mode,
+              float inv_tau, const float* __restrict__ noise, uint64_t seed, uint64_t nstream,
+              const float* __restrict__ ymax, const float* __restrict__ ysum,
+              const uint8_t* __restrict__ unf, bf16* __restrict__ dz) {
+  extern __shared__ float s_y[];   // [V1]
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  bf16* dr = dz + int64_t(b) * V1;
+  if (!unf[b]) {
+    for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) store_bf16x4(dr + 4 * v4, 0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float* zr = z + int64_t(b) * V1;
+  const float* gr = g + int64_t(b) * ldg;
+  const float* nr = noise ? noise + int64_t(b) * V1 : nullptr;
+  const float m = ymax[b], inv_s = 1.f / ysum[b];
+  float dot = 0.f;
+  for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
+    const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
+    const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
+    const float g4[4] = {gr[4 * v4], gr[4 * v4 + 1], gr[4 * v4 + 2], gr[4 * v4 + 3]};
+    float u4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (mode == COOPCAP_SAMPLE_ST_GUMBEL) noise4(nr, v4, seed, nstream, uint64_t(b) * (V1 / 4) + v4, u4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float score = (mode == COOPCAP_SAMPLE_ST_GUMBEL) ? (x4[q] + gumbel_of(u4[q])) * inv_tau
+                                                              : x4[q] * inv_tau;
+      const float y = __expf(score - m) * inv_s;
+      s_y[4 * v4 + q] = y;
+      dot += y * g4[q];
+    }
+  }
+  dot = block_sum_256(dot, red);
+  for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
+    const float4 yv = *reinterpret_cast<const float4*>(s_y + 4 * v4);
+    store_bf16x4(dr + 4 * v4, inv_tau * yv.x * (gr[4 * v4] - dot), inv_tau * yv.y * (gr[4 * v4 + 1] - dot),
+                 inv_tau * yv.z * (gr[4 * v4 + 2] - dot), inv_tau * yv.w * (gr[4 * v4 + 3] - dot));
+  }
+}
+
+// dz = coef * (onehot(tok) - softmax(z))   (REINFORCE / XE), one CTA per (step, row)
+__global__ void __launch_bounds__(256)
+logp_bwd_kernel(const float* __restrict__ z, int V1, const float* __restrict__ lse,
+                const int64_t* __restrict__ tok, const float* __restrict__ coef,
+                bf16* __restrict__ dz) {
+  const int64_t row = blockIdx.x;
+  bf16* dr = dz + row * V1;
+  const float c = coef[row];
+  if (c == 0.f) {
+    for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) store_bf16x4(dr + 4 * v4, 0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float* zr = z + row * V1;
+  const float l = lse[row];
+  const int t = int(tok[row]);
+  for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
+    const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
+    const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = c * ((4 * v4 + q == t ? 1.f : 0.f) - __expf(x4[q] - l));
+    store_bf16x4(dr + 4 * v4, o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// maxout-LSTM pointwise backward (one step)
+// ------------------------------------------------------------------------------------------
+__global__ void lstm_bwd_kernel(const float* __restrict__ d_out, const bf16* __restrict__ out16,
+                                const float* __restrict__ dh_next, int64_t ld_dh,
+                                const float* __restrict__ dc_in, float* __restrict__ dc_out,
+                                const float* __restrict__ s, int64_t lds, const float* __restrict__ u,
+                                const float* __restrict__ c_prev, const float* __restrict__ c_cur,
+                                bf16* __restrict__ dscat, float drop_p, int B, int R) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * R) return;
+  const int b = idx / R, j = idx % R;
+  float dh = d_out[idx];
+  if (drop_p > 0.f)
+    dh = (__bfloat162float(out16[idx]) != 0.f) ? dh * (1.f / (1.f - drop_p)) : 0.f;
+  if (dh_next) dh += dh_next[int64_t(b) * ld_dh + j];
+  const float* sr = s + int64_t(b) * lds;
+  const float ig = 1.f / (1.f + expf(-sr[j]));
+  const float fg = 1.f / (1.f + expf(-sr[R + j]));
+  const float og = 1.f / (1.f + expf(-sr[2 * R + j]));
+  const float a1 = sr[3 * R + j] + u[int64_t(b) * 2 * R + j];
+  const float a2 = sr[4 * R + j] + u[int64_t(b) * 2 * R + R + j];
+  const float g = fmaxf(a1, a2);
+  const float tc = tanhf(c_cur[idx]);
+  float dc = (dc_in ? dc_in[idx] : 0.f) + dh * og * (1.f - tc * tc);
+  const float d_o = dh * tc;
+  const float d_f = dc * c_prev[idx];
+  const float d_i = dc * g;
+  const float d_g = dc * ig;
+  dc_out[idx] = dc * fg;
+  bf16* dr = dscat + int64_t(b) * lds;
+  dr[j] = __float2bfloat16_rn(d_i * ig * (1.f - ig));
+  dr[R + j] = __float2bfloat16_rn(d_f * fg * (1.f - fg));
+  dr[2 * R + j] = __float2bfloat16_rn(d_o * og * (1.f - og));
+  const bool first = a1 >= a2;
+  dr[3 * R + j] = __float2bfloat16_rn(first ? d_g : 0.f);
+  dr[4 * R + j] = __float2bfloat16_rn(first ? 0.f : d_g);
+}
+
+// ------------------------------------------------------------------------------------------
+// additive attention backward for one step (inside the BPTT chain): produces d(scores) and
+// d(att_h); the region-tensor gradients are accumulated over all steps by the deferred kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int ATT_THREADS = 256;
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_bwd_kernel(const bf16* __restrict__ p_att16, const bf16* __restrict__ att_e16,
+                     const int* __restrict__ off, int Lfix, const float* __restrict__ s_row0,
+                     int64_t lds, int att_h_col, const float* __restrict__ w_alpha,
+                     const float* __restrict__ d_att_res, const float* __restrict__ att_w,
+                     float* __restrict__ de_out, bf16* __restrict__ dscat, int A, int R) {
+  extern __shared__ float sm[];
+  float* s_ah = sm;              // [A]
+  float* s_dr = sm + A;          // [R] d_att_res   (A == R is not assumed: sized 2*max below)
+  const int mx = A > R ? A : R;
+  s_dr = sm + mx;
+  float* s_red = sm + 2 * mx;    // [8]
+  float* s_e = sm + 2 * mx + 8;  // [Lb] dw -> de
+  const int b = blockIdx.x;
+  const int r0 = off ? off[b] : b * Lfix;
+  const int Lb = off ? off[b + 1] - r0 : Lfix;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* att_h = s_row0 + int64_t(b) * lds + att_h_col;
+  for (int i = threadIdx.x; i < A; i += ATT_THREADS) s_ah[i] = att_h[i];
+  for (int i = threadIdx.x; i < R; i += ATT_THREADS) s_dr[i] = d_att_res[int64_t(b) * R + i];
+  __syncthreads();
+  // dw_l = <d_att_res, att_e[l]>
+  for (int l = warp; l < Lb; l += ATT_THREADS / 32) {
+    const uint4* erow = reinterpret_cast<const uint4*>(att_e16 + int64_t(r0 + l) * R);
+    float acc = 0.f;
+    for (int c = lane; c < R / 8; c += 32) {
+      float f[8];
+      bf16x8_to_float(__ldg(erow + c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += s_dr[c * 8 + j] * f[j];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_e[l] = acc;
+  }
+  __syncthreads();
+  float dotw = 0.f;
+  for (int l = threadIdx.x; l < Lb; l += ATT_THREADS) dotw += att_w[r0 + l] * s_e[l];
+  dotw = block_sum_256(dotw, s_red);
+  __syncthreads();
+  for (int l = threadIdx.x; l < Lb; l += ATT_THREADS) {
+    const float de = att_w[r0 + l] * (s_e[l] - dotw);
+    s_e[l] = de;
+    de_out[r0 + l] = de;
+  }
+  __syncthreads();
+  // d_att_h[j] = alpha_j * sum_l de_l (1 - tanh^2(p_att[l,j] + att_h[j]))
+  const int tpr = A / 8, groups = ATT_THREADS / tpr;
+  const int g = threadIdx.x / tpr, c = threadIdx.x % tpr;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (g < groups) {
+    for (int l = g; l < Lb; l += groups) {
+      float f[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p_att16 + int64_t(r0 + l) * A) + c), f);
+      const float de = s_e[l];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float th = tanh_fast(f[j] + s_ah[c * 8 + j]);
+        acc[j] += de * (1.f - th * th);
+      }
+    }
+  }
+  float* s_acc = s_e + ((Lb + 3) & ~3);  // [groups][A]
+  if (g < groups) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_acc[g * A + c * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < A; j += ATT_THREADS) {
+    float t = 0.f;
+    for (int gg = 0; gg < groups; ++gg) t += s_acc[gg * A + j];
+    dscat[int64_t(b) * lds + att_h_col + j] = __float2bfloat16_rn(t * w_alpha[j]);
+  }
+}
+
+// Deferred accumulation over all steps, one CTA per batch row (each region tensor is read once):
+//   d_att_e[l,:]  = sum_t w_t[l] * d_att_res_t[:]
+//   d_p_att[l,j]  = alpha_j * sum_t de_t[l] (1 - tanh^2(p_att[l,j] + att_h_t[j]))
+//   galpha[b, j]  = sum_t sum_l de_t[l] tanh(p_att[l,j] + att_h_t[j])     (per-row partial)
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_deferred_bwd_kernel(const bf16* __restrict__ p_att16, const int* __restrict__ off, int Lfix,
+                              const float* __restrict__ s_all, int64_t lds, int att_h_col,
+                              int64_t step_stride_s, const float* __restrict__ w_alpha,
+                              const float* __restrict__ d_att_res, const float* __restrict__ att_w,
+                              const float* __restrict__ de, int NL, int n_steps, int B,
+                              float* __restrict__ d_att_e, bf16* __restrict__ d_p_att16,
+                              float* __restrict__ galpha_part, float* __restrict__ gbias_part,
+                              int A, int R) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x;
+  const int r0 = off ? off[b] : b * Lfix;
+  const int Lb = off ? off[b + 1] - r0 : Lfix;
+  float* s_ah = sm;                              // [n_steps][A]
+  float* s_dr = s_ah + n_steps * A;              // [n_steps][R]
+  float* s_w = s_dr + n_steps * R;               // [n_steps][Lb]
+  float* s_de = s_w + n_steps * ((Lb + 3) & ~3); // [n_steps][Lb]
+  float* s_acc = s_de + n_steps * ((Lb + 3) & ~3);  // [groups][A]
+  const int Lp = (Lb + 3) & ~3;
+  for (int i = threadIdx.x; i < n_steps * A; i += ATT_THREADS) {
+    const int t = i / A, j = i % A;
+    s_ah[i] = s_all[int64_t(t) * step_stride_s + int64_t(b) * lds + att_h_col + j];
+  }
+  for (int i = threadIdx.x; i < n_steps * R; i += ATT_THREADS) {
+    const int t = i / R, j = i % R;
+    s_dr[i] = d_att_res[(int64_t(t) * B + b) * R + j];
+  }
+  for (int i = threadIdx.x; i < n_steps * Lb; i += ATT_THREADS) {
+    const int t = i / Lb, l = i % Lb;
+    s_w[t * Lp + l] = att_w[int64_t(t) * NL + r0 + l];
+    s_de[t * Lp + l] = de[int64_t(t) * NL + r0 + l];
+  }
+  __syncthreads();
+  const int tpr = A / 8, groups = ATT_THREADS / tpr;   // requires A == R (checked on the host)
+  const int g = threadIdx.x / tpr, c = threadIdx.x % tpr;
+  float al[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) al[j] = w_alpha[c * 8 + j];
+  float ga[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float gb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (g < groups) {
+    for (int l = g; l < Lb; l += groups) {
+      float p[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p_att16 + int64_t(r0 + l) * A) + c), p);
+      float ap[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float ae[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int t = 0; t < n_steps; ++t) {
+        const float w = s_w[t * Lp + l], d = s_de[t * Lp + l];
+        const float* ah = s_ah + t * A + c * 8;
+        const float* dr = s_dr + t * R + c * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float th = tanh_fast(p[j] + ah[j]);
+          ap[j] += d * (1.f - th * th);
+          ga[j] += d * th;
+          ae[j] += w * dr[j];
+        }
+      }
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o[j] = ap[j] * al[j]; gb[j] += o[j]; }
+      *(reinterpret_cast<uint4*>(d_p_att16 + int64_t(r0 + l) * A) + c) = float8_to_bf16x8(o);
+      float4* dst = reinterpret_cast<float4*>(d_att_e + int64_t(r0 + l) * R + c * 8);
+      dst[0] = make_float4(ae[0], ae[1], ae[2], ae[3]);
+      dst[1] = make_float4(ae[4], ae[5], ae[6], ae[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_acc[g * A + c * 8 + j] = ga[j];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < A; j += ATT_THREADS) {
+    float t = 0.f;
+    for (int gg = 0; gg < groups; ++gg) t += s_acc[gg * A + j];
+    galpha_part[int64_t(b) * A + j] = t;
+  }
+  // second reduction: fp32 column sums of d_p_att (the ctx2att bias gradient cancels heavily, so
+  // it is not taken from the bf16-rounded tensor)
+  __syncthreads();
+  if (g < groups) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_acc[g * A + c * 8 + j] = gb[j];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < A; j += ATT_THREADS) {
+    float t = 0.f;
+    for (int gg = 0; gg < groups; ++gg) t += s_acc[gg * A + j];
+    gbias_part[int64_t(b) * A + j] = t;
+  }
+}
+
+// d_pre16 = bf16(d_att_e * scale * [att_e > 0])   (relu and dropout share the "output > 0" mask)
+__global__ void mask_pre_kernel(const float* __restrict__ d_att_e, const bf16* __restrict__ att_e16,
+                                int64_t n4, float scale, bf16* __restrict__ d_pre16) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const float4 d = *reinterpret_cast<const float4*>(d_att_e + 4 * i);
+    const uint2 e = *reinterpret_cast<const uint2*>(att_e16 + 4 * i);
+    const __nv_bfloat162* eh = reinterpret_cast<const __nv_bfloat162*>(&e);
+    const float2 e0 = __bfloat1622float2(eh[0]), e1 = __bfloat1622float2(eh[1]);
+    store_bf16x4(d_pre16 + 4 * i, e0.x > 0.f ? d.x * scale : 0.f, e0.y > 0.f ? d.y * scale : 0.f,
+                 e1.x > 0.f ? d.z * scale : 0.f, e1.y > 0.f ? d.w * scale : 0.f);
+  }
+}
+
+// g_embed[tok_fed[t,b], :] += d_x[t,b,:] * scale * [x16 > 0]
+__global__ void embed_grad_kernel(const int64_t* __restrict__ tok_fed, const float* __restrict__ d_xh,
+                                  const bf16* __restrict__ xh16, int E, int XH, float scale,
+                                  float* __restrict__ g_embed) {
+  const int64_t row = blockIdx.x;
+  float* dst = g_embed + tok_fed[row] * E;
+  const float* dx = d_xh + row * XH;
+  const bf16* x = xh16 + row * XH;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    if (__bfloat162float(x[i]) > 0.f) atomicAdd(dst + i, dx[i] * scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// orchestration
+// ------------------------------------------------------------------------------------------
+static int check_dims(const coopcap_speaker* c) {
+  CC_REQUIRE(c != nullptr, "speaker: null context");
+  CC_REQUIRE(c->A == c->R, "speaker backward assumes att_hid_size == rnn_size (A=%d R=%d)", c->A,
+             c->R);
+  CC_REQUIRE(c->n_steps >= 1 && c->n_steps <= c->cap, "speaker backward: n_steps %d", c->n_steps);
+  return CC_OK;
+}
+
+int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb16, float* g_ws,
+                int64_t ldg, void* dz16, cudaStream_t s) {
+  int rc = check_dims(c);
+  if (rc) return rc;
+  CC_REQUIRE(c->mode == COOPCAP_SAMPLE_ST_GUMBEL || c->mode == COOPCAP_SAMPLE_ST_MULTINOMIAL,
+             "st_backward: context was not sampled in a straight-through mode (%d)", c->mode);
+  const int B = c->B, V1 = c->V1, E = c->E;
+  const size_t smem = sizeof(float) * V1;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(st_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(smem)));
+    smem_set = smem;
+  }
+  for (int t = 0; t < c->n_steps; ++t) {
+    const float* g_t = g_ws;
+    if (demb16) {
+      // g = demb[t] . W_emb^T   ([B,E] x [V1,E]^T), kept L2-resident for the row kernel below
+      EpiStoreParams e = {};
+      e.alpha = 1.f; e.C = g_ws; e.ldc = V1;
+      rc = gemm_run(0, 0, 0, reinterpret_cast<const bf16*>(demb16) + int64_t(t) * B * E, E, w_emb16,
+                    E, B, V1, E, 1, 0, e, s);
+      if (rc) return rc;
+    } else {
+      g_t = g_ws + int64_t(t) * B * ldg;   // dense upstream gradient, all steps
+    }
+    st_bwd_kernel<<<B, 256, smem, s>>>(
+        c->z_all + int64_t(t) * B * V1, g_t, ldg, V1, c->mode, c->inv_tau,
+        c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed, SITE_NOISE + t,
+        c->y_max + int64_t(t) * B, c->y_sum + int64_t(t) * B, c->unfinished + int64_t(t) * B,
+        reinterpret_cast<bf16*>(dz16) + int64_t(t) * B * V1);
+    CC_LAUNCH_CHECK();
+  }
+  return CC_OK;
+}
+
+int logp_backward(const coopcap_speaker* c, const int64_t* tok, const float* coef, void* dz16,
+                  cudaStream_t s) {
+  int rc = check_dims(c);
+  if (rc) return rc;
+  logp_bwd_kernel<<<c->n_steps * c->B, 256, 0, s>>>(c->z_all, c->V1, c->lse, tok, coef,
+                                                    reinterpret_cast<bf16*>(dz16));
+  CC_LAUNCH_CHECK();
+  return CC_OK;
+}
+
+int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g, cudaStream_t s) {
+  int rc = check_dims(c);
+  if (rc) return rc;
+  CC_REQUIRE(g != nullptr && g->dz16 != nullptr, "speaker_decode_bwd: null grads / dz16");
+  const int B = c->B, R = c->R, E = c->E, A = c->A, V1 = c->V1, NL = c->NL, n = c->n_steps;
+  const int NS = 5 * R + A, XH = E + R;
+  const int64_t rows = int64_t(n) * B;
+  const bf16* dz16 = reinterpret_cast<const bf16*>(g->dz16);
+  bf16* dscat16 = reinterpret_cast<bf16*>(g->dscat16);
+  const bf16* xh16 = reinterpret_cast<const bf16*>(c->xh16);
+  const bf16* out16 = reinterpret_cast<const bf16*>(c->out16);
+  const float scale = c->drop_p > 0.f ? 1.f / (1.f - c->drop_p) : 1.f;
+
+  // logit layer: d_out = dz . W_logit ; g_w_logit = dz^T . out ; g_b_logit = colsum(dz)
+  {
+    EpiStoreParams e = {};
+    e.alpha = 1.f; e.C = g->d_out; e.ldc = R;
+    if ((rc = gemm_run(0, 0, 1, dz16, V1, c->w_logit16, R, int(rows), R, V1, 1, 0, e, s))) return rc;
+    if ((rc = wgrad(dz16, V1, out16, R, V1, R, int(rows), g->g_w_logit, R, s))) return rc;
+    if ((rc = colsum_bf16(dz16, rows, V1, V1, g->g_b_logit, s))) return rc;
+  }
+
+  const size_t att_smem = attention_smem_bytes(A, R, c->L);
+  static size_t att_smem_set = 0;
+  if (att_smem > 48 * 1024 && att_smem > att_smem_set) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(att_smem)));
+    att_smem_set = att_smem;
+  }
+  // BPTT
+  for (int t = n - 1; t >= 0; --t) {
+    const float* s_t = c->s_all + int64_t(t) * B * NS;
+    bf16* ds_t = dscat16 + int64_t(t) * B * NS;
+    float* dc_in = (t == n - 1) ? nullptr : g->dc + int64_t((t + 1) & 1) * B * R;
+    float* dc_out = g->dc + int64_t(t & 1) * B * R;
+    const float* dh_next = (t == n - 1) ? nullptr : g->d_xh + int64_t(t + 1) * B * XH + E;
+    {
+      const int nthr = B * R;
+      lstm_bwd_kernel<<<(nthr + 255) / 256, 256, 0, s>>>(
+          g->d_out + int64_t(t) * B * R, out16 + int64_t(t) * B * R, dh_next, XH, dc_in, dc_out, s_t,
+          NS, c->u_all + int64_t(t) * B * 2 * R, c->c_all + int64_t(t) * B * R,
+          c->c_all + int64_t(t + 1) * B * R, ds_t, c->drop_p, B, R);
+      CC_LAUNCH_CHECK();
+    }
+    // d_att_res = d_u . W_a2c      ([B,2R] x [2R,R])
+    float* dres_t = g->d_att_res + int64_t(t) * B * R;
+    {
+      EpiStoreParams e = {};
+      e.alpha = 1.f; e.C = dres_t; e.ldc = R;
+      if ((rc = gemm_run(0, 0, 1, ds_t + 3 * R, NS, c->w_a2c16, R, B, R, 2 * R, 1, 0, e, s))) return rc;
+    }
+    attention_bwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
+        reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
+        c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, dres_t, c->att_w + int64_t(t) * NL,
+        g->de + int64_t(t) * NL, ds_t, A, R);
+    CC_LAUNCH_CHECK();
+    // d[x_t | h_{t-1}] = dscat . w_cat      ([B,5R+A] x [5R+A,E+R])
+    {
+      EpiStoreParams e = {};
+      e.alpha = 1.f; e.C = g->d_xh + int64_t(t) * B * XH; e.ldc = XH;
+      if ((rc = gemm_run(0, 0, 1, ds_t, NS, c->w_cat16, XH, B, XH, NS, 1, 0, e, s))) return rc;
+    }
+  }
+  // step-batched weight gradients
+  if ((rc = wgrad(dscat16, NS, xh16, XH, 5 * R, E, int(rows), g->g_w_i2h, E, s))) return rc;
+  if ((rc = wgrad(dscat16, NS, xh16 + E, XH, 5 * R, R, int(rows), g->g_w_h2h, R, s))) return rc;
+  if ((rc = wgrad(dscat16 + 5 * R, NS, xh16 + E, XH, A, R, int(rows), g->g_w_h2att, R, s))) return rc;
+  if ((rc = wgrad(dscat16 + 3 * R, NS, c->att_res16, R, 2 * R, R, int(rows), g->g_w_a2c, R, s))) return rc;
+  if ((rc = colsum_bf16(dscat16, rows, 5 * R, NS, g->g_b_gates, s))) return rc;
+  if ((rc = colsum_bf16(dscat16 + 5 * R, rows, A, NS, g->g_b_h2att, s))) return rc;
+  if ((rc = colsum_bf16(dscat16 + 3 * R, rows, 2 * R, NS, g->g_b_a2c, s))) return rc;
+  // input embedding
+  embed_grad_kernel<<<(unsigned)rows, 128, 0, s>>>(c->tok_fed, g->d_xh, xh16, E, XH, scale, g->g_embed);
+  CC_LAUNCH_CHECK();
+  // region tensors: deferred accumulation over the steps, then the prologue layers
+  {
+    const int Lp = (c->L + 3) & ~3;
+    const int groups = ATT_THREADS / (A / 8);
+    const size_t smem = sizeof(float) * (size_t(n) * (A + R) + 2 * size_t(n) * Lp + size_t(groups) * A);
+    CC_REQUIRE(smem <= 227 * 1024, "deferred attention backward needs %zu B of shared memory", smem);
+    static size_t set = 0;
+    if (smem > 48 * 1024 && smem > set) {
+      CC_CHECK_CUDA(cudaFuncSetAttribute(attention_deferred_bwd_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      set = smem;
+    }
+    // galpha / bias partials live in d_out (free after the BPTT loop): 2 x [B, A] <= [cap*B, R]
+    float* galpha_part = g->d_out;
+    float* gbias_part = g->d_out + int64_t(B) * A;
+    attention_deferred_bwd_kernel<<<B, ATT_THREADS, smem, s>>>(
+        reinterpret_cast<const bf16*>(c->p_att16), c->att_off, c->L, c->s_all, NS, 5 * R,
+        int64_t(B) * NS, c->w_alpha, g->d_att_res, c->att_w, g->de, NL, n, B, g->d_att_e,
+        reinterpret_cast<bf16*>(g->d_p_att16), galpha_part, gbias_part, A, R);
+    CC_LAUNCH_CHECK();
+    if ((rc = colsum_f32(galpha_part, B, A, A, g->g_w_alpha, s))) return rc;
+    if ((rc = colsum_f32(gbias_part, B, A, A, g->g_b_ctx2att, s))) return rc;
+  }
+  {
+    // d_att_e += d_p_att . W_ctx2att     ([NL,A] x [A,R])
+    EpiStoreParams e = {};
+    e.alpha = 1.f; e.C = g->d_att_e; e.ldc = R; e.mode = 1;
+    if ((rc = gemm_run(0, 0, 1, g->d_p_att16, A, c->w_ctx2att16, R, NL, R, A, 1, 0, e, s))) return rc;
+    const int64_t n4 = int64_t(NL) * R / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > int64_t(num_sms()) * 16) blocks = int64_t(num_sms()) * 16;
+    mask_pre_kernel<<<(unsigned)blocks, 256, 0, s>>>(g->d_att_e,
+                                                     reinterpret_cast<const bf16*>(c->att_e16), n4,
+                                                     scale, reinterpret_cast<bf16*>(g->d_pre16));
+    CC_LAUNCH_CHECK();
+    if ((rc = wgrad(g->d_p_att16, A, c->att_e16, R, A, R, NL, g->g_w_ctx2att, R, s))) return rc;
+    if ((rc = wgrad(g->d_pre16, R, c->att16, c->D, R, c->D, NL, g->g_w_att_embed, c->D, s))) return rc;
+    if ((rc = colsum_bf16(g->d_pre16, NL, R, R, g->g_b_att_embed, s))) return rc;
+  }
+  return CC_OK;
+}
+
+// flat fp32 bucket: g *= grad_scale; clamp; Adam  (optimizer.py:233-242, misc/utils.py:65-69)
+__global__ void clamp_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                  float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                  float grad_scale, float clip, float lr, float b1, float b2, float eps,
+                                  float wd, float bc1, float bc2_sqrt) {
+  const int64_t n4 = n / 4;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float pp[4] = {pv.x, pv.y, pv.z, pv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+    float mm[4] = {mv.x, mv.y, mv.z, mv.w}, vq[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float x = gg[q] * grad_scale;
+      if (clip > 0.f) x = fminf(fmaxf(x, -clip), clip);
+      x += wd * pp[q];
+      mm[q] = b1 * mm[q] + (1.f - b1) * x;
+      vq[q] = b2 * vq[q] + (1.f - b2) * x * x;
+      const float denom = sqrtf(vq[q]) / bc2_sqrt + eps;
+      pp[q] -= (lr / bc1) * (mm[q] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(vq[0], vq[1], vq[2], vq[3]);
+  }
+  // tail
+  if (blockIdx.x == 0) {
+    for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      float x = g[i] * grad_scale;
+      if (clip > 0.f) x = fminf(fmaxf(x, -clip), clip);
+      x += wd * p[i];
+      const float mq = b1 * m[i] + (1.f - b1) * x;
+      const float vq = b2 * v[i] + (1.f - b2) * x * x;
+      m[i] = mq; v[i] = vq;
+      p[i] -= (lr / bc1) * (mq / (sqrtf(vq) / bc2_sqrt + eps));
+    }
+  }
+}
+
+}  // namespace coopcap
+
+extern "C" {
+
+int coopcap_st_backward(const coopcap_speaker* ctx, const void* demb16, const void* w_emb16,
+                        float* g_ws, void* dz16, coopcap_stream_t stream) {
+  if (!demb16 || !w_emb16 || !g_ws) {
+    coopcap::set_last_error("st_backward: null demb16 / w_emb16 / g_ws");
+    return coopcap::CC_ERR_ARG;
+  }
+  return coopcap::st_backward(ctx, demb16, w_emb16, g_ws, ctx ? ctx->V1 : 0, dz16,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int coopcap_st_backward_dense(const coopcap_speaker* ctx, const float* g, int64_t ldg, void* dz16,
+                              coopcap_stream_t stream) {
+  if (!g) {
+    coopcap::set_last_error("st_backward_dense: null g");
+    return coopcap::CC_ERR_ARG;
+  }
+  return coopcap::st_backward(ctx, nullptr, nullptr, const_cast<float*>(g), ldg, dz16,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int coopcap_logp_backward(const coopcap_speaker* ctx, const int64_t* tok, const float* coef,
+                          void* dz16, coopcap_stream_t stream) {
+  return coopcap::logp_backward(ctx, tok, coef, dz16, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int coopcap_speaker_decode_bwd(const coopcap_speaker* ctx, const coopcap_speaker_grads* gr,
+                               coopcap_stream_t stream) {
+  return coopcap::speaker_decode_bwd(ctx, gr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int coopcap_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       float grad_scale, float clip, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int step, coopcap_stream_t stream) {
+  using namespace coopcap;
+  if (n <= 0) return CC_OK;
+  CC_REQUIRE(step >= 1, "clamp_adam: step must be >= 1");
+  CC_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+               reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
+             "clamp_adam: buffers must be 16-byte aligned");
+  const float bc1 = 1.f - powf(beta1, float(step));
+  const float bc2 = 1.f - powf(beta2, float(step));
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > int64_t(num_sms()) * 8) blocks = int64_t(num_sms()) * 8;
+  if (blocks < 1) blocks = 1;
+  clamp_adam_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, n, grad_scale, clip, lr, beta1, beta2, eps, weight_decay,
+      bc1, sqrtf(bc2));
+  CC_LAUNCH_CHECK();
+  return CC_OK;
+}
+
+}  // extern "C"

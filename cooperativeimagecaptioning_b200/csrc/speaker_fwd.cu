@@ -113,11 +113,13 @@ __device__ __forceinline__ void embed_row(const float* __restrict__ embed, int64
 }
 
 // step 0: feed the start token, zero h_{-1} and c_{-1}
-__global__ void start_step_kernel(const float* __restrict__ embed, int64_t start, int B, int E, int R,
+__global__ void start_step_kernel(const float* __restrict__ embed, int64_t start_scalar,
+                                  const int64_t* __restrict__ start_rows, int B, int E, int R,
                                   const uint8_t* __restrict__ keep_embed, uint64_t seed,
                                   float drop_p, bf16* __restrict__ xh0, float* __restrict__ c0,
                                   int64_t* __restrict__ tok_fed0) {
   const int b = blockIdx.x;
+  const int64_t start = start_rows ? start_rows[b] : start_scalar;
   bf16* row = xh0 + int64_t(b) * (E + R);
   embed_row(embed, start, E, keep_embed ? keep_embed + int64_t(b) * E : nullptr, seed,
             SITE_DROP_EMBED, int64_t(b) * E, drop_p, row);
@@ -493,7 +495,7 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(att_smem)));
     att_smem_set = att_smem;
   }
-  start_step_kernel<<<B, 128, 0, s>>>(c->embed, c->start_token, B, E, R, c->keep_embed, c->seed,
+  start_step_kernel<<<B, 128, 0, s>>>(c->embed, c->start_token, c->start_tokens, B, E, R, c->keep_embed, c->seed,
                                       c->drop_p, xh16, c->c_all, c->tok_fed);
   CC_LAUNCH_CHECK();
   for (int t = 0; t < c->n_steps; ++t) {
@@ -535,7 +537,7 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
         c->lse + int64_t(t) * B, c->y_max + int64_t(t) * B, c->y_sum + int64_t(t) * B,
         c->unfinished + int64_t(t) * B, c->embed, E,
         c->keep_embed ? c->keep_embed + int64_t(t + 1) * B * E : nullptr, SITE_DROP_EMBED + t + 1,
-        c->drop_p, xh16 + int64_t(t + 1) * B * XH, XH);
+        c->drop_p, (t + 1 < c->n_steps) ? xh16 + int64_t(t + 1) * B * XH : nullptr, XH);
     CC_LAUNCH_CHECK();
   }
   if (c->n_out && c->cap_len) {

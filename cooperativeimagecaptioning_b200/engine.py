@@ -147,9 +147,11 @@ def region_offsets(att_masks: Optional[torch.Tensor], B: int, L: int):
 def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.Tensor,
                     att_off: Optional[torch.Tensor], NL: int, *, n_steps: int, mode: int,
                     inv_tau: float, start_token: int, rnd: SpeakerRandom,
-                    forced: Optional[torch.Tensor] = None) -> SpeakerPass:
-    """Prologue + n_steps decode steps.  `forced` int64 [n_steps, B] (time-major)."""
-    _need_cuda(att_feats, att_off, forced)
+                    forced: Optional[torch.Tensor] = None,
+                    start_tokens: Optional[torch.Tensor] = None) -> SpeakerPass:
+    """Prologue + n_steps decode steps.  `forced` int64 [n_steps, B] (time-major);
+    `start_tokens` int64 [B] overrides the scalar start id per row."""
+    _need_cuda(att_feats, att_off, forced, start_tokens)
     d: SpeakerDims = packed["dims"]
     att_feats = _f32c(att_feats)
     B, L, D = att_feats.shape
@@ -187,23 +189,265 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     for n in ("w_att_embed16", "w_ctx2att16", "w_cat16", "w_a2c16", "w_logit16"):
         setattr(c, n, _p(packed[n]))
     c.seed, c.drop_p = int(rnd.seed) & (2 ** 64 - 1), float(rnd.drop_p)
+    want = {"keep_att": (NL, d.R), "keep_embed": (n_steps, B, d.E), "keep_core": (n_steps, B, d.R)}
     for n in ("keep_att", "keep_embed", "keep_core"):
         k = getattr(rnd, n)
         if k is not None:
             assert k.dtype == torch.uint8 and k.is_contiguous() and k.is_cuda
+            w = want[n]
+            if k.shape[0] < w[0] or tuple(k.shape[1:]) != tuple(w[1:]):
+                raise _lib.CoopcapError(f"injected {n} has shape {tuple(k.shape)}, need >= {w}")
         setattr(c, n, _p(k))
-    if rnd.noise is not None:
+    uses_noise = mode in (MODE_MULTINOMIAL, MODE_ST_GUMBEL, MODE_ST_MULTINOMIAL)
+    if rnd.noise is not None and uses_noise:
         _f32c(rnd.noise)
-    c.noise = _p(rnd.noise)
+        if rnd.noise.shape[0] < n_steps or tuple(rnd.noise.shape[1:]) != (B, d.V1):
+            raise _lib.CoopcapError(f"injected noise has shape {tuple(rnd.noise.shape)}, "
+                                    f"need >= {(n_steps, B, d.V1)}")
+    c.noise = _p(rnd.noise) if uses_noise else None
     c.mode, c.inv_tau, c.start_token = mode, float(inv_tau), int(start_token)
     if forced is not None:
         assert forced.dtype == torch.int64 and forced.is_contiguous() and forced.shape == (n_steps, B)
     c.forced = _p(forced)
+    if start_tokens is not None:
+        assert start_tokens.dtype == torch.int64 and start_tokens.is_contiguous()
+        assert start_tokens.shape == (B,)
+    c.start_tokens = _p(start_tokens)
     for n, tsr in T.items():
         setattr(c, n, _p(tsr))
     sp = SpeakerPass(ctx=c, dims=d, B=B, L=L, NL=NL, cap=cap, n_steps=n_steps, t=T,
-                     keep=[att_feats, att_off, forced, rnd, packed, P])
+                     keep=[att_feats, att_off, forced, start_tokens, rnd, packed, P])
     lib = _lib.load()
     check(lib.coopcap_speaker_prologue_fwd(C.byref(c), _stream()))
     check(lib.coopcap_speaker_decode_fwd(C.byref(c), _stream()))
     return sp
+
+
+def st_logit_grads(sp: SpeakerPass, demb16: torch.Tensor, w_emb16: torch.Tensor) -> torch.Tensor:
+    """dz16 [n_steps*B, V1] for the straight-through samplers from the listener's embedding
+    gradient demb16 [n_steps, B, E] (caption positions 1..n_steps)."""
+    d = sp.dims
+    dev = demb16.device
+    assert demb16.dtype == torch.bfloat16 and demb16.is_contiguous()
+    assert demb16.shape == (sp.n_steps, sp.B, d.E)
+    g_ws = torch.empty(sp.B, d.V1, dtype=torch.float32, device=dev)
+    dz16 = torch.empty(sp.n_steps * sp.B, d.V1, dtype=torch.bfloat16, device=dev)
+    check(_lib.load().coopcap_st_backward(C.byref(sp.ctx), _p(demb16), _p(w_emb16), _p(g_ws),
+                                          _p(dz16), _stream()))
+    return dz16
+
+
+def st_logit_grads_dense(sp: SpeakerPass, g: torch.Tensor) -> torch.Tensor:
+    """Same from a dense upstream gradient g fp32 [n_steps, B, >=V1] (d loss / d one_hots)."""
+    d = sp.dims
+    g = _f32c(g)
+    assert g.shape[0] == sp.n_steps and g.shape[1] == sp.B and g.shape[2] >= d.V1
+    dz16 = torch.empty(sp.n_steps * sp.B, d.V1, dtype=torch.bfloat16, device=g.device)
+    check(_lib.load().coopcap_st_backward_dense(C.byref(sp.ctx), _p(g), g.shape[2], _p(dz16),
+                                                _stream()))
+    return dz16
+
+
+def logp_logit_grads(sp: SpeakerPass, tok: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
+    """dz16 for sum coef[t,b] * log_softmax(z[t,b])[tok[t,b]]; tok int64 / coef fp32 [n_steps, B]."""
+    d = sp.dims
+    assert tok.dtype == torch.int64 and tok.is_contiguous() and tok.shape == (sp.n_steps, sp.B)
+    coef = _f32c(coef)
+    assert coef.shape == (sp.n_steps, sp.B)
+    dz16 = torch.empty(sp.n_steps * sp.B, d.V1, dtype=torch.bfloat16, device=tok.device)
+    check(_lib.load().coopcap_logp_backward(C.byref(sp.ctx), _p(tok), _p(coef), _p(dz16), _stream()))
+    return dz16
+
+
+def speaker_backward(sp: SpeakerPass, dz16: torch.Tensor, P: Dict[str, torch.Tensor]
+                     ) -> Dict[str, torch.Tensor]:
+    """BPTT + prologue backward.  Returns {reference parameter name: fp32 gradient}."""
+    d = sp.dims
+    dev = dz16.device
+    B, cap, NL = sp.B, sp.cap, sp.NL
+    NS, XH = 5 * d.R + d.A, d.E + d.R
+    f32 = dict(dtype=torch.float32, device=dev)
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    ws = dict(
+        d_out=torch.empty(max(cap, 2) * B, d.R, **f32), dscat16=torch.empty(cap * B, NS, **bf),
+        d_att_res=torch.empty(cap * B, d.R, **f32), de=torch.empty(cap, NL, **f32),
+        d_xh=torch.empty(cap * B, XH, **f32), dc=torch.empty(2, B, d.R, **f32),
+        d_att_e=torch.empty(NL, d.R, **f32), d_p_att16=torch.empty(NL, d.A, **bf),
+        d_pre16=torch.empty(NL, d.R, **bf))
+    G = {n: torch.empty_like(P[n], dtype=torch.float32) for n in SPEAKER_PARAM_NAMES
+         if n not in ("embed.0.weight", "core.attention.alpha_net.bias", "core.h2h.bias")}
+    G["embed.0.weight"] = torch.zeros_like(P["embed.0.weight"], dtype=torch.float32)
+    # the alpha_net bias shifts every score of a row equally: its gradient is identically 0
+    G["core.attention.alpha_net.bias"] = torch.zeros_like(P["core.attention.alpha_net.bias"])
+    g = _lib.SpeakerGrads()
+    g.dz16 = _p(dz16)
+    for n, tsr in ws.items():
+        setattr(g, n, _p(tsr))
+    g.g_embed = _p(G["embed.0.weight"])
+    g.g_w_att_embed, g.g_b_att_embed = _p(G["att_embed.0.weight"]), _p(G["att_embed.0.bias"])
+    g.g_w_ctx2att, g.g_b_ctx2att = _p(G["ctx2att.weight"]), _p(G["ctx2att.bias"])
+    g.g_w_i2h, g.g_w_h2h = _p(G["core.i2h.weight"]), _p(G["core.h2h.weight"])
+    g.g_b_gates = _p(G["core.i2h.bias"])
+    g.g_w_h2att, g.g_b_h2att = (_p(G["core.attention.h2att.weight"]),
+                                _p(G["core.attention.h2att.bias"]))
+    g.g_w_a2c, g.g_b_a2c = _p(G["core.a2c.weight"]), _p(G["core.a2c.bias"])
+    g.g_w_logit, g.g_b_logit = _p(G["logit.weight"]), _p(G["logit.bias"])
+    g.g_w_alpha = _p(G["core.attention.alpha_net.weight"])
+    check(_lib.load().coopcap_speaker_decode_bwd(C.byref(sp.ctx), C.byref(g), _stream()))
+    G["core.h2h.bias"] = G["core.i2h.bias"]     # both biases enter the same sum
+    return G
+
+
+# =============================================================================================
+# listener
+# =============================================================================================
+LISTENER_PARAM_NAMES = [
+    "img_enc.fc.weight", "img_enc.fc.bias", "txt_enc.embed.weight", "txt_enc.rnn.weight_ih_l0",
+    "txt_enc.rnn.weight_hh_l0", "txt_enc.rnn.bias_ih_l0", "txt_enc.rnn.bias_hh_l0",
+]
+
+
+@dataclass
+class ListenerDims:
+    F: int
+    M: int
+    E: int
+    V2: int
+
+    @staticmethod
+    def of(P) -> "ListenerDims":
+        return ListenerDims(F=P["img_enc.fc.weight"].shape[1], M=P["img_enc.fc.weight"].shape[0],
+                            E=P["txt_enc.embed.weight"].shape[1],
+                            V2=P["txt_enc.embed.weight"].shape[0])
+
+
+class PackedListener:
+    def __init__(self):
+        self.key = None
+        self.buf = {}
+
+    def get(self, P):
+        key = tuple((P[n].data_ptr(), P[n]._version) for n in LISTENER_PARAM_NAMES)
+        if key == self.key:
+            return self.buf
+        d = ListenerDims.of(P)
+        _need_cuda(*[P[n] for n in LISTENER_PARAM_NAMES])
+        dev = P["img_enc.fc.weight"].device
+        if not self.buf or self.buf["dims"] != d:
+            bf = dict(dtype=torch.bfloat16, device=dev)
+            self.buf = dict(dims=d, w_img16=torch.empty(d.M, d.F, **bf),
+                            w_ih16=torch.empty(3 * d.M, d.E, **bf),
+                            w_hh16=torch.empty(3 * d.M, d.M, **bf),
+                            w_emb16=torch.empty(d.V2, d.E, **bf))
+        b = self.buf
+        a = _lib.ListenerPack()
+        a.F, a.M, a.E, a.V2 = d.F, d.M, d.E, d.V2
+        a.w_img = _p(_f32c(P["img_enc.fc.weight"].detach()))
+        a.w_ih = _p(_f32c(P["txt_enc.rnn.weight_ih_l0"].detach()))
+        a.w_hh = _p(_f32c(P["txt_enc.rnn.weight_hh_l0"].detach()))
+        a.w_emb = _p(_f32c(P["txt_enc.embed.weight"].detach()))
+        a.w_img16, a.w_ih16, a.w_hh16, a.w_emb16 = (_p(b["w_img16"]), _p(b["w_ih16"]),
+                                                    _p(b["w_hh16"]), _p(b["w_emb16"]))
+        check(_lib.load().coopcap_listener_pack_weights(C.byref(a), _stream()))
+        self.key = key
+        return b
+
+
+@dataclass
+class ListenerPass:
+    ctx: object = None
+    dims: ListenerDims = None
+    B: int = 0
+    S: int = 0
+    t: Dict[str, torch.Tensor] = field(default_factory=dict)
+    keep: list = field(default_factory=list)
+
+
+ONLY = {"off": 0, "image": 1, "caption": 2}
+
+
+def listener_forward(P, packed, fc_feats, tok_sb, lens, *, margin=0.2, only_one_retrieval="off",
+                     no_imgnorm=False) -> ListenerPass:
+    """tok_sb int64 [S, B] time-major ids, lens int32 [B].  Results in .t['loss'] ([1]) and
+    .t['loss_rows'] ([B])."""
+    _need_cuda(fc_feats, tok_sb, lens)
+    d: ListenerDims = packed["dims"]
+    fc_feats = _f32c(fc_feats)
+    assert tok_sb.dtype == torch.int64 and tok_sb.is_contiguous()
+    assert lens.dtype == torch.int32 and lens.is_contiguous()
+    S, B = tok_sb.shape
+    dev = fc_feats.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    T = dict(
+        fc16=torch.empty(B, d.F, **bf), img_pre=torch.empty(B, d.M, **f32),
+        im=torch.empty(B, d.M, **f32), emb16=torch.empty(S, B, d.E, **bf),
+        gi_all=torch.empty(S, B, 3 * d.M, **f32), gh=torch.empty(B, 3 * d.M, **f32),
+        gates=torch.empty(S, B, 4 * d.M, **f32), h32=torch.empty(S + 1, B, d.M, **f32),
+        h16=torch.empty(S + 1, B, d.M, **bf), cap=torch.empty(B, d.M, **f32),
+        scores=torch.empty(B, B, **f32), cost_s=torch.empty(B, **f32),
+        cost_im=torch.empty(B, **f32), arg_s=torch.empty(B, dtype=torch.int32, device=dev),
+        arg_im=torch.empty(B, dtype=torch.int32, device=dev), loss_rows=torch.empty(B, **f32),
+        loss=torch.empty(1, **f32))
+    c = _lib.Listener()
+    c.B, c.S, c.F, c.M, c.E, c.V2 = B, S, d.F, d.M, d.E, d.V2
+    c.margin, c.only_one_retrieval, c.no_imgnorm = float(margin), ONLY[only_one_retrieval], int(no_imgnorm)
+    c.fc_feats, c.tok, c.len = _p(fc_feats), _p(tok_sb), _p(lens)
+    c.w_emb = _p(_f32c(P["txt_enc.embed.weight"].detach()))
+    c.b_img = _p(_f32c(P["img_enc.fc.bias"].detach()))
+    c.b_ih = _p(_f32c(P["txt_enc.rnn.bias_ih_l0"].detach()))
+    c.b_hh = _p(_f32c(P["txt_enc.rnn.bias_hh_l0"].detach()))
+    c.w_img16, c.w_ih16, c.w_hh16 = _p(packed["w_img16"]), _p(packed["w_ih16"]), _p(packed["w_hh16"])
+    for n, tsr in T.items():
+        setattr(c, n, _p(tsr))
+    lp = ListenerPass(ctx=c, dims=d, B=B, S=S, t=T, keep=[fc_feats, tok_sb, lens, packed, P])
+    check(_lib.load().coopcap_listener_fwd(C.byref(c), _stream()))
+    return lp
+
+
+def listener_backward(lp: ListenerPass, P, *, g_loss=None, g_rows=None, need_param_grads=True):
+    """Returns (grads {name: tensor} or None, demb16 [S, B, E] bf16)."""
+    d = lp.dims
+    B, S = lp.B, lp.S
+    dev = lp.t["im"].device
+    f32 = dict(dtype=torch.float32, device=dev)
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    ws = dict(d_im=torch.empty(B, d.M, **f32), d_cap=torch.empty(B, d.M, **f32),
+              dh=torch.empty(B, d.M, **f32), d_img_pre16=torch.empty(B, d.M, **bf),
+              d_gi16=torch.empty(S, B, 3 * d.M, **bf), d_gh16=torch.empty(S, B, 3 * d.M, **bf),
+              demb16=torch.empty(S, B, d.E, **bf))
+    g = _lib.ListenerGrads()
+    if g_loss is not None:
+        g_loss = _f32c(g_loss.reshape(1))
+    if g_rows is not None:
+        g_rows = _f32c(g_rows)
+        assert g_rows.shape == (B,)
+    g.g_loss, g.g_rows = _p(g_loss), _p(g_rows)
+    g.need_param_grads = int(need_param_grads)
+    for n, tsr in ws.items():
+        setattr(g, n, _p(tsr))
+    G = None
+    if need_param_grads:
+        G = {n: torch.empty_like(P[n], dtype=torch.float32) for n in LISTENER_PARAM_NAMES
+             if n != "txt_enc.embed.weight"}
+        G["txt_enc.embed.weight"] = torch.zeros_like(P["txt_enc.embed.weight"], dtype=torch.float32)
+        g.g_w_img, g.g_b_img = _p(G["img_enc.fc.weight"]), _p(G["img_enc.fc.bias"])
+        g.g_w_emb = _p(G["txt_enc.embed.weight"])
+        g.g_w_ih, g.g_w_hh = _p(G["txt_enc.rnn.weight_ih_l0"]), _p(G["txt_enc.rnn.weight_hh_l0"])
+        g.g_b_ih, g.g_b_hh = _p(G["txt_enc.rnn.bias_ih_l0"]), _p(G["txt_enc.rnn.bias_hh_l0"])
+    check(_lib.load().coopcap_listener_bwd(C.byref(lp.ctx), C.byref(g), _stream()))
+    return G, ws["demb16"]
+
+
+def clamp_adam_(param, grad, exp_avg, exp_avg_sq, *, step, lr, grad_scale=1.0, clip=0.0,
+                beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+    """In-place fused (grad * scale) -> clamp -> Adam over flat fp32 buffers."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        _f32c(t)
+    n = param.numel()
+    assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    check(_lib.load().coopcap_clamp_adam(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), n,
+                                         float(grad_scale), float(clip), float(lr), float(beta1),
+                                         float(beta2), float(eps), float(weight_decay), int(step),
+                                         _stream()))

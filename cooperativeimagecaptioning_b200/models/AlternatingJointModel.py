@@ -1,0 +1,305 @@
+"""Drop-in joint speaker-listener model (reference: models/AlternatingJointModel.py).
+
+Keeps the reference's constructor, `forward(fc_feats, seq, masks, data, att_feats, att_masks,
+is_alternating, alternating_turn)` turn logic (:433-555), the loss recipes of the hot path
+(`ce_loss`, `vse_loss`, `reinforce_disc`, `gt/greedy/no_baseline`, `loss_configuration`,
+`st_and_ps_methods`), `sample`, `loss()`, `get/setLossFlages`.  Out of scope:
+the CIDEr self-critical terms (`cider_optimization` must be 0) and the partial-sampling modes.
+
+The straight-through joint step (`retrieval_reward` in {'gumbel','multinomial'}) runs as ONE fused
+autograd node: speaker decode -> listener loss forward; listener backward -> factored
+straight-through gradient (demb . W_emb^T formed tile by tile, never a dense [B,n,V+2] tensor) ->
+speaker BPTT.  The reference hands a dense one-hot tensor across this boundary
+(AttModel.py:445-452 -> VSEFCModel.py:104); that path still exists (speaker.sample with
+use_one_hot=1 + vse(one_hots)) for callers that want the tensors.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import engine as EN
+from .AttModel import _ordered as _ordered_s
+
+
+def _setup(*a, **k):
+    from . import setup
+    return setup(*a, **k)
+
+
+class _StJointFn(torch.autograd.Function):
+    """loss_vse of st_and_ps_methods (:343-376) as a function of speaker + listener parameters."""
+
+    @staticmethod
+    def forward(ctx, owner, sp, lp, *params):
+        ctx.owner, ctx.sp, ctx.lp = owner, sp, lp
+        return lp.t["loss"][0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        owner, sp, lp = ctx.owner, ctx.sp, ctx.lp
+        spk, lis = owner.caption_generator, owner.vse
+        Ps, Pl = spk._params(), lis._params()
+        need_l = any(p.requires_grad for p in Pl.values())
+        need_s = any(p.requires_grad for p in Ps.values())
+        Gl, demb16 = EN.listener_backward(lp, Pl, g_loss=g.contiguous().float().reshape(1),
+                                          need_param_grads=need_l)
+        gs = (None,) * len(EN.SPEAKER_PARAM_NAMES)
+        if need_s:
+            T = sp.n_steps
+            dz16 = EN.st_logit_grads(sp, demb16[1:T + 1], lis._packed.get(Pl)["w_emb16"])
+            Gs = EN.speaker_backward(sp, dz16, Ps)
+            gs = tuple(Gs[n].view_as(Ps[n]) for n in EN.SPEAKER_PARAM_NAMES)
+        gl = tuple((Gl[n].view_as(Pl[n]) if need_l else None) for n in EN.LISTENER_PARAM_NAMES)
+        return (None, None, None) + gs + gl
+
+
+class AlternatingJointModel(nn.Module):
+    def __init__(self, opt, iteration=None):
+        super().__init__()
+        self.opt = opt
+        self.use_word_weights = getattr(opt, "use_word_weights", 0)
+        self.caption_generator = _setup(opt, opt.caption_model, "caption_model")       # :78
+        if opt.vse_model != "None":
+            self.vse = _setup(opt, opt.vse_model, "vse_model")                         # :82
+            self.share_embed = opt.share_embed
+            if self.share_embed:
+                self.caption_generator.embed[0] = self.vse.txt_enc.embed               # :85-88
+                if self.opt.phase == 2:
+                    for p in self.caption_generator.embed.parameters():
+                        p.requires_grad = False
+        else:
+            raise NotImplementedError("vse_model='None' (speaker only) : use models.setup directly")
+        if opt.retrieval_reward == "reinforce":
+            if opt.vse_loss_weight == 0:
+                for p in self.vse.parameters():
+                    p.requires_grad = False                                            # :96-99
+        self.batch_size = opt.batch_size
+        self.vse_loss_weight = opt.vse_loss_weight
+        self.caption_loss_weight = opt.caption_loss_weight
+        self.retrieval_reward = opt.retrieval_reward
+        if getattr(opt, "alternating_turn", None) is not None:
+            if len(opt.alternating_turn) == 1 and opt.retrieval_reward == "reinforce":
+                if opt.alternating_turn[0] == "listener":
+                    opt.retrieval_reward_weight = 0                                    # :110-114
+        self.retrieval_reward_weight = opt.retrieval_reward_weight
+        self.reinforce_baseline_type = getattr(opt, "reinforce_baseline_type", "greedy")
+        self.only_one_retrieval = getattr(opt, "only_one_retrieval", "off")
+        self.cider_optimization = getattr(opt, "cider_optimization", 0)
+        self.use_gen_cider_scores = getattr(opt, "use_gen_cider_scores", 0)
+        self._loss = {}
+        self._load_checkpoints(opt, iteration)
+
+    # checkpoint loading (:131-177): same file names, tolerant state-dict loader
+    def _load_checkpoints(self, opt, iteration):
+        from . import load_state_dict
+        start = vars(opt).get("start_from", None)
+        if start is not None and os.path.isdir(start):
+            name = "alternatingModel.pth" if iteration is None else f"alternatingModel-{iteration}.pth"
+            path = os.path.join(start, name)
+            if not os.path.isfile(path):
+                path = os.path.join(start, "model.pth" if iteration is None else f"model-{iteration}.pth")
+            if os.path.isfile(path):
+                load_state_dict(self, torch.load(path, map_location="cpu"))
+        init = vars(opt).get("initialize_retrieval", None)
+        if init is not None and os.path.isfile(str(init)):
+            sd = torch.load(init, map_location="cpu")
+            load_state_dict(self, {k: v for k, v in sd.items() if k.startswith("vse.")})
+
+    # ------------------------------------------------------------------ flags (:180-194)
+    def getLossFlags(self):
+        return [self.vse_loss_weight, self.caption_loss_weight, self.cider_optimization,
+                self.retrieval_reward_weight]
+
+    def setLossFlages(self, VSEWeight, MLEWeight, ciderFlag, DISCWeight):
+        self.vse_loss_weight = VSEWeight
+        self.caption_loss_weight = MLEWeight
+        self.cider_optimization = ciderFlag
+        self.retrieval_reward_weight = DISCWeight
+
+    def _zero(self, ref):
+        return torch.zeros(1, device=ref.device)
+
+    # ------------------------------------------------------------------ loss terms
+    def ce_loss(self, fc_feats, att_feats, att_masks, seq, masks):                     # :196-207
+        if self.caption_loss_weight > 0:
+            loss_cap = self.caption_generator(fc_feats, att_feats, att_masks, seq, masks)
+            self._loss["loss_cap"] = loss_cap.detach()
+            return loss_cap
+        return self._zero(fc_feats)
+
+    def vse_loss(self, fc_feats, att_feats, seq, masks, only_one_retrieval):            # :209-224
+        if self.vse_loss_weight > 0:
+            loss_vse = self.vse(fc_feats, att_feats, seq, masks,
+                                only_one_retrieval=self.only_one_retrieval)
+            self._loss["loss_vse"] = loss_vse.detach()
+            return loss_vse
+        return self._zero(fc_feats)
+
+    @staticmethod
+    def _caption_masks(seqs):
+        """[1, 1, (w_1>0), ..., (w_{n-1}>0)]                                  (:232-234,353-355)"""
+        B = seqs.size(0)
+        return torch.cat([torch.ones(B, 2, device=seqs.device), (seqs > 0).float()[:, :-1]], 1)
+
+    def _with_bos(self, seqs):
+        bos = torch.full((seqs.size(0), 1), self.caption_generator.vocab_size + 1,
+                         dtype=seqs.dtype, device=seqs.device)
+        return torch.cat([bos, seqs], 1)
+
+    def reinforce_disc(self, fc_feats, att_feats, att_masks):                           # :226-247
+        _seqs, _sampleLogProbs = self.caption_generator.sample(
+            fc_feats, att_feats, att_masks, {"sample_max": 0, "temperature": 1})
+        gen_result, sample_logprobs = _seqs, _sampleLogProbs
+        _masks = self._caption_masks(_seqs)
+        gen_masks = _masks
+        _seqs = self._with_bos(_seqs)
+        retrieval_loss = self.vse(fc_feats, att_feats, _seqs, _masks, True,
+                                  only_one_retrieval=self.only_one_retrieval)
+        return retrieval_loss, _seqs, _masks, gen_result, sample_logprobs, gen_masks
+
+    def greedy_baseline(self, fc_feats, att_feats, att_masks, retrieval_loss, _seqs,
+                        _sampleLogProbs, _masks):                                       # :250-298
+        with torch.no_grad():
+            _seqs_greedy, _ = self.caption_generator.sample(
+                fc_feats, att_feats, att_masks, opt={"sample_max": 1, "temperature": 1})
+            greedy_res = _seqs_greedy
+            _masks_greedy = self._caption_masks(_seqs_greedy)
+            baseline = self.vse(fc_feats, att_feats, self._with_bos(_seqs_greedy), _masks_greedy,
+                                True, only_one_retrieval=self.only_one_retrieval)
+        sc_loss = _sampleLogProbs * (retrieval_loss - baseline).detach().unsqueeze(1) * \
+            _masks[:, 1:].detach().float()
+        return baseline, sc_loss, greedy_res
+
+    def gt_baseline(self, fc_feats, att_feats, att_masks, retrieval_loss, _seqs, _sampleLogProbs,
+                    _masks, seq, masks):                                                # :300-310
+        baseline = self.vse(fc_feats, att_feats, seq, masks, True,
+                            only_one_retrieval=self.only_one_retrieval)
+        sc_loss = _sampleLogProbs * (retrieval_loss - baseline).detach().unsqueeze(1) * \
+            _masks[:, 1:].detach().float()
+        return baseline, sc_loss
+
+    def no_baseline(self, retrieval_loss, _sampleLogProbs, _masks):                     # :312-319
+        sc_loss = _sampleLogProbs * retrieval_loss.detach().unsqueeze(1) * \
+            _masks[:, 1:].detach().float()
+        return 0, sc_loss
+
+    def loss_configuration(self, loss, sc_loss, baseline, retrieval_loss, _masks):      # :321-332
+        sc_loss = sc_loss.sum() / _masks[:, 1:].float().sum()
+        loss = loss + self.retrieval_reward_weight * sc_loss
+        self._loss["retrieval_sc_loss"] = sc_loss.detach()
+        self._loss["retrieval_loss"] = retrieval_loss.sum().detach()
+        self._loss["retrieval_loss_greedy"] = baseline.sum().detach() \
+            if torch.is_tensor(baseline) else baseline
+        return loss
+
+    def reinforce(self, fc_feats, att_feats, att_masks, seq, masks, data, loss):        # :334-341
+        retrieval_loss, _seqs, _masks, gen_result, sample_logprobs, gen_masks = \
+            self.reinforce_disc(fc_feats, att_feats, att_masks)
+        return loss, gen_result, sample_logprobs, _masks, gen_result, gen_masks, _seqs, \
+            retrieval_loss
+
+    def st_and_ps_methods(self, fc_feats, att_feats, att_masks, seq, masks, data, loss):
+        """gumbel / multinomial joint loss (:343-376), fused (see module docstring).  Returns
+        (loss, word_index, logprobs, masks, _seqs) with the caption tensors left time-major and
+        unsliced on the device (they only feed the out-of-scope CIDEr branch in the reference)."""
+        spk, lis = self.caption_generator, self.vse
+        if self.retrieval_reward not in ("gumbel", "multinomial"):
+            raise NotImplementedError(
+                f"retrieval_reward={self.retrieval_reward!r} is not on the B200 path yet")
+        sp, st_mode = spk._sample_pass(att_feats, att_masks, 0, 1, 1)                   # :346-348
+        assert st_mode
+        B, V = sp.B, spk.vocab_size
+        tok_sb = torch.cat([torch.full((1, B), V + 1, dtype=torch.int64, device=fc_feats.device),
+                            sp.t["tok_out"][: sp.n_steps]], 0)                          # :360-370
+        Pl = lis._params()
+        lp = EN.listener_forward(Pl, lis._packed.get(Pl), fc_feats.detach().float().contiguous(),
+                                 tok_sb, sp.t["cap_len"], margin=lis.margin,
+                                 only_one_retrieval=self.only_one_retrieval,
+                                 no_imgnorm=bool(lis.img_enc.no_imgnorm))               # :371-373
+        Ps = spk._params()
+        if torch.is_grad_enabled():
+            loss_vse = _StJointFn.apply(self, sp, lp, *_ordered_s(Ps),
+                                        *[Pl[n] for n in EN.LISTENER_PARAM_NAMES])
+        else:
+            loss_vse = lp.t["loss"][0].clone()
+        lis._loss["contrastive"] = loss_vse.detach()
+        loss = loss + loss_vse * self.retrieval_reward_weight                           # :374
+        return loss, sp.t["tok_out"], sp.t["logp"], sp.t["cap_len"], tok_sb
+
+    # ------------------------------------------------------------------ forward (:433-555)
+    def forward(self, fc_feats, seq, masks, data, att_feats, att_masks, is_alternating=False,
+                alternating_turn=None):
+        if not is_alternating:
+            if self.cider_optimization:
+                raise NotImplementedError("CIDEr self-critical terms are outside the hot path "
+                                          "(SURVEY.md §2 row 8): run with cider_optimization=0")
+            loss_cap = self.ce_loss(fc_feats, att_feats, att_masks, seq, masks)
+            loss_vse = self.vse_loss(fc_feats, att_feats, seq, masks,
+                                     only_one_retrieval=self.only_one_retrieval)
+            loss = self.caption_loss_weight * loss_cap + self.vse_loss_weight * loss_vse
+            if self.retrieval_reward_weight > 0:
+                if self.retrieval_reward == "reinforce":
+                    loss, gen_result, sample_logprobs, _masks, gen_result, gen_masks, _seqs, \
+                        retrieval_loss = self.reinforce(fc_feats, att_feats, att_masks, seq, masks,
+                                                        data, loss)
+                    if self.reinforce_baseline_type == "greedy":
+                        baseline, sc_loss, _ = self.greedy_baseline(
+                            fc_feats, att_feats, att_masks, retrieval_loss, _seqs, sample_logprobs,
+                            _masks)
+                    elif self.reinforce_baseline_type == "gt":
+                        baseline, sc_loss = self.gt_baseline(
+                            fc_feats, att_feats, att_masks, retrieval_loss, _seqs, sample_logprobs,
+                            _masks, seq, masks)
+                    else:
+                        baseline, sc_loss = self.no_baseline(retrieval_loss, sample_logprobs, _masks)
+                    loss = self.loss_configuration(loss, sc_loss, baseline, retrieval_loss, _masks)
+                else:
+                    loss, *_ = self.st_and_ps_methods(fc_feats, att_feats, att_masks, seq, masks,
+                                                      data, loss)
+            return loss
+        if alternating_turn == "speaker":                                               # :508-526
+            if self.retrieval_reward == "reinforce":
+                self.changeModelUpdateStatus({"vseModel": False, "captionModel": True})
+            old = self.getLossFlags()
+            self.setLossFlages(VSEWeight=0, MLEWeight=old[1], ciderFlag=old[2], DISCWeight=old[3])
+            try:
+                return self.forward(fc_feats, seq, masks, data, att_feats, att_masks,
+                                    is_alternating=False, alternating_turn=alternating_turn)
+            finally:
+                self.setLossFlages(*old)
+        if alternating_turn == "listener":                                              # :528-555
+            self.changeModelUpdateStatus({"vseModel": True, "captionModel": False})
+            old = self.getLossFlags()
+            self.setLossFlages(VSEWeight=old[0], MLEWeight=0, ciderFlag=0, DISCWeight=0)
+            try:
+                with torch.no_grad():
+                    _seqs, _ = self.caption_generator.sample(
+                        fc_feats, att_feats, att_masks, {"sample_max": 0, "temperature": 1})
+                _masks = self._caption_masks(_seqs)
+                _seqs = self._with_bos(_seqs)
+                return self.forward(fc_feats, _seqs, _masks, data, att_feats, att_masks,
+                                    is_alternating=False, alternating_turn=alternating_turn)
+            finally:
+                self.setLossFlages(*old)
+        raise ValueError(f"alternating_turn must be 'speaker' or 'listener', got {alternating_turn!r}")
+
+    def sample(self, fc_feats, att_feats, att_masks, opt={}):                           # :557-560
+        return self.caption_generator.sample(fc_feats, att_feats, att_masks, opt)
+
+    def loss(self):                                                                     # :562-568
+        out = {}
+        out.update(self._loss)
+        out.update({"cap_" + k: v for k, v in self.caption_generator._loss.items()})
+        out.update({"vse_" + k: v for k, v in self.vse._loss.items()})
+        return out
+
+    def changeModelUpdateStatus(self, gradientsDic, printWeights=False):
+        """requires_grad toggling of :571-633; the deep-copy consistency check (:584-586,
+        :680-685) is not reproduced."""
+        for p in self.vse.parameters():
+            p.requires_grad = bool(gradientsDic["vseModel"])
+        for p in self.caption_generator.parameters():
+            p.requires_grad = bool(gradientsDic["captionModel"])

@@ -181,13 +181,14 @@ typedef struct coopcap_speaker {
   uint64_t seed;
   float drop_p;
   const uint8_t* keep_att;   /* [NL, R] packed, or NULL */
-  const uint8_t* keep_embed; /* [cap+1, B, E] or NULL */
+  const uint8_t* keep_embed; /* [>= n_steps, B, E] or NULL */
   const uint8_t* keep_core;  /* [cap, B, R] or NULL */
   const float* noise;        /* [cap, B, V1] uniforms (gumbel) / Exp(1) draws (multinomial) or NULL */
   /* decode configuration */
   int mode;                  /* COOPCAP_SAMPLE_* */
   float inv_tau;             /* 1/gumbel_temp, 1/multinomial_temp or 1/temperature */
   int64_t start_token;       /* V+1 for `sample` (AttModel.py:324-326), 0 for `forward` (:131) */
+  const int64_t* start_tokens; /* [B] per-row start ids (seq[:,0], AttModel.py:131) or NULL -> start_token */
   const int64_t* forced;     /* [cap, B] ids that replace the drawn ones (teacher forcing / replay) or NULL */
   /* saved activations / outputs (see layout above) */
   void* att16;
@@ -229,6 +230,10 @@ int coopcap_speaker_decode_fwd(const coopcap_speaker* ctx, coopcap_stream_t stre
  * 1..n_steps; w_emb16: bf16 [>=V1, E]; g_ws: fp32 [B, V1] workspace; dz16: bf16 [n_steps*B, V1]. */
 int coopcap_st_backward(const coopcap_speaker* ctx, const void* demb16, const void* w_emb16,
                         float* g_ws, void* dz16, coopcap_stream_t stream);
+/* Same with a dense upstream gradient g = d(loss)/d(one_hots[:, :, :V1]) given explicitly
+ * (fp32 [n_steps*B, ldg]); used when foreign code consumed the dense one-hot tensor. */
+int coopcap_st_backward_dense(const coopcap_speaker* ctx, const float* g, int64_t ldg, void* dz16,
+                              coopcap_stream_t stream);
 /* d(loss)/d(logits) of sum_{t,b} coef[t,b] * log_softmax(z[t,b])[tok[t,b]]
  * (REINFORCE: AlternatingJointModel.py:305-309,324; XE: misc/utils.py:49-58 with coef = -mask/sum).
  * tok: int64 [n_steps, B]; coef: fp32 [n_steps, B]. */
@@ -239,7 +244,7 @@ typedef struct coopcap_speaker_grads {
   /* input */
   const void* dz16;     /* bf16 [n_steps*B, V1] */
   /* workspaces */
-  float* d_out;         /* [cap*B, R]  d(loss)/d(dropout(h_t)) from the logit layer */
+  float* d_out;         /* [max(cap,2)*B, R]  d(loss)/d(dropout(h_t)) from the logit layer (reused as scratch) */
   void* dscat16;        /* bf16 [cap*B, 5R+A] : d(gate pre-acts) | d(att_h) */
   float* d_att_res;     /* [cap*B, R] */
   float* de;            /* [cap, NL] d(attention scores) */
@@ -249,7 +254,7 @@ typedef struct coopcap_speaker_grads {
   void* d_p_att16;      /* bf16 [NL, A] */
   void* d_pre16;        /* bf16 [NL, R] */
   /* outputs: gradients, fp32, reference parameter shapes; written (overwritten), except g_embed
-   * and g_w_alpha which are accumulated into (the caller zeroes them) */
+   * which is accumulated into (the caller zeroes it) */
   float* g_embed;       /* [V+2, E] */
   float* g_w_att_embed;
   float* g_b_att_embed;

@@ -44,6 +44,13 @@ class SpeakerNoise:
     U: Optional[torch.Tensor] = None
     E: Optional[torch.Tensor] = None
     part_u: Optional[torch.Tensor] = None
+    # --- branch replay (test aid, like forced_tokens): decisions of the non-smooth ops taken from
+    # the implementation under test, so that a near-tie flip (bf16 vs fp32 pre-activations) does
+    # not masquerade as a gradient error.  None -> the oracle decides itself (reference behaviour).
+    relu_att: Optional[torch.Tensor] = None      # bool [B, L, R]: att_embed pre-activation > 0
+    maxout_first: Optional[torch.Tensor] = None  # bool [steps, B, R]: u[:, :R] >= u[:, R:]
+    # filled by the oracle for diagnostics: margins of its own decisions
+    margins: Optional[dict] = None
 
 
 def _dropout(x, keep, p):
@@ -64,7 +71,13 @@ def prologue(P: Params, att_feats, att_masks, noise: SpeakerNoise, drop_p: float
     """att_e = dropout(relu(att W^T + b)) on valid regions, exactly 0 on padded regions, width
     clipped to the longest row (pack_wrapper, AttModel.py:44-51); p_att = ctx2att(att_e)
     (AttModel.py:114) -- so padded positions of p_att hold ctx2att's bias."""
-    x = torch.relu(_linear(att_feats, P, "att_embed.0"))
+    pre = _linear(att_feats, P, "att_embed.0")
+    if noise.margins is not None:
+        noise.margins["relu_att"] = pre.detach()
+    if noise.relu_att is not None:
+        x = pre * noise.relu_att.to(pre.dtype)           # replayed ReLU decision
+    else:
+        x = torch.relu(pre)
     x = _dropout(x, noise.drop_att, drop_p)
     if att_masks is not None:
         lens = att_masks.long().sum(1)                    # AttModel.py:47
@@ -94,14 +107,20 @@ def attention(P: Params, h, att_e, p_att, att_masks):
 # --------------------------------------------------------------------------------------------
 # Att2in2Core.forward                                                      (AttModel.py:510-531)
 # --------------------------------------------------------------------------------------------
-def core_step(P: Params, xt, h, c, att_e, p_att, att_masks, keep_core, drop_p):
+def core_step(P: Params, xt, h, c, att_e, p_att, att_masks, keep_core, drop_p, maxout_first=None,
+              margins=None):
     R = h.size(1)
     att_res, w = attention(P, h, att_e, p_att, att_masks)               # :511
     s = _linear(xt, P, "core.i2h") + _linear(h, P, "core.h2h")          # :514
     sig = torch.sigmoid(s[:, : 3 * R])                                  # :515-516
     i, f, o = sig[:, :R], sig[:, R:2 * R], sig[:, 2 * R:3 * R]          # :517-519
     u = s[:, 3 * R:] + _linear(att_res, P, "core.a2c")                  # :521-522
-    g = torch.max(u[:, :R], u[:, R:])                                   # :523-525 (maxout)
+    if margins is not None:
+        margins.setdefault("maxout", []).append((u[:, :R] - u[:, R:]).detach())
+    if maxout_first is not None:
+        g = torch.where(maxout_first, u[:, :R], u[:, R:])               # replayed maxout decision
+    else:
+        g = torch.max(u[:, :R], u[:, R:])                               # :523-525 (maxout)
     c2 = f * c + i * g                                                  # :526
     h2 = o * torch.tanh(c2)                                             # :527
     out = _dropout(h2, keep_core, drop_p)                               # :529
@@ -268,7 +287,10 @@ def sample(P: Params, att_feats, att_masks, *, mode: str, seq_length: int, vocab
                     vec = torch.where(unfinished[:, None], vec, eos_one_hot)  # :419-420,:431-432
                 seq.append(vec)
             seq_lp.append(sample_lp)                                          # :413,:423,:434
-        out, h, c, _ = core_step(P, xt, h, c, att_e, p_att, att_masks, keep_c, drop_p)  # :436
+        mf = None if noise.maxout_first is None or t >= noise.maxout_first.size(0) \
+            else noise.maxout_first[t]
+        out, h, c, _ = core_step(P, xt, h, c, att_e, p_att, att_masks, keep_c, drop_p, mf,
+                                 noise.margins)                                         # :436
         logprobs = F.log_softmax(logits_of(P, out), dim=1)                    # :444
         res.step_logprobs.append(logprobs)
         res.n_steps += 1
@@ -314,7 +336,10 @@ def forward_xe(P: Params, att_feats, att_masks, seq, masks, *, noise: SpeakerNoi
         keep_e = None if noise.drop_embed is None else noise.drop_embed[i]
         keep_c = None if noise.drop_core is None else noise.drop_core[i]
         xt = embed_tokens(P, it, keep_e, drop_p)                              # :136
-        out, h, c, _ = core_step(P, xt, h, c, att_e, p_att, att_masks, keep_c, drop_p)  # :138
+        mf = None if noise.maxout_first is None or i >= noise.maxout_first.size(0) \
+            else noise.maxout_first[i]
+        out, h, c, _ = core_step(P, xt, h, c, att_e, p_att, att_masks, keep_c, drop_p, mf,
+                                 noise.margins)                                         # :138
         outputs.append(F.log_softmax(logits_of(P, out), dim=1))               # :140
     logp = torch.stack(outputs, 1)                                            # :143
     loss = language_model_criterion(logp, seq[:, 1:], masks[:, 1:])           # :144

@@ -25,3 +25,54 @@ def rel_err(a, b):
 
 
 REAL = synth.Dims()
+
+
+def branch_replay(sp, att_masks, noise):
+    """Copy of `noise` that makes the oracle replay the CUDA pass's non-smooth decisions (maxout
+    branch, att_embed ReLU) and record its own margins -- the gradient analogue of forced tokens."""
+    import copy
+    R = sp.dims.R
+    n = sp.n_steps
+    s = sp.t["s_all"][:n].float().cpu()
+    u = sp.t["u_all"][:n].float().cpu()
+    first = (s[:, :, 3 * R:4 * R] + u[:, :, :R]) >= (s[:, :, 4 * R:5 * R] + u[:, :, R:])
+    on = (sp.t["att_e16"].float() > 0).cpu()                 # packed [NL, R]
+    B, L = sp.B, sp.L
+    if att_masks is None:
+        relu = on.view(B, L, R)
+    else:
+        relu = torch.zeros(B, L, R, dtype=torch.bool)
+        relu[att_masks[:, :L] > 0] = on
+    if noise.drop_att is not None:
+        # a dropped unit hides the ReLU decision; it carries no gradient either way
+        relu = relu | (noise.drop_att == 0)
+    out = copy.copy(noise)
+    out.maxout_first, out.relu_att, out.margins = first, relu, {}
+    return out
+
+
+def check_near_ties(replay_noise, att_masks, tol):
+    """The replayed decisions may differ from the oracle's own only at near-ties (|margin| < tol
+    relative to the typical margin)."""
+    mg = replay_noise.margins
+    stats = {}
+    m = torch.stack(mg["maxout"], 0)[: replay_noise.maxout_first.size(0)]
+    dec = replay_noise.maxout_first[: m.size(0)]
+    flipped = dec != (m >= 0)
+    scale = float(m.abs().median())
+    stats["maxout_flips"] = int(flipped.sum())
+    stats["maxout_total"] = flipped.numel()
+    if flipped.any():
+        assert float(m[flipped].abs().max()) <= tol * scale, "maxout decision differs away from a tie"
+    pre = mg["relu_att"]
+    dec = replay_noise.relu_att
+    valid = torch.ones_like(dec) if att_masks is None else (att_masks[:, :dec.size(1)] > 0)[:, :, None].expand_as(dec)
+    if replay_noise.drop_att is not None:
+        valid = valid & (replay_noise.drop_att > 0)
+    flipped = (dec != (pre > 0)) & valid
+    scale = float(pre.abs().median())
+    stats["relu_flips"] = int(flipped.sum())
+    stats["relu_total"] = int(valid.sum())
+    if flipped.any():
+        assert float(pre[flipped].abs().max()) <= tol * scale, "ReLU decision differs away from a tie"
+    return stats

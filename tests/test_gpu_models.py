@@ -1,0 +1,227 @@
+"""GPU: the drop-in modules (models.setup / AlternatingJointModel) against the CPU oracle on the
+same seeded inputs and injected noise.  These read like a user of the reference would call it."""
+import pytest
+import torch
+
+from oracle import joint as OJ
+from oracle import speaker as OS
+from oracle import synth
+from oracle.ref_loader import reference_opt
+from gpu_util import REAL, branch_replay, check_near_ties, pack_keep, u8
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 2e-2     # bf16-operand path (north star: 2e-2 relative)
+GRAD_L2_TOL = 2e-2  # ||g - g_ref||_2 / ||g_ref||_2 per parameter tensor, decisions replayed
+GRAD_COS = 0.9995
+NEAR_TIE = 5e-2     # a maxout / ReLU decision may differ only if |margin| < 5% of the median margin
+
+
+def _build(mode, B, L, seed, *, varlen, dropout, tau=1.0, eos_bias=7.5, **optkw):
+    import cooperativeimagecaptioning_b200.models as models
+    from cooperativeimagecaptioning_b200 import engine as EN
+    d = REAL
+    Ps = synth.speaker_params(d, seed=seed, eos_bias=eos_bias)
+    Pl = synth.listener_params(d, seed=seed + 1)
+    batch = synth.make_batch(d, B, L, seed + 2, varlen=varlen, min_regions=2)
+    noise = synth.make_noise(d, B, L, seed + 3, dropout=dropout, gumbel=(mode == "gumbel"),
+                             multinomial=(mode in ("multinomial", "reinforce")))
+    drop_p = 0.5 if dropout else 0.0
+    opt = reference_opt(retrieval_reward=mode, gumbel_temp=tau, multinomial_temp=tau,
+                        drop_prob_lm=drop_p, batch_size=B, **optkw)
+    model = models.AlternatingJointModel(opt)
+    sd = {"caption_generator." + k: v for k, v in Ps.items()}
+    sd.update({"vse." + k: v for k, v in Pl.items()})
+    model.load_state_dict(sd)
+    model.cuda().train()
+    T = d.seq_length
+    rnd = EN.SpeakerRandom(seed=1, drop_p=drop_p)
+    if dropout:
+        rnd.keep_att = pack_keep(noise.drop_att, batch.att_masks)
+        rnd.keep_embed = u8(noise.drop_embed)
+        rnd.keep_core = u8(noise.drop_core)
+    if mode == "gumbel":
+        rnd.noise = noise.U.cuda().contiguous()
+    elif mode in ("multinomial", "reinforce"):
+        rnd.noise = noise.E.cuda().contiguous()
+    model.caption_generator.injected = rnd
+    model.caption_generator.keep_passes = True
+    cfg = OJ.JointCfg(drop_p=drop_p, retrieval_reward=mode, gumbel_temp=tau, multinomial_temp=tau,
+                      retrieval_reward_weight=opt.retrieval_reward_weight,
+                      vse_loss_weight=opt.vse_loss_weight,
+                      caption_loss_weight=opt.caption_loss_weight,
+                      reinforce_baseline_type=opt.reinforce_baseline_type)
+    return model, Ps, Pl, batch, noise, cfg
+
+
+def _oracle_grads(loss, Pso, Plo):
+    ts = list(Pso.values()) + list(Plo.values())
+    names = ["caption_generator." + k for k in Pso] + ["vse." + k for k in Plo]
+    gs = torch.autograd.grad(loss, ts, allow_unused=True)
+    return {n: (torch.zeros_like(t) if g is None else g) for n, t, g in zip(names, ts, gs)}
+
+
+def _check_grads(model, ref, tag):
+    worst_l2, worst_cos = 0.0, 1.0
+    for name, p in model.named_parameters():
+        r = ref[name].double().flatten()
+        g = torch.zeros_like(r) if p.grad is None else p.grad.detach().double().cpu().flatten()
+        if name.endswith("alpha_net.bias") or float(r.abs().max()) < 1e-11:
+            # alpha_net.bias: analytically 0 (softmax shift invariance); the reference only
+            # accumulates rounding noise there
+            assert float(g.abs().max()) < 1e-7, name
+            continue
+        l2 = float((g - r).norm() / r.norm())
+        cos = float((g @ r) / (g.norm() * r.norm()))
+        worst_l2, worst_cos = max(worst_l2, l2), min(worst_cos, cos)
+        assert l2 <= GRAD_L2_TOL and cos >= GRAD_COS, f"{tag} {name}: l2 {l2:.3e} cos {cos:.6f}"
+    print(f"[{tag}] worst grad l2 rel err {worst_l2:.3e}, worst cosine {worst_cos:.6f}")
+
+
+def _cuda_batch(batch):
+    return (batch.fc_feats.cuda(), batch.labels.cuda(), batch.masks.cuda(), None,
+            batch.att_feats.cuda(), None if batch.att_masks is None else batch.att_masks.cuda())
+
+
+def _replay_tokens(Ps, batch, noise, mode, drop_p, tau, sample_max=0):
+    d = REAL
+    free = OS.sample(Ps, batch.att_feats, batch.att_masks, mode=mode, seq_length=d.seq_length,
+                     vocab_size=d.vocab_size, noise=noise, drop_p=drop_p, sample_max=sample_max,
+                     use_one_hot=0 if mode == "reinforce" else 1, gumbel_temp=tau,
+                     multinomial_temp=tau, keep_all_steps=True)
+    return torch.stack(free.tokens_raw, 1)
+
+
+@pytest.mark.parametrize("mode,varlen,dropout,tau", [("gumbel", True, True, 0.75),
+                                                     ("multinomial", False, True, 1.0)])
+def test_joint_st_speaker_turn(mode, varlen, dropout, tau):
+    model, Ps, Pl, batch, noise, cfg = _build(mode, 12, 8, 31, varlen=varlen, dropout=dropout, tau=tau)
+    forced = _replay_tokens(Ps, batch, noise, mode, cfg.drop_p, tau)
+    model.caption_generator.forced_tokens = forced.cuda()
+    fc, labels, masks, data, att, am = _cuda_batch(batch)
+    loss = model(fc, labels, masks, data, att, am, is_alternating=True, alternating_turn="speaker")
+    loss.backward()
+    rn = branch_replay(model.caption_generator._passes[0], batch.att_masks, noise)
+    Pso = {k: v.clone().requires_grad_(True) for k, v in Ps.items()}
+    Plo = {k: v.clone().requires_grad_(True) for k, v in Pl.items()}
+    loss_ref, res, _, _ = OJ.st_joint_loss(Pso, Plo, batch.fc_feats, batch.att_feats,
+                                           batch.att_masks, rn, cfg, forced)
+    ref = _oracle_grads(loss_ref, Pso, Plo)
+    print(check_near_ties(rn, batch.att_masks, NEAR_TIE))
+    assert abs(float(loss) - float(loss_ref)) <= LOSS_TOL * abs(float(loss_ref))
+    _check_grads(model, ref, f"st-{mode}")
+    out = model.loss()
+    assert "vse_contrastive" in out
+
+
+def test_mle_step():
+    model, Ps, Pl, batch, noise, cfg = _build("gumbel", 10, 6, 41, varlen=True, dropout=True,
+                                              caption_loss_weight=1.0, retrieval_reward_weight=0.0)
+    fc, labels, masks, data, att, am = _cuda_batch(batch)
+    loss = model(fc, labels, masks, data, att, am)
+    loss.backward()
+    rn = branch_replay(model.caption_generator._passes[0], batch.att_masks, noise)
+    Pso = {k: v.clone().requires_grad_(True) for k, v in Ps.items()}
+    Plo = {k: v.clone().requires_grad_(True) for k, v in Pl.items()}
+    loss_ref = OJ.mle_loss(Pso, batch.att_feats, batch.att_masks, batch.labels, batch.masks, rn, cfg)
+    ref = _oracle_grads(loss_ref, Pso, Plo)
+    print(check_near_ties(rn, batch.att_masks, NEAR_TIE))
+    assert abs(float(loss) - float(loss_ref)) <= LOSS_TOL * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    _check_grads(model, ref, "mle")
+    assert abs(float(model.loss()["cap_xe"]) - float(loss_ref)) <= LOSS_TOL * abs(float(loss_ref))
+
+
+@pytest.mark.parametrize("baseline", ["gt", "greedy", "none"])
+def test_reinforce_speaker_turn(baseline):
+    model, Ps, Pl, batch, noise, cfg = _build("reinforce", 10, 6, 51, varlen=False, dropout=False,
+                                              retrieval_reward_weight=0.8, vse_loss_weight=0.1,
+                                              reinforce_baseline_type=baseline,
+                                              is_alternating=1,
+                                              eos_bias=0.0 if baseline == "greedy" else 7.5)
+    # the reference freezes the listener only when vse_loss_weight == 0; the speaker turn freezes it
+    forced = _replay_tokens(Ps, batch, noise, "reinforce", cfg.drop_p, 1.0)
+    cfg.vse_loss_weight = 0.0           # speaker turn forces the VSE weight to 0 (:516-518)
+    forced_g = None
+    if baseline == "greedy":
+        forced_g = _replay_tokens(Ps, batch, synth.SpeakerNoise(), "reinforce", 0.0, 1.0, sample_max=1)
+    spk = model.caption_generator
+    spk.forced_tokens = forced.cuda()
+    if baseline == "greedy":
+        # the greedy pass must not be forced with the sampled ids: patch sample to swap them
+        orig = spk._sample_pass
+
+        def patched(att_feats, att_masks, sample_max, temperature, use_one_hot):
+            spk.forced_tokens = (forced_g if sample_max else forced).cuda()
+            return orig(att_feats, att_masks, sample_max, temperature, use_one_hot)
+        spk._sample_pass = patched
+    fc, labels, masks, data, att, am = _cuda_batch(batch)
+    loss = model(fc, labels, masks, data, att, am, is_alternating=True, alternating_turn="speaker")
+    loss.backward()
+    rn = branch_replay(spk._passes[0], batch.att_masks, noise)
+    Pso = {k: v.clone().requires_grad_(True) for k, v in Ps.items()}
+    Plo = {k: v.clone().requires_grad_(True) for k, v in Pl.items()}
+    loss_ref, res, r, b = OJ.reinforce_speaker_loss(
+        Pso, Plo, batch.fc_feats, batch.att_feats, batch.att_masks, batch.labels, batch.masks,
+        rn, cfg, noise_greedy=synth.SpeakerNoise(), forced_tokens=forced,
+        forced_tokens_greedy=forced_g)
+    ref = _oracle_grads(loss_ref, Pso, Plo)
+    print(check_near_ties(rn, batch.att_masks, NEAR_TIE))
+    denom = max(abs(float(loss_ref)), 1e-3)
+    assert abs(float(loss) - float(loss_ref)) <= LOSS_TOL * denom, (float(loss), float(loss_ref))
+    _check_grads(model, ref, f"reinforce-{baseline}")
+
+
+def test_listener_turn():
+    model, Ps, Pl, batch, noise, cfg = _build("reinforce", 10, 6, 61, varlen=True, dropout=True,
+                                              retrieval_reward_weight=0.8, vse_loss_weight=0.1)
+    forced = _replay_tokens(Ps, batch, noise, "reinforce", cfg.drop_p, 1.0)
+    Pso = {k: v.clone().requires_grad_(True) for k, v in Ps.items()}
+    Plo = {k: v.clone().requires_grad_(True) for k, v in Pl.items()}
+    loss_ref, res, loss_vse = OJ.listener_turn_loss(Pso, Plo, batch.fc_feats, batch.att_feats,
+                                                    batch.att_masks, noise, cfg, forced)
+    ref = _oracle_grads(loss_ref, Pso, Plo)
+    model.caption_generator.forced_tokens = forced.cuda()
+    fc, labels, masks, data, att, am = _cuda_batch(batch)
+    loss = model(fc, labels, masks, data, att, am, is_alternating=True, alternating_turn="listener")
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= LOSS_TOL * abs(float(loss_ref))
+    _check_grads(model, ref, "listener-turn")
+    assert all(p.grad is None for p in model.caption_generator.parameters())
+
+
+def test_dense_one_hot_boundary_matches_fused_path():
+    """speaker.sample(use_one_hot=1) -> vse(one_hots) (the reference's dense hand-off) gives the
+    same loss and gradients as the fused joint node."""
+    model, Ps, Pl, batch, noise, cfg = _build("gumbel", 8, 5, 71, varlen=False, dropout=True)
+    forced = _replay_tokens(Ps, batch, noise, "gumbel", cfg.drop_p, 1.0)
+    spk, lis = model.caption_generator, model.vse
+    spk.forced_tokens = forced.cuda()
+    fc, labels, masks, data, att, am = _cuda_batch(batch)
+    loss_f = model(fc, labels, masks, data, att, am, is_alternating=True, alternating_turn="speaker")
+    loss_f.backward()
+    g_fused = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    word_index, one_hots, logprobs = spk.sample(fc, att, am, {"sample_max": 0, "temperature": 1,
+                                                              "use_one_hot": 1})
+    B, V = word_index.size(0), spk.vocab_size
+    _masks = torch.cat([torch.ones(B, 2, device="cuda"), (word_index > 0).float()[:, :-1]], 1)
+    bos = torch.zeros(B, 1, V + 2, device="cuda")
+    bos[:, 0, V + 1] = 1.0
+    _seqs = torch.cat([bos, one_hots], 1)
+    loss_d = lis(fc, att, _seqs, _masks) * model.retrieval_reward_weight
+    loss_d.backward()
+    assert abs(float(loss_d) - float(loss_f)) <= 1e-5 * abs(float(loss_f))
+    for n, p in model.named_parameters():
+        a, b = p.grad.double().flatten(), g_fused[n].double().flatten()
+        if float(b.norm()) == 0:
+            continue
+        assert float((a - b).norm() / b.norm()) <= 2e-2, n
+
+
+def test_cpu_tensors_fail_loudly():
+    import cooperativeimagecaptioning_b200.models as models
+    from cooperativeimagecaptioning_b200._lib import CoopcapError
+    opt = reference_opt()
+    spk = models.setup(opt, "att2in2", "caption_model")
+    with pytest.raises(CoopcapError):
+        spk.sample(torch.zeros(2, 2048), torch.zeros(2, 4, 2048), None, {"sample_max": 1})

@@ -34,7 +34,7 @@ def _run(mode, varlen, dropout, tau, B=6, L=9, seed=11):
     if dropout:
         rnd.keep_att = pack_keep(noise.drop_att, batch.att_masks)
         rnd.keep_embed = u8(noise.drop_embed)
-        rnd.keep_core = u8(noise.drop_core[:T])
+        rnd.keep_core = u8(noise.drop_core)
     rnd.noise = (noise.U if mode == "gumbel" else noise.E).cuda().contiguous()
     cmode = {"gumbel": EN.MODE_ST_GUMBEL, "multinomial": EN.MODE_ST_MULTINOMIAL,
              "reinforce": EN.MODE_MULTINOMIAL}[mode]
