@@ -40,7 +40,36 @@ void set_last_error(const char* fmt, ...);
     }                                                                                        \
   } while (0)
 
-#define CC_LAUNCH_CHECK() CC_CHECK_CUDA(cudaGetLastError())
+// Kernel classes for the launch counter / event timeline (coopcap_prof_* in include/coopcap.h).
+enum ProfKind : int {
+  PROF_MISC = 0,
+  PROF_GEMM,
+  PROF_ATT_FWD,
+  PROF_ATT_BWD,
+  PROF_ATT_DEFERRED,
+  PROF_LSTM,
+  PROF_SAMPLE,
+  PROF_ST_BWD,
+  PROF_LOGP_BWD,
+  PROF_GRU,
+  PROF_HINGE,
+  PROF_REDUCE,
+  PROF_PACK,
+  PROF_ADAM,
+  PROF_NKINDS
+};
+// counts the launch; when the timeline is enabled also records an event on `stream` so that the
+// time between consecutive markers (one stream, back-to-back launches) is this launch's duration
+void prof_mark(int kind, cudaStream_t stream, double flops, double bytes);
+
+#define CC_LAUNCH_CHECK_K(kind, stream, flops, bytes)                                        \
+  do {                                                                                       \
+    CC_CHECK_CUDA(cudaGetLastError());                                                       \
+    ::coopcap::prof_mark((kind), (stream), (flops), (bytes));                                \
+  } while (0)
+// torch's default stream is the null handle, so "no stream known" needs its own sentinel
+#define CC_NO_STREAM (reinterpret_cast<cudaStream_t>(static_cast<intptr_t>(-1)))
+#define CC_LAUNCH_CHECK() CC_LAUNCH_CHECK_K(::coopcap::PROF_MISC, CC_NO_STREAM, 0.0, 0.0)
 
 int num_sms();
 
@@ -117,6 +146,29 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// 2D tile store / reduce-add from shared memory (bulk async-group completion).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0,
+                                             int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src,
+                                                  int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM

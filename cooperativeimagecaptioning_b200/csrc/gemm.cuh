@@ -15,9 +15,12 @@
 namespace coopcap {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM_STAGE_BUDGET = 196608;  // 192 KB of operand stages
+constexpr int GEMM_THREADS = 320;              // TMA warp + MMA warp + 8 epilogue warps
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_SMEM_TOTAL = 232448;         // 227 KB opt-in limit per CTA
 constexpr int GEMM_SMEM_EXTRA = 2048;           // barriers + alignment slack
+// epilogue staging: per epilogue warp EPI_BUFS buffers of [32 rows][128 B] fp32, 128B-swizzled
+// (chunk j of row r lives at chunk j ^ (r & 7)); read by TMA stores or by the manual store path
 
 template <int KIND, int BN>
 struct GemmCfg {
@@ -28,12 +31,16 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = GEMM_SMEM_STAGE_BUDGET / STAGE_BYTES;
+  static constexpr int EPI_BUFS = (BN <= 128) ? 2 : 1;
+  static constexpr int EPI_STAGE_BYTES = GEMM_EPI_WARPS * EPI_BUFS * 4096;
+  static constexpr int STAGES_RAW =
+      (GEMM_SMEM_TOTAL - GEMM_SMEM_EXTRA - 1024 - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_SMEM_EXTRA + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_SMEM_EXTRA + EPI_STAGE_BYTES + 1024;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32,256]");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 
 // ------------------------------------------------------------------------------------------
@@ -59,99 +66,158 @@ struct EpiStoreParams {
   int philox_dropout;
   float drop_p;
   uint64_t seed, stream;
+  int tma_store;         // set by the launcher: fp32 C is written / reduced by TMA from swizzled smem
 };
 
 struct EpiStore {
   using Params = EpiStoreParams;
   __device__ __forceinline__ void begin(const Params&, int, int, int, int, int) {}
   __device__ __forceinline__ void end(const Params&, int, int, int, int, int) {}
+  // One 32x32 chunk of the accumulator tile: this thread holds row `row` (= row0 + lane), columns
+  // col0..col0+31.  The per-row transform runs in registers; the chunk is then staged through
+  // shared memory ([32][36] fp32 per warp) so that every global store instruction of the warp
+  // covers whole 128-byte lines (4 rows x 128 B for fp32, 8 rows x 64 B for bf16).
   __device__ __forceinline__ void chunk(const Params& p, int row, int col0, float (&v)[32], int M,
-                                        int N) {
-    if (row >= M) return;
+                                        int N, float* stage, int lane, int row0) {
     const int ncols = min(32, N - col0);
-    if (ncols <= 0) return;
-    float rs = p.row_scale ? p.row_scale[row] : 1.f;
-    if (p.seg_lens && (row % p.seg_L) >= p.seg_lens[row / p.seg_L]) rs = 0.f;
+    if (ncols <= 0 || row0 >= M) return;        // warp-uniform
+    transform(p, row, col0, ncols, v, M, N);
+    store(p, row, col0, ncols, v, M, N, stage, lane, row0);
+  }
+  __device__ __forceinline__ void transform(const Params& p, int row, int col0, int ncols,
+                                            float (&v)[32], int M, int N) {
+    if (row < M) {
+      float rs = p.row_scale ? p.row_scale[row] : 1.f;
+      if (p.seg_lens && (row % p.seg_L) >= p.seg_lens[row / p.seg_L]) rs = 0.f;
+      if (p.bias && ncols == 32 && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);   // warp-uniform address
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = v[j] * p.alpha;
-      if (p.bias && j < ncols) x += __ldg(p.bias + col0 + j);
-      if (p.relu) x = fmaxf(x, 0.f);
-      v[j] = x * rs;
-    }
-    if (p.keep) {
-      const float sc = 1.f / (1.f - p.drop_p);
-      const uint8_t* k = p.keep + int64_t(row) * p.ld_keep + col0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) v[j] = k[j] ? v[j] * sc : 0.f;
-    } else if (p.philox_dropout) {
-      const float sc = 1.f / (1.f - p.drop_p);
-      const uint64_t base = (uint64_t(row) * uint64_t(N) + uint64_t(col0)) >> 2;  // N % 4 == 0
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const uint4 r = Philox::gen(p.seed, p.stream, base + j4);
-        v[4 * j4 + 0] = Philox::u01(r.x) >= p.drop_p ? v[4 * j4 + 0] * sc : 0.f;
-        v[4 * j4 + 1] = Philox::u01(r.y) >= p.drop_p ? v[4 * j4 + 1] * sc : 0.f;
-        v[4 * j4 + 2] = Philox::u01(r.z) >= p.drop_p ? v[4 * j4 + 2] * sc : 0.f;
-        v[4 * j4 + 3] = Philox::u01(r.w) >= p.drop_p ? v[4 * j4 + 3] * sc : 0.f;
-      }
-    }
-    if (p.C) {
-      float* dst = p.C + int64_t(row) * p.ldc + col0;
-      if (p.mode == 2) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) atomicAdd(dst + j, v[j]);
-      } else {
-        const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-        if (vec) {
-          float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (p.mode == 1) {
-              float4 old = d4[j];
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            d4[j] = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) dst[j] = (p.mode == 1) ? dst[j] + v[j] : v[j];
-        }
-      }
-    }
-    if (p.C16) {
-      __nv_bfloat16* dst = p.C16 + int64_t(row) * p.ldc16 + col0;
-      const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-      if (vec) {
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
-          __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-          __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-          __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-          uint4 o;
-          o.x = *reinterpret_cast<uint32_t*>(&a);
-          o.y = *reinterpret_cast<uint32_t*>(&b);
-          o.z = *reinterpret_cast<uint32_t*>(&c);
-          o.w = *reinterpret_cast<uint32_t*>(&d);
-          d4[j] = o;
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          v[4 * j + 0] = v[4 * j + 0] * p.alpha + b.x;
+          v[4 * j + 1] = v[4 * j + 1] * p.alpha + b.y;
+          v[4 * j + 2] = v[4 * j + 2] * p.alpha + b.z;
+          v[4 * j + 3] = v[4 * j + 3] * p.alpha + b.w;
         }
       } else {
 #pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = v[j] * p.alpha;
+          if (p.bias && j < ncols) x += __ldg(p.bias + col0 + j);
+          v[j] = x;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = v[j];
+        if (p.relu) x = fmaxf(x, 0.f);
+        v[j] = x * rs;
+      }
+      if (p.keep) {
+        const float sc = 1.f / (1.f - p.drop_p);
+        const uint8_t* k = p.keep + int64_t(row) * p.ld_keep + col0;
+#pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
+          if (j < ncols) v[j] = k[j] ? v[j] * sc : 0.f;
+      } else if (p.philox_dropout) {
+        const float sc = 1.f / (1.f - p.drop_p);
+        const uint64_t base = (uint64_t(row) * uint64_t(N) + uint64_t(col0)) >> 2;  // N % 4 == 0
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const uint4 r = Philox::gen(p.seed, p.stream, base + j4);
+          v[4 * j4 + 0] = Philox::u01(r.x) >= p.drop_p ? v[4 * j4 + 0] * sc : 0.f;
+          v[4 * j4 + 1] = Philox::u01(r.y) >= p.drop_p ? v[4 * j4 + 1] * sc : 0.f;
+          v[4 * j4 + 2] = Philox::u01(r.z) >= p.drop_p ? v[4 * j4 + 2] * sc : 0.f;
+          v[4 * j4 + 3] = Philox::u01(r.w) >= p.drop_p ? v[4 * j4 + 3] * sc : 0.f;
+        }
       }
     }
-    if (p.Ct16) {
+  }
+  __device__ __forceinline__ void store(const Params& p, int row, int col0, int ncols, float (&v)[32],
+                                        int M, int N, float* stage, int lane, int row0) {
+    if (p.Ct16 && row < M) {
       // for a fixed column the 32 lanes of a warp hold 32 consecutive rows -> coalesced
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j < ncols) p.Ct16[int64_t(col0 + j) * p.ldct + row] = __float2bfloat16_rn(v[j]);
+    }
+    if (!p.C && !p.C16) return;
+    // stage: thread r writes its row, 16-byte chunk j at position j ^ (r & 7) (conflict-free)
+    __syncwarp();
+    {
+      uint8_t* dst = reinterpret_cast<uint8_t*>(stage) + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __syncwarp();
+    auto st4 = [&](int r, int c4) -> float4 {
+      return *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stage) + r * 128 +
+                                              ((c4 ^ (r & 7)) << 4));
+    };
+    auto st1 = [&](int r, int col) -> float {
+      return stage[r * 32 + ((((col >> 2) ^ (r & 7)) << 2) | (col & 3))];
+    };
+    const int rows_here = min(32, M - row0);
+    if (p.C) {
+      float* base = p.C + int64_t(row0) * p.ldc + col0;
+      const bool vec = (ncols == 32) && ((p.ldc & 3) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+      if (p.mode == 2) {
+        // split-K reduction: one row per instruction, 32 consecutive addresses per warp
+        for (int r = 0; r < rows_here; ++r)
+          if (lane < ncols) atomicAdd(base + int64_t(r) * p.ldc + lane, st1(r, lane));
+      } else if (vec) {
+        const int rsub = lane >> 3, c4 = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + rsub;
+          if (r < rows_here) {
+            float4 o = st4(r, c4);
+            float4* d = reinterpret_cast<float4*>(base + int64_t(r) * p.ldc) + c4;
+            if (p.mode == 1) {
+              const float4 old = *d;
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *d = o;
+          }
+        }
+      } else {
+        for (int r = 0; r < rows_here; ++r)
+          if (lane < ncols) {
+            float* d = base + int64_t(r) * p.ldc + lane;
+            const float x = st1(r, lane);
+            *d = (p.mode == 1) ? *d + x : x;
+          }
+      }
+    }
+    if (p.C16) {
+      __nv_bfloat16* base = p.C16 + int64_t(row0) * p.ldc16 + col0;
+      const bool vec = (ncols == 32) && ((p.ldc16 & 7) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+      if (vec) {
+        const int rsub = lane >> 2, c8 = lane & 3;   // 8 rows x (4 lanes x 8 bf16) per instruction
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + rsub;
+          if (r < rows_here) {
+            const float4 a = st4(r, 2 * c8);
+            const float4 b = st4(r, 2 * c8 + 1);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+            uint4 o;
+            o.x = *reinterpret_cast<uint32_t*>(&h0);
+            o.y = *reinterpret_cast<uint32_t*>(&h1);
+            o.z = *reinterpret_cast<uint32_t*>(&h2);
+            o.w = *reinterpret_cast<uint32_t*>(&h3);
+            *(reinterpret_cast<uint4*>(base + int64_t(r) * p.ldc16) + c8) = o;
+          }
+        }
+      } else {
+        for (int r = 0; r < rows_here; ++r)
+          if (lane < ncols) base[int64_t(r) * p.ldc16 + lane] = __float2bfloat16_rn(st1(r, lane));
+      }
     }
   }
 };
@@ -162,7 +228,8 @@ struct EpiStore {
 template <int KIND, int BN, int AMAJ, int BMAJ, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               int M, int N, int K, int split_k, typename Epi::Params ep) {
+               const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int split_k,
+               typename Epi::Params ep) {
   using Cfg = GemmCfg<KIND, BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -176,6 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES + GEMM_SMEM_EXTRA;   // 1024-aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -189,13 +257,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (ep.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS * 32);
     }
     fence_barrier_init();
   }
@@ -283,8 +352,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9: two warps per TMEM lane quarter) =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the 32-column chunks this warp handles
     Epi epi;
     int as = 0;
     uint32_t aph = 0;
@@ -302,19 +372,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       epi.begin(ep, row, n0, M, N, ks);
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(t_addr + c * 32, v);
+      uint8_t* wstage = epi_stage + (warp - 2) * Cfg::EPI_BUFS * 4096;
+      const int row0 = m_blk * GEMM_BM + q * 32;
+      constexpr int NC = BN / 32 / 2;    // chunks per warp: c = half, half + 2, ...
+      float v[2][32];
+      tmem_ld32(t_addr + half * 32, v[0]);
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
         tmem_ld_wait();
-        epi.chunk(ep, row, n0 + c * 32, v, M, N);
+        if (i + 1 < NC) tmem_ld32(t_addr + (half + 2 * (i + 1)) * 32, v[(i + 1) & 1]);
+        else {
+          // this thread has read all of its accumulator columns: hand the TMEM buffer back to the
+          // MMA warp now, the stores of this chunk overlap the next tile's MMAs
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[as]);
+        }
+        const int col0 = n0 + (half + 2 * i) * 32;
+        if (ep.tma_store) {
+          if (col0 < N && row0 < M) {            // warp-uniform
+            epi.transform(ep, row, col0, min(32, N - col0), v[i & 1], M, N);
+            uint8_t* buf = wstage + (Cfg::EPI_BUFS == 2 ? (i & 1) * 4096 : 0);
+            // the bulk store that last read this buffer must have drained
+            if (lane == 0) bulk_wait_read<Cfg::EPI_BUFS - 1>();
+            __syncwarp();
+            // row `lane` -> 128 B, 16-byte chunk j stored at (j ^ (lane & 7)): SWIZZLE_128B layout
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[i & 1][4 * j], v[i & 1][4 * j + 1], v[i & 1][4 * j + 2],
+                              v[i & 1][4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (ep.mode == 0) tma_store_2d(&tmC, buf, col0, row0);
+              else tma_reduce_add_2d(&tmC, buf, col0, row0);
+              bulk_commit();
+            }
+          }
+        } else {
+          epi.chunk(ep, row, col0, v[i & 1], M, N, reinterpret_cast<float*>(wstage), lane, row0);
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
       epi.end(ep, row, n0, M, N, n_blk);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   }
+  if (warp >= 2 && lane == 0 && ep.tma_store) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -333,8 +436,9 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, int64_t r
 
 template <int KIND, int BN, int AMAJ, int BMAJ, class Epi>
 int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
-                   int split_k, const typename Epi::Params& ep, cudaStream_t stream,
+                   int split_k, const typename Epi::Params& ep_in, cudaStream_t stream,
                    int max_ctas = 0) {
+  typename Epi::Params ep = ep_in;
   using Cfg = GemmCfg<KIND, BN>;
   CC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   CC_REQUIRE(split_k >= 1, "gemm: split_k must be >= 1");
@@ -351,6 +455,15 @@ int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int M
     rc = encode_tmap_2d(&tmB, B, Cfg::EB, K, N, ldb, Cfg::BK, Cfg::MN_ATOM);
   if (rc) return rc;
 
+  // fp32-only output with a TMA-compatible pitch: the epilogue stores / reduces through TMA
+  CUtensorMap tmC = tmA;
+  ep.tma_store = 0;
+  if (ep.C && !ep.C16 && !ep.Ct16 && (ep.ldc % 4) == 0 &&
+      (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) {
+    rc = encode_tmap_2d(&tmC, ep.C, 4, M, N, ep.ldc, 32, 32);
+    if (rc) return rc;
+    ep.tma_store = 1;
+  }
   auto kern = gemm_tc_kernel<KIND, BN, AMAJ, BMAJ, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -365,8 +478,9 @@ int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int M
   int grid = num_sms();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (tiles < grid) grid = tiles;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, split_k, ep);
-  CC_LAUNCH_CHECK();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, split_k, ep);
+  CC_LAUNCH_CHECK_K(PROF_GEMM, stream, 2.0 * double(M) * double(N) * double(K),
+                    double(Cfg::EB) * (double(M) * K + double(N) * K));
   return CC_OK;
 }
 

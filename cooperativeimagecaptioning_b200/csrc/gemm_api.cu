@@ -67,15 +67,30 @@ static int dispatch_major(const coopcap_gemm_args* a, const EpiStoreParams& ep, 
   return CC_ERR_ARG;
 }
 
-int pick_tile_n(int M, int N, int requested) {
-  if (requested == 64 || requested == 128 || requested == 256) return requested;
+// Tile width from a small cost model: persistent CTAs process ceil(tiles / SMs) waves of tiles; a
+// tile costs max(MMA time, epilogue time) (they overlap through the double-buffered accumulator)
+// plus a pipeline-fill term.  Narrow tiles fill the machine better, wide tiles feed the tensor
+// pipe better (operand smem traffic per MAC falls with N).
+int pick_tile_n(int M, int N, int K, int split_k, int requested) {
+  if (requested == 64 || requested == 128 || requested == 192 || requested == 256) return requested;
   const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
   const int sms = num_sms();
-  // prefer the widest tile that still fills ~one wave of SMs
-  if (num_m * ((N + 255) / 256) >= sms) return 256;
-  if (num_m * ((N + 127) / 128) >= (sms * 3) / 4) return 128;
-  if (N <= 64) return 64;
-  return num_m * ((N + 127) / 128) >= sms / 3 ? 128 : 64;
+  const int cand[4] = {64, 128, 192, 256};
+  const double eff[4] = {0.55, 0.80, 0.92, 1.00};
+  double best = 1e30;
+  int best_bn = 128;
+  const double kk = double((K + split_k - 1) / split_k);
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    if (bn > 64 && bn >= 2 * N) continue;   // do not pad tiny N into a wide tile
+    const int tiles = num_m * ((N + bn - 1) / bn) * split_k;
+    const int waves = (tiles + sms - 1) / sms;
+    const double mma = kk * bn * 1.68e-11 / eff[i];
+    const double epi = bn * 5.1e-9;
+    const double cost = waves * (mma > epi ? mma : epi) + (mma > epi ? epi : mma) + 1.5e-6;
+    if (cost < best) { best = cost; best_bn = bn; }
+  }
+  return best_bn;
 }
 
 // internal entry used by the orchestration code (speaker.cu, listener.cu)
@@ -90,9 +105,10 @@ int gemm_run(int kind, int a_major, int b_major, const void* A, int64_t lda, con
              "gemm: tf32 operands must be K-major (MN-major tf32 needs the 32B-atom swizzle)");
   CC_REQUIRE(a.split_k <= 1 || (ep.mode == 2 && ep.C16 == nullptr && ep.Ct16 == nullptr),
              "gemm: split_k > 1 needs mode 2 (atomicAdd) and fp32 output only");
-  const int bn = pick_tile_n(M, N, tile_n);
+  const int bn = pick_tile_n(M, N, K, a.split_k, tile_n);
   if (kind == 0) {
     if (bn == 256) return dispatch_major<0, 256>(&a, ep, s);
+    if (bn == 192) return dispatch_major<0, 192>(&a, ep, s);
     if (bn == 128) return dispatch_major<0, 128>(&a, ep, s);
     return dispatch_major<0, 64>(&a, ep, s);
   }
@@ -126,7 +142,7 @@ int gemm_store(const coopcap_gemm_args* a, cudaStream_t s) {
       gemm_simt_kernel<float><<<grd, blk, 0, s>>>(reinterpret_cast<const float*>(a->A), a->lda,
                                                   a->a_major, reinterpret_cast<const float*>(a->B),
                                                   a->ldb, a->b_major, a->M, a->N, a->K, ep);
-    CC_LAUNCH_CHECK();
+    CC_LAUNCH_CHECK_K(PROF_MISC, s, 0.0, 0.0);
     return CC_OK;
   }
   return gemm_run(a->kind, a->a_major, a->b_major, a->A, a->lda, a->B, a->ldb, a->M, a->N, a->K,
@@ -173,7 +189,7 @@ int coopcap_cast_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_s
   cast_bf16_kernel<<<grd, blk, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src, rows, cols, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst,
       reinterpret_cast<__nv_bfloat16*>(dst_t), ld_dst_t);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_PACK, reinterpret_cast<cudaStream_t>(stream), 0.0, 0.0);
   return CC_OK;
 }
 

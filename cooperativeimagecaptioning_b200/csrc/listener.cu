@@ -297,10 +297,10 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
     if ((rc = gemm_run(0, 0, 0, c->fc16, F, c->w_img16, F, B, M, F, 1, 0, e, s))) return rc;
   }
   l2norm_fwd_kernel<<<B, 256, 0, s>>>(c->img_pre, c->im, M, c->no_imgnorm);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   // caption branch                                                    (VSEFCModel.py:83-140)
   gather_embed_kernel<<<S * B, 128, 0, s>>>(c->tok, c->w_emb, E, reinterpret_cast<bf16*>(c->emb16));
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
   {
     EpiStoreParams e = {};
     e.alpha = 1.f; e.bias = c->b_ih; e.C = c->gi_all; e.ldc = 3 * M;
@@ -318,10 +318,10 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
         c->gi_all + int64_t(t) * B * 3 * M, c->gh, c->h32 + int64_t(t) * B * M, c->len, t,
         c->gates + int64_t(t) * B * 4 * M, c->h32 + int64_t(t + 1) * B * M,
         h16 + int64_t(t + 1) * B * M, B, M);
-    CC_LAUNCH_CHECK();
+    CC_LAUNCH_CHECK_K(PROF_GRU, s, 0.0, 0.0);
   }
   l2norm_fwd_kernel<<<B, 256, 0, s>>>(c->h32 + int64_t(S) * B * M, c->cap, M, 0);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   // scores (tf32 operands: the hinge compares score differences against a 0.2 margin)
   {
     EpiStoreParams e = {};
@@ -329,13 +329,13 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
     if ((rc = gemm_run(1, 0, 0, c->im, M, c->cap, M, B, B, M, 1, 0, e, s))) return rc;
   }
   hinge_rows_kernel<<<B, 256, 0, s>>>(c->scores, B, c->margin, c->cost_s, c->arg_s);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   hinge_cols_kernel<<<(B + 31) / 32, dim3(32, 8), 0, s>>>(c->scores, B, c->margin, c->cost_im,
                                                            c->arg_im);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   hinge_finish_kernel<<<1, 256, 0, s>>>(c->cost_s, c->cost_im, B, c->only_one_retrieval,
                                         c->loss_rows, c->loss);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   return CC_OK;
 }
 
@@ -354,22 +354,22 @@ int listener_bwd(const coopcap_listener* c, const coopcap_listener_grads* g, cud
   hinge_bwd_kernel<<<B, 256, 0, s>>>(c->im, c->cap, c->cost_s, c->cost_im, c->arg_s, c->arg_im,
                                      g->g_loss, g->g_rows, c->only_one_retrieval, M, g->d_im,
                                      g->d_cap);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   if (g->need_param_grads) {
     l2norm_bwd_kernel<<<B, 256, 0, s>>>(c->img_pre, g->d_im, nullptr,
                                         reinterpret_cast<bf16*>(g->d_img_pre16), M, c->no_imgnorm);
-    CC_LAUNCH_CHECK();
+    CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
     if ((rc = wgrad(g->d_img_pre16, M, c->fc16, F, M, F, B, g->g_w_img, F, s))) return rc;
     if ((rc = colsum_bf16(g->d_img_pre16, B, M, M, g->g_b_img, s))) return rc;
   }
   l2norm_bwd_kernel<<<B, 256, 0, s>>>(c->h32 + int64_t(S) * B * M, g->d_cap, g->dh, nullptr, M, 0);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   for (int t = S - 1; t >= 0; --t) {
     const int n = B * M;
     gru_bwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(
         g->dh, c->gates + int64_t(t) * B * 4 * M, c->h32 + int64_t(t) * B * M, c->len, t,
         d_gi16 + int64_t(t) * B * 3 * M, d_gh16 + int64_t(t) * B * 3 * M, B, M);
-    CC_LAUNCH_CHECK();
+    CC_LAUNCH_CHECK_K(PROF_GRU, s, 0.0, 0.0);
     if (t > 0) {
       // dh += d_gh . W_hh        ([B,3M] x [3M,M]; W_hh stored [K, N])
       EpiStoreParams e = {};
@@ -394,7 +394,7 @@ int listener_bwd(const coopcap_listener* c, const coopcap_listener_grads* g, cud
     embed_scatter_kernel<<<S * B, 128, 0, s>>>(c->tok, c->len,
                                                reinterpret_cast<const bf16*>(g->demb16), B, E,
                                                g->g_w_emb);
-    CC_LAUNCH_CHECK();
+    CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
   }
   return CC_OK;
 }

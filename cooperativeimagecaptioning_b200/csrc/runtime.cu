@@ -4,6 +4,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "../../include/coopcap.h"
 #include "common.cuh"
 #include "gemm.cuh"
@@ -17,6 +20,26 @@ void set_last_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
   va_end(ap);
+}
+
+// ---- launch counter + event timeline -----------------------------------------------------------
+struct ProfRec { int kind; cudaEvent_t ev; double flops, bytes; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t g_prof_begin = nullptr;
+static bool g_prof_on = false;
+static long long g_launches[PROF_NKINDS] = {0};
+
+void prof_mark(int kind, cudaStream_t stream, double flops, double bytes) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (kind >= 0 && kind < PROF_NKINDS) ++g_launches[kind];
+  if (!g_prof_on || stream == CC_NO_STREAM) return;
+  cudaEvent_t ev;
+  if (!g_prof_pool.empty()) { ev = g_prof_pool.back(); g_prof_pool.pop_back(); }
+  else if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, stream);
+  g_prof.push_back({kind, ev, flops, bytes});
 }
 
 int num_sms() {
@@ -81,6 +104,47 @@ extern "C" {
 const char* coopcap_last_error(void) { return coopcap::g_last_error; }
 
 int coopcap_version(void) { return COOPCAP_VERSION; }
+
+long long coopcap_launch_count(void) {
+  std::lock_guard<std::mutex> lk(coopcap::g_prof_mu);
+  long long t = 0;
+  for (int i = 0; i < coopcap::PROF_NKINDS; ++i) t += coopcap::g_launches[i];
+  return t;
+}
+
+int coopcap_prof_kinds(void) { return coopcap::PROF_NKINDS; }
+
+int coopcap_prof_enable(int on, coopcap_stream_t stream) {
+  using namespace coopcap;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) g_prof_pool.push_back(r.ev);
+  g_prof.clear();
+  g_prof_on = on != 0;
+  if (g_prof_on) {
+    if (!g_prof_begin) CC_CHECK_CUDA(cudaEventCreate(&g_prof_begin));
+    CC_CHECK_CUDA(cudaEventRecord(g_prof_begin, reinterpret_cast<cudaStream_t>(stream)));
+  }
+  return CC_OK;
+}
+
+int coopcap_prof_report(double* ms, double* flops, double* bytes, long long* launches, int nkinds) {
+  using namespace coopcap;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  CC_REQUIRE(nkinds >= PROF_NKINDS, "prof_report: need %d slots", PROF_NKINDS);
+  for (int i = 0; i < nkinds; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+  if (g_prof.empty()) return CC_OK;
+  CC_CHECK_CUDA(cudaEventSynchronize(g_prof.back().ev));
+  cudaEvent_t prev = g_prof_begin;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    CC_CHECK_CUDA(cudaEventElapsedTime(&t, prev, r.ev));
+    ms[r.kind] += t; flops[r.kind] += r.flops; bytes[r.kind] += r.bytes; ++launches[r.kind];
+    prev = r.ev;
+  }
+  for (auto& r : g_prof) g_prof_pool.push_back(r.ev);
+  g_prof.clear();
+  return CC_OK;
+}
 
 int coopcap_sizeof(int which) {
   switch (which) {

@@ -51,7 +51,7 @@ static int colsum_impl(const T* src, int64_t rows, int cols, int64_t ld, float* 
   const int64_t rpb = (rows + row_blocks - 1) / row_blocks;
   colsum_kernel<T><<<dim3(col_blocks, (unsigned)row_blocks), dim3(32, 8), 0, s>>>(src, rows, cols,
                                                                                   ld, out, rpb);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
   return CC_OK;
 }
 int colsum_bf16(const void* src, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t s) {
@@ -66,7 +66,7 @@ int colsum_f32(const float* src, int64_t rows, int cols, int64_t ld, float* out,
 int wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                  float* C, int64_t ldc, cudaStream_t s) {
   const int bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
-  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);  // split-K sizing at the widest tile
   int split = num_sms() / tiles;
   const int max_split = (K + 255) / 256;
   if (split > max_split) split = max_split;
@@ -453,7 +453,8 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
         c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed, SITE_NOISE + t,
         c->y_max + int64_t(t) * B, c->y_sum + int64_t(t) * B, c->unfinished + int64_t(t) * B,
         reinterpret_cast<bf16*>(dz16) + int64_t(t) * B * V1);
-    CC_LAUNCH_CHECK();
+    // logits + upstream gradient (+ injected noise) read, bf16 dz written
+    CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(B) * V1 * (4.0 + 4.0 + 2.0 + (c->noise ? 4.0 : 0.0)));
   }
   return CC_OK;
 }
@@ -464,7 +465,7 @@ int logp_backward(const coopcap_speaker* c, const int64_t* tok, const float* coe
   if (rc) return rc;
   logp_bwd_kernel<<<c->n_steps * c->B, 256, 0, s>>>(c->z_all, c->V1, c->lse, tok, coef,
                                                     reinterpret_cast<bf16*>(dz16));
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_LOGP_BWD, s, 0.0, 0.0);
   return CC_OK;
 }
 
@@ -510,7 +511,7 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
           g->d_out + int64_t(t) * B * R, out16 + int64_t(t) * B * R, dh_next, XH, dc_in, dc_out, s_t,
           NS, c->u_all + int64_t(t) * B * 2 * R, c->c_all + int64_t(t) * B * R,
           c->c_all + int64_t(t + 1) * B * R, ds_t, c->drop_p, B, R);
-      CC_LAUNCH_CHECK();
+      CC_LAUNCH_CHECK_K(PROF_LSTM, s, 0.0, 0.0);
     }
     // d_att_res = d_u . W_a2c      ([B,2R] x [2R,R])
     float* dres_t = g->d_att_res + int64_t(t) * B * R;
@@ -523,7 +524,8 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
         reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
         c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, dres_t, c->att_w + int64_t(t) * NL,
         g->de + int64_t(t) * NL, ds_t, A, R);
-    CC_LAUNCH_CHECK();
+    CC_LAUNCH_CHECK_K(PROF_ATT_BWD, s, 0.0,
+                      2.0 * NL * (A + R) + 4.0 * B * (A + R) + 8.0 * NL + 2.0 * B * A);
     // d[x_t | h_{t-1}] = dscat . w_cat      ([B,5R+A] x [5R+A,E+R])
     {
       EpiStoreParams e = {};
@@ -541,7 +543,7 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
   if ((rc = colsum_bf16(dscat16 + 3 * R, rows, 2 * R, NS, g->g_b_a2c, s))) return rc;
   // input embedding
   embed_grad_kernel<<<(unsigned)rows, 128, 0, s>>>(c->tok_fed, g->d_xh, xh16, E, XH, scale, g->g_embed);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
   // region tensors: deferred accumulation over the steps, then the prologue layers
   {
     const int Lp = (c->L + 3) & ~3;
@@ -561,7 +563,10 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
         reinterpret_cast<const bf16*>(c->p_att16), c->att_off, c->L, c->s_all, NS, 5 * R,
         int64_t(B) * NS, c->w_alpha, g->d_att_res, c->att_w, g->de, NL, n, B, g->d_att_e,
         reinterpret_cast<bf16*>(g->d_p_att16), galpha_part, gbias_part, A, R);
-    CC_LAUNCH_CHECK();
+    // p_att read, d_p_att (bf16) + d_att_e (fp32) written, per-step vectors read
+    CC_LAUNCH_CHECK_K(PROF_ATT_DEFERRED, s, 0.0,
+                      2.0 * NL * A + 2.0 * NL * A + 4.0 * NL * R +
+                          double(n) * (4.0 * B * (A + R) + 8.0 * NL));
     if ((rc = colsum_f32(galpha_part, B, A, A, g->g_w_alpha, s))) return rc;
     if ((rc = colsum_f32(gbias_part, B, A, A, g->g_b_ctx2att, s))) return rc;
   }
@@ -576,7 +581,7 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
     mask_pre_kernel<<<(unsigned)blocks, 256, 0, s>>>(g->d_att_e,
                                                      reinterpret_cast<const bf16*>(c->att_e16), n4,
                                                      scale, reinterpret_cast<bf16*>(g->d_pre16));
-    CC_LAUNCH_CHECK();
+    CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
     if ((rc = wgrad(g->d_p_att16, A, c->att_e16, R, A, R, NL, g->g_w_ctx2att, R, s))) return rc;
     if ((rc = wgrad(g->d_pre16, R, c->att16, c->D, R, c->D, NL, g->g_w_att_embed, c->D, s))) return rc;
     if ((rc = colsum_bf16(g->d_pre16, NL, R, R, g->g_b_att_embed, s))) return rc;
@@ -677,7 +682,7 @@ int coopcap_clamp_adam(float* param, const float* grad, float* exp_avg, float* e
   clamp_adam_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       param, grad, exp_avg, exp_avg_sq, n, grad_scale, clip, lr, beta1, beta2, eps, weight_decay,
       bc1, sqrtf(bc2));
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_ADAM, reinterpret_cast<cudaStream_t>(stream), 0.0, 28.0 * double(n));
   return CC_OK;
 }
 

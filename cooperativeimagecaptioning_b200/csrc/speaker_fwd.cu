@@ -40,7 +40,7 @@ int cast_block(const float* src, int64_t rows, int cols, void* dst, int64_t ld_d
   int64_t want = (n4 + 255) / 256, cap_blocks = int64_t(num_sms()) * 16;
   int grid = int(want < cap_blocks ? want : cap_blocks);
   cast_block_kernel<<<grid, 256, 0, s>>>(src, rows, cols, reinterpret_cast<bf16*>(dst), ld_dst);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
   return CC_OK;
 }
 
@@ -458,7 +458,7 @@ int speaker_prologue_fwd(const coopcap_speaker* c, cudaStream_t s) {
   if (rc) return rc;
   pack_att_kernel<<<c->NL, 256, 0, s>>>(c->att_feats, c->att_off, c->B, c->L, c->D,
                                         reinterpret_cast<bf16*>(c->att16));
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
   EpiStoreParams ep = {};
   ep.alpha = 1.f;
   ep.bias = c->b_att_embed;
@@ -497,7 +497,7 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
   }
   start_step_kernel<<<B, 128, 0, s>>>(c->embed, c->start_token, c->start_tokens, B, E, R, c->keep_embed, c->seed,
                                       c->drop_p, xh16, c->c_all, c->tok_fed);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 0.0);
   for (int t = 0; t < c->n_steps; ++t) {
     float* s_t = c->s_all + int64_t(t) * B * NS;
     float* u_t = c->u_all + int64_t(t) * B * 2 * R;
@@ -510,7 +510,9 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
         reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
         c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, att_res16 + int64_t(t) * B * R,
         c->att_w + int64_t(t) * c->NL, A, R);
-    CC_LAUNCH_CHECK();
+    // algorithmic bytes: p_att + att_e read once (bf16), att_h in, att_res + weights out
+    CC_LAUNCH_CHECK_K(PROF_ATT_FWD, s, 0.0,
+                      2.0 * c->NL * (A + R) + 4.0 * B * A + 2.0 * B * R + 4.0 * c->NL);
     EpiStoreParams e2 = {};
     e2.alpha = 1.f; e2.bias = c->b_a2c; e2.C = u_t; e2.ldc = 2 * R;
     rc = gemm_run(0, 0, 0, att_res16 + int64_t(t) * B * R, R, c->w_a2c16, R, B, 2 * R, R, 1, 0, e2, s);
@@ -522,7 +524,7 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
           xh16 + int64_t(t + 1) * B * XH + E, XH, out16 + int64_t(t) * B * R,
           c->keep_core ? c->keep_core + int64_t(t) * B * R : nullptr, c->seed, SITE_DROP_CORE + t,
           c->drop_p, B, R);
-      CC_LAUNCH_CHECK();
+      CC_LAUNCH_CHECK_K(PROF_LSTM, s, 0.0, 0.0);
     }
     float* z_t = c->z_all + int64_t(t) * B * V1;
     EpiStoreParams e3 = {};
@@ -538,11 +540,12 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
         c->unfinished + int64_t(t) * B, c->embed, E,
         c->keep_embed ? c->keep_embed + int64_t(t + 1) * B * E : nullptr, SITE_DROP_EMBED + t + 1,
         c->drop_p, (t + 1 < c->n_steps) ? xh16 + int64_t(t + 1) * B * XH : nullptr, XH);
-    CC_LAUNCH_CHECK();
+    // algorithmic bytes: logits (+ injected noise) read once
+    CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 4.0 * B * V1 * (c->noise ? 2.0 : 1.0));
   }
   if (c->n_out && c->cap_len) {
     caption_summary_kernel<<<1, 256, 0, s>>>(c->tok_out, B, c->n_steps, c->n_out, c->cap_len);
-    CC_LAUNCH_CHECK();
+    CC_LAUNCH_CHECK_K(PROF_MISC, s, 0.0, 0.0);
   }
   return CC_OK;
 }
@@ -569,7 +572,7 @@ int coopcap_speaker_pack_weights(const coopcap_speaker_pack* p, coopcap_stream_t
   if ((rc = cast_block(p->w_logit, p->V1, R, p->w_logit16, R, s))) return rc;
   const int n = 5 * R + A;
   bias_cat_kernel<<<(n + 255) / 256, 256, 0, s>>>(p->b_i2h, p->b_h2h, p->b_h2att, 5 * R, A, p->b_cat);
-  CC_LAUNCH_CHECK();
+  CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
   return CC_OK;
 }
 

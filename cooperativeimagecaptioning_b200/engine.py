@@ -18,6 +18,16 @@ from ._lib import check
 MODE_GREEDY, MODE_MULTINOMIAL, MODE_ST_GUMBEL, MODE_ST_MULTINOMIAL, MODE_NONE = 0, 1, 2, 3, 4
 
 
+_weights_epoch = 0
+
+
+def bump_weights_epoch():
+    """Called by anything that modifies parameters outside autograd's version tracking (the fused
+    optimizer kernel); invalidates the packed bf16 operand copies."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -72,7 +82,7 @@ class PackedSpeaker:
         self.buf = {}
 
     def get(self, P: Dict[str, torch.Tensor]):
-        key = tuple((P[n].data_ptr(), P[n]._version) for n in SPEAKER_PARAM_NAMES)
+        key = (_weights_epoch,) + tuple((P[n].data_ptr(), P[n]._version) for n in SPEAKER_PARAM_NAMES)
         if key == self.key:
             return self.buf
         d = SpeakerDims.of(P)
@@ -327,7 +337,7 @@ class PackedListener:
         self.buf = {}
 
     def get(self, P):
-        key = tuple((P[n].data_ptr(), P[n]._version) for n in LISTENER_PARAM_NAMES)
+        key = (_weights_epoch,) + tuple((P[n].data_ptr(), P[n]._version) for n in LISTENER_PARAM_NAMES)
         if key == self.key:
             return self.buf
         d = ListenerDims.of(P)

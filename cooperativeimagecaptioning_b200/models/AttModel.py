@@ -173,10 +173,14 @@ class AttModel(nn.Module):
         packed = self._packed.get(P)
         att_feats = att_feats.detach().float().contiguous()
         B, L = att_feats.shape[:2]
-        if att_masks is not None:
-            # precondition of the reference (Appendix D): padded width == longest row
-            att_masks = att_masks[:, :L]
-        off, NL = EN.region_offsets(att_masks, B, L)
+        pre = getattr(att_masks, "_coopcap_off", None) if att_masks is not None else None
+        if pre is not None:
+            off, NL = pre         # offsets supplied by the loader side: no device sync
+        else:
+            if att_masks is not None:
+                # precondition of the reference (Appendix D): padded width == longest row
+                att_masks = att_masks[:, :L]
+            off, NL = EN.region_offsets(att_masks, B, L)
         sp = EN.speaker_forward(P, packed, att_feats, off, NL, n_steps=n_steps, mode=mode,
                                 inv_tau=inv_tau, start_token=start_token, rnd=self._random(),
                                 forced=forced, start_tokens=start_tokens)

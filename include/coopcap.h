@@ -73,7 +73,7 @@ typedef struct coopcap_gemm_args {
   void* Ct16;  /* bf16 transposed [N, ldct] or NULL */
   int64_t ldct;
   int split_k; /* >= 1 */
-  int tile_n;  /* 0 = auto, else 64 / 128 / 256 */
+  int tile_n;  /* 0 = auto, else 64 / 128 / 192 / 256 */
   int backend; /* 0 tcgen05, 1 SIMT cross-check */
 } coopcap_gemm_args;
 
@@ -392,6 +392,19 @@ int coopcap_listener_bwd(const coopcap_listener* ctx, const coopcap_listener_gra
 int coopcap_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                        int64_t n, float grad_scale, float clip, float lr, float beta1, float beta2,
                        float eps, float weight_decay, int step, coopcap_stream_t stream);
+
+/* ---- instrumentation ---------------------------------------------------------------------------
+ * coopcap_launch_count: kernels launched by this library since load (all streams).
+ * coopcap_prof_enable(1, stream): start an event timeline on `stream` (one event after every
+ * launch; the library's launches on one stream run back to back, so the gap between consecutive
+ * events is that launch's duration); coopcap_prof_report sums per kernel class (index = ProfKind in
+ * csrc/common.cuh: 0 misc, 1 gemm, 2 att_fwd, 3 att_bwd, 4 att_deferred, 5 lstm, 6 sample,
+ * 7 st_bwd, 8 logp_bwd, 9 gru, 10 hinge, 11 reduce, 12 pack, 13 adam) the elapsed ms, the
+ * algorithmic FLOPs / bytes the launches declared, and the launch count, then clears the timeline. */
+long long coopcap_launch_count(void);
+int coopcap_prof_kinds(void);
+int coopcap_prof_enable(int on, coopcap_stream_t stream);
+int coopcap_prof_report(double* ms, double* flops, double* bytes, long long* launches, int nkinds);
 
 /* sizeof() of the structs above, for binding self-checks: which = 0 gemm_args, 1 speaker_pack,
  * 2 speaker, 3 speaker_grads, 4 listener_pack, 5 listener, 6 listener_grads. */

@@ -28,6 +28,9 @@ CASES = [
     (torch.bfloat16, 1, 1, 2560, 512, 1111, 0, 1),
     (torch.bfloat16, 1, 1, 512, 2048, 4000, 128, 4),
     (torch.bfloat16, 1, 0, 256, 192, 320, 64, 1),
+    (torch.bfloat16, 0, 0, 1024, 9488, 512, 192, 1),
+    (torch.bfloat16, 0, 1, 1000, 1024, 3072, 192, 1),
+    (torch.bfloat16, 1, 1, 9488, 512, 2000, 192, 2),
     (torch.float32, 0, 0, 130, 1024, 2048, 0, 1),
     (torch.float32, 0, 0, 96, 200, 300, 128, 1),
     (torch.float32, 0, 0, 512, 2048, 776, 0, 2),
@@ -98,3 +101,28 @@ def test_cast_bf16():
     torch.cuda.synchronize()
     assert torch.equal(d, x.bfloat16())
     assert torch.equal(dt, x.bfloat16().t().contiguous())
+
+
+@pytest.mark.parametrize("M,N,K,tile_n", [(1024, 9488, 512, 0), (333, 1000, 192, 64), (1000, 520, 256, 192)])
+def test_gemm_bf16_output_and_accumulate(M, N, K, tile_n):
+    """bf16 row-major output (C16), relu + bias, and the read-add-write mode (mode 1) of the
+    coalesced epilogue."""
+    from cooperativeimagecaptioning_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, generator=gen, device="cuda").bfloat16()
+    B = torch.randn(N, K, generator=gen, device="cuda").bfloat16()
+    bias = torch.randn(N, generator=gen, device="cuda")
+    ref = torch.relu(A.float() @ B.float().t() + bias)
+    out16 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(A, B, M, N, K, bias=bias, relu=True, out=out, out16=out16, tile_n=tile_n)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (out - ref).abs().max().item() <= 2e-5 * scale * K ** 0.5
+    assert (out16.float() - ref).abs().max().item() <= 1e-2 * scale
+    base = torch.randn(M, N, generator=gen, device="cuda")
+    acc = base.clone()
+    ops.gemm(A, B, M, N, K, alpha=0.25, mode=1, out=acc, tile_n=tile_n)
+    torch.cuda.synchronize()
+    ref2 = base + 0.25 * (A.float() @ B.float().t())
+    assert (acc - ref2).abs().max().item() <= 2e-5 * ref2.abs().max().item() * K ** 0.5
