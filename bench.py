@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prof", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
+    ap.add_argument("--upload-ctas", type=int, default=64, help="CTAs of the zero-copy upload kernel")
     ap.add_argument("--clock-period", type=float, default=0.05, help="NVML sampling period (s); 0 = off")
     return ap.parse_args()
 
@@ -283,10 +284,21 @@ def main():
     resident = [to_device(h, False) for h in hb]
     torch.cuda.synchronize()
     clocks = ClockSampler(local, args.clock_period) if (rank == 0 and args.clock_period > 0) else None
-    # setup: a few untimed priming steps so that the caching allocator has seen both batch shapes
-    # (not part of the W warm-up steps, which follow)
-    for i in range(4):
-        train_step(resident[i % 2])
+    # setup (untimed, before the W warm-up steps): prime until the step time has settled -- the
+    # caching allocator must have seen both batch shapes, and a freshly booted box takes a few
+    # hundred ms of work before clocks / driver state stop moving
+    prev = None
+    for _ in range(12):
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(4):
+            train_step(resident[i % 2])
+        p1.record()
+        torch.cuda.synchronize()
+        cur = p0.elapsed_time(p1)
+        if prev is not None and abs(cur - prev) <= 0.03 * prev:
+            break
+        prev = cur
     for i in range(args.warmup):
         train_step(resident[i % 2])
     barrier()
@@ -316,17 +328,20 @@ def main():
         # every step is read back to pinned host memory (async, drained at the end of the region)
         copy_stream = torch.cuda.Stream()
         loss_host = torch.zeros(args.steps, pin_memory=True)
-        h2d = sum(hb[0][k].numel() * hb[0][k].element_size() for k in ("fc", "att", "att_masks", "labels", "masks")) \
-            + 4 * (B + 1)
+        h2d = 0
         resident = None
         torch.cuda.empty_cache()
 
+        from cooperativeimagecaptioning_b200.data import record_stream, upload_batch
+
         def upload(i):
-            with torch.cuda.stream(copy_stream):
-                d = to_device(hb[i % 2], True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return d, ev
+            # the repo's own load_data: only the valid regions of att_feats cross PCIe
+            h = hb[i % 2]
+            fc, att, am, lab, msk = upload_batch(h["fc"], h["att"], h["att_masks"], h["labels"],
+                                                 h["masks"], dev, stream=copy_stream, ctas=args.upload_ctas)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            return dict(fc=fc, att=att, att_masks=am, labels=lab, masks=msk), ev
 
         def e2e_loop(n, record):
             nxt = upload(0)
@@ -336,8 +351,7 @@ def main():
                     nxt = upload(i + 1)
                 torch.cuda.current_stream().wait_event(ev)
                 loss = train_step(d)
-                for v in d.values():
-                    v.record_stream(torch.cuda.current_stream())
+                record_stream(d.values(), torch.cuda.current_stream())
                 if record:
                     loss_host[i].copy_(loss.detach().reshape(()), non_blocking=True)
 
@@ -347,6 +361,7 @@ def main():
         t0.record()
         e2e_loop(args.steps, True)
         t1.record()
+        h2d = upload_batch.last_bytes
         barrier()
         t = torch.tensor([t0.elapsed_time(t1)], device=dev)
         if world > 1:
@@ -426,7 +441,7 @@ def main():
                      value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
                      ms_per_step=e2e_ms / args.steps,
                      note="public API (AlternatingJointModel.forward + backward + optimizer.step) "
-                          "from pinned host buffers, upload double-buffered on a copy stream"),
+                          "from pinned host buffers, valid regions only (data.upload_batch), upload double-buffered on a copy stream"),
             gpu_launches=int(launches), loss=loss_value, clocks=clk, roofline=roof,
             cpu_baseline=cpu, breakdown=breakdown)
         print(json.dumps(line), flush=True)

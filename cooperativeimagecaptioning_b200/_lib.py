@@ -22,7 +22,7 @@ class CoopcapError(RuntimeError):
 
 _SCALARS = {
     "int": C.c_int, "float": C.c_float, "int64_t": C.c_int64, "uint64_t": C.c_uint64,
-    "coopcap_stream_t": C.c_void_p,
+    "coopcap_stream_t": C.c_void_p, "long long": C.c_longlong,
 }
 
 
@@ -72,7 +72,7 @@ def _parse_header(path):
         order.append(name)
     funcs = {}
     body = re.sub(r"typedef\s+struct\s+\w+\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
-    for m in re.finditer(r"\b(int|const char\s*\*)\s+(coopcap_\w+)\s*\(([^)]*)\)\s*;", body):
+    for m in re.finditer(r"\b(int|long long|const char\s*\*)\s+(coopcap_\w+)\s*\(([^)]*)\)\s*;", body):
         ret, fname, args = m.group(1), m.group(2), m.group(3).strip()
         argtypes = []
         if args and args != "void":
@@ -80,7 +80,8 @@ def _parse_header(path):
                 a = " ".join(a.split())
                 am = re.match(r"^(.*?[\s\*])(\w+)$", a)
                 argtypes.append(_ctype_of(am.group(1).strip(), structs))
-        funcs[fname] = (C.c_char_p if "char" in ret else C.c_int, argtypes)
+        restype = C.c_char_p if "char" in ret else (C.c_longlong if "long" in ret else C.c_int)
+        funcs[fname] = (restype, argtypes)
     return structs, order, funcs
 
 

@@ -105,6 +105,31 @@ const char* coopcap_last_error(void) { return coopcap::g_last_error; }
 
 int coopcap_version(void) { return COOPCAP_VERSION; }
 
+int coopcap_h2d_ragged_rows(void* dst, const void* src_host, const int* lens_host, int B,
+                            int64_t row_stride_bytes, int64_t unit_bytes, coopcap_stream_t stream) {
+  using namespace coopcap;
+  CC_REQUIRE(dst && src_host && lens_host && B >= 0, "h2d_ragged_rows: null argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // coalesce runs of full rows into one copy; otherwise one copy per row
+  int b = 0;
+  while (b < B) {
+    int64_t bytes = int64_t(lens_host[b]) * unit_bytes;
+    CC_REQUIRE(bytes >= 0 && bytes <= row_stride_bytes, "h2d_ragged_rows: row %d has %lld B > pitch",
+               b, (long long)bytes);
+    int e = b + 1;
+    if (bytes == row_stride_bytes) {
+      while (e < B && int64_t(lens_host[e]) * unit_bytes == row_stride_bytes) ++e;
+      bytes = int64_t(e - b) * row_stride_bytes;
+    }
+    if (bytes > 0)
+      CC_CHECK_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + int64_t(b) * row_stride_bytes,
+                                    static_cast<const char*>(src_host) + int64_t(b) * row_stride_bytes,
+                                    size_t(bytes), cudaMemcpyHostToDevice, s));
+    b = e;
+  }
+  return CC_OK;
+}
+
 long long coopcap_launch_count(void) {
   std::lock_guard<std::mutex> lk(coopcap::g_prof_mu);
   long long t = 0;

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "speaker_kernels.cuh"
+#include "attention.cuh"
 
 namespace coopcap {
 
@@ -80,18 +81,6 @@ int wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, 
   return gemm_run(0, 1, 1, A, lda, B, ldb, M, N, K, split, bn, e, s);
 }
 
-__device__ __forceinline__ float gumbel_of(float u) { return -logf(-logf(u + 1e-20f) + 1e-20f); }
-__device__ __forceinline__ void noise4(const float* inj_row, int v4, uint64_t seed, uint64_t stream,
-                                       uint64_t ctr, float (&u)[4]) {
-  if (inj_row) {
-    const float4 t = *reinterpret_cast<const float4*>(inj_row + 4 * v4);
-    u[0] = t.x; u[1] = t.y; u[2] = t.z; u[3] = t.w;
-  } else {
-    const uint4 r = Philox::gen(seed, stream, ctr);
-    u[0] = Philox::u01(r.x); u[1] = Philox::u01(r.y); u[2] = Philox::u01(r.z); u[3] = Philox::u01(r.w);
-  }
-}
-
 __device__ __forceinline__ void store_bf16x4(bf16* dst, float a, float b, float c, float d) {
   __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
   uint2 o;
@@ -122,6 +111,7 @@ st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t 
   const float* gr = g + int64_t(b) * ldg;
   const float* nr = noise ? noise + int64_t(b) * V1 : nullptr;
   const float m = ymax[b], inv_s = 1.f / ysum[b];
+  const bool fast = (noise == nullptr);
   float dot = 0.f;
   for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
     const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
@@ -131,8 +121,7 @@ st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t 
     if (mode == COOPCAP_SAMPLE_ST_GUMBEL) noise4(nr, v4, seed, nstream, uint64_t(b) * (V1 / 4) + v4, u4);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float score = (mode == COOPCAP_SAMPLE_ST_GUMBEL) ? (x4[q] + gumbel_of(u4[q])) * inv_tau
-                                                              : x4[q] * inv_tau;
+      const float score = st_score(mode, x4[q], u4[q], inv_tau, fast);
       const float y = __expf(score - m) * inv_s;
       s_y[4 * v4 + q] = y;
       dot += y * g4[q];
@@ -214,8 +203,6 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ d_out, const bf16* __r
 // additive attention backward for one step (inside the BPTT chain): produces d(scores) and
 // d(att_h); the region-tensor gradients are accumulated over all steps by the deferred kernel.
 // ------------------------------------------------------------------------------------------
-constexpr int ATT_THREADS = 256;
-
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_bwd_kernel(const bf16* __restrict__ p_att16, const bf16* __restrict__ att_e16,
                      const int* __restrict__ off, int Lfix, const float* __restrict__ s_row0,
@@ -520,10 +507,25 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
       e.alpha = 1.f; e.C = dres_t; e.ldc = R;
       if ((rc = gemm_run(0, 0, 1, ds_t + 3 * R, NS, c->w_a2c16, R, B, R, 2 * R, 1, 0, e, s))) return rc;
     }
-    attention_bwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
-        reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
-        c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, dres_t, c->att_w + int64_t(t) * NL,
-        g->de + int64_t(t) * NL, ds_t, A, R);
+    if (A == 512 && R == 512) {
+      constexpr int ST = 4;
+      const size_t sm2 = attention_bwd2_smem<512, ST>(c->L);
+      static size_t sm2_set = 0;
+      if (sm2 > sm2_set) {
+        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd2_kernel<512, ST>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2)));
+        sm2_set = sm2;
+      }
+      attention_bwd2_kernel<512, ST><<<B, ATT_THREADS, sm2, s>>>(
+          reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
+          c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, dres_t, c->att_w + int64_t(t) * NL,
+          g->de + int64_t(t) * NL, ds_t);
+    } else {
+      attention_bwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
+          reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
+          c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, dres_t, c->att_w + int64_t(t) * NL,
+          g->de + int64_t(t) * NL, ds_t, A, R);
+    }
     CC_LAUNCH_CHECK_K(PROF_ATT_BWD, s, 0.0,
                       2.0 * NL * (A + R) + 4.0 * B * (A + R) + 8.0 * NL + 2.0 * B * A);
     // d[x_t | h_{t-1}] = dscat . w_cat      ([B,5R+A] x [5R+A,E+R])
@@ -546,23 +548,39 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
   CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
   // region tensors: deferred accumulation over the steps, then the prologue layers
   {
-    const int Lp = (c->L + 3) & ~3;
-    const int groups = ATT_THREADS / (A / 8);
-    const size_t smem = sizeof(float) * (size_t(n) * (A + R) + 2 * size_t(n) * Lp + size_t(groups) * A);
-    CC_REQUIRE(smem <= 227 * 1024, "deferred attention backward needs %zu B of shared memory", smem);
-    static size_t set = 0;
-    if (smem > 48 * 1024 && smem > set) {
-      CC_CHECK_CUDA(cudaFuncSetAttribute(attention_deferred_bwd_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      set = smem;
-    }
     // galpha / bias partials live in d_out (free after the BPTT loop): 2 x [B, A] <= [cap*B, R]
     float* galpha_part = g->d_out;
     float* gbias_part = g->d_out + int64_t(B) * A;
-    attention_deferred_bwd_kernel<<<B, ATT_THREADS, smem, s>>>(
-        reinterpret_cast<const bf16*>(c->p_att16), c->att_off, c->L, c->s_all, NS, 5 * R,
-        int64_t(B) * NS, c->w_alpha, g->d_att_res, c->att_w, g->de, NL, n, B, g->d_att_e,
-        reinterpret_cast<bf16*>(g->d_p_att16), galpha_part, gbias_part, A, R);
+    if (A == 512 && R == 512) {
+      constexpr int ST = 3;
+      const size_t smem = attention_deferred2_smem<512, ST>(c->L, n);
+      CC_REQUIRE(smem <= 227 * 1024, "deferred attention backward needs %zu B of shared memory", smem);
+      static size_t set = 0;
+      if (smem > set) {
+        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_deferred2_kernel<512, ST>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        set = smem;
+      }
+      attention_deferred2_kernel<512, ST><<<B, ATT_THREADS, smem, s>>>(
+          reinterpret_cast<const bf16*>(c->p_att16), c->att_off, c->L, c->s_all, NS, 5 * R,
+          int64_t(B) * NS, c->w_alpha, g->d_att_res, c->att_w, g->de, NL, n, B, g->d_att_e,
+          reinterpret_cast<bf16*>(g->d_p_att16), galpha_part, gbias_part);
+    } else {
+      const int Lp = (c->L + 3) & ~3;
+      const int groups = ATT_THREADS / (A / 8);
+      const size_t smem = sizeof(float) * (size_t(n) * (A + R) + 2 * size_t(n) * Lp + size_t(groups) * A);
+      CC_REQUIRE(smem <= 227 * 1024, "deferred attention backward needs %zu B of shared memory", smem);
+      static size_t set = 0;
+      if (smem > 48 * 1024 && smem > set) {
+        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_deferred_bwd_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        set = smem;
+      }
+      attention_deferred_bwd_kernel<<<B, ATT_THREADS, smem, s>>>(
+          reinterpret_cast<const bf16*>(c->p_att16), c->att_off, c->L, c->s_all, NS, 5 * R,
+          int64_t(B) * NS, c->w_alpha, g->d_att_res, c->att_w, g->de, NL, n, B, g->d_att_e,
+          reinterpret_cast<bf16*>(g->d_p_att16), galpha_part, gbias_part, A, R);
+    }
     // p_att read, d_p_att (bf16) + d_att_e (fp32) written, per-step vectors read
     CC_LAUNCH_CHECK_K(PROF_ATT_DEFERRED, s, 0.0,
                       2.0 * NL * A + 2.0 * NL * A + 4.0 * NL * R +

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "speaker_kernels.cuh"
+#include "attention.cuh"
 
 namespace coopcap {
 
@@ -65,25 +66,58 @@ __device__ __forceinline__ int find_row(const int* __restrict__ off, int B, int 
   return lo;
 }
 
-__global__ void pack_att_kernel(const float* __restrict__ att, const int* __restrict__ off, int B,
-                                int L, int D, bf16* __restrict__ out) {
-  const int r = blockIdx.x;
-  int64_t src_row;
-  if (off) {
-    const int b = find_row(off, B, r);
-    src_row = int64_t(b) * L + (r - off[b]);
-  } else {
-    src_row = r;
-  }
-  const float4* src = reinterpret_cast<const float4*>(att + src_row * D);
-  uint2* dst = reinterpret_cast<uint2*>(out + int64_t(r) * D);
-  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
-    const float4 v = __ldcs(src + i);  // streamed once
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b2 = __floats2bfloat162_rn(v.z, v.w);
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&a);
-    o.y = *reinterpret_cast<uint32_t*>(&b2);
-    dst[i] = o;
+// Cast + pack: packed row r (valid region l of batch row b) <- att[b, l, :].  Work item = 2
+// consecutive packed rows; every thread first issues all of its 16-byte loads for the item
+// (8 independent loads in flight at D = 2048 -- this kernel also runs as the zero-copy PCIe
+// reader), then converts and stores.  128 threads / <= 64 registers per CTA so that a resident
+// pack CTA still leaves room for a 320-thread GEMM CTA on the same SM (the upload overlaps compute).
+constexpr int PACK_ROWS = 1;
+constexpr int PACK_THREADS = 128;
+__global__ void __launch_bounds__(PACK_THREADS)
+pack_att_kernel(const float* __restrict__ att, const int* __restrict__ off, int B, int L, int D,
+                int NL, bf16* __restrict__ out) {
+  const int d4 = D / 4;                      // float4 per row
+  const int n_items = (NL + PACK_ROWS - 1) / PACK_ROWS;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int r0 = item * PACK_ROWS;
+    const float4* src[PACK_ROWS];
+#pragma unroll
+    for (int k = 0; k < PACK_ROWS; ++k) {
+      const int r = min(r0 + k, NL - 1);
+      int64_t src_row = r;
+      if (off) {
+        const int b = find_row(off, B, r);
+        src_row = int64_t(b) * L + (r - off[b]);
+      }
+      src[k] = reinterpret_cast<const float4*>(att + src_row * D);
+    }
+    for (int i0 = 0; i0 < d4; i0 += 4 * PACK_THREADS) {   // 4 float4 per thread per row
+      float4 v[PACK_ROWS][4];
+#pragma unroll
+      for (int k = 0; k < PACK_ROWS; ++k)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int i = i0 + h * PACK_THREADS + threadIdx.x;
+          v[k][h] = (i < d4) ? __ldcs(src[k] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int k = 0; k < PACK_ROWS; ++k) {
+        if (r0 + k >= NL) break;
+        uint2* dst = reinterpret_cast<uint2*>(out + int64_t(r0 + k) * D);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int i = i0 + h * PACK_THREADS + threadIdx.x;
+          if (i < d4) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(v[k][h].x, v[k][h].y);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[k][h].z, v[k][h].w);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&a);
+            o.y = *reinterpret_cast<uint32_t*>(&b2);
+            dst[i] = o;
+          }
+        }
+      }
+    }
   }
 }
 
@@ -136,8 +170,6 @@ __global__ void start_step_kernel(const float* __restrict__ embed, int64_t start
 //   att_res[j] = sum_l w_l att_e[l,j]
 // one CTA per batch row; HBM-bound: reads p_att[b] and att_e[b] once (bf16, 16-byte loads).
 // ------------------------------------------------------------------------------------------
-constexpr int ATT_THREADS = 256;
-
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_fwd_kernel(const bf16* __restrict__ p_att16, const bf16* __restrict__ att_e16,
                      const int* __restrict__ off, int Lfix, const float* __restrict__ s_row0,
@@ -289,39 +321,28 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ s, int64_t lds, const 
 //   ST gumbel     : id = argmax (z+G), y = softmax((z+G)/tau)              (gumbel.py:6-30)
 //   ST multinomial: id = argmax (z/tau - log E), y = softmax(z/tau)        (multinomial.py:4-27)
 // ------------------------------------------------------------------------------------------
-struct OnlineLse {
-  float m, s;
+constexpr int SAMPLE_THREADS = 256;
+
+// running (max, sum of exp) pair; exponentials in base 2 on pre-scaled inputs
+struct OnlineLse2 {
+  float m, s;   // m in log2 units
   __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
-  __device__ __forceinline__ void add(float x) {
-    if (x > m) { s = s * __expf(m - x) + 1.f; m = x; }
-    else s += __expf(x - m);
+  __device__ __forceinline__ void add4(const float (&x2)[4]) {      // x2 = x * log2(e)
+    const float nm = fmaxf(fmaxf(fmaxf(x2[0], x2[1]), fmaxf(x2[2], x2[3])), m);
+    s = s * exp2f(m - nm) + exp2f(x2[0] - nm) + exp2f(x2[1] - nm) + exp2f(x2[2] - nm) + exp2f(x2[3] - nm);
+    m = nm;
   }
   __device__ __forceinline__ void merge(float m2, float s2) {
-    if (m2 == -INFINITY) return;
-    if (m2 > m) { s = s * __expf(m - m2) + s2; m = m2; }
-    else s += s2 * __expf(m2 - m);
+    const float nm = fmaxf(m, m2);
+    if (nm == -INFINITY) return;
+    s = s * exp2f(m - nm) + s2 * exp2f(m2 - nm);
+    m = nm;
   }
 };
 
-__device__ __forceinline__ float gumbel_of(float u) {
-  return -logf(-logf(u + 1e-20f) + 1e-20f);   // gumbel.py:6-11
-}
-
-// 4 noise values for elements [4*v4, 4*v4+3] of a row: injected (fp32 row) or Philox uniforms
-__device__ __forceinline__ void noise4(const float* inj_row, int v4, uint64_t seed, uint64_t stream,
-                                       uint64_t ctr, float (&u)[4]) {
-  if (inj_row) {
-    const float4 t = *reinterpret_cast<const float4*>(inj_row + 4 * v4);
-    u[0] = t.x; u[1] = t.y; u[2] = t.z; u[3] = t.w;
-  } else {
-    const uint4 r = Philox::gen(seed, stream, ctr);
-    u[0] = Philox::u01(r.x); u[1] = Philox::u01(r.y); u[2] = Philox::u01(r.z); u[3] = Philox::u01(r.w);
-  }
-}
-__device__ __forceinline__ float exp1_of_u(float u) { return -logf(1.f - u); }  // Exp(1) from U[0,1)
-
-constexpr int SAMPLE_THREADS = 256;
-
+// One CTA per row, one streaming pass over the logits (one global read, few registers -> high
+// occupancy): per 4 elements one Philox call, the perturbed scores, an online (max, sum) for
+// log-sum-exp and for the relaxed sample y, and the running argmax.
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
               const float* __restrict__ noise, uint64_t seed, uint64_t nstream,
@@ -335,39 +356,43 @@ sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
   __shared__ float s_m1[8], s_s1[8], s_m2[8], s_s2[8], s_bv[8];
   __shared__ int s_bi[8];
   __shared__ int64_t s_fed;
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   const int b = blockIdx.x;
   const float* zr = z + int64_t(b) * V1;
   const float* nr = noise ? noise + int64_t(b) * V1 : nullptr;
-  OnlineLse l1, l2;
+  const bool fast = (noise == nullptr);
+  const bool st = (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL);
+  const bool race = (mode == COOPCAP_SAMPLE_MULTINOMIAL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL);
+  const bool use_noise = (mode == COOPCAP_SAMPLE_ST_GUMBEL) || race;
+  const int nv4 = V1 / 4;
+  OnlineLse2 l1, l2;
   l1.init();
   l2.init();
   float bv = -INFINITY;
   int bi = 0x7fffffff;
-  const bool need_y = (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL);
-  const bool use_noise = (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_MULTINOMIAL ||
-                          mode == COOPCAP_SAMPLE_ST_MULTINOMIAL);
-  for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += SAMPLE_THREADS) {
+#pragma unroll 2
+  for (int v4 = threadIdx.x; v4 < nv4; v4 += SAMPLE_THREADS) {
     const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
     const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
     float u4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (use_noise) noise4(nr, v4, seed, nstream, uint64_t(b) * (V1 / 4) + v4, u4);
+    if (use_noise) noise4(nr, v4, seed, nstream, uint64_t(b) * nv4 + v4, u4);
+    float a4[4], y4[4], xs[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float x = x4[q];
-      l1.add(x);
-      float score = x;
-      if (mode == COOPCAP_SAMPLE_ST_GUMBEL) {
-        score = (x + gumbel_of(u4[q])) * inv_tau;
-        l2.add(score);
-      } else if (mode == COOPCAP_SAMPLE_MULTINOMIAL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL) {
-        const float e = nr ? u4[q] : exp1_of_u(u4[q]);
-        score = x * inv_tau - logf(e);
-        if (need_y) l2.add(x * inv_tau);
-      }
-      if (mode != COOPCAP_SAMPLE_NONE && (score > bv)) { bv = score; bi = 4 * v4 + q; }
+      xs[q] = x4[q] * LOG2E;
+      a4[q] = x4[q];
+      y4[q] = 0.f;
+      if (st) { y4[q] = st_score(mode, x4[q], u4[q], inv_tau, fast); a4[q] = y4[q]; y4[q] *= LOG2E; }
+      if (race) a4[q] = x4[q] * inv_tau + neg_log_exp1(u4[q], nr != nullptr);
+    }
+    l1.add4(xs);
+    if (st) l2.add4(y4);
+    if (mode != COOPCAP_SAMPLE_NONE) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (a4[q] > bv) { bv = a4[q]; bi = 4 * v4 + q; }
     }
   }
-  // warp then block merge
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float m1 = __shfl_xor_sync(0xffffffffu, l1.m, o), s1 = __shfl_xor_sync(0xffffffffu, l1.s, o);
@@ -390,7 +415,7 @@ sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
       l2.merge(s_m2[w], s_s2[w]);
       if (s_bv[w] > bv || (s_bv[w] == bv && s_bi[w] < bi)) { bv = s_bv[w]; bi = s_bi[w]; }
     }
-    const float lse = l1.m + logf(l1.s);
+    const float lse = (l1.m + log2f(l1.s)) * LN2;
     const int64_t raw = (mode == COOPCAP_SAMPLE_NONE) ? 0 : int64_t(bi);
     const int64_t fed = forced ? forced[b] : raw;
     const bool up = unf_prev ? (unf_prev[b] != 0) : true;
@@ -400,7 +425,7 @@ sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
     tok_fed_next[b] = fed;
     logp[b] = zr[fed] - lse;
     lse_o[b] = lse;
-    ymax_o[b] = l2.m;
+    ymax_o[b] = l2.m * LN2;                          // back to natural-log units (st_bwd_kernel)
     ysum_o[b] = l2.s;
     unf[b] = un ? 1 : 0;
     s_fed = fed;
@@ -456,9 +481,12 @@ size_t attention_smem_bytes(int A, int R, int L) {
 int speaker_prologue_fwd(const coopcap_speaker* c, cudaStream_t s) {
   int rc = check_dims(c);
   if (rc) return rc;
-  pack_att_kernel<<<c->NL, 256, 0, s>>>(c->att_feats, c->att_off, c->B, c->L, c->D,
-                                        reinterpret_cast<bf16*>(c->att16));
-  CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
+  if (!c->att_prepacked) {
+    CC_REQUIRE(c->att_feats != nullptr, "speaker: att_feats is null and att16 is not pre-packed");
+    pack_att_kernel<<<(c->NL + PACK_ROWS - 1) / PACK_ROWS, PACK_THREADS, 0, s>>>(c->att_feats, c->att_off, c->B, c->L, c->D, c->NL,
+                                          reinterpret_cast<bf16*>(c->att16));
+    CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 6.0 * c->NL * c->D);
+  }
   EpiStoreParams ep = {};
   ep.alpha = 1.f;
   ep.bias = c->b_att_embed;
@@ -506,10 +534,25 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     e1.alpha = 1.f; e1.bias = c->b_cat; e1.C = s_t; e1.ldc = NS;
     rc = gemm_run(0, 0, 0, xh16 + int64_t(t) * B * XH, XH, c->w_cat16, XH, B, NS, XH, 1, 0, e1, s);
     if (rc) return rc;
-    attention_fwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
-        reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
-        c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, att_res16 + int64_t(t) * B * R,
-        c->att_w + int64_t(t) * c->NL, A, R);
+    if (A == 512 && R == 512) {
+      constexpr int ST = 3;
+      const size_t sm2 = attention_fwd2_smem<512, ST>(c->L);
+      static size_t sm2_set = 0;
+      if (sm2 > sm2_set) {
+        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd2_kernel<512, ST>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2)));
+        sm2_set = sm2;
+      }
+      attention_fwd2_kernel<512, ST><<<B, ATT_THREADS, sm2, s>>>(
+          reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
+          c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, att_res16 + int64_t(t) * B * R,
+          c->att_w + int64_t(t) * c->NL);
+    } else {
+      attention_fwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
+          reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
+          c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, att_res16 + int64_t(t) * B * R,
+          c->att_w + int64_t(t) * c->NL, A, R);
+    }
     // algorithmic bytes: p_att + att_e read once (bf16), att_h in, att_res + weights out
     CC_LAUNCH_CHECK_K(PROF_ATT_FWD, s, 0.0,
                       2.0 * c->NL * (A + R) + 4.0 * B * A + 2.0 * B * R + 4.0 * c->NL);
@@ -573,6 +616,23 @@ int coopcap_speaker_pack_weights(const coopcap_speaker_pack* p, coopcap_stream_t
   const int n = 5 * R + A;
   bias_cat_kernel<<<(n + 255) / 256, 256, 0, s>>>(p->b_i2h, p->b_h2h, p->b_h2att, 5 * R, A, p->b_cat);
   CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
+  return CC_OK;
+}
+
+int coopcap_pack_att_from_host(const float* att_feats_pinned, const int* att_off, int B, int L, int D,
+                               int NL, void* att16, int ctas, coopcap_stream_t stream) {
+  using namespace coopcap;
+  CC_REQUIRE(att_feats_pinned && att16 && B > 0 && L > 0 && NL > 0 && D % 4 == 0,
+             "pack_att_from_host: bad arguments");
+  void* dptr = nullptr;
+  // the host buffer must be pinned + mapped (UVA): ask the runtime for its device alias
+  CC_CHECK_CUDA(cudaHostGetDevicePointer(&dptr, const_cast<float*>(att_feats_pinned), 0));
+  if (ctas <= 0) ctas = 64;
+  if (ctas > (NL + PACK_ROWS - 1) / PACK_ROWS) ctas = (NL + PACK_ROWS - 1) / PACK_ROWS;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  pack_att_kernel<<<ctas, PACK_THREADS, 0, s>>>(reinterpret_cast<const float*>(dptr), att_off, B, L, D, NL,
+                                       reinterpret_cast<bf16*>(att16));
+  CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 4.0 * NL * D);
   return CC_OK;
 }
 

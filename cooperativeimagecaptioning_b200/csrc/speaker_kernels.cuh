@@ -53,6 +53,47 @@ __device__ __forceinline__ void keep4(const uint8_t* inj, int64_t idx4, uint64_t
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// noise transforms shared by the sampler (forward) and the straight-through backward, which must
+// rebuild bit-identical scores.  `fast` selects hardware approximations (Philox noise: production)
+// versus libm-accurate logs (injected noise: parity with the reference's torch.log).
+// ---------------------------------------------------------------------------------------------
+// Exp(1) draw from a uniform in [0,1): -log(1-u) ~ -log(u'); accurate near u' -> 1 via log1p series
+__device__ __forceinline__ float neg_log_fast(float u) {
+  // -log(u) for u in (0, 1]; lg2.approx has a 2^-22 absolute error, useless for u -> 1
+  const float d = 1.f - u;
+  if (d < 0.0625f) return d * (1.f + d * (0.5f + d * (0.33333334f + d * 0.25f)));
+  return -0.69314718f * __log2f(u);
+}
+__device__ __forceinline__ float gumbel_of(float u, bool fast) {
+  if (fast) {
+    const float e = neg_log_fast(fmaxf(u, 1e-20f));          // Exp(1)
+    return -0.69314718f * __log2f(e);
+  }
+  return -logf(-logf(u + 1e-20f) + 1e-20f);                  // gumbel.py:6-11
+}
+// -log(E) for the multinomial race; E injected (precise) or E = -log(1-u) from a Philox uniform
+__device__ __forceinline__ float neg_log_exp1(float n, bool injected) {
+  if (injected) return -logf(n);
+  const float e = neg_log_fast(fmaxf(1.f - n, 1e-20f));
+  return -0.69314718f * __log2f(e);
+}
+// 4 noise values for elements [4*v4, 4*v4+3] of a row: injected (fp32 row) or Philox uniforms
+__device__ __forceinline__ void noise4(const float* inj_row, int v4, uint64_t seed, uint64_t stream,
+                                       uint64_t ctr, float (&u)[4]) {
+  if (inj_row) {
+    const float4 t = *reinterpret_cast<const float4*>(inj_row + 4 * v4);
+    u[0] = t.x; u[1] = t.y; u[2] = t.z; u[3] = t.w;
+  } else {
+    const uint4 r = Philox::gen(seed, stream, ctr);
+    u[0] = Philox::u01(r.x); u[1] = Philox::u01(r.y); u[2] = Philox::u01(r.z); u[3] = Philox::u01(r.w);
+  }
+}
+// score whose softmax is y (straight-through modes) for one logit
+__device__ __forceinline__ float st_score(int mode, float x, float u, float inv_tau, bool fast) {
+  return (mode == 2 /*ST_GUMBEL*/) ? (x + gumbel_of(u, fast)) * inv_tau : x * inv_tau;
+}
+
 // block-wide reductions for 256-thread CTAs (8 warps)
 __device__ __forceinline__ float block_sum_256(float v, float* sm /*[8]*/) {
   v = warp_sum(v);

@@ -158,22 +158,27 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
                     att_off: Optional[torch.Tensor], NL: int, *, n_steps: int, mode: int,
                     inv_tau: float, start_token: int, rnd: SpeakerRandom,
                     forced: Optional[torch.Tensor] = None,
-                    start_tokens: Optional[torch.Tensor] = None) -> SpeakerPass:
+                    start_tokens: Optional[torch.Tensor] = None,
+                    att16: Optional[torch.Tensor] = None) -> SpeakerPass:
     """Prologue + n_steps decode steps.  `forced` int64 [n_steps, B] (time-major);
     `start_tokens` int64 [B] overrides the scalar start id per row."""
     _need_cuda(att_feats, att_off, forced, start_tokens)
     d: SpeakerDims = packed["dims"]
-    att_feats = _f32c(att_feats)
     B, L, D = att_feats.shape
     assert D == d.D
-    dev = att_feats.device
+    if att16 is None:
+        att_feats = _f32c(att_feats)       # `att16` given: att_feats is only a shape carrier
+    else:
+        assert att16.dtype == torch.bfloat16 and att16.is_contiguous() and att16.shape == (NL, d.D)
+    dev = att16.device if att16 is not None else att_feats.device
     cap = max(n_steps, 1)
     f32 = dict(dtype=torch.float32, device=dev)
     bf = dict(dtype=torch.bfloat16, device=dev)
     i64 = dict(dtype=torch.int64, device=dev)
     NS, XH = 5 * d.R + d.A, d.E + d.R
     T = dict(
-        att16=torch.empty(NL, d.D, **bf), att_e16=torch.empty(NL, d.R, **bf),
+        att16=att16 if att16 is not None else torch.empty(NL, d.D, **bf),
+        att_e16=torch.empty(NL, d.R, **bf),
         p_att16=torch.empty(NL, d.A, **bf), xh16=torch.empty(cap + 1, B, XH, **bf),
         s_all=torch.empty(cap, B, NS, **f32), u_all=torch.empty(cap, B, 2 * d.R, **f32),
         c_all=torch.empty(cap + 1, B, d.R, **f32), att_res16=torch.empty(cap, B, d.R, **bf),
@@ -188,7 +193,8 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     c = _lib.Speaker()
     c.B, c.L, c.D, c.R, c.E, c.A, c.V1 = B, L, d.D, d.R, d.E, d.A, d.V1
     c.NL, c.cap, c.n_steps = NL, cap, n_steps
-    c.att_feats, c.att_off = _p(att_feats), _p(att_off)
+    c.att_feats, c.att_off = (None if att16 is not None else _p(att_feats)), _p(att_off)
+    c.att_prepacked = int(att16 is not None)
     c.embed = _p(_f32c(P["embed.0.weight"].detach()))
     c.b_att_embed = _p(_f32c(P["att_embed.0.bias"].detach()))
     c.b_ctx2att = _p(_f32c(P["ctx2att.bias"].detach()))

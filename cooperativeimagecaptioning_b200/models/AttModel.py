@@ -171,7 +171,9 @@ class AttModel(nn.Module):
             raise EN._lib.CoopcapError("Att2in2Model runs on CUDA only (no CPU path)")
         P = self._params()
         packed = self._packed.get(P)
-        att_feats = att_feats.detach().float().contiguous()
+        att16 = getattr(att_masks, "_coopcap_att16", None) if att_masks is not None else None
+        if att16 is None:
+            att_feats = att_feats.detach().float().contiguous()
         B, L = att_feats.shape[:2]
         pre = getattr(att_masks, "_coopcap_off", None) if att_masks is not None else None
         if pre is not None:
@@ -183,7 +185,7 @@ class AttModel(nn.Module):
             off, NL = EN.region_offsets(att_masks, B, L)
         sp = EN.speaker_forward(P, packed, att_feats, off, NL, n_steps=n_steps, mode=mode,
                                 inv_tau=inv_tau, start_token=start_token, rnd=self._random(),
-                                forced=forced, start_tokens=start_tokens)
+                                forced=forced, start_tokens=start_tokens, att16=att16)
         if self.keep_passes:
             self._passes.append(sp)
         return sp

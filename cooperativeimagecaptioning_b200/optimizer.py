@@ -32,8 +32,8 @@ class FlatAdam:
         if not self.params:
             raise ValueError("FlatAdam: no parameters")
         dev = self.params[0].device
-        if dev.type != "cuda":
-            raise EN._lib.CoopcapError("FlatAdam needs CUDA parameters (there is no CPU path)")
+        # the bucket plumbing (flattening, all-reduce) is device-agnostic torch code and is
+        # exercised on CPU/gloo by tests/test_dist_cpu.py; step() itself needs the CUDA kernel
         # 16-byte aligned segments so every parameter view is vector-load friendly
         self.offsets, n = [], 0
         for p in self.params:
@@ -72,6 +72,8 @@ class FlatAdam:
 
     def step(self, grad_clip: Optional[float] = None, world_size: Optional[int] = None):
         """clamp + Adam; `world_size` > 1 divides the (already all-reduced) gradient first."""
+        if self.flat_param.device.type != "cuda":
+            raise EN._lib.CoopcapError("FlatAdam.step needs CUDA parameters (there is no CPU path)")
         if world_size is None:
             world_size = self.all_reduce()
         g = self.param_groups[0]

@@ -164,6 +164,7 @@ typedef struct coopcap_speaker {
   /* inputs */
   const float* att_feats; /* [B, L, D] */
   const int* att_off;     /* [B+1] packed-row offsets, or NULL */
+  int att_prepacked;      /* 1: att16 already holds the packed bf16 regions (att_feats unused) */
   /* parameters */
   const float* embed;     /* [V+2, E] fp32 */
   const float* b_att_embed;
@@ -392,6 +393,24 @@ int coopcap_listener_bwd(const coopcap_listener* ctx, const coopcap_listener_gra
 int coopcap_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                        int64_t n, float grad_scale, float clip, float lr, float beta1, float beta2,
                        float eps, float weight_decay, int step, coopcap_stream_t stream);
+
+/* ---- host -> device staging (train.py:162-178 `load_data` / misc/utils.py:72-87 `var_wrapper`) ----
+ * The loader zero-pads att_feats to the longest image of the batch (dataloader.py:220-229); only
+ * the valid prefix of every row needs to cross PCIe.  Copies lens_host[b] * unit_bytes bytes of row
+ * b (row pitch row_stride_bytes in both buffers) from pinned host memory, one cudaMemcpyAsync per
+ * row on `stream`.  lens_host is a HOST array.  Padded tails of dst are left untouched (the kernels
+ * never read them: they work on the packed valid regions). */
+int coopcap_h2d_ragged_rows(void* dst, const void* src_host, const int* lens_host, int B,
+                            int64_t row_stride_bytes, int64_t unit_bytes, coopcap_stream_t stream);
+
+/* Zero-copy variant: a small persistent grid reads the valid regions of a PINNED host tensor
+ * att_feats [B, L, D] fp32 straight over PCIe and writes the packed bf16 operand att16 [NL, D]
+ * (the same result coopcap_speaker_prologue_fwd's pack step produces from a device tensor), so the
+ * padded fp32 tensor never exists in HBM.  att_off is a DEVICE array [B+1] (or NULL: all L valid).
+ * Meant to run on a copy stream while the previous step computes; `ctas` bounds the SMs it uses
+ * (0 = default 64; 128-thread CTAs that co-reside with the GEMM CTAs).  Pass the result as coopcap_speaker.att16 with att_prepacked = 1. */
+int coopcap_pack_att_from_host(const float* att_feats_pinned, const int* att_off, int B, int L, int D,
+                               int NL, void* att16, int ctas, coopcap_stream_t stream);
 
 /* ---- instrumentation ---------------------------------------------------------------------------
  * coopcap_launch_count: kernels launched by this library since load (all streams).

@@ -1,0 +1,71 @@
+"""CPU / gloo, world_size 2: the data-parallel host logic (flat gradient bucket, one all-reduce,
+1/N scaling) of optimizer.FlatAdam -- SURVEY.md §8(e)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cooperativeimagecaptioning_b200 import optimizer as OPT
+        from cooperativeimagecaptioning_b200._lib import CoopcapError
+        torch.manual_seed(0)                                  # identical weights on every rank
+        net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+        w0 = [p.detach().clone() for p in net.parameters()]
+        opt = OPT.FlatAdam(net.parameters(), lr=1e-3, grad_clip=0.1)
+        # parameters and gradients are views of the flat buckets
+        for p, o in zip(opt.params, opt.offsets):
+            assert p.data_ptr() == opt.flat_param.data_ptr() + 4 * o
+            assert p.grad.data_ptr() == opt.flat_grad.data_ptr() + 4 * o
+            assert o % 4 == 0
+        for p, w in zip(net.parameters(), w0):
+            assert torch.equal(p, w)
+        # rank-local "shard" loss -> rank-local gradients accumulate INTO the bucket
+        opt.zero_grad()
+        g = torch.Generator().manual_seed(100 + rank)
+        x = torch.randn(4, 7, generator=g)
+        net(x).square().sum().backward()
+        local = opt.flat_grad.clone()
+        n = opt.all_reduce()
+        assert n == world
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        assert torch.allclose(opt.flat_grad, sum(gathered))   # one SUM all-reduce of the bucket
+        # the fused clamp+Adam kernel is CUDA-only: the CPU path must fail loudly
+        try:
+            opt.step(world_size=n)
+            raise AssertionError("FlatAdam.step must not run on CPU")
+        except CoopcapError:
+            pass
+        # checkpoint layout is torch.optim-shaped
+        sd = opt.state_dict()
+        assert set(sd) == {"state", "param_groups"} and len(sd["state"]) == 4
+        out.put((rank, float(opt.flat_grad.abs().sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    res = dict(q.get() for _ in range(2))
+    assert abs(res[0] - res[1]) < 1e-6                        # both ranks hold the same sum
