@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--no-prof", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
     ap.add_argument("--upload-ctas", type=int, default=64, help="CTAs of the zero-copy upload kernel")
-    ap.add_argument("--clock-period", type=float, default=0.05, help="NVML sampling period (s); 0 = off")
+    ap.add_argument("--clock-samples", type=int, default=1, help="NVML samples inside the timed region; 0 = off")
     return ap.parse_args()
 
 
@@ -111,15 +111,14 @@ def host_batch(rows, lmax, lmin, seed, pin):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled through NVML (in-process thread, started before the
-    warm-up so that NVML initialisation is outside the timed region) DURING the timed region."""
+    """SM clock / throttle reasons through NVML, sampled from the launching thread at a few points
+    INSIDE the timed region (between steps).  A background poller is deliberately not used: on
+    these hosts NVML queries contend with kernel launches (a 50 ms poller doubled the step time at
+    N = 2); the launch queue runs several ms ahead of the GPU, so three short inline queries do not
+    starve it.  NVML is initialised before the warm-up."""
 
-    def __init__(self, index, period_s=0.05):
-        import threading
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._active = threading.Event()
-        self._h = None
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._h = [], set(), None, None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -128,15 +127,9 @@ class ClockSampler:
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:       # pragma: no cover - NVML missing: report nulls
             self._h = None
-        self._period = period_s
-        self._t = threading.Thread(target=self._loop, daemon=True)
-        self._t.start()
-
-    def _loop(self):
-        nv = getattr(self, "_nv", None)
-        if self._h is None:
             return
-        bits = {}
+        nv = self._nv
+        self._bits = {}
         for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
                            ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
                            ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
@@ -145,29 +138,25 @@ class ClockSampler:
             if v is None:
                 v = getattr(nv, attr.replace("ClocksEventReason", "ClocksThrottleReason"), None)
             if v is not None:
-                bits[name] = v
-        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                self._bits[name] = v
+        self._get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
             getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
-        while not self._stop.is_set():
-            if self._active.is_set():
-                try:
-                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
-                    if get_reasons is not None:
-                        r = get_reasons(self._h)
-                        for name, bit in bits.items():
-                            if r & bit:
-                                self.reasons.add(name)
-                except Exception:
-                    pass
-            self._stop.wait(self._period)
 
-    def begin(self):
-        self._active.set()
+    def sample(self):
+        if self._h is None:
+            return
+        try:
+            nv = self._nv
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            if self._get_reasons is not None:
+                r = self._get_reasons(self._h)
+                for name, bit in self._bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+        except Exception:
+            pass
 
-    def stop(self):
-        self._active.clear()
-        self._stop.set()
-        self._t.join(timeout=2)
+    def result(self):
         out = dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
                    samples=len(self.samples))
         if self.samples:
@@ -228,6 +217,11 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: anything else a library prints (the NCCL version banner)
+    # goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -241,7 +235,8 @@ def main():
     import torch.distributed as dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
 
     import cooperativeimagecaptioning_b200.models as models
     from cooperativeimagecaptioning_b200 import _lib, engine as EN
@@ -283,7 +278,7 @@ def main():
     # ---------------- device-resident throughput (`value`) ----------------
     resident = [to_device(h, False) for h in hb]
     torch.cuda.synchronize()
-    clocks = ClockSampler(local, args.clock_period) if (rank == 0 and args.clock_period > 0) else None
+    clocks = ClockSampler(local) if (rank == 0 and args.clock_samples > 0) else None
     # setup (untimed, before the W warm-up steps): prime until the step time has settled -- the
     # caching allocator must have seen both batch shapes, and a freshly booted box takes a few
     # hundred ms of work before clocks / driver state stop moving
@@ -295,28 +290,39 @@ def main():
             train_step(resident[i % 2])
         p1.record()
         torch.cuda.synchronize()
-        cur = p0.elapsed_time(p1)
+        cur_t = torch.tensor([p0.elapsed_time(p1)], device=dev)
+        if world > 1:
+            dist.all_reduce(cur_t, op=dist.ReduceOp.MAX)     # every rank takes the same decision
+        cur = float(cur_t)
         if prev is not None and abs(cur - prev) <= 0.03 * prev:
             break
         prev = cur
     for i in range(args.warmup):
         train_step(resident[i % 2])
     barrier()
+    sample_at = set()
     if clocks:
-        clocks.begin()
+        n = args.clock_samples
+        sample_at = {max(1, (k + 1) * args.steps // (n + 1)) for k in range(n)}
     l0 = lib.coopcap_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
+        if i in sample_at:
+            clocks.sample()                    # GPU is busy with the steps already queued
         loss = train_step(resident[i % 2])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.coopcap_launch_count() - l0
-    clk = clocks.stop() if clocks else None
+    clk = clocks.result() if clocks else None
     loss_value = float(loss.detach())
     t = torch.tensor([ms], device=dev)
+    ms_ranks = [ms]
     if world > 1:
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        ms_ranks = [float(x) for x in gathered]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t)
     value = args.rows * world * args.steps / (ms_max * 1e-3)
@@ -371,16 +377,19 @@ def main():
 
     # ---------------- per-kernel timeline (roofline of the dominant kernel) ----------------
     roof, breakdown = None, None
-    if rank == 0 and not args.no_prof:
+    if not args.no_prof:
+        # every rank runs the same steps (they contain the all-reduce); rank 0 records the timeline
         resident = [to_device(h, False) for h in hb]
         torch.cuda.synchronize()
         nk = lib.coopcap_prof_kinds()
         psteps = min(args.steps, 5)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(lib.coopcap_prof_enable(1, stream))
+        if rank == 0:
+            _lib.check(lib.coopcap_prof_enable(1, stream))
         for i in range(psteps):
             train_step(resident[i % 2])
         torch.cuda.synchronize()
+    if rank == 0 and not args.no_prof:
         arr = lambda ty: (ty * nk)()
         pms, pfl, pby, pln = arr(C.c_double), arr(C.c_double), arr(C.c_double), arr(C.c_longlong)
         _lib.check(lib.coopcap_prof_report(pms, pfl, pby, pln, nk))
@@ -442,7 +451,8 @@ def main():
                      ms_per_step=e2e_ms / args.steps,
                      note="public API (AlternatingJointModel.forward + backward + optimizer.step) "
                           "from pinned host buffers, valid regions only (data.upload_batch), upload double-buffered on a copy stream"),
-            gpu_launches=int(launches), loss=loss_value, clocks=clk, roofline=roof,
+            gpu_launches=int(launches), ms_per_step_by_rank=[m / args.steps for m in ms_ranks],
+            loss=loss_value, clocks=clk, roofline=roof,
             cpu_baseline=cpu, breakdown=breakdown)
         print(json.dumps(line), flush=True)
     if world > 1:
