@@ -56,11 +56,13 @@ attention_fwd2_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bflo
   const __nv_bfloat16* pg = p_att16 + int64_t(r0) * AR;
   const __nv_bfloat16* eg = att_e16 + int64_t(r0) * AR;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();
   auto issue = [&](int c) {
     const int st = c % STAGES;
     const int rows = min(ATT_CH, Lb - c * ATT_CH);
@@ -175,11 +177,13 @@ attention_bwd2_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bflo
   const int nch = (Lb + ATT_CH - 1) / ATT_CH;
   const __nv_bfloat16* pg = p_att16 + int64_t(r0) * AR;
   const __nv_bfloat16* eg = att_e16 + int64_t(r0) * AR;
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();
   // item i in [0, 2*nch): att_e chunks first, then p_att chunks
   auto issue = [&](int i) {
     const int st = i % STAGES;
@@ -298,11 +302,13 @@ attention_deferred2_kernel(const __nv_bfloat16* __restrict__ p_att16, const int*
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_de + n_steps * Lp);
   const int nch = (Lb + ATT_CH - 1) / ATT_CH;
   const __nv_bfloat16* pg = p_att16 + int64_t(r0) * AR;
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();
   auto issue = [&](int c) {
     const int st = c % STAGES;
     const int rows = min(ATT_CH, Lb - c * ATT_CH);

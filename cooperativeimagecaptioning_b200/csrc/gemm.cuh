@@ -268,11 +268,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
+  pdl_launch_dependents();
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // setup above overlapped the previous kernel's tail; from here on global memory is touched
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -478,7 +481,8 @@ int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int M
   int grid = num_sms();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (tiles < grid) grid = tiles;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, split_k, ep);
+  CC_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC,
+                           M, N, K, split_k, ep));
   CC_LAUNCH_CHECK_K(PROF_GEMM, stream, 2.0 * double(M) * double(N) * double(K),
                     double(Cfg::EB) * (double(M) * K + double(N) * K));
   return CC_OK;

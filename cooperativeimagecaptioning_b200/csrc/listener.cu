@@ -40,6 +40,8 @@ __global__ void gru_fwd_kernel(const float* __restrict__ gi, const float* __rest
                                const float* __restrict__ h_prev, const int* __restrict__ len, int t,
                                float* __restrict__ gates, float* __restrict__ h_next,
                                bf16* __restrict__ h_next16, int B, int M) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int per_row = M / 4;
   if (idx >= B * per_row) return;
@@ -232,6 +234,8 @@ __global__ void hinge_bwd_kernel(const float* __restrict__ im, const float* __re
 __global__ void gru_bwd_kernel(float* __restrict__ dh, const float* __restrict__ gates,
                                const float* __restrict__ h_prev, const int* __restrict__ len, int t,
                                bf16* __restrict__ d_gi16, bf16* __restrict__ d_gh16, int B, int M) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * M) return;
   const int b = idx / M, j = idx % M;
@@ -314,10 +318,10 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
     if ((rc = gemm_run(0, 0, 0, h16 + int64_t(t) * B * M, M, c->w_hh16, M, B, 3 * M, M, 1, 0, e, s)))
       return rc;
     const int n = B * (M / 4);
-    gru_fwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(
-        c->gi_all + int64_t(t) * B * 3 * M, c->gh, c->h32 + int64_t(t) * B * M, c->len, t,
-        c->gates + int64_t(t) * B * 4 * M, c->h32 + int64_t(t + 1) * B * M,
-        h16 + int64_t(t + 1) * B * M, B, M);
+    CC_CHECK_CUDA(launch_pdl(gru_fwd_kernel, dim3((n + 255) / 256), dim3(256), 0, s,
+                             c->gi_all + int64_t(t) * B * 3 * M, c->gh, c->h32 + int64_t(t) * B * M,
+                             c->len, t, c->gates + int64_t(t) * B * 4 * M,
+                             c->h32 + int64_t(t + 1) * B * M, h16 + int64_t(t + 1) * B * M, B, M));
     CC_LAUNCH_CHECK_K(PROF_GRU, s, 0.0, 0.0);
   }
   l2norm_fwd_kernel<<<B, 256, 0, s>>>(c->h32 + int64_t(S) * B * M, c->cap, M, 0);
@@ -366,9 +370,9 @@ int listener_bwd(const coopcap_listener* c, const coopcap_listener_grads* g, cud
   CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   for (int t = S - 1; t >= 0; --t) {
     const int n = B * M;
-    gru_bwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(
-        g->dh, c->gates + int64_t(t) * B * 4 * M, c->h32 + int64_t(t) * B * M, c->len, t,
-        d_gi16 + int64_t(t) * B * 3 * M, d_gh16 + int64_t(t) * B * 3 * M, B, M);
+    CC_CHECK_CUDA(launch_pdl(gru_bwd_kernel, dim3((n + 255) / 256), dim3(256), 0, s, g->dh,
+                             c->gates + int64_t(t) * B * 4 * M, c->h32 + int64_t(t) * B * M, c->len, t,
+                             d_gi16 + int64_t(t) * B * 3 * M, d_gh16 + int64_t(t) * B * 3 * M, B, M));
     CC_LAUNCH_CHECK_K(PROF_GRU, s, 0.0, 0.0);
     if (t > 0) {
       // dh += d_gh . W_hh        ([B,3M] x [3M,M]; W_hh stored [K, N])

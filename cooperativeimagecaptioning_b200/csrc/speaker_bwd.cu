@@ -99,6 +99,8 @@ st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t 
               float inv_tau, const float* __restrict__ noise, uint64_t seed, uint64_t nstream,
               const float* __restrict__ ymax, const float* __restrict__ ysum,
               const uint8_t* __restrict__ unf, bf16* __restrict__ dz) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_y[];   // [V1]
   __shared__ float red[8];
   const int b = blockIdx.x;
@@ -169,6 +171,8 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ d_out, const bf16* __r
                                 const float* __restrict__ s, int64_t lds, const float* __restrict__ u,
                                 const float* __restrict__ c_prev, const float* __restrict__ c_cur,
                                 bf16* __restrict__ dscat, float drop_p, int B, int R) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * R) return;
   const int b = idx / R, j = idx % R;
@@ -435,11 +439,11 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
     } else {
       g_t = g_ws + int64_t(t) * B * ldg;   // dense upstream gradient, all steps
     }
-    st_bwd_kernel<<<B, 256, smem, s>>>(
-        c->z_all + int64_t(t) * B * V1, g_t, ldg, V1, c->mode, c->inv_tau,
-        c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed, SITE_NOISE + t,
-        c->y_max + int64_t(t) * B, c->y_sum + int64_t(t) * B, c->unfinished + int64_t(t) * B,
-        reinterpret_cast<bf16*>(dz16) + int64_t(t) * B * V1);
+    CC_CHECK_CUDA(launch_pdl(
+        st_bwd_kernel, dim3(B), dim3(256), smem, s, c->z_all + int64_t(t) * B * V1, g_t, ldg, V1,
+        c->mode, c->inv_tau, c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed,
+        uint64_t(SITE_NOISE + t), c->y_max + int64_t(t) * B, c->y_sum + int64_t(t) * B,
+        c->unfinished + int64_t(t) * B, reinterpret_cast<bf16*>(dz16) + int64_t(t) * B * V1));
     // logits + upstream gradient (+ injected noise) read, bf16 dz written
     CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(B) * V1 * (4.0 + 4.0 + 2.0 + (c->noise ? 4.0 : 0.0)));
   }
@@ -494,10 +498,11 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
     const float* dh_next = (t == n - 1) ? nullptr : g->d_xh + int64_t(t + 1) * B * XH + E;
     {
       const int nthr = B * R;
-      lstm_bwd_kernel<<<(nthr + 255) / 256, 256, 0, s>>>(
-          g->d_out + int64_t(t) * B * R, out16 + int64_t(t) * B * R, dh_next, XH, dc_in, dc_out, s_t,
-          NS, c->u_all + int64_t(t) * B * 2 * R, c->c_all + int64_t(t) * B * R,
-          c->c_all + int64_t(t + 1) * B * R, ds_t, c->drop_p, B, R);
+      CC_CHECK_CUDA(launch_pdl(
+          lstm_bwd_kernel, dim3((nthr + 255) / 256), dim3(256), 0, s, g->d_out + int64_t(t) * B * R,
+          out16 + int64_t(t) * B * R, dh_next, int64_t(XH), dc_in, dc_out, s_t, int64_t(NS),
+          c->u_all + int64_t(t) * B * 2 * R, c->c_all + int64_t(t) * B * R,
+          c->c_all + int64_t(t + 1) * B * R, ds_t, c->drop_p, B, R));
       CC_LAUNCH_CHECK_K(PROF_LSTM, s, 0.0, 0.0);
     }
     // d_att_res = d_u . W_a2c      ([B,2R] x [2R,R])
@@ -516,10 +521,11 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2)));
         sm2_set = sm2;
       }
-      attention_bwd2_kernel<512, ST><<<B, ATT_THREADS, sm2, s>>>(
-          reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
-          c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, dres_t, c->att_w + int64_t(t) * NL,
-          g->de + int64_t(t) * NL, ds_t);
+      CC_CHECK_CUDA(launch_pdl(attention_bwd2_kernel<512, ST>, dim3(B), dim3(ATT_THREADS), sm2, s,
+                               reinterpret_cast<const bf16*>(c->p_att16),
+                               reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L, s_t,
+                               int64_t(NS), 5 * R, c->w_alpha, dres_t, c->att_w + int64_t(t) * NL,
+                               g->de + int64_t(t) * NL, ds_t));
     } else {
       attention_bwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
           reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),

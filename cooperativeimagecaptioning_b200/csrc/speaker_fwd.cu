@@ -263,6 +263,8 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ s, int64_t lds, const 
                                 bf16* __restrict__ h_dst, int64_t ld_h, bf16* __restrict__ out16,
                                 const uint8_t* __restrict__ keep, uint64_t seed, uint64_t stream,
                                 float drop_p, int B, int R) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // 4 units per thread
   const int per_row = R / 4;
   if (idx >= B * per_row) return;
@@ -353,6 +355,8 @@ sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
               // next-step input
               const float* __restrict__ embed, int E, const uint8_t* __restrict__ keep_embed_next,
               uint64_t estream, float drop_p, bf16* __restrict__ xh_next, int64_t ld_xh) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_m1[8], s_s1[8], s_m2[8], s_s2[8], s_bv[8];
   __shared__ int s_bi[8];
   __shared__ int64_t s_fed;
@@ -543,10 +547,11 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2)));
         sm2_set = sm2;
       }
-      attention_fwd2_kernel<512, ST><<<B, ATT_THREADS, sm2, s>>>(
-          reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
-          c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, att_res16 + int64_t(t) * B * R,
-          c->att_w + int64_t(t) * c->NL);
+      CC_CHECK_CUDA(launch_pdl(attention_fwd2_kernel<512, ST>, dim3(B), dim3(ATT_THREADS), sm2, s,
+                               reinterpret_cast<const bf16*>(c->p_att16),
+                               reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L, s_t,
+                               int64_t(NS), 5 * R, c->w_alpha, att_res16 + int64_t(t) * B * R,
+                               c->att_w + int64_t(t) * c->NL));
     } else {
       attention_fwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
           reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
@@ -562,11 +567,12 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     if (rc) return rc;
     {
       const int n = B * (R / 4);
-      lstm_fwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(
-          s_t, NS, u_t, c->c_all + int64_t(t) * B * R, c->c_all + int64_t(t + 1) * B * R,
-          xh16 + int64_t(t + 1) * B * XH + E, XH, out16 + int64_t(t) * B * R,
-          c->keep_core ? c->keep_core + int64_t(t) * B * R : nullptr, c->seed, SITE_DROP_CORE + t,
-          c->drop_p, B, R);
+      CC_CHECK_CUDA(launch_pdl(
+          lstm_fwd_kernel, dim3((n + 255) / 256), dim3(256), 0, s, s_t, int64_t(NS), u_t,
+          c->c_all + int64_t(t) * B * R, c->c_all + int64_t(t + 1) * B * R,
+          xh16 + int64_t(t + 1) * B * XH + E, int64_t(XH), out16 + int64_t(t) * B * R,
+          c->keep_core ? c->keep_core + int64_t(t) * B * R : nullptr, c->seed,
+          uint64_t(SITE_DROP_CORE + t), c->drop_p, B, R));
       CC_LAUNCH_CHECK_K(PROF_LSTM, s, 0.0, 0.0);
     }
     float* z_t = c->z_all + int64_t(t) * B * V1;
@@ -574,15 +580,17 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     e3.alpha = 1.f; e3.bias = c->b_logit; e3.C = z_t; e3.ldc = V1;
     rc = gemm_run(0, 0, 0, out16 + int64_t(t) * B * R, R, c->w_logit16, R, B, V1, R, 1, 0, e3, s);
     if (rc) return rc;
-    sample_kernel<<<B, SAMPLE_THREADS, 0, s>>>(
-        z_t, V1, c->mode, c->inv_tau, c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed,
-        SITE_NOISE + t, c->forced ? c->forced + int64_t(t) * B : nullptr,
+    CC_CHECK_CUDA(launch_pdl(
+        sample_kernel, dim3(B), dim3(SAMPLE_THREADS), 0, s, z_t, V1, c->mode, c->inv_tau,
+        c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed, uint64_t(SITE_NOISE + t),
+        c->forced ? c->forced + int64_t(t) * B : nullptr,
         t > 0 ? c->unfinished + int64_t(t - 1) * B : nullptr, c->tok_raw + int64_t(t) * B,
         c->tok_out + int64_t(t) * B, c->tok_fed + int64_t(t + 1) * B, c->logp + int64_t(t) * B,
         c->lse + int64_t(t) * B, c->y_max + int64_t(t) * B, c->y_sum + int64_t(t) * B,
         c->unfinished + int64_t(t) * B, c->embed, E,
-        c->keep_embed ? c->keep_embed + int64_t(t + 1) * B * E : nullptr, SITE_DROP_EMBED + t + 1,
-        c->drop_p, (t + 1 < c->n_steps) ? xh16 + int64_t(t + 1) * B * XH : nullptr, XH);
+        c->keep_embed ? c->keep_embed + int64_t(t + 1) * B * E : nullptr,
+        uint64_t(SITE_DROP_EMBED + t + 1), c->drop_p,
+        (t + 1 < c->n_steps) ? xh16 + int64_t(t + 1) * B * XH : nullptr, int64_t(XH)));
     // algorithmic bytes: logits (+ injected noise) read once
     CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 4.0 * B * V1 * (c->noise ? 2.0 : 1.0));
   }
