@@ -376,10 +376,12 @@ int listener_bwd(const coopcap_listener* c, const coopcap_listener_grads* g, cud
     CC_LAUNCH_CHECK_K(PROF_GRU, s, 0.0, 0.0);
     if (t > 0) {
       // dh += d_gh . W_hh        ([B,3M] x [3M,M]; W_hh stored [K, N])
+      // few output tiles, deep K: split along K, both halves reduce-add onto dh
+      const int split = (int64_t(B) * M <= int64_t(128) * 128 * 74 && 3 * M >= 2048) ? 2 : 1;
       EpiStoreParams e = {};
-      e.alpha = 1.f; e.C = g->dh; e.ldc = M; e.mode = 1;
+      e.alpha = 1.f; e.C = g->dh; e.ldc = M; e.mode = split > 1 ? 2 : 1;
       if ((rc = gemm_run(0, 0, 1, d_gh16 + int64_t(t) * B * 3 * M, 3 * M, c->w_hh16, M, B, M, 3 * M,
-                         1, 0, e, s)))
+                         split, split > 1 ? 128 : 0, e, s)))
         return rc;
     }
   }

@@ -2,6 +2,7 @@
 // resolved through the runtime so the library does not link libcuda directly).
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -40,6 +41,15 @@ void prof_mark(int kind, cudaStream_t stream, double flops, double bytes) {
   else if (cudaEventCreate(&ev) != cudaSuccess) return;
   cudaEventRecord(ev, stream);
   g_prof.push_back({kind, ev, flops, bytes});
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("COOPCAP_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int num_sms() {

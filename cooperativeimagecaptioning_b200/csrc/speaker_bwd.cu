@@ -489,7 +489,11 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(att_smem)));
     att_smem_set = att_smem;
   }
-  // BPTT
+  // BPTT.  d[x|h] = dscat . w_cat has only 8 x 8 output tiles for K = 5R+A: it runs split along K
+  // with TMA reduce-add into a zeroed buffer so that the whole machine works on it.
+  const int dxh_split = (int64_t(B) * XH <= int64_t(128) * 128 * 74 && NS >= 2048) ? 2 : 1;
+  if (dxh_split > 1)
+    CC_CHECK_CUDA(cudaMemsetAsync(g->d_xh, 0, sizeof(float) * size_t(n) * B * XH, s));
   for (int t = n - 1; t >= 0; --t) {
     const float* s_t = c->s_all + int64_t(t) * B * NS;
     bf16* ds_t = dscat16 + int64_t(t) * B * NS;
@@ -538,7 +542,10 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
     {
       EpiStoreParams e = {};
       e.alpha = 1.f; e.C = g->d_xh + int64_t(t) * B * XH; e.ldc = XH;
-      if ((rc = gemm_run(0, 0, 1, ds_t, NS, c->w_cat16, XH, B, XH, NS, 1, 0, e, s))) return rc;
+      e.mode = dxh_split > 1 ? 2 : 0;
+      if ((rc = gemm_run(0, 0, 1, ds_t, NS, c->w_cat16, XH, B, XH, NS, dxh_split,
+                         dxh_split > 1 ? 128 : 0, e, s)))
+        return rc;
     }
   }
   // step-batched weight gradients
