@@ -121,6 +121,8 @@ class VSEFCModel(nn.Module):
         self.margin = opt.vse_margin
         self.embed_size = opt.vse_embed_size
         self._loss = {}
+        self.keep_passes = False          # tests: retain every ListenerPass in self._passes
+        self._passes = []
         self._packed = EN.PackedListener()
 
     def _params(self) -> Dict[str, torch.Tensor]:
@@ -141,6 +143,8 @@ class VSEFCModel(nn.Module):
         lp = EN.listener_forward(P, packed, fc_feats.detach().float().contiguous(), tok_sb, lens,
                                  margin=self.margin, only_one_retrieval=only_one_retrieval,
                                  no_imgnorm=bool(self.img_enc.no_imgnorm))
+        if self.keep_passes:
+            self._passes.append(lp)
         needs = torch.is_grad_enabled() and (
             any(p.requires_grad for p in P.values()) or
             (dense_seq is not None and dense_seq.requires_grad))
