@@ -307,11 +307,13 @@ def main():
     l0 = lib.coopcap_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    h0 = time.perf_counter()
     for i in range(args.steps):
         if i in sample_at:
             clocks.sample()                    # GPU is busy with the steps already queued
         loss = train_step(resident[i % 2])
     e1.record()
+    host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / args.steps   # CPU time to queue one step
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.coopcap_launch_count() - l0
@@ -451,7 +453,8 @@ def main():
                      ms_per_step=e2e_ms / args.steps,
                      note="public API (AlternatingJointModel.forward + backward + optimizer.step) "
                           "from pinned host buffers, valid regions only (data.upload_batch), upload double-buffered on a copy stream"),
-            gpu_launches=int(launches), ms_per_step_by_rank=[m / args.steps for m in ms_ranks],
+            gpu_launches=int(launches), host_enqueue_ms_per_step=host_enqueue_ms,
+            ms_per_step_by_rank=[m / args.steps for m in ms_ranks],
             loss=loss_value, clocks=clk, roofline=roof,
             cpu_baseline=cpu, breakdown=breakdown)
         print(json.dumps(line), flush=True)

@@ -96,23 +96,26 @@ __device__ __forceinline__ void store_bf16x4(bf16* dst, float a, float b, float 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t ldg, int V1, int mode,
-              float inv_tau, const float* __restrict__ noise, uint64_t seed, uint64_t nstream,
-              const float* __restrict__ ymax, const float* __restrict__ ysum,
+              float inv_tau, const float* __restrict__ noise, uint64_t seed, uint64_t nstream0,
+              int B, const float* __restrict__ ymax, const float* __restrict__ ysum,
               const uint8_t* __restrict__ unf, bf16* __restrict__ dz) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float s_y[];   // [V1]
   __shared__ float red[8];
-  const int b = blockIdx.x;
-  bf16* dr = dz + int64_t(b) * V1;
-  if (!unf[b]) {
+  // rows are (step, batch row) pairs of consecutive steps: row = (t - t0) * B + b
+  const int64_t row = blockIdx.x;
+  const int b = int(row % B);
+  const uint64_t nstream = nstream0 + uint64_t(row / B);
+  bf16* dr = dz + row * V1;
+  if (!unf[row]) {
     for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) store_bf16x4(dr + 4 * v4, 0.f, 0.f, 0.f, 0.f);
     return;
   }
-  const float* zr = z + int64_t(b) * V1;
-  const float* gr = g + int64_t(b) * ldg;
-  const float* nr = noise ? noise + int64_t(b) * V1 : nullptr;
-  const float m = ymax[b], inv_s = 1.f / ysum[b];
+  const float* zr = z + row * V1;
+  const float* gr = g + row * ldg;
+  const float* nr = noise ? noise + row * V1 : nullptr;
+  const float m = ymax[row], inv_s = 1.f / ysum[row];
   const bool fast = (noise == nullptr);
   float dot = 0.f;
   for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
@@ -414,7 +417,7 @@ static int check_dims(const coopcap_speaker* c) {
 }
 
 int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb16, float* g_ws,
-                int64_t ldg, void* dz16, cudaStream_t s) {
+                int g_chunk_steps, int64_t ldg, void* dz16, cudaStream_t s) {
   int rc = check_dims(c);
   if (rc) return rc;
   CC_REQUIRE(c->mode == COOPCAP_SAMPLE_ST_GUMBEL || c->mode == COOPCAP_SAMPLE_ST_MULTINOMIAL,
@@ -427,25 +430,30 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
                                        int(smem)));
     smem_set = smem;
   }
-  for (int t = 0; t < c->n_steps; ++t) {
+  // several steps per launch: M = chunk * B rows give properly sized GEMM tiles instead of
+  // n_steps launches at the latency floor (g_ws holds `g_chunk_steps` steps)
+  const int chunk = demb16 ? (g_chunk_steps < 1 ? 1 : g_chunk_steps) : c->n_steps;
+  for (int t0 = 0; t0 < c->n_steps; t0 += chunk) {
+    const int nt = min(chunk, c->n_steps - t0);
+    const int64_t rows = int64_t(nt) * B;
     const float* g_t = g_ws;
     if (demb16) {
-      // g = demb[t] . W_emb^T   ([B,E] x [V1,E]^T), kept L2-resident for the row kernel below
+      // g = demb[t0..] . W_emb^T   ([rows,E] x [V1,E]^T)
       EpiStoreParams e = {};
       e.alpha = 1.f; e.C = g_ws; e.ldc = V1;
-      rc = gemm_run(0, 0, 0, reinterpret_cast<const bf16*>(demb16) + int64_t(t) * B * E, E, w_emb16,
-                    E, B, V1, E, 1, 0, e, s);
+      rc = gemm_run(0, 0, 0, reinterpret_cast<const bf16*>(demb16) + int64_t(t0) * B * E, E, w_emb16,
+                    E, int(rows), V1, E, 1, 0, e, s);
       if (rc) return rc;
     } else {
-      g_t = g_ws + int64_t(t) * B * ldg;   // dense upstream gradient, all steps
+      g_t = g_ws + int64_t(t0) * B * ldg;   // dense upstream gradient, all steps
     }
     CC_CHECK_CUDA(launch_pdl(
-        st_bwd_kernel, dim3(B), dim3(256), smem, s, c->z_all + int64_t(t) * B * V1, g_t, ldg, V1,
-        c->mode, c->inv_tau, c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed,
-        uint64_t(SITE_NOISE + t), c->y_max + int64_t(t) * B, c->y_sum + int64_t(t) * B,
-        c->unfinished + int64_t(t) * B, reinterpret_cast<bf16*>(dz16) + int64_t(t) * B * V1));
+        st_bwd_kernel, dim3((unsigned)rows), dim3(256), smem, s, c->z_all + int64_t(t0) * B * V1, g_t,
+        ldg, V1, c->mode, c->inv_tau, c->noise ? c->noise + int64_t(t0) * B * V1 : nullptr, c->seed,
+        uint64_t(SITE_NOISE + t0), B, c->y_max + int64_t(t0) * B, c->y_sum + int64_t(t0) * B,
+        c->unfinished + int64_t(t0) * B, reinterpret_cast<bf16*>(dz16) + int64_t(t0) * B * V1));
     // logits + upstream gradient (+ injected noise) read, bf16 dz written
-    CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(B) * V1 * (4.0 + 4.0 + 2.0 + (c->noise ? 4.0 : 0.0)));
+    CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(rows) * V1 * (4.0 + 4.0 + 2.0 + (c->noise ? 4.0 : 0.0)));
   }
   return CC_OK;
 }
@@ -667,12 +675,12 @@ __global__ void clamp_adam_kernel(float* __restrict__ p, const float* __restrict
 extern "C" {
 
 int coopcap_st_backward(const coopcap_speaker* ctx, const void* demb16, const void* w_emb16,
-                        float* g_ws, void* dz16, coopcap_stream_t stream) {
+                        float* g_ws, int g_chunk_steps, void* dz16, coopcap_stream_t stream) {
   if (!demb16 || !w_emb16 || !g_ws) {
     coopcap::set_last_error("st_backward: null demb16 / w_emb16 / g_ws");
     return coopcap::CC_ERR_ARG;
   }
-  return coopcap::st_backward(ctx, demb16, w_emb16, g_ws, ctx ? ctx->V1 : 0, dz16,
+  return coopcap::st_backward(ctx, demb16, w_emb16, g_ws, g_chunk_steps, ctx ? ctx->V1 : 0, dz16,
                               reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -682,7 +690,7 @@ int coopcap_st_backward_dense(const coopcap_speaker* ctx, const float* g, int64_
     coopcap::set_last_error("st_backward_dense: null g");
     return coopcap::CC_ERR_ARG;
   }
-  return coopcap::st_backward(ctx, nullptr, nullptr, const_cast<float*>(g), ldg, dz16,
+  return coopcap::st_backward(ctx, nullptr, nullptr, const_cast<float*>(g), 0, ldg, dz16,
                               reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -239,6 +239,9 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     return sp
 
 
+ST_CHUNK_ROWS = 4096   # rows of the upstream-gradient scratch per launch (155 MB fp32 at V1 = 9488)
+
+
 def st_logit_grads(sp: SpeakerPass, demb16: torch.Tensor, w_emb16: torch.Tensor) -> torch.Tensor:
     """dz16 [n_steps*B, V1] for the straight-through samplers from the listener's embedding
     gradient demb16 [n_steps, B, E] (caption positions 1..n_steps)."""
@@ -246,10 +249,11 @@ def st_logit_grads(sp: SpeakerPass, demb16: torch.Tensor, w_emb16: torch.Tensor)
     dev = demb16.device
     assert demb16.dtype == torch.bfloat16 and demb16.is_contiguous()
     assert demb16.shape == (sp.n_steps, sp.B, d.E)
-    g_ws = torch.empty(sp.B, d.V1, dtype=torch.float32, device=dev)
+    chunk = max(1, min(sp.n_steps, ST_CHUNK_ROWS // max(sp.B, 1)))
+    g_ws = torch.empty(chunk * sp.B, d.V1, dtype=torch.float32, device=dev)
     dz16 = torch.empty(sp.n_steps * sp.B, d.V1, dtype=torch.bfloat16, device=dev)
     check(_lib.load().coopcap_st_backward(C.byref(sp.ctx), _p(demb16), _p(w_emb16), _p(g_ws),
-                                          _p(dz16), _stream()))
+                                          chunk, _p(dz16), _stream()))
     return dz16
 
 

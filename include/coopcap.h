@@ -228,9 +228,11 @@ int coopcap_speaker_decode_fwd(const coopcap_speaker* ctx, coopcap_stream_t stre
  *   g  = demb[t+1] . W_emb^T                  (listener-embedding dgrad, VSEFCModel.py:104)
  *   dz = inv_tau * y * (g - <y, g>) on unfinished rows, 0 elsewhere, y = softmax((z+G)*inv_tau)
  * demb16: bf16 [n_steps*B, E] gradient w.r.t. the listener's word embedding at caption positions
- * 1..n_steps; w_emb16: bf16 [>=V1, E]; g_ws: fp32 [B, V1] workspace; dz16: bf16 [n_steps*B, V1]. */
+ * 1..n_steps; w_emb16: bf16 [>=V1, E]; g_ws: fp32 [g_chunk_steps*B, V1] workspace (g is formed for
+ * g_chunk_steps steps per launch: larger GEMM tiles, scratch mostly L2-resident);
+ * dz16: bf16 [n_steps*B, V1]. */
 int coopcap_st_backward(const coopcap_speaker* ctx, const void* demb16, const void* w_emb16,
-                        float* g_ws, void* dz16, coopcap_stream_t stream);
+                        float* g_ws, int g_chunk_steps, void* dz16, coopcap_stream_t stream);
 /* Same with a dense upstream gradient g = d(loss)/d(one_hots[:, :, :V1]) given explicitly
  * (fp32 [n_steps*B, ldg]); used when foreign code consumed the dense one-hot tensor. */
 int coopcap_st_backward_dense(const coopcap_speaker* ctx, const float* g, int64_t ldg, void* dz16,
