@@ -127,7 +127,7 @@ st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t 
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float score = st_score(mode, x4[q], u4[q], inv_tau, fast);
-      const float y = __expf(score - m) * inv_s;
+      const float y = ex2_ftz((score - m) * 1.4426950408889634f) * inv_s;
       s_y[4 * v4 + q] = y;
       dot += y * g4[q];
     }
@@ -160,7 +160,8 @@ logp_bwd_kernel(const float* __restrict__ z, int V1, const float* __restrict__ l
     const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
     float o[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) o[q] = c * ((4 * v4 + q == t ? 1.f : 0.f) - __expf(x4[q] - l));
+    for (int q = 0; q < 4; ++q)
+      o[q] = c * ((4 * v4 + q == t ? 1.f : 0.f) - ex2_ftz((x4[q] - l) * 1.4426950408889634f));
     store_bf16x4(dr + 4 * v4, o[0], o[1], o[2], o[3]);
   }
 }

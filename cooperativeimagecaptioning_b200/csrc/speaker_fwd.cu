@@ -331,13 +331,14 @@ struct OnlineLse2 {
   __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
   __device__ __forceinline__ void add4(const float (&x2)[4]) {      // x2 = x * log2(e)
     const float nm = fmaxf(fmaxf(fmaxf(x2[0], x2[1]), fmaxf(x2[2], x2[3])), m);
-    s = s * exp2f(m - nm) + exp2f(x2[0] - nm) + exp2f(x2[1] - nm) + exp2f(x2[2] - nm) + exp2f(x2[3] - nm);
+    s = s * ex2_ftz(m - nm) + ex2_ftz(x2[0] - nm) + ex2_ftz(x2[1] - nm) + ex2_ftz(x2[2] - nm) +
+        ex2_ftz(x2[3] - nm);
     m = nm;
   }
   __device__ __forceinline__ void merge(float m2, float s2) {
     const float nm = fmaxf(m, m2);
     if (nm == -INFINITY) return;
-    s = s * exp2f(m - nm) + s2 * exp2f(m2 - nm);
+    s = s * ex2_ftz(m - nm) + s2 * ex2_ftz(m2 - nm);
     m = nm;
   }
 };

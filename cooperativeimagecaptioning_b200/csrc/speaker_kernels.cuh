@@ -58,17 +58,30 @@ __device__ __forceinline__ void keep4(const uint8_t* inj, int64_t idx4, uint64_t
 // rebuild bit-identical scores.  `fast` selects hardware approximations (Philox noise: production)
 // versus libm-accurate logs (injected noise: parity with the reference's torch.log).
 // ---------------------------------------------------------------------------------------------
-// Exp(1) draw from a uniform in [0,1): -log(1-u) ~ -log(u'); accurate near u' -> 1 via log1p series
+// single-instruction base-2 transcendentals (the libm-style wrappers add range / denormal
+// handling worth ~6 instructions per call, which made the sampler issue-bound)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// -log(u) for u in (0, 1]; lg2.approx has a 2^-22 absolute error, useless for u -> 1, where the
+// log1p series takes over (branch-free select)
 __device__ __forceinline__ float neg_log_fast(float u) {
-  // -log(u) for u in (0, 1]; lg2.approx has a 2^-22 absolute error, useless for u -> 1
   const float d = 1.f - u;
-  if (d < 0.0625f) return d * (1.f + d * (0.5f + d * (0.33333334f + d * 0.25f)));
-  return -0.69314718f * __log2f(u);
+  const float series = d * (1.f + d * (0.5f + d * (0.33333334f + d * 0.25f)));
+  const float direct = -0.69314718f * lg2_ftz(u);
+  return d < 0.0625f ? series : direct;
 }
 __device__ __forceinline__ float gumbel_of(float u, bool fast) {
   if (fast) {
     const float e = neg_log_fast(fmaxf(u, 1e-20f));          // Exp(1)
-    return -0.69314718f * __log2f(e);
+    return -0.69314718f * lg2_ftz(e);
   }
   return -logf(-logf(u + 1e-20f) + 1e-20f);                  // gumbel.py:6-11
 }
@@ -76,7 +89,7 @@ __device__ __forceinline__ float gumbel_of(float u, bool fast) {
 __device__ __forceinline__ float neg_log_exp1(float n, bool injected) {
   if (injected) return -logf(n);
   const float e = neg_log_fast(fmaxf(1.f - n, 1e-20f));
-  return -0.69314718f * __log2f(e);
+  return -0.69314718f * lg2_ftz(e);
 }
 // 4 noise values for elements [4*v4, 4*v4+3] of a row: injected (fp32 row) or Philox uniforms
 __device__ __forceinline__ void noise4(const float* inj_row, int v4, uint64_t seed, uint64_t stream,
