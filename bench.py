@@ -112,21 +112,24 @@ def host_batch(rows, lmax, lmin, seed, pin):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons through NVML, sampled from the launching thread at a few points
-    INSIDE the timed region (between steps).  A background poller is deliberately not used: on
-    these hosts NVML queries contend with kernel launches (a 50 ms poller doubled the step time at
-    N = 2); the launch queue runs several ms ahead of the GPU, so three short inline queries do not
-    starve it.  NVML is initialised before the warm-up."""
+    """Clocks DURING the timed region without touching the driver: the SM clock is measured on the
+    device (coopcap_measure_sm_clock: a 20 us one-warp kernel comparing clock64 with globaltimer,
+    queued between steps of the timed loop).  NVML is only queried immediately before and after
+    the region (max clock, throttle reasons): on these hosts an NVML query can stall kernel
+    launches for 10-200 ms, which wrecked timed loops that sampled it inline or from a thread."""
 
-    def __init__(self, index):
-        self.samples, self.reasons, self.max_mhz, self._h = [], set(), None, None
+    def __init__(self, index, lib, n):
+        self.lib, self.n = lib, max(n, 1)
+        self.buf = torch.zeros(self.n, device=torch.device("cuda", index))
+        self.used = 0
+        self.reasons, self.max_mhz, self._h, self.nvml_mhz = set(), None, None, []
         try:
             import pynvml
             pynvml.nvmlInit()
             self._nv = pynvml
             self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
-        except Exception:       # pragma: no cover - NVML missing: report nulls
+        except Exception:       # pragma: no cover - NVML missing: device-side clock only
             self._h = None
             return
         nv = self._nv
@@ -143,20 +146,13 @@ class ClockSampler:
         self._get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
             getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
 
-    def warm(self):
-        """First NVML queries pay a one-time initialisation cost (seen: ~170 ms): pay it in setup."""
-        self.sample()
-        self.samples.clear()
-        self.reasons.clear()
-        self.query_ms = []
-
-    def sample(self):
+    def nvml_edge(self):
+        """NVML snapshot at the edge of the timed region (the GPU is still / already busy)."""
         if self._h is None:
             return
-        t0 = time.perf_counter()
         try:
             nv = self._nv
-            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            self.nvml_mhz.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
             if self._get_reasons is not None:
                 r = self._get_reasons(self._h)
                 for name, bit in self._bits.items():
@@ -164,15 +160,21 @@ class ClockSampler:
                         self.reasons.add(name)
         except Exception:
             pass
-        if hasattr(self, "query_ms"):
-            self.query_ms.append((time.perf_counter() - t0) * 1e3)
+
+    def sample(self):
+        """Queue one device-side clock measurement on the current stream (inside the region)."""
+        if self.used < self.n:
+            _ptr = C.c_void_p(self.buf.data_ptr() + 4 * self.used)
+            self.lib.coopcap_measure_sm_clock(_ptr, 20000, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            self.used += 1
 
     def result(self):
-        out = dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
-                   samples=len(self.samples), query_ms=[round(q, 2) for q in getattr(self, "query_ms", [])])
-        if self.samples:
-            out["sm_mhz"] = float(np.median(self.samples))
-        return out
+        vals = self.buf[: self.used].cpu().tolist()
+        return dict(sm_mhz=float(np.median(vals)) if vals else None, sm_max_mhz=self.max_mhz,
+                    reasons=sorted(self.reasons), samples=len(vals),
+                    how="device-side clock64/globaltimer kernels inside the timed region; NVML "
+                        "throttle reasons read right before and after it",
+                    nvml_sm_mhz_at_edges=self.nvml_mhz)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -289,9 +291,7 @@ def main():
     # ---------------- device-resident throughput (`value`) ----------------
     resident = [to_device(h, False) for h in hb]
     torch.cuda.synchronize()
-    clocks = ClockSampler(local) if (rank == 0 and args.clock_samples > 0) else None
-    if clocks:
-        clocks.warm()
+    clocks = ClockSampler(local, lib, args.clock_samples) if (rank == 0 and args.clock_samples > 0) else None
     # setup (untimed, before the W warm-up steps): prime until the step time has settled -- the
     # caching allocator must have seen both batch shapes, and a freshly booted box takes a few
     # hundred ms of work before clocks / driver state stop moving
@@ -317,6 +317,9 @@ def main():
     if clocks:
         n = args.clock_samples
         sample_at = {max(1, (k + 1) * args.steps // (n + 1)) for k in range(n)}
+    if clocks:
+        clocks.nvml_edge()                     # GPU busy with the warm-up steps still draining
+        torch.cuda.synchronize()
     l0 = lib.coopcap_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -327,9 +330,11 @@ def main():
         loss = train_step(resident[i % 2])
     e1.record()
     host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / args.steps   # CPU time to queue one step
+    if clocks:
+        clocks.nvml_edge()                     # the tail of the timed steps is still executing
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = lib.coopcap_launch_count() - l0
+    launches = lib.coopcap_launch_count() - l0 - (clocks.used if clocks else 0)
     clk = clocks.result() if clocks else None
     loss_value = float(loss.detach())
     t = torch.tensor([ms], device=dev)

@@ -172,9 +172,31 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int64_t rows, in
   }
 }
 
+__global__ void sm_clock_kernel(float* out, long long spin_ns) {
+  if (threadIdx.x != 0) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const long long c0 = clock64();
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while ((long long)(t1 - t0) < spin_ns);
+  const long long c1 = clock64();
+  *out = float(double(c1 - c0) / double(t1 - t0) * 1e3);
+}
+
 }  // namespace coopcap
 
 extern "C" {
+
+int coopcap_measure_sm_clock(float* mhz_out, int spin_ns, coopcap_stream_t stream) {
+  using namespace coopcap;
+  CC_REQUIRE(mhz_out != nullptr, "measure_sm_clock: null output");
+  if (spin_ns <= 0) spin_ns = 20000;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  sm_clock_kernel<<<1, 32, 0, s>>>(mhz_out, spin_ns);
+  CC_LAUNCH_CHECK_K(PROF_MISC, s, 0.0, 0.0);
+  return CC_OK;
+}
 
 int coopcap_gemm(const coopcap_gemm_args* args, coopcap_stream_t stream) {
   return coopcap::gemm_store(args, reinterpret_cast<cudaStream_t>(stream));

@@ -427,6 +427,11 @@ int coopcap_prof_kinds(void);
 int coopcap_prof_enable(int on, coopcap_stream_t stream);
 int coopcap_prof_report(double* ms, double* flops, double* bytes, long long* launches, int nkinds);
 
+/* SM clock measured on the device: one warp spins for ~spin_ns and compares clock64 with
+ * globaltimer; writes MHz to *mhz_out (device float).  Costs ~spin_ns of stream time and no driver
+ * query, so it can be dropped between steps of a timed region. */
+int coopcap_measure_sm_clock(float* mhz_out, int spin_ns, coopcap_stream_t stream);
+
 /* sizeof() of the structs above, for binding self-checks: which = 0 gemm_args, 1 speaker_pack,
  * 2 speaker, 3 speaker_grads, 4 listener_pack, 5 listener, 6 listener_grads. */
 int coopcap_sizeof(int which);
