@@ -281,7 +281,7 @@ def main():
                      is_alternating=True, alternating_turn="speaker")
         loss.backward()
         optim.step()                           # all-reduce (N > 1) + /N + clamp + Adam
-        return loss
+        return loss.detach()
 
     def barrier():
         if world > 1:
@@ -322,14 +322,26 @@ def main():
         torch.cuda.synchronize()
     l0 = lib.coopcap_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st0 = torch.cuda.memory_stats()
+    import gc
+    gc_before = gc.get_count()
     e0.record()
     h0 = time.perf_counter()
+    gaps = []
     for i in range(args.steps):
         if i in sample_at:
             clocks.sample()                    # GPU is busy with the steps already queued
+        g0 = time.perf_counter()
         loss = train_step(resident[i % 2])
+        gaps.append((time.perf_counter() - g0) * 1e3)
     e1.record()
     host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / args.steps   # CPU time to queue one step
+    st1 = torch.cuda.memory_stats()
+    loop_debug = dict(host_ms_per_step=[round(g, 2) for g in gaps],
+                      device_allocs=st1["num_device_alloc"] - st0["num_device_alloc"],
+                      device_frees=st1["num_device_free"] - st0["num_device_free"],
+                      alloc_retries=st1["num_alloc_retries"] - st0["num_alloc_retries"],
+                      gc_counts=[gc_before, gc.get_count()])
     if clocks:
         clocks.nvml_edge()                     # the tail of the timed steps is still executing
     barrier()
@@ -348,7 +360,7 @@ def main():
     value = args.rows * world * args.steps / (ms_max * 1e-3)
 
     # ---------------- end to end from pinned host buffers (`e2e`) ----------------
-    e2e_value, e2e_ms, h2d = None, None, 0
+    e2e_value, e2e_ms, h2d, e2e_allocs = None, None, 0, None
     if not args.no_e2e:
         # double-buffered: batch i+1 is uploaded on a copy stream while batch i computes; the loss of
         # every step is read back to pinned host memory (async, drained at the end of the region)
@@ -356,7 +368,6 @@ def main():
         loss_host = torch.zeros(args.steps, pin_memory=True)
         h2d = 0
         resident = None
-        torch.cuda.empty_cache()
 
         from cooperativeimagecaptioning_b200.data import record_stream, upload_batch
 
@@ -381,12 +392,16 @@ def main():
                 if record:
                     loss_host[i].copy_(loss.detach().reshape(()), non_blocking=True)
 
-        e2e_loop(max(2, min(args.warmup, 3)), False)
+        # warm-up: the upload buffers live in the copy stream's allocator pool and are recycled
+        # through record_stream, which needs a few rounds to reach its steady state
+        e2e_loop(max(8, args.warmup), False)
         barrier()
+        a0 = torch.cuda.memory_stats()["num_device_alloc"]
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         e2e_loop(args.steps, True)
         t1.record()
+        e2e_allocs = torch.cuda.memory_stats()["num_device_alloc"] - a0
         h2d = upload_batch.last_bytes
         barrier()
         t = torch.tensor([t0.elapsed_time(t1)], device=dev)
@@ -513,10 +528,11 @@ def main():
                         accumulate="fp32 accumulation, bf16 tensor-core operands, fp32 master weights"),
             e2e=None if e2e_value is None else dict(
                      value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
-                     ms_per_step=e2e_ms / args.steps,
+                     ms_per_step=e2e_ms / args.steps, device_allocs_in_region=e2e_allocs,
                      note="public API (AlternatingJointModel.forward + backward + optimizer.step) "
                           "from pinned host buffers, valid regions only (data.upload_batch), upload double-buffered on a copy stream"),
             gpu_launches=int(launches), host_enqueue_ms_per_step=host_enqueue_ms,
+            value_loop_debug=loop_debug,
             ms_per_step_by_rank=[m / args.steps for m in ms_ranks],
             loss=loss_value, clocks=clk, roofline=roof,
             cpu_baseline=cpu, decode=decode, breakdown=breakdown)

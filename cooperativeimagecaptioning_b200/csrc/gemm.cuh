@@ -31,7 +31,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BUFS = (BN <= 128) ? 2 : 1;
+  static constexpr int EPI_BUFS = (BN <= 192) ? 2 : 1;
   static constexpr int EPI_STAGE_BYTES = GEMM_EPI_WARPS * EPI_BUFS * 4096;
   static constexpr int STAGES_RAW =
       (GEMM_SMEM_TOTAL - GEMM_SMEM_EXTRA - 1024 - EPI_STAGE_BYTES) / STAGE_BYTES;
@@ -67,7 +67,16 @@ struct EpiStoreParams {
   float drop_p;
   uint64_t seed, stream;
   int tma_store;         // set by the launcher: fp32 C is written / reduced by TMA from swizzled smem
+  unsigned long long* dbg;  // optional globaltimer stamps of CTA 0 (tuning aid), else null
 };
+
+__device__ __forceinline__ void dbg_stamp(unsigned long long* dbg, int slot) {
+  if (dbg && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[slot] = t;
+  }
+}
 
 struct EpiStore {
   using Params = EpiStoreParams;
@@ -81,32 +90,22 @@ struct EpiStore {
                                         int N, float* stage, int lane, int row0) {
     const int ncols = min(32, N - col0);
     if (ncols <= 0 || row0 >= M) return;        // warp-uniform
-    transform(p, row, col0, ncols, v, M, N);
+    transform(p, row, col0, ncols, v, M, N, prefetch_bias(p, col0, N, lane));
     store(p, row, col0, ncols, v, M, N, stage, lane, row0);
   }
+  // bias for one 32-column chunk, one value per lane (loaded early, before the accumulator is
+  // ready, so that its global-load latency is off the epilogue's critical path)
+  __device__ __forceinline__ float prefetch_bias(const Params& p, int col0, int N, int lane) {
+    return (p.bias && col0 + lane < N) ? __ldg(p.bias + col0 + lane) : 0.f;
+  }
   __device__ __forceinline__ void transform(const Params& p, int row, int col0, int ncols,
-                                            float (&v)[32], int M, int N) {
+                                            float (&v)[32], int M, int N, float bias_lane) {
+    // all lanes take part in the shuffles (rows beyond M included)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] * p.alpha + __shfl_sync(0xffffffffu, bias_lane, j);
     if (row < M) {
       float rs = p.row_scale ? p.row_scale[row] : 1.f;
       if (p.seg_lens && (row % p.seg_L) >= p.seg_lens[row / p.seg_L]) rs = 0.f;
-      if (p.bias && ncols == 32 && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);   // warp-uniform address
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(b4 + j);
-          v[4 * j + 0] = v[4 * j + 0] * p.alpha + b.x;
-          v[4 * j + 1] = v[4 * j + 1] * p.alpha + b.y;
-          v[4 * j + 2] = v[4 * j + 2] * p.alpha + b.z;
-          v[4 * j + 3] = v[4 * j + 3] * p.alpha + b.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = v[j] * p.alpha;
-          if (p.bias && j < ncols) x += __ldg(p.bias + col0 + j);
-          v[j] = x;
-        }
-      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float x = v[j];
@@ -226,7 +225,7 @@ struct EpiStore {
 // kernel
 // ------------------------------------------------------------------------------------------
 template <int KIND, int BN, int AMAJ, int BMAJ, class Epi>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)   // 10 warps are allocated as 12: 168 regs/thread
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int split_k,
                typename Epi::Params ep) {
@@ -268,6 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
+  if (threadIdx.x == 0) dbg_stamp(ep.dbg, 0);
   pdl_launch_dependents();
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
@@ -276,6 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   // setup above overlapped the previous kernel's tail; from here on global memory is touched
   pdl_wait();
+  if (threadIdx.x == 0) dbg_stamp(ep.dbg, 1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -314,6 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (++st == STAGES) { st = 0; ph ^= 1; }
         }
+        if (t / gridDim.x < 6) dbg_stamp(ep.dbg, 8 + int(t / gridDim.x));       // loads of tile i issued
       }
     }
   } else if (warp == 1) {
@@ -351,6 +353,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++st == STAGES) { st = 0; ph ^= 1; }
         }
         umma_commit(&tfull_bar[as]);
+        if (t / gridDim.x < 6) dbg_stamp(ep.dbg, 16 + int(t / gridDim.x));      // MMAs of tile i issued
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
@@ -361,6 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     Epi epi;
     int as = 0;
     uint32_t aph = 0;
+    int ebuf = 0;   // staging buffer of the next TMA store; alternates across chunks AND tiles
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t % num_m;
       const int rest = t / num_m;
@@ -371,8 +375,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (kb0 >= kb1) continue;
       const int row = m_blk * GEMM_BM + q * 32 + lane;
       const int n0 = n_blk * BN;
+      float bias_pf[BN / 64];
+#pragma unroll
+      for (int i = 0; i < BN / 64; ++i) bias_pf[i] = epi.prefetch_bias(ep, n0 + (half + 2 * i) * 32, N, lane);
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
+      if (warp == 2 && lane == 0 && t / gridDim.x < 6) dbg_stamp(ep.dbg, 24 + int(t / gridDim.x));  // accumulator ready
       epi.begin(ep, row, n0, M, N, ks);
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
       uint8_t* wstage = epi_stage + (warp - 2) * Cfg::EPI_BUFS * 4096;
@@ -393,8 +401,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int col0 = n0 + (half + 2 * i) * 32;
         if (ep.tma_store) {
           if (col0 < N && row0 < M) {            // warp-uniform
-            epi.transform(ep, row, col0, min(32, N - col0), v[i & 1], M, N);
-            uint8_t* buf = wstage + (Cfg::EPI_BUFS == 2 ? (i & 1) * 4096 : 0);
+            epi.transform(ep, row, col0, min(32, N - col0), v[i & 1], M, N, bias_pf[i]);
+            uint8_t* buf = wstage + (Cfg::EPI_BUFS == 2 ? ebuf * 4096 : 0);
+            ebuf ^= 1;
             // the bulk store that last read this buffer must have drained
             if (lane == 0) bulk_wait_read<Cfg::EPI_BUFS - 1>();
             __syncwarp();
@@ -413,16 +422,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         } else {
-          epi.chunk(ep, row, col0, v[i & 1], M, N, reinterpret_cast<float*>(wstage), lane, row0);
+          if (col0 < N && row0 < M) {
+            epi.transform(ep, row, col0, min(32, N - col0), v[i & 1], M, N, bias_pf[i]);
+            epi.store(ep, row, col0, min(32, N - col0), v[i & 1], M, N,
+                      reinterpret_cast<float*>(wstage), lane, row0);
+          }
         }
       }
       epi.end(ep, row, n0, M, N, n_blk);
+      if (warp == 2 && lane == 0 && t / gridDim.x < 6) dbg_stamp(ep.dbg, 32 + int(t / gridDim.x));  // epilogue of tile i issued
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   }
   if (warp >= 2 && lane == 0 && ep.tma_store) bulk_wait_all();
+  if (warp == 2 && lane == 0) dbg_stamp(ep.dbg, 2);     // stores drained
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) dbg_stamp(ep.dbg, 3);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);

@@ -257,6 +257,23 @@ def st_logit_grads(sp: SpeakerPass, demb16: torch.Tensor, w_emb16: torch.Tensor)
     return dz16
 
 
+def retain(p):
+    """Register one more autograd node that will need the pass `p` in its backward."""
+    p.users = getattr(p, "users", 0) + 1
+    return p
+
+
+def release(p):
+    """Called at the end of a node's backward: when the last registered user is done the
+    multi-GB workspaces of the pass are dropped right away (autograd only frees saved tensors,
+    and a caller holding on to `loss` would otherwise keep a whole step of buffers alive)."""
+    p.users = getattr(p, "users", 1) - 1
+    if p.users <= 0 and not getattr(p, "pinned", False):   # tests pin passes they inspect later
+        p.t.clear()
+        p.keep.clear()
+        p.ctx = None
+
+
 def st_logit_grads_dense(sp: SpeakerPass, g: torch.Tensor) -> torch.Tensor:
     """Same from a dense upstream gradient g fp32 [n_steps, B, >=V1] (d loss / d one_hots)."""
     d = sp.dims

@@ -34,7 +34,7 @@ class _StJointFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, owner, sp, lp, *params):
-        ctx.owner, ctx.sp, ctx.lp = owner, sp, lp
+        ctx.owner, ctx.sp, ctx.lp = owner, EN.retain(sp), EN.retain(lp)
         return lp.t["loss"][0].clone()
 
     @staticmethod
@@ -53,6 +53,9 @@ class _StJointFn(torch.autograd.Function):
             Gs = EN.speaker_backward(sp, dz16, Ps)
             gs = tuple(Gs[n].view_as(Ps[n]) for n in EN.SPEAKER_PARAM_NAMES)
         gl = tuple((Gl[n].view_as(Pl[n]) if need_l else None) for n in EN.LISTENER_PARAM_NAMES)
+        EN.release(sp)
+        EN.release(lp)
+        ctx.sp = ctx.lp = None
         return (None, None, None) + gs + gl
 
 

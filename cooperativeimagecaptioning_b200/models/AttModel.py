@@ -69,15 +69,19 @@ class _SpeakerLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, sp, tok, owner, *params):
-        ctx.sp, ctx.tok, ctx.owner = sp, tok, owner
+        ctx.sp, ctx.tok, ctx.owner = EN.retain(sp), tok, owner
         return sp.t["logp"][: sp.n_steps].clone()
 
     @staticmethod
     def backward(ctx, d_logp):
         sp = ctx.sp
+        if sp is None or not sp.t:
+            raise RuntimeError("the speaker pass was already released (backward a second time?)")
         P = ctx.owner._params()
         dz16 = EN.logp_logit_grads(sp, ctx.tok, d_logp.contiguous().float())
         G = EN.speaker_backward(sp, dz16, P)
+        EN.release(sp)
+        ctx.sp = None
         return (None, None, None) + tuple(G[n].view_as(P[n]) for n in EN.SPEAKER_PARAM_NAMES)
 
 
@@ -87,6 +91,8 @@ class _SampleSTFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, sp, n, owner, *params):
+        if not isinstance(ctx, _Dummy):
+            EN.retain(sp)
         ctx.sp, ctx.n, ctx.owner = sp, n, owner
         B, V2 = sp.B, sp.dims.V1 + 1
         tok = sp.t["tok_out"][:n].t()                      # [B, n]
@@ -102,6 +108,8 @@ class _SampleSTFn(torch.autograd.Function):
         gt[:n] = g.transpose(0, 1)
         dz16 = EN.st_logit_grads_dense(sp, gt)
         G = EN.speaker_backward(sp, dz16, P)
+        EN.release(sp)
+        ctx.sp = None
         return (None, None, None) + tuple(G[n_].view_as(P[n_]) for n_ in EN.SPEAKER_PARAM_NAMES)
 
 
@@ -187,6 +195,7 @@ class AttModel(nn.Module):
                                 inv_tau=inv_tau, start_token=start_token, rnd=self._random(),
                                 forced=forced, start_tokens=start_tokens, att16=att16)
         if self.keep_passes:
+            sp.pinned = True
             self._passes.append(sp)
         return sp
 

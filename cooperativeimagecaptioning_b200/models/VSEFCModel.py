@@ -71,7 +71,7 @@ class _ListenerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, owner, lp, whole_batch, dense_seq, *params):
-        ctx.owner, ctx.lp, ctx.whole_batch = owner, lp, whole_batch
+        ctx.owner, ctx.lp, ctx.whole_batch = owner, EN.retain(lp), whole_batch
         ctx.dense = dense_seq is not None and dense_seq.requires_grad
         ctx.dense_shape = None if dense_seq is None else dense_seq.shape
         out = lp.t["loss_rows"] if whole_batch else lp.t["loss"][0]
@@ -98,6 +98,8 @@ class _ListenerFn(torch.autograd.Function):
                 ops.gemm(demb16.view(S * B, -1), w16, S * B, V2, demb16.shape[-1], out=flat)
             g_seq = flat.view(S, B, V2).transpose(0, 1).contiguous()
         grads = tuple((G[n].view_as(P[n]) if need else None) for n in EN.LISTENER_PARAM_NAMES)
+        EN.release(lp)
+        ctx.lp = None
         return (None, None, None, g_seq) + grads
 
 
@@ -144,6 +146,7 @@ class VSEFCModel(nn.Module):
                                  margin=self.margin, only_one_retrieval=only_one_retrieval,
                                  no_imgnorm=bool(self.img_enc.no_imgnorm))
         if self.keep_passes:
+            lp.pinned = True
             self._passes.append(lp)
         needs = torch.is_grad_enabled() and (
             any(p.requires_grad for p in P.values()) or

@@ -75,6 +75,7 @@ typedef struct coopcap_gemm_args {
   int split_k; /* >= 1 */
   int tile_n;  /* 0 = auto, else 64 / 128 / 192 / 256 */
   int backend; /* 0 tcgen05, 1 SIMT cross-check */
+  void* dbg;   /* NULL, or device uint64[64]: CTA 0 writes globaltimer stamps of its pipeline (tuning aid) */
 } coopcap_gemm_args;
 
 int coopcap_gemm(const coopcap_gemm_args* args, coopcap_stream_t stream);
