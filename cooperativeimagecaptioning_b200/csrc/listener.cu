@@ -303,8 +303,10 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
   l2norm_fwd_kernel<<<B, 256, 0, s>>>(c->img_pre, c->im, M, c->no_imgnorm);
   CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   // caption branch                                                    (VSEFCModel.py:83-140)
-  gather_embed_kernel<<<S * B, 128, 0, s>>>(c->tok, c->w_emb, E, reinterpret_cast<bf16*>(c->emb16));
-  CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
+  if (!c->emb_given) {
+    gather_embed_kernel<<<S * B, 128, 0, s>>>(c->tok, c->w_emb, E, reinterpret_cast<bf16*>(c->emb16));
+    CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
+  }
   {
     EpiStoreParams e = {};
     e.alpha = 1.f; e.bias = c->b_ih; e.C = c->gi_all; e.ldc = 3 * M;
@@ -397,10 +399,12 @@ int listener_bwd(const coopcap_listener* c, const coopcap_listener_grads* g, cud
     if ((rc = wgrad(d_gh16, 3 * M, h16, M, 3 * M, M, K, g->g_w_hh, M, s))) return rc;
     if ((rc = colsum_bf16(d_gi16, K, 3 * M, 3 * M, g->g_b_ih, s))) return rc;
     if ((rc = colsum_bf16(d_gh16, K, 3 * M, 3 * M, g->g_b_hh, s))) return rc;
-    embed_scatter_kernel<<<S * B, 128, 0, s>>>(c->tok, c->len,
-                                               reinterpret_cast<const bf16*>(g->demb16), B, E,
-                                               g->g_w_emb);
-    CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
+    if (!c->emb_given) {   // dense captions: coopcap_caption_embed_dense_bwd forms this gradient
+      embed_scatter_kernel<<<S * B, 128, 0, s>>>(c->tok, c->len,
+                                                 reinterpret_cast<const bf16*>(g->demb16), B, E,
+                                                 g->g_w_emb);
+      CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
+    }
   }
   return CC_OK;
 }
@@ -419,6 +423,39 @@ int coopcap_listener_pack_weights(const coopcap_listener_pack* p, coopcap_stream
   if ((rc = cast_block(p->w_hh, 3 * p->M, p->M, p->w_hh16, p->M, s))) return rc;
   if (p->w_emb16 && (rc = cast_block(p->w_emb, p->V2, p->E, p->w_emb16, p->E, s))) return rc;
   return CC_OK;
+}
+
+// emb16[row, :] = bf16(w_emb[id, :]) for `rows` rows (the prepended BOS position)
+__global__ void fill_embed_kernel(const float* __restrict__ w_row, int E,
+                                  __nv_bfloat16* __restrict__ emb16) {
+  __nv_bfloat16* dst = emb16 + int64_t(blockIdx.x) * E;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) dst[i] = __float2bfloat16_rn(w_row[i]);
+}
+
+int coopcap_caption_embed_dense(const void* soft16, const float* w_emb, const void* w_emb16, int n,
+                                int B, int V1, int E, int64_t bos_id, void* emb16,
+                                coopcap_stream_t stream) {
+  using namespace coopcap;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  CC_REQUIRE(soft16 && w_emb && w_emb16 && emb16 && n >= 1 && B > 0 && V1 % 8 == 0 && E % 8 == 0,
+             "caption_embed_dense: bad arguments");
+  __nv_bfloat16* e16 = reinterpret_cast<__nv_bfloat16*>(emb16);
+  fill_embed_kernel<<<B, 128, 0, s>>>(w_emb + bos_id * E, E, e16);
+  CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
+  EpiStoreParams e = {};
+  e.alpha = 1.f; e.C16 = e16 + int64_t(B) * E; e.ldc16 = E;
+  return gemm_run(0, 0, 1, soft16, V1, w_emb16, E, n * B, E, V1, 1, 0, e, s);
+}
+
+int coopcap_caption_embed_dense_bwd(const void* soft16, const void* demb16, int n, int B, int V1,
+                                    int E, int64_t bos_id, float* g_w_emb, coopcap_stream_t stream) {
+  using namespace coopcap;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  CC_REQUIRE(soft16 && demb16 && g_w_emb && n >= 1 && B > 0, "caption_embed_dense_bwd: bad arguments");
+  const __nv_bfloat16* d16 = reinterpret_cast<const __nv_bfloat16*>(demb16);
+  int rc = wgrad(soft16, V1, d16 + int64_t(B) * E, E, V1, E, n * B, g_w_emb, E, s);
+  if (rc) return rc;
+  return colsum_bf16(d16, B, E, E, g_w_emb + bos_id * E, s);
 }
 
 int coopcap_listener_fwd(const coopcap_listener* ctx, coopcap_stream_t stream) {

@@ -81,14 +81,6 @@ int wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, 
   return gemm_run(0, 1, 1, A, lda, B, ldb, M, N, K, split, bn, e, s);
 }
 
-__device__ __forceinline__ void store_bf16x4(bf16* dst, float a, float b, float c, float d) {
-  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
-  uint2 o;
-  o.x = *reinterpret_cast<uint32_t*>(&lo);
-  o.y = *reinterpret_cast<uint32_t*>(&hi);
-  *reinterpret_cast<uint2*>(dst) = o;
-}
-
 // ------------------------------------------------------------------------------------------
 // d(loss)/d(logits) of the straight-through samplers, one CTA per row:
 //   y = softmax(score), score = (z+G)/tau (gumbel) or z/tau (multinomial), rebuilt from the saved
@@ -98,7 +90,8 @@ __global__ void __launch_bounds__(256)
 st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t ldg, int V1, int mode,
               float inv_tau, const float* __restrict__ noise, uint64_t seed, uint64_t nstream0,
               int B, const float* __restrict__ ymax, const float* __restrict__ ysum,
-              const uint8_t* __restrict__ unf, bf16* __restrict__ dz) {
+              const uint8_t* __restrict__ unf, bf16* __restrict__ dz,
+              const float* __restrict__ lse) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float s_y[];   // [V1]
@@ -123,7 +116,8 @@ st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t 
     const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
     const float g4[4] = {gr[4 * v4], gr[4 * v4 + 1], gr[4 * v4 + 2], gr[4 * v4 + 3]};
     float u4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (mode == COOPCAP_SAMPLE_ST_GUMBEL) noise4(nr, v4, seed, nstream, uint64_t(b) * (V1 / 4) + v4, u4);
+    if (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_PS_GUMBEL)
+      noise4(nr, v4, seed, nstream, uint64_t(b) * (V1 / 4) + v4, u4);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float score = st_score(mode, x4[q], u4[q], inv_tau, fast);
@@ -133,11 +127,36 @@ st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t 
     }
   }
   dot = block_sum_256(dot, red);
+  if (mode == COOPCAP_SAMPLE_PS_MULTINOMIAL) {
+    // y = exp(lp / tau) with lp = log_softmax(z):  d lp = y g / tau,  dz = d lp - softmax(z) sum(d lp)
+    const float l = lse[row];
+    for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
+      const float4 yv = *reinterpret_cast<const float4*>(s_y + 4 * v4);
+      const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
+      const float p0 = ex2_ftz((zv.x - l) * 1.4426950408889634f), p1 = ex2_ftz((zv.y - l) * 1.4426950408889634f);
+      const float p2 = ex2_ftz((zv.z - l) * 1.4426950408889634f), p3 = ex2_ftz((zv.w - l) * 1.4426950408889634f);
+      store_bf16x4(dr + 4 * v4, inv_tau * (yv.x * gr[4 * v4] - p0 * dot),
+                   inv_tau * (yv.y * gr[4 * v4 + 1] - p1 * dot),
+                   inv_tau * (yv.z * gr[4 * v4 + 2] - p2 * dot),
+                   inv_tau * (yv.w * gr[4 * v4 + 3] - p3 * dot));
+    }
+    return;
+  }
   for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
     const float4 yv = *reinterpret_cast<const float4*>(s_y + 4 * v4);
     store_bf16x4(dr + 4 * v4, inv_tau * yv.x * (gr[4 * v4] - dot), inv_tau * yv.y * (gr[4 * v4 + 1] - dot),
                  inv_tau * yv.z * (gr[4 * v4 + 2] - dot), inv_tau * yv.w * (gr[4 * v4 + 3] - dot));
   }
+}
+
+// d(loss)/d(v . embed) of the partial-sampling next input x = dropout(relu(v . embed)): the ReLU
+// and dropout decisions are both recovered from the saved x (x > 0)
+__global__ void ps_dpre_kernel(const float* __restrict__ d_xh, const bf16* __restrict__ xh16, int E,
+                               int XH, float scale, bf16* __restrict__ dpre16) {
+  const int64_t row = blockIdx.x;
+  for (int i = threadIdx.x; i < E; i += blockDim.x)
+    dpre16[row * E + i] = __float2bfloat16_rn(
+        __bfloat162float(xh16[row * XH + i]) > 0.f ? d_xh[row * XH + i] * scale : 0.f);
 }
 
 // dz = coef * (onehot(tok) - softmax(z))   (REINFORCE / XE), one CTA per (step, row)
@@ -421,8 +440,10 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
                 int g_chunk_steps, int64_t ldg, void* dz16, cudaStream_t s) {
   int rc = check_dims(c);
   if (rc) return rc;
-  CC_REQUIRE(c->mode == COOPCAP_SAMPLE_ST_GUMBEL || c->mode == COOPCAP_SAMPLE_ST_MULTINOMIAL,
-             "st_backward: context was not sampled in a straight-through mode (%d)", c->mode);
+  CC_REQUIRE(c->mode == COOPCAP_SAMPLE_ST_GUMBEL || c->mode == COOPCAP_SAMPLE_ST_MULTINOMIAL ||
+                 c->mode == COOPCAP_SAMPLE_PS_GUMBEL || c->mode == COOPCAP_SAMPLE_PS_MULTINOMIAL,
+             "st_backward: context was not sampled in a straight-through / partial-sampling mode (%d)",
+             c->mode);
   const int B = c->B, V1 = c->V1, E = c->E;
   const size_t smem = sizeof(float) * V1;
   static size_t smem_set = 0;
@@ -452,7 +473,8 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
         st_bwd_kernel, dim3((unsigned)rows), dim3(256), smem, s, c->z_all + int64_t(t0) * B * V1, g_t,
         ldg, V1, c->mode, c->inv_tau, c->noise ? c->noise + int64_t(t0) * B * V1 : nullptr, c->seed,
         uint64_t(SITE_NOISE + t0), B, c->y_max + int64_t(t0) * B, c->y_sum + int64_t(t0) * B,
-        c->unfinished + int64_t(t0) * B, reinterpret_cast<bf16*>(dz16) + int64_t(t0) * B * V1));
+        c->unfinished + int64_t(t0) * B, reinterpret_cast<bf16*>(dz16) + int64_t(t0) * B * V1,
+        c->lse + int64_t(t0) * B));
     // logits + upstream gradient (+ injected noise) read, bf16 dz written
     CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(rows) * V1 * (4.0 + 4.0 + 2.0 + (c->noise ? 4.0 : 0.0)));
   }
@@ -473,6 +495,11 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
   int rc = check_dims(c);
   if (rc) return rc;
   CC_REQUIRE(g != nullptr && g->dz16 != nullptr, "speaker_decode_bwd: null grads / dz16");
+  const bool ps = (c->mode == COOPCAP_SAMPLE_PS_GUMBEL || c->mode == COOPCAP_SAMPLE_PS_MULTINOMIAL);
+  if (ps)
+    CC_REQUIRE(g->ps_g && g->ps_dpre16 && c->soft16 && c->w_embed16 &&
+                   (g->ps_demb16 == nullptr || g->ps_w_emb16 != nullptr),
+               "speaker_decode_bwd: partial-sampling pass needs ps_g, ps_dpre16 (+ ps_w_emb16)");
   const int B = c->B, R = c->R, E = c->E, A = c->A, V1 = c->V1, NL = c->NL, n = c->n_steps;
   const int NS = 5 * R + A, XH = E + R;
   const int64_t rows = int64_t(n) * B;
@@ -483,12 +510,22 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
   const float scale = c->drop_p > 0.f ? 1.f / (1.f - c->drop_p) : 1.f;
 
   // logit layer: d_out = dz . W_logit ; g_w_logit = dz^T . out ; g_b_logit = colsum(dz)
-  {
+  if (!ps) {
     EpiStoreParams e = {};
     e.alpha = 1.f; e.C = g->d_out; e.ldc = R;
     if ((rc = gemm_run(0, 0, 1, dz16, V1, c->w_logit16, R, int(rows), R, V1, 1, 0, e, s))) return rc;
     if ((rc = wgrad(dz16, V1, out16, R, V1, R, int(rows), g->g_w_logit, R, s))) return rc;
     if ((rc = colsum_bf16(dz16, rows, V1, V1, g->g_b_logit, s))) return rc;
+  }
+  bf16* ps_dpre16 = reinterpret_cast<bf16*>(g->ps_dpre16);
+  if (ps) {
+    const size_t smem = sizeof(float) * V1;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+      CC_CHECK_CUDA(cudaFuncSetAttribute(st_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(smem)));
+      smem_set = smem;
+    }
   }
 
   const size_t att_smem = attention_smem_bytes(A, R, c->L);
@@ -509,6 +546,41 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
     float* dc_in = (t == n - 1) ? nullptr : g->dc + int64_t((t + 1) & 1) * B * R;
     float* dc_out = g->dc + int64_t(t & 1) * B * R;
     const float* dh_next = (t == n - 1) ? nullptr : g->d_xh + int64_t(t + 1) * B * XH + E;
+    if (ps) {
+      // d(loss)/d(v_t) = consumer gradient + d(x_{t+1} pre-activation) . embed^T, then the sampler's
+      // softmax backward and the logit dgrad of this step
+      const bool dense = (g->ps_demb16 == nullptr);
+      const int64_t ldg = dense ? g->ps_ldg : V1;
+      float* g_t = dense ? g->ps_g + int64_t(t) * B * ldg : g->ps_g;
+      if (!dense) {
+        EpiStoreParams e = {};
+        e.alpha = 1.f; e.C = g_t; e.ldc = ldg;
+        if ((rc = gemm_run(0, 0, 0, reinterpret_cast<const bf16*>(g->ps_demb16) + int64_t(t) * B * E, E,
+                           g->ps_w_emb16, E, B, V1, E, 1, 0, e, s)))
+          return rc;
+      }
+      if (t + 1 < n) {
+        EpiStoreParams e = {};
+        e.alpha = 1.f; e.C = g_t; e.ldc = ldg; e.mode = 1;
+        if ((rc = gemm_run(0, 0, 0, ps_dpre16 + int64_t(t + 1) * B * E, E, c->w_embed16, E, B, V1, E,
+                           1, 0, e, s)))
+          return rc;
+      }
+      bf16* dz_t = const_cast<bf16*>(dz16) + int64_t(t) * B * V1;
+      CC_CHECK_CUDA(launch_pdl(
+          st_bwd_kernel, dim3((unsigned)B), dim3(256), sizeof(float) * V1, s,
+          static_cast<const float*>(c->z_all + int64_t(t) * B * V1), static_cast<const float*>(g_t),
+          ldg, V1, c->mode, c->inv_tau,
+          c->noise ? c->noise + int64_t(t) * B * V1 : static_cast<const float*>(nullptr), c->seed,
+          uint64_t(SITE_NOISE + t), B, static_cast<const float*>(c->y_max + int64_t(t) * B),
+          static_cast<const float*>(c->y_sum + int64_t(t) * B),
+          static_cast<const uint8_t*>(c->unfinished + int64_t(t) * B), dz_t,
+          static_cast<const float*>(c->lse + int64_t(t) * B)));
+      CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(B) * V1 * 10.0);
+      EpiStoreParams e = {};
+      e.alpha = 1.f; e.C = g->d_out + int64_t(t) * B * R; e.ldc = R;
+      if ((rc = gemm_run(0, 0, 1, dz_t, V1, c->w_logit16, R, B, R, V1, 1, 0, e, s))) return rc;
+    }
     {
       const int nthr = B * R;
       CC_CHECK_CUDA(launch_pdl(
@@ -556,6 +628,15 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
                          dxh_split > 1 ? 128 : 0, e, s)))
         return rc;
     }
+    if (ps && t > 0) {
+      ps_dpre_kernel<<<B, 128, 0, s>>>(g->d_xh + int64_t(t) * B * XH, xh16 + int64_t(t) * B * XH, E, XH,
+                                       scale, ps_dpre16 + int64_t(t) * B * E);
+      CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
+    }
+  }
+  if (ps) {
+    if ((rc = wgrad(dz16, V1, out16, R, V1, R, int(rows), g->g_w_logit, R, s))) return rc;
+    if ((rc = colsum_bf16(dz16, rows, V1, V1, g->g_b_logit, s))) return rc;
   }
   // step-batched weight gradients
   if ((rc = wgrad(dscat16, NS, xh16, XH, 5 * R, E, int(rows), g->g_w_i2h, E, s))) return rc;
@@ -566,7 +647,15 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
   if ((rc = colsum_bf16(dscat16 + 5 * R, rows, A, NS, g->g_b_h2att, s))) return rc;
   if ((rc = colsum_bf16(dscat16 + 3 * R, rows, 2 * R, NS, g->g_b_a2c, s))) return rc;
   // input embedding
-  embed_grad_kernel<<<(unsigned)rows, 128, 0, s>>>(c->tok_fed, g->d_xh, xh16, E, XH, scale, g->g_embed);
+  if (ps) {
+    // steps >= 1 were fed v_{t-1} . embed:  g_embed[:V1] = sum_t v_{t-1}^T . dpre_t ; step 0 is a lookup
+    if (n > 1 &&
+        (rc = wgrad(c->soft16, V1, ps_dpre16 + int64_t(B) * E, E, V1, E, int(rows - B), g->g_embed, E, s)))
+      return rc;
+    embed_grad_kernel<<<(unsigned)B, 128, 0, s>>>(c->tok_fed, g->d_xh, xh16, E, XH, scale, g->g_embed);
+  } else {
+    embed_grad_kernel<<<(unsigned)rows, 128, 0, s>>>(c->tok_fed, g->d_xh, xh16, E, XH, scale, g->g_embed);
+  }
   CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
   // region tensors: deferred accumulation over the steps, then the prologue layers
   {

@@ -347,7 +347,7 @@ struct OnlineLse2 {
 // occupancy): per 4 elements one Philox call, the perturbed scores, an online (max, sum) for
 // log-sum-exp and for the relaxed sample y, and the running argmax.
 __global__ void __launch_bounds__(SAMPLE_THREADS)
-sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
+sample_kernel(float* __restrict__ z, int V1, int mode, float inv_tau,
               const float* __restrict__ noise, uint64_t seed, uint64_t nstream,
               const int64_t* __restrict__ forced, const uint8_t* __restrict__ unf_prev,
               int64_t* __restrict__ tok_raw, int64_t* __restrict__ tok_out,
@@ -355,7 +355,10 @@ sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
               float* __restrict__ ymax_o, float* __restrict__ ysum_o, uint8_t* __restrict__ unf,
               // next-step input
               const float* __restrict__ embed, int E, const uint8_t* __restrict__ keep_embed_next,
-              uint64_t estream, float drop_p, bf16* __restrict__ xh_next, int64_t ld_xh) {
+              uint64_t estream, float drop_p, bf16* __restrict__ xh_next, int64_t ld_xh,
+              // scheduled sampling (AttModel.py:119-131) and decoding_constraint (:437-442)
+              float ss_prob, const float* __restrict__ ss_u, uint64_t ss_stream,
+              const int64_t* __restrict__ prev_out) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_m1[8], s_s1[8], s_m2[8], s_s2[8], s_bv[8];
@@ -363,13 +366,16 @@ sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
   __shared__ int64_t s_fed;
   constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   const int b = blockIdx.x;
-  const float* zr = z + int64_t(b) * V1;
+  float* zr = z + int64_t(b) * V1;
   const float* nr = noise ? noise + int64_t(b) * V1 : nullptr;
   const bool fast = (noise == nullptr);
-  const bool st = (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL);
-  const bool race = (mode == COOPCAP_SAMPLE_MULTINOMIAL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL);
-  const bool use_noise = (mode == COOPCAP_SAMPLE_ST_GUMBEL) || race;
+  const bool gum = (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_PS_GUMBEL);
+  const bool race = (mode == COOPCAP_SAMPLE_MULTINOMIAL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL ||
+                     mode == COOPCAP_SAMPLE_PS_MULTINOMIAL);
+  const bool st = gum || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL || mode == COOPCAP_SAMPLE_PS_MULTINOMIAL;
+  const bool use_noise = gum || race;
   const int nv4 = V1 / 4;
+  const int banned = prev_out ? int(prev_out[b]) : -1;   // decoding_constraint: logit := -inf
   OnlineLse2 l1, l2;
   l1.init();
   l2.init();
@@ -378,7 +384,11 @@ sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
 #pragma unroll 2
   for (int v4 = threadIdx.x; v4 < nv4; v4 += SAMPLE_THREADS) {
     const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
-    const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
+    float x4[4] = {zv.x, zv.y, zv.z, zv.w};
+    if ((banned >> 2) == v4) {          // banned = -1 never matches
+      x4[banned & 3] = -INFINITY;
+      zr[banned] = -INFINITY;           // the saved logits are what backward differentiates
+    }
     float u4[4] = {0.f, 0.f, 0.f, 0.f};
     if (use_noise) noise4(nr, v4, seed, nstream, uint64_t(b) * nv4 + v4, u4);
     float a4[4], y4[4], xs[4];
@@ -422,16 +432,27 @@ sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
     }
     const float lse = (l1.m + log2f(l1.s)) * LN2;
     const int64_t raw = (mode == COOPCAP_SAMPLE_NONE) ? 0 : int64_t(bi);
-    const int64_t fed = forced ? forced[b] : raw;
+    const int64_t tgt = forced ? forced[b] : raw;
+    int64_t fed = tgt;
+    if (ss_prob > 0.f) {               // scheduled sampling: feed the drawn id instead of the target
+      const float u = ss_u ? ss_u[b] : Philox::u01(Philox::gen(seed, ss_stream, uint64_t(b)).x);
+      if (u < ss_prob) fed = raw;
+    }
     const bool up = unf_prev ? (unf_prev[b] != 0) : true;
     const bool un = up && (fed > 0);                 // AttModel.py:403-406
     tok_raw[b] = raw;
     tok_out[b] = un ? fed : 0;                       // :409
     tok_fed_next[b] = fed;
-    logp[b] = zr[fed] - lse;
+    logp[b] = zr[tgt] - lse;
     lse_o[b] = lse;
-    ymax_o[b] = l2.m * LN2;                          // back to natural-log units (st_bwd_kernel)
-    ysum_o[b] = l2.s;
+    if (mode == COOPCAP_SAMPLE_PS_MULTINOMIAL) {
+      // y = exp(log_softmax(z) / tau), unnormalised for tau != 1  (multinomial_soft.py:12-15)
+      ymax_o[b] = lse * inv_tau;
+      ysum_o[b] = 1.f;
+    } else {
+      ymax_o[b] = l2.m * LN2;                        // back to natural-log units (st_bwd_kernel)
+      ysum_o[b] = l2.s;
+    }
     unf[b] = un ? 1 : 0;
     s_fed = fed;
   }
@@ -440,6 +461,63 @@ sample_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
     embed_row(embed, s_fed, E, keep_embed_next ? keep_embed_next + int64_t(b) * E : nullptr, seed,
               estream, int64_t(b) * E, drop_p, xh_next + int64_t(b) * ld_xh);
   }
+}
+
+// Partial-sampling modes: the vector a step emits (gumbel_softmax.py:28-40, multinomial_soft.py:21-33).
+// One CTA per row; y is rebuilt from the logits, the regenerated / injected noise and the saved
+// (max, sum) exactly like the straight-through backward does.  Rows with part_u < ps_prob emit
+// one_hot(id), the others y.
+__global__ void __launch_bounds__(256)
+ps_vec_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
+              const float* __restrict__ noise, uint64_t seed, uint64_t nstream,
+              const float* __restrict__ ymax, const float* __restrict__ ysum,
+              const int64_t* __restrict__ tok_fed_next, float ps_prob,
+              const float* __restrict__ part_u, uint64_t pstream, bf16* __restrict__ soft16,
+              uint8_t* __restrict__ ps_sel) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const float* zr = z + int64_t(b) * V1;
+  const float* nr = noise ? noise + int64_t(b) * V1 : nullptr;
+  bf16* dr = soft16 + int64_t(b) * V1;
+  const bool fast = (noise == nullptr);
+  const int nv4 = V1 / 4;
+  bool hard = false;
+  if (ps_prob > 0.f) {
+    const float u = part_u ? part_u[b] : Philox::u01(Philox::gen(seed, pstream, uint64_t(b)).x);
+    hard = u < ps_prob;
+  }
+  if (threadIdx.x == 0) ps_sel[b] = hard ? 1 : 0;
+  if (hard) {
+    const int id = int(tok_fed_next[b]);
+    for (int v4 = threadIdx.x; v4 < nv4; v4 += 256)
+      store_bf16x4(dr + 4 * v4, 4 * v4 == id ? 1.f : 0.f, 4 * v4 + 1 == id ? 1.f : 0.f,
+                   4 * v4 + 2 == id ? 1.f : 0.f, 4 * v4 + 3 == id ? 1.f : 0.f);
+    return;
+  }
+  const float m = ymax[b], inv_s = 1.f / ysum[b];
+  for (int v4 = threadIdx.x; v4 < nv4; v4 += 256) {
+    const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
+    const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
+    float u4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (mode == COOPCAP_SAMPLE_PS_GUMBEL) noise4(nr, v4, seed, nstream, uint64_t(b) * nv4 + v4, u4);
+    float y[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      y[q] = ex2_ftz((st_score(mode, x4[q], u4[q], inv_tau, fast) - m) * 1.4426950408889634f) * inv_s;
+    store_bf16x4(dr + 4 * v4, y[0], y[1], y[2], y[3]);
+  }
+}
+
+// finished rows emit the EOS one-hot (AttModel.py:428-432); runs after the next-input GEMM has
+// consumed the unmasked vectors
+__global__ void __launch_bounds__(256)
+ps_mask_kernel(const uint8_t* __restrict__ unf, int V1, bf16* __restrict__ soft16) {
+  const int b = blockIdx.x;
+  if (unf[b]) return;
+  bf16* dr = soft16 + int64_t(b) * V1;
+  for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256)
+    store_bf16x4(dr + 4 * v4, v4 == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
 }
 
 // caption summary after the last step: k_b = number of leading non-zero ids, n = max_b k_b,
@@ -475,6 +553,11 @@ static int check_dims(const coopcap_speaker* c) {
   CC_REQUIRE(c->n_steps >= 0 && c->n_steps <= c->cap, "speaker: n_steps %d > cap %d", c->n_steps,
              c->cap);
   CC_REQUIRE(c->drop_p >= 0.f && c->drop_p < 1.f, "speaker: drop_p %f", c->drop_p);
+  if (c->mode == COOPCAP_SAMPLE_PS_GUMBEL || c->mode == COOPCAP_SAMPLE_PS_MULTINOMIAL)
+    CC_REQUIRE(c->soft16 && c->ps_sel && c->w_embed16 && c->V1 % 8 == 0,
+               "speaker: partial-sampling modes need soft16, ps_sel, w_embed16 and V1 %% 8 == 0");
+  CC_REQUIRE(c->ss_prob <= 0.f || (c->mode == COOPCAP_SAMPLE_MULTINOMIAL && c->forced),
+             "speaker: scheduled sampling needs mode MULTINOMIAL and forced targets");
   return CC_OK;
 }
 
@@ -581,6 +664,8 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     e3.alpha = 1.f; e3.bias = c->b_logit; e3.C = z_t; e3.ldc = V1;
     rc = gemm_run(0, 0, 0, out16 + int64_t(t) * B * R, R, c->w_logit16, R, B, V1, R, 1, 0, e3, s);
     if (rc) return rc;
+    const bool ps = (c->mode == COOPCAP_SAMPLE_PS_GUMBEL || c->mode == COOPCAP_SAMPLE_PS_MULTINOMIAL);
+    bf16* x_next = (t + 1 < c->n_steps) ? xh16 + int64_t(t + 1) * B * XH : nullptr;
     CC_CHECK_CUDA(launch_pdl(
         sample_kernel, dim3(B), dim3(SAMPLE_THREADS), 0, s, z_t, V1, c->mode, c->inv_tau,
         c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed, uint64_t(SITE_NOISE + t),
@@ -590,10 +675,35 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
         c->lse + int64_t(t) * B, c->y_max + int64_t(t) * B, c->y_sum + int64_t(t) * B,
         c->unfinished + int64_t(t) * B, c->embed, E,
         c->keep_embed ? c->keep_embed + int64_t(t + 1) * B * E : nullptr,
-        uint64_t(SITE_DROP_EMBED + t + 1), c->drop_p,
-        (t + 1 < c->n_steps) ? xh16 + int64_t(t + 1) * B * XH : nullptr, int64_t(XH)));
+        uint64_t(SITE_DROP_EMBED + t + 1), c->drop_p, ps ? nullptr : x_next, int64_t(XH),
+        c->ss_prob, c->ss_u ? c->ss_u + int64_t(t) * B : nullptr, uint64_t(SITE_SCHED + t),
+        (c->no_repeat && t > 0) ? c->tok_out + int64_t(t - 1) * B : nullptr));
     // algorithmic bytes: logits (+ injected noise) read once
     CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 4.0 * B * V1 * (c->noise ? 2.0 : 1.0));
+    if (ps) {
+      bf16* v_t = reinterpret_cast<bf16*>(c->soft16) + int64_t(t) * B * V1;
+      CC_CHECK_CUDA(launch_pdl(
+          ps_vec_kernel, dim3(B), dim3(256), 0, s, z_t, V1, c->mode, c->inv_tau,
+          c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed, uint64_t(SITE_NOISE + t),
+          c->y_max + int64_t(t) * B, c->y_sum + int64_t(t) * B, c->tok_fed + int64_t(t + 1) * B,
+          c->ps_prob, c->part_u ? c->part_u + int64_t(t) * B : nullptr, uint64_t(SITE_PARTIAL + t),
+          v_t, c->ps_sel + int64_t(t) * B));
+      CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 6.0 * B * V1);
+      if (x_next) {
+        // x_{t+1} = dropout(relu(v_t . embed))                        (AttModel.py:395-397)
+        EpiStoreParams e = {};
+        e.alpha = 1.f; e.relu = 1; e.C16 = x_next; e.ldc16 = XH;
+        if (c->drop_p > 0.f) {
+          e.drop_p = c->drop_p;
+          if (c->keep_embed) { e.keep = c->keep_embed + int64_t(t + 1) * B * E; e.ld_keep = E; }
+          else { e.philox_dropout = 1; e.seed = c->seed; e.stream = SITE_DROP_EMBED + t + 1; }
+        }
+        rc = gemm_run(0, 0, 1, v_t, V1, c->w_embed16, E, B, E, V1, 1, 64, e, s);
+        if (rc) return rc;
+      }
+      ps_mask_kernel<<<B, 256, 0, s>>>(c->unfinished + int64_t(t) * B, V1, v_t);
+      CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 0.0);
+    }
   }
   if (c->n_out && c->cap_len) {
     caption_summary_kernel<<<1, 256, 0, s>>>(c->tok_out, B, c->n_steps, c->n_out, c->cap_len);

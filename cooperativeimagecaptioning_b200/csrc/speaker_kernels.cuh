@@ -15,6 +15,8 @@ enum : uint64_t {
   SITE_DROP_EMBED = 2ull << 32,
   SITE_DROP_CORE = 3ull << 32,
   SITE_NOISE = 4ull << 32,
+  SITE_PARTIAL = 5ull << 32,    // partial-sampling row selection
+  SITE_SCHED = 6ull << 32,      // scheduled-sampling row selection
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -38,6 +40,14 @@ __device__ __forceinline__ uint4 float8_to_bf16x8(const float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return u;
+}
+
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&lo);
+  o.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = o;
 }
 
 // 4 dropout keep decisions for elements [4*g, 4*g+3] of a site
@@ -104,7 +114,8 @@ __device__ __forceinline__ void noise4(const float* inj_row, int v4, uint64_t se
 }
 // score whose softmax is y (straight-through modes) for one logit
 __device__ __forceinline__ float st_score(int mode, float x, float u, float inv_tau, bool fast) {
-  return (mode == 2 /*ST_GUMBEL*/) ? (x + gumbel_of(u, fast)) * inv_tau : x * inv_tau;
+  return (mode == 2 /*ST_GUMBEL*/ || mode == 5 /*PS_GUMBEL*/) ? (x + gumbel_of(u, fast)) * inv_tau
+                                                              : x * inv_tau;
 }
 
 // block-wide reductions for 256-thread CTAs (8 warps)

@@ -16,6 +16,8 @@ from . import _lib
 from ._lib import check
 
 MODE_GREEDY, MODE_MULTINOMIAL, MODE_ST_GUMBEL, MODE_ST_MULTINOMIAL, MODE_NONE = 0, 1, 2, 3, 4
+MODE_PS_GUMBEL, MODE_PS_MULTINOMIAL = 5, 6
+PS_MODES = (MODE_PS_GUMBEL, MODE_PS_MULTINOMIAL)
 
 
 _weights_epoch = 0
@@ -80,6 +82,21 @@ class PackedSpeaker:
     def __init__(self):
         self.key = None
         self.buf = {}
+        self.embed_key = None
+        self.embed16 = None
+
+    def get_embed16(self, P: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """bf16 copy of `embed` [V+2, E]: the operand of the partial-sampling next-input GEMM."""
+        w = P["embed.0.weight"]
+        key = (_weights_epoch, w.data_ptr(), w._version)
+        if key != self.embed_key:
+            _need_cuda(w)
+            if self.embed16 is None or self.embed16.shape != w.shape:
+                self.embed16 = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+            from . import ops
+            ops.cast_bf16(_f32c(w.detach()), dst=self.embed16)
+            self.embed_key = key
+        return self.embed16
 
     def get(self, P: Dict[str, torch.Tensor]):
         key = (_weights_epoch,) + tuple((P[n].data_ptr(), P[n]._version) for n in SPEAKER_PARAM_NAMES)
@@ -126,6 +143,8 @@ class SpeakerRandom:
     keep_embed: Optional[torch.Tensor] = None   # uint8 [steps+1, B, E]
     keep_core: Optional[torch.Tensor] = None    # uint8 [steps, B, R]
     noise: Optional[torch.Tensor] = None        # fp32 [steps, B, V1]
+    part_u: Optional[torch.Tensor] = None       # fp32 [steps, B] partial-sampling row selection
+    ss_u: Optional[torch.Tensor] = None         # fp32 [steps, B] scheduled-sampling row selection
 
 
 @dataclass
@@ -159,7 +178,9 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
                     inv_tau: float, start_token: int, rnd: SpeakerRandom,
                     forced: Optional[torch.Tensor] = None,
                     start_tokens: Optional[torch.Tensor] = None,
-                    att16: Optional[torch.Tensor] = None) -> SpeakerPass:
+                    att16: Optional[torch.Tensor] = None, ps_prob: float = 0.0,
+                    w_embed16: Optional[torch.Tensor] = None, ss_prob: float = 0.0,
+                    no_repeat: bool = False) -> SpeakerPass:
     """Prologue + n_steps decode steps.  `forced` int64 [n_steps, B] (time-major);
     `start_tokens` int64 [B] overrides the scalar start id per row."""
     _need_cuda(att_feats, att_off, forced, start_tokens)
@@ -190,6 +211,11 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
         unfinished=torch.empty(cap, B, dtype=torch.uint8, device=dev),
         n_out=torch.empty(1, dtype=torch.int32, device=dev),
         cap_len=torch.empty(B, dtype=torch.int32, device=dev))
+    if mode in PS_MODES:
+        if w_embed16 is None:
+            raise _lib.CoopcapError("partial-sampling modes need the bf16 embedding copy")
+        T["soft16"] = torch.empty(cap, B, d.V1, **bf)
+        T["ps_sel"] = torch.empty(cap, B, dtype=torch.uint8, device=dev)
     c = _lib.Speaker()
     c.B, c.L, c.D, c.R, c.E, c.A, c.V1 = B, L, d.D, d.R, d.E, d.A, d.V1
     c.NL, c.cap, c.n_steps = NL, cap, n_steps
@@ -214,7 +240,7 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
             if k.shape[0] < w[0] or tuple(k.shape[1:]) != tuple(w[1:]):
                 raise _lib.CoopcapError(f"injected {n} has shape {tuple(k.shape)}, need >= {w}")
         setattr(c, n, _p(k))
-    uses_noise = mode in (MODE_MULTINOMIAL, MODE_ST_GUMBEL, MODE_ST_MULTINOMIAL)
+    uses_noise = mode in (MODE_MULTINOMIAL, MODE_ST_GUMBEL, MODE_ST_MULTINOMIAL) + PS_MODES
     if rnd.noise is not None and uses_noise:
         _f32c(rnd.noise)
         if rnd.noise.shape[0] < n_steps or tuple(rnd.noise.shape[1:]) != (B, d.V1):
@@ -222,6 +248,15 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
                                     f"need >= {(n_steps, B, d.V1)}")
     c.noise = _p(rnd.noise) if uses_noise else None
     c.mode, c.inv_tau, c.start_token = mode, float(inv_tau), int(start_token)
+    c.ps_prob, c.ss_prob, c.no_repeat = float(ps_prob), float(ss_prob), int(bool(no_repeat))
+    c.w_embed16 = _p(w_embed16)
+    for n, on in (("part_u", mode in PS_MODES), ("ss_u", ss_prob > 0.0)):
+        u = getattr(rnd, n)
+        if u is not None and on:
+            _f32c(u)
+            if u.shape[0] < n_steps or tuple(u.shape[1:]) != (B,):
+                raise _lib.CoopcapError(f"injected {n} has shape {tuple(u.shape)}, need >= {(n_steps, B)}")
+            setattr(c, n, _p(u))
     if forced is not None:
         assert forced.dtype == torch.int64 and forced.is_contiguous() and forced.shape == (n_steps, B)
     c.forced = _p(forced)
@@ -232,7 +267,7 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     for n, tsr in T.items():
         setattr(c, n, _p(tsr))
     sp = SpeakerPass(ctx=c, dims=d, B=B, L=L, NL=NL, cap=cap, n_steps=n_steps, t=T,
-                     keep=[att_feats, att_off, forced, start_tokens, rnd, packed, P])
+                     keep=[att_feats, att_off, forced, start_tokens, rnd, packed, P, w_embed16])
     lib = _lib.load()
     check(lib.coopcap_speaker_prologue_fwd(C.byref(c), _stream()))
     check(lib.coopcap_speaker_decode_fwd(C.byref(c), _stream()))
@@ -296,11 +331,21 @@ def logp_logit_grads(sp: SpeakerPass, tok: torch.Tensor, coef: torch.Tensor) -> 
     return dz16
 
 
-def speaker_backward(sp: SpeakerPass, dz16: torch.Tensor, P: Dict[str, torch.Tensor]
-                     ) -> Dict[str, torch.Tensor]:
-    """BPTT + prologue backward.  Returns {reference parameter name: fp32 gradient}."""
+def speaker_backward(sp: SpeakerPass, dz16: Optional[torch.Tensor], P: Dict[str, torch.Tensor],
+                     ps_demb16: Optional[torch.Tensor] = None,
+                     ps_w_emb16: Optional[torch.Tensor] = None,
+                     ps_g_dense: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """BPTT + prologue backward.  Returns {reference parameter name: fp32 gradient}.
+
+    Partial-sampling passes take the upstream gradient of the emitted vectors instead of dz16:
+    factored (`ps_demb16` bf16 [n_steps, B, E] + `ps_w_emb16`) or dense (`ps_g_dense` fp32
+    [n_steps, B, ld >= V1], modified in place)."""
     d = sp.dims
-    dev = dz16.device
+    dev = sp.t["z_all"].device
+    is_ps = sp.ctx.mode in PS_MODES
+    if is_ps:
+        assert dz16 is None and ((ps_demb16 is None) != (ps_g_dense is None))
+        dz16 = torch.empty(sp.n_steps * sp.B, d.V1, dtype=torch.bfloat16, device=dev)
     B, cap, NL = sp.B, sp.cap, sp.NL
     NS, XH = 5 * d.R + d.A, d.E + d.R
     f32 = dict(dtype=torch.float32, device=dev)
@@ -318,6 +363,19 @@ def speaker_backward(sp: SpeakerPass, dz16: torch.Tensor, P: Dict[str, torch.Ten
     G["core.attention.alpha_net.bias"] = torch.zeros_like(P["core.attention.alpha_net.bias"])
     g = _lib.SpeakerGrads()
     g.dz16 = _p(dz16)
+    if is_ps:
+        ws["ps_dpre16"] = torch.zeros(sp.n_steps * sp.B, d.E, **bf)
+        if ps_demb16 is not None:
+            assert ps_demb16.dtype == torch.bfloat16 and ps_demb16.is_contiguous()
+            assert ps_demb16.shape == (sp.n_steps, sp.B, d.E) and ps_w_emb16 is not None
+            ws["ps_g"] = torch.empty(sp.B, d.V1, **f32)
+            g.ps_demb16, g.ps_w_emb16, g.ps_ldg = _p(ps_demb16), _p(ps_w_emb16), d.V1
+        else:
+            _f32c(ps_g_dense)
+            assert ps_g_dense.shape[:2] == (sp.n_steps, sp.B) and ps_g_dense.shape[2] >= d.V1
+            assert ps_g_dense.shape[2] % 4 == 0, "dense upstream gradient needs a 16-byte row pitch"
+            ws["ps_g"] = ps_g_dense
+            g.ps_ldg = ps_g_dense.shape[2]
     for n, tsr in ws.items():
         setattr(g, n, _p(tsr))
     g.g_embed = _p(G["embed.0.weight"])
@@ -331,6 +389,8 @@ def speaker_backward(sp: SpeakerPass, dz16: torch.Tensor, P: Dict[str, torch.Ten
     g.g_w_logit, g.g_b_logit = _p(G["logit.weight"]), _p(G["logit.bias"])
     g.g_w_alpha = _p(G["core.attention.alpha_net.weight"])
     check(_lib.load().coopcap_speaker_decode_bwd(C.byref(sp.ctx), C.byref(g), _stream()))
+    if getattr(sp, "pinned", False):     # tests inspect the logit gradient of pinned passes
+        sp.t["dz16"] = dz16
     G["core.h2h.bias"] = G["core.i2h.bias"]     # both biases enter the same sum
     return G
 
@@ -404,21 +464,26 @@ ONLY = {"off": 0, "image": 1, "caption": 2}
 
 
 def listener_forward(P, packed, fc_feats, tok_sb, lens, *, margin=0.2, only_one_retrieval="off",
-                     no_imgnorm=False) -> ListenerPass:
+                     no_imgnorm=False, emb16: Optional[torch.Tensor] = None) -> ListenerPass:
     """tok_sb int64 [S, B] time-major ids, lens int32 [B].  Results in .t['loss'] ([1]) and
-    .t['loss_rows'] ([B])."""
-    _need_cuda(fc_feats, tok_sb, lens)
+    .t['loss_rows'] ([B]).  `emb16` bf16 [S, B, E]: caption embeddings computed by the caller
+    (dense caption vectors); tok_sb is then None."""
+    _need_cuda(fc_feats, tok_sb, lens, emb16)
     d: ListenerDims = packed["dims"]
     fc_feats = _f32c(fc_feats)
-    assert tok_sb.dtype == torch.int64 and tok_sb.is_contiguous()
     assert lens.dtype == torch.int32 and lens.is_contiguous()
-    S, B = tok_sb.shape
+    if emb16 is None:
+        assert tok_sb.dtype == torch.int64 and tok_sb.is_contiguous()
+        S, B = tok_sb.shape
+    else:
+        assert emb16.dtype == torch.bfloat16 and emb16.is_contiguous() and emb16.shape[2] == d.E
+        S, B = emb16.shape[:2]
     dev = fc_feats.device
     f32 = dict(dtype=torch.float32, device=dev)
     bf = dict(dtype=torch.bfloat16, device=dev)
     T = dict(
         fc16=torch.empty(B, d.F, **bf), img_pre=torch.empty(B, d.M, **f32),
-        im=torch.empty(B, d.M, **f32), emb16=torch.empty(S, B, d.E, **bf),
+        im=torch.empty(B, d.M, **f32), emb16=emb16 if emb16 is not None else torch.empty(S, B, d.E, **bf),
         gi_all=torch.empty(S, B, 3 * d.M, **f32), gh=torch.empty(B, 3 * d.M, **f32),
         gates=torch.empty(S, B, 4 * d.M, **f32), h32=torch.empty(S + 1, B, d.M, **f32),
         h16=torch.empty(S + 1, B, d.M, **bf), cap=torch.empty(B, d.M, **f32),
@@ -430,6 +495,7 @@ def listener_forward(P, packed, fc_feats, tok_sb, lens, *, margin=0.2, only_one_
     c.B, c.S, c.F, c.M, c.E, c.V2 = B, S, d.F, d.M, d.E, d.V2
     c.margin, c.only_one_retrieval, c.no_imgnorm = float(margin), ONLY[only_one_retrieval], int(no_imgnorm)
     c.fc_feats, c.tok, c.len = _p(fc_feats), _p(tok_sb), _p(lens)
+    c.emb_given = int(emb16 is not None)
     c.w_emb = _p(_f32c(P["txt_enc.embed.weight"].detach()))
     c.b_img = _p(_f32c(P["img_enc.fc.bias"].detach()))
     c.b_ih = _p(_f32c(P["txt_enc.rnn.bias_ih_l0"].detach()))
@@ -474,6 +540,30 @@ def listener_backward(lp: ListenerPass, P, *, g_loss=None, g_rows=None, need_par
         g.g_b_ih, g.g_b_hh = _p(G["txt_enc.rnn.bias_ih_l0"]), _p(G["txt_enc.rnn.bias_hh_l0"])
     check(_lib.load().coopcap_listener_bwd(C.byref(lp.ctx), C.byref(g), _stream()))
     return G, ws["demb16"]
+
+
+def caption_embed_dense(soft16: torch.Tensor, n: int, P, packed, bos_id: int) -> torch.Tensor:
+    """emb16 bf16 [n+1, B, E] of the caption [BOS, v_0 .. v_{n-1}] given dense vectors soft16
+    bf16 [>= n, B, V1] (VSEFCModel.py:102-104 with AlternatingJointModel.py:356-370)."""
+    d: ListenerDims = packed["dims"]
+    _need_cuda(soft16)
+    assert soft16.dtype == torch.bfloat16 and soft16.is_contiguous() and soft16.shape[0] >= n
+    B, V1 = soft16.shape[1:]
+    emb16 = torch.empty(n + 1, B, d.E, dtype=torch.bfloat16, device=soft16.device)
+    check(_lib.load().coopcap_caption_embed_dense(
+        _p(soft16), _p(_f32c(P["txt_enc.embed.weight"].detach())), _p(packed["w_emb16"]), n, B, V1,
+        d.E, int(bos_id), _p(emb16), _stream()))
+    return emb16
+
+
+def caption_embed_dense_bwd(soft16: torch.Tensor, demb16: torch.Tensor, n: int, bos_id: int,
+                            g_w_emb: torch.Tensor) -> None:
+    """g_w_emb (fp32 [V2, E], zero-initialised) <- embedding weight gradient of caption_embed_dense."""
+    B, V1 = soft16.shape[1:]
+    assert demb16.dtype == torch.bfloat16 and demb16.is_contiguous() and demb16.shape[0] == n + 1
+    check(_lib.load().coopcap_caption_embed_dense_bwd(_p(soft16), _p(demb16), n, B, V1,
+                                                      demb16.shape[2], int(bos_id),
+                                                      _p(_f32c(g_w_emb)), _stream()))
 
 
 def clamp_adam_(param, grad, exp_avg, exp_avg_sq, *, step, lr, grad_scale=1.0, clip=0.0,

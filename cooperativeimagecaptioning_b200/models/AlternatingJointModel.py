@@ -4,7 +4,7 @@ Keeps the reference's constructor, `forward(fc_feats, seq, masks, data, att_feat
 is_alternating, alternating_turn)` turn logic (:433-555), the loss recipes of the hot path
 (`ce_loss`, `vse_loss`, `reinforce_disc`, `gt/greedy/no_baseline`, `loss_configuration`,
 `st_and_ps_methods`), `sample`, `loss()`, `get/setLossFlages`.  Out of scope:
-the CIDEr self-critical terms (`cider_optimization` must be 0) and the partial-sampling modes.
+the CIDEr self-critical terms (`cider_optimization` must be 0).
 
 The straight-through joint step (`retrieval_reward` in {'gumbel','multinomial'}) runs as ONE fused
 autograd node: speaker decode -> listener loss forward; listener backward -> factored
@@ -51,6 +51,41 @@ class _StJointFn(torch.autograd.Function):
             T = sp.n_steps
             dz16 = EN.st_logit_grads(sp, demb16[1:T + 1], lis._packed.get(Pl)["w_emb16"])
             Gs = EN.speaker_backward(sp, dz16, Ps)
+            gs = tuple(Gs[n].view_as(Ps[n]) for n in EN.SPEAKER_PARAM_NAMES)
+        gl = tuple((Gl[n].view_as(Pl[n]) if need_l else None) for n in EN.LISTENER_PARAM_NAMES)
+        EN.release(sp)
+        EN.release(lp)
+        ctx.sp = ctx.lp = None
+        return (None, None, None) + gs + gl
+
+
+class _PsJointFn(torch.autograd.Function):
+    """loss_vse of st_and_ps_methods for the partial-sampling modes (gumbel_softmax /
+    multinomial_soft): the listener embeds the emitted vectors with a dense contraction and the
+    speaker's BPTT forms d(loss)/d(logits) step by step (the vectors also feed the next input)."""
+
+    @staticmethod
+    def forward(ctx, owner, sp, lp, *params):
+        ctx.owner, ctx.sp, ctx.lp = owner, EN.retain(sp), EN.retain(lp)
+        return lp.t["loss"][0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        owner, sp, lp = ctx.owner, ctx.sp, ctx.lp
+        spk, lis = owner.caption_generator, owner.vse
+        Ps, Pl = spk._params(), lis._params()
+        need_l = any(p.requires_grad for p in Pl.values())
+        need_s = any(p.requires_grad for p in Ps.values())
+        Gl, demb16 = EN.listener_backward(lp, Pl, g_loss=g.contiguous().float().reshape(1),
+                                          need_param_grads=need_l)
+        T = sp.n_steps
+        if need_l:
+            EN.caption_embed_dense_bwd(sp.t["soft16"], demb16, T, spk.vocab_size + 1,
+                                       Gl["txt_enc.embed.weight"])
+        gs = (None,) * len(EN.SPEAKER_PARAM_NAMES)
+        if need_s:
+            Gs = EN.speaker_backward(sp, None, Ps, ps_demb16=demb16[1:T + 1],
+                                     ps_w_emb16=lis._packed.get(Pl)["w_emb16"])
             gs = tuple(Gs[n].view_as(Ps[n]) for n in EN.SPEAKER_PARAM_NAMES)
         gl = tuple((Gl[n].view_as(Pl[n]) if need_l else None) for n in EN.LISTENER_PARAM_NAMES)
         EN.release(sp)
@@ -209,23 +244,29 @@ class AlternatingJointModel(nn.Module):
         (loss, word_index, logprobs, masks, _seqs) with the caption tensors left time-major and
         unsliced on the device (they only feed the out-of-scope CIDEr branch in the reference)."""
         spk, lis = self.caption_generator, self.vse
-        if self.retrieval_reward not in ("gumbel", "multinomial"):
-            raise NotImplementedError(
-                f"retrieval_reward={self.retrieval_reward!r} is not on the B200 path yet")
         sp, st_mode = spk._sample_pass(att_feats, att_masks, 0, 1, 1)                   # :346-348
         assert st_mode
         B, V = sp.B, spk.vocab_size
         tok_sb = torch.cat([torch.full((1, B), V + 1, dtype=torch.int64, device=fc_feats.device),
                             sp.t["tok_out"][: sp.n_steps]], 0)                          # :360-370
         Pl = lis._params()
+        is_ps = sp.ctx.mode in EN.PS_MODES
+        emb16 = None
+        if is_ps:
+            # dense caption vectors: seqs_embed = _seqs @ embed.weight (VSEFCModel.py:102-104)
+            emb16 = EN.caption_embed_dense(sp.t["soft16"], sp.n_steps, Pl, lis._packed.get(Pl), V + 1)
         lp = EN.listener_forward(Pl, lis._packed.get(Pl), fc_feats.detach().float().contiguous(),
-                                 tok_sb, sp.t["cap_len"], margin=lis.margin,
+                                 None if is_ps else tok_sb, sp.t["cap_len"], margin=lis.margin,
                                  only_one_retrieval=self.only_one_retrieval,
-                                 no_imgnorm=bool(lis.img_enc.no_imgnorm))               # :371-373
+                                 no_imgnorm=bool(lis.img_enc.no_imgnorm), emb16=emb16)  # :371-373
+        if lis.keep_passes:
+            lp.pinned = True
+            lis._passes.append(lp)
         Ps = spk._params()
         if torch.is_grad_enabled():
-            loss_vse = _StJointFn.apply(self, sp, lp, *_ordered_s(Ps),
-                                        *[Pl[n] for n in EN.LISTENER_PARAM_NAMES])
+            fn = _PsJointFn if is_ps else _StJointFn
+            loss_vse = fn.apply(self, sp, lp, *_ordered_s(Ps),
+                                *[Pl[n] for n in EN.LISTENER_PARAM_NAMES])
         else:
             loss_vse = lp.t["loss"][0].clone()
         lis._loss["contrastive"] = loss_vse.detach()

@@ -113,6 +113,35 @@ class _SampleSTFn(torch.autograd.Function):
         return (None, None, None) + tuple(G[n_].view_as(P[n_]) for n_ in EN.SPEAKER_PARAM_NAMES)
 
 
+class _SamplePSFn(torch.autograd.Function):
+    """Dense partial-sampling vectors [B, n, V+2] (gumbel_softmax.py:28-40 / multinomial_soft.py:21-33
+    + AttModel.py:373-378,425-434): one-hot values on the selected rows, the relaxed sample y on
+    the others, EOS one-hot on finished rows.  Backward: the upstream gradient plus the gradient
+    that reaches v_t through the next input relu(v_t . embed) -> softmax backward -> BPTT."""
+
+    @staticmethod
+    def forward(ctx, sp, n, owner, *params):
+        if not isinstance(ctx, _Dummy):
+            EN.retain(sp)
+        ctx.sp, ctx.n, ctx.owner = sp, n, owner
+        B, V1 = sp.B, sp.dims.V1
+        out = torch.zeros(B, n, V1 + 1, device=sp.t["soft16"].device)
+        out[:, :, :V1] = sp.t["soft16"][:n].transpose(0, 1)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        sp, n = ctx.sp, ctx.n
+        P = ctx.owner._params()
+        V1 = sp.dims.V1
+        gt = torch.zeros(sp.n_steps, sp.B, (V1 + 3) // 4 * 4, device=g.device)
+        gt[:n, :, :V1] = g[:, :, :V1].transpose(0, 1)
+        G = EN.speaker_backward(sp, None, P, ps_g_dense=gt)
+        EN.release(sp)
+        ctx.sp = None
+        return (None, None, None) + tuple(G[n_].view_as(P[n_]) for n_ in EN.SPEAKER_PARAM_NAMES)
+
+
 class AttModel(nn.Module):
     def __init__(self, opt):
         super().__init__()
@@ -174,7 +203,7 @@ class AttModel(nn.Module):
         return EN.SpeakerRandom(seed=_next_seed(), drop_p=p)
 
     def _run(self, att_feats, att_masks, *, n_steps, mode, inv_tau, start_token, forced=None,
-             start_tokens=None) -> EN.SpeakerPass:
+             start_tokens=None, ps_prob=0.0, ss_prob=0.0, no_repeat=False) -> EN.SpeakerPass:
         if not att_feats.is_cuda:
             raise EN._lib.CoopcapError("Att2in2Model runs on CUDA only (no CPU path)")
         P = self._params()
@@ -193,7 +222,9 @@ class AttModel(nn.Module):
             off, NL = EN.region_offsets(att_masks, B, L)
         sp = EN.speaker_forward(P, packed, att_feats, off, NL, n_steps=n_steps, mode=mode,
                                 inv_tau=inv_tau, start_token=start_token, rnd=self._random(),
-                                forced=forced, start_tokens=start_tokens, att16=att16)
+                                forced=forced, start_tokens=start_tokens, att16=att16,
+                                ps_prob=ps_prob, ss_prob=ss_prob, no_repeat=no_repeat,
+                                w_embed16=self._packed.get_embed16(P) if mode in EN.PS_MODES else None)
         if self.keep_passes:
             sp.pinned = True
             self._passes.append(sp)
@@ -205,8 +236,6 @@ class AttModel(nn.Module):
     # ------------------------------------------------------------------ AttModel.forward
     def forward(self, fc_feats, att_feats, att_masks, seq, masks):
         """Teacher-forced XE loss (AttModel.py:103-148 + misc/utils.py:49-58)."""
-        if self.training and self.ss_prob > 0.0:
-            raise NotImplementedError("scheduled sampling (ss_prob > 0) is not on the B200 path yet")
         seq = seq.long()
         T1 = seq.size(1) - 1
         # stop at the first i >= 1 whose whole column is 0 (AttModel.py:133): one small D2H
@@ -217,8 +246,12 @@ class AttModel(nn.Module):
                 break
             n_steps = i + 1
         forced = seq[:, 1:n_steps + 1].t().contiguous()                    # targets = next inputs
-        sp = self._run(att_feats, att_masks, n_steps=n_steps, mode=EN.MODE_NONE, inv_tau=1.0,
-                       start_token=0, forced=forced, start_tokens=seq[:, 0].contiguous())
+        # scheduled sampling (:119-131): with probability ss_prob a row is fed the id drawn from
+        # the previous step's distribution instead of the ground truth (no gradient through it)
+        ss = float(self.ss_prob) if self.training else 0.0
+        sp = self._run(att_feats, att_masks, n_steps=n_steps,
+                       mode=EN.MODE_MULTINOMIAL if ss > 0.0 else EN.MODE_NONE, inv_tau=1.0,
+                       start_token=0, forced=forced, start_tokens=seq[:, 0].contiguous(), ss_prob=ss)
         if self._needs_grad():
             logp = _SpeakerLossFn.apply(sp, forced, self, *_ordered(self._params()))
         else:
@@ -238,9 +271,9 @@ class AttModel(nn.Module):
         use_one_hot = opt.get("use_one_hot", 0)
         if beam_size > 1:
             raise NotImplementedError("beam search is evaluation-only and outside the hot path")
-        if opt.get("decoding_constraint", 0):
-            raise NotImplementedError("decoding_constraint is outside the hot path")
-        sp, st_mode = self._sample_pass(att_feats, att_masks, sample_max, temperature, use_one_hot)
+        no_repeat = bool(opt.get("decoding_constraint", self.decoding_constraint))      # :305-306
+        sp, st_mode = self._sample_pass(att_feats, att_masks, sample_max, temperature, use_one_hot,
+                                        **({"no_repeat": True} if no_repeat else {}))
         n = int(sp.t["n_out"].item())                       # the one host sync (output width)
         seq = sp.t["tok_out"][:n].t().contiguous()
         if n == 0:
@@ -248,26 +281,32 @@ class AttModel(nn.Module):
             z = torch.zeros(sp.B, 0, device=seq.device)
             return (seq, torch.zeros(sp.B, 0, sp.dims.V1 + 1, device=seq.device), z) if st_mode \
                 else (seq, z)
-        if self._needs_grad() and not sample_max:
+        if self._needs_grad() and not sample_max and sp.ctx.mode not in EN.PS_MODES:
+            # (partial-sampling passes return sampleLogprobs detached: their BPTT is driven by the
+            # gradient of the emitted vectors, the only use the reference's joint step makes of them)
             logp_all = _SpeakerLossFn.apply(sp, sp.t["tok_fed"][1:sp.n_steps + 1].contiguous(), self,
                                             *_ordered(self._params()))
         else:
             logp_all = sp.t["logp"][: sp.n_steps]
         logprobs = logp_all[:n].t()
         if st_mode:
+            fn = _SamplePSFn if sp.ctx.mode in EN.PS_MODES else _SampleSTFn
             if self._needs_grad():
-                one_hots = _SampleSTFn.apply(sp, n, self, *_ordered(self._params()))
+                one_hots = fn.apply(sp, n, self, *_ordered(self._params()))
             else:
-                one_hots = _SampleSTFn.forward(_Dummy(), sp, n, self)
+                one_hots = fn.forward(_Dummy(), sp, n, self)
             return seq, one_hots, logprobs
         return seq, logprobs
 
     _sample = sample
 
-    def _sample_pass(self, att_feats, att_masks, sample_max, temperature, use_one_hot):
-        """Run the decode loop in the mode AttModel.sample would pick; returns (pass, is_ST)."""
+    def _sample_pass(self, att_feats, att_masks, sample_max, temperature, use_one_hot,
+                     no_repeat=False):
+        """Run the decode loop in the mode AttModel.sample would pick; returns (pass, is_ST) with
+        is_ST true for the modes that return dense vectors (straight-through / partial sampling)."""
         T = self.seq_length
         st_mode = False
+        ps_prob = 0.0
         if sample_max:
             mode, inv_tau = EN.MODE_GREEDY, 1.0
         elif self.retrieval_reward == "reinforce" or not use_one_hot:
@@ -276,15 +315,23 @@ class AttModel(nn.Module):
             mode, inv_tau, st_mode = EN.MODE_ST_GUMBEL, 1.0 / float(self.gumbel_temp), True
         elif self.retrieval_reward == "multinomial":
             mode, inv_tau, st_mode = EN.MODE_ST_MULTINOMIAL, 1.0 / float(self.multinomial_temp), True
+        elif self.retrieval_reward == "gumbel_softmax":                             # :367-378
+            mode, inv_tau, st_mode = EN.MODE_PS_GUMBEL, 1.0 / float(self.gumbel_temp), True
+            ps_prob = float(self.prob_gumbel_softmax)
+        elif self.retrieval_reward == "multinomial_soft":                           # :381-392
+            mode, inv_tau, st_mode = EN.MODE_PS_MULTINOMIAL, 1.0 / float(self.multinomial_temp), True
+            ps_prob = float(self.prob_multinomial_soft)
         else:
-            raise NotImplementedError(
-                f"retrieval_reward={self.retrieval_reward!r}: the partial-sampling variants "
-                "(gumbel_softmax / multinomial_soft) are not on the B200 path yet")
+            raise ValueError(f"unknown retrieval_reward {self.retrieval_reward!r}")
+        if no_repeat and st_mode:
+            # the reference scatters with seq[-1], a dense tensor in these modes, and crashes
+            raise ValueError("decoding_constraint needs index outputs (sample_max or use_one_hot=0)")
         forced = None
         if self.forced_tokens is not None:
             forced = self.forced_tokens.t().contiguous()
         sp = self._run(att_feats, att_masks, n_steps=T, mode=mode, inv_tau=inv_tau,
-                       start_token=self.vocab_size + 1, forced=forced)
+                       start_token=self.vocab_size + 1, forced=forced, ps_prob=ps_prob,
+                       no_repeat=no_repeat)
         return sp, st_mode
 
 

@@ -3,8 +3,9 @@
 Same constructor, parameter names / shapes (`img_enc.fc`, `txt_enc.embed`, `txt_enc.rnn.*_l0`),
 same `forward(fc_feats, att_feats, seq, masks, whole_batch=False, only_one_retrieval='off')`
 (VSEFCModel.py:230-241).  `seq` is int64 [B, S] ids or a float one-hot tensor [B, S, V+2]
-(VSEFCModel.py:102-106); a one-hot input is consumed as a gather (its argmax), and its gradient
-is returned densely (demb . W_emb^T) so foreign callers still see the reference's autograd graph.
+(VSEFCModel.py:102-106); a dense input (one-hot or soft vectors) is embedded by the dense
+contraction `seq @ embed.weight` like the reference does, and its gradient is returned densely
+(demb . W_emb^T) so foreign callers still see the reference's autograd graph.
 All arithmetic runs in libcoopcap; there is no CPU path.
 """
 from __future__ import annotations
@@ -97,6 +98,13 @@ class _ListenerFn(torch.autograd.Function):
             else:
                 ops.gemm(demb16.view(S * B, -1), w16, S * B, V2, demb16.shape[-1], out=flat)
             g_seq = flat.view(S, B, V2).transpose(0, 1).contiguous()
+        x16 = getattr(lp, "dense_x16", None)
+        if need and x16 is not None:
+            # embedding weight gradient of the dense contraction: x^T . demb   ([V2, S*B] x [S*B, E])
+            S, B, V2p = x16.shape
+            V2 = P["txt_enc.embed.weight"].shape[0]
+            ops.gemm(x16.view(S * B, V2p), demb16.view(S * B, -1), V2, demb16.shape[-1], S * B,
+                     a_major=1, b_major=1, out=G["txt_enc.embed.weight"])
         grads = tuple((G[n].view_as(P[n]) if need else None) for n in EN.LISTENER_PARAM_NAMES)
         EN.release(lp)
         ctx.lp = None
@@ -137,14 +145,28 @@ class VSEFCModel(nn.Module):
         }
 
     def _forward_ids(self, fc_feats, tok_sb, lens, whole_batch, only_one_retrieval, dense_seq=None):
-        """tok_sb int64 [S, B] time-major, lens int32 [B]."""
+        """tok_sb int64 [S, B] time-major, lens int32 [B]; or dense_seq float [B, S, V+2]."""
         if not fc_feats.is_cuda:
             raise EN._lib.CoopcapError("VSEFCModel runs on CUDA only (no CPU path)")
         P = self._params()
         packed = self._packed.get(P)
+        emb16 = x16 = None
+        if dense_seq is not None:
+            # seqs.dim() > 2: seqs_embed = seqs @ embed.weight (VSEFCModel.py:102-104); the dense
+            # tensor is re-laid time-major in bf16 (row pitch padded to 16 bytes for TMA)
+            B, S, V2 = dense_seq.shape
+            d = packed["dims"]
+            if V2 != d.V2:
+                raise EN._lib.CoopcapError(f"dense captions have width {V2}, the embedding has {d.V2} rows")
+            x16 = torch.zeros(S, B, (V2 + 7) // 8 * 8, dtype=torch.bfloat16, device=dense_seq.device)
+            x16[:, :, :V2] = dense_seq.detach().transpose(0, 1)
+            emb16 = torch.empty(S, B, d.E, dtype=torch.bfloat16, device=dense_seq.device)
+            ops.gemm(x16.view(S * B, -1), packed["w_emb16"], S * B, d.E, V2, b_major=1,
+                     out16=emb16.view(S * B, d.E))
         lp = EN.listener_forward(P, packed, fc_feats.detach().float().contiguous(), tok_sb, lens,
                                  margin=self.margin, only_one_retrieval=only_one_retrieval,
-                                 no_imgnorm=bool(self.img_enc.no_imgnorm))
+                                 no_imgnorm=bool(self.img_enc.no_imgnorm), emb16=emb16)
+        lp.dense_x16 = x16
         if self.keep_passes:
             lp.pinned = True
             self._passes.append(lp)
@@ -161,13 +183,11 @@ class VSEFCModel(nn.Module):
                 only_one_retrieval="off"):
         """VSEFCModel.py:230-241 (att_feats is ignored, as in the reference)."""
         lens = (masks > 0).sum(1).to(torch.int32).contiguous()                     # :84
-        dense = None
+        dense, tok_sb = None, None
         if seq.dim() > 2:
             dense = seq
-            ids = seq.detach().argmax(-1)
         else:
-            ids = seq.long()
-        tok_sb = ids.t().contiguous()
+            tok_sb = seq.long().t().contiguous()
         loss, _ = self._forward_ids(fc_feats, tok_sb, lens, whole_batch, only_one_retrieval, dense)
         if not whole_batch:
             self._loss["contrastive"] = loss.detach()                               # :238-239

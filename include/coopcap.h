@@ -122,6 +122,8 @@ int coopcap_cast_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_s
 #define COOPCAP_SAMPLE_ST_GUMBEL 2      /* gumbel.py:17-30 */
 #define COOPCAP_SAMPLE_ST_MULTINOMIAL 3 /* multinomial.py:4-27 */
 #define COOPCAP_SAMPLE_NONE 4           /* teacher forcing: only lse / logp of the forced id */
+#define COOPCAP_SAMPLE_PS_GUMBEL 5      /* gumbel_softmax.py:17-42 (partial sampling) */
+#define COOPCAP_SAMPLE_PS_MULTINOMIAL 6 /* multinomial_soft.py:5-35 (partial sampling) */
 
 /* fp32 master parameters -> packed bf16 operand copies (run after every optimizer step). */
 typedef struct coopcap_speaker_pack {
@@ -217,6 +219,23 @@ typedef struct coopcap_speaker {
    * positions of [BOS, w_1..w_n] under _masks = [1,1,(w_1>0),..] (AlternatingJointModel.py:353-355) */
   int* n_out;                /* [1] */
   int* cap_len;              /* [B] */
+  /* partial-sampling modes (COOPCAP_SAMPLE_PS_*; AttModel.py:367-399,425-434): step t emits the
+   * vector v_t = one_hot(id) on rows with part_u < ps_prob and the relaxed sample y on the others
+   * (y = softmax((z+G)/tau) resp. exp(log_softmax(z)/tau)); the next input is
+   * dropout(relu(v_t . embed)) instead of an embedding lookup.  After that GEMM, finished rows of
+   * v_t are replaced by the EOS one-hot (:428-432), which is what `sample` returns. */
+  float ps_prob;             /* prob_gumbel_softmax / prob_multinomial_soft; <= 0: every row stays soft */
+  const float* part_u;       /* [cap, B] injected uniforms or NULL -> Philox */
+  void* soft16;              /* bf16 [cap, B, V1]  v_t (the BOS column V+1 is always 0 and not stored) */
+  uint8_t* ps_sel;           /* [cap, B] 1 = row emitted the hard one-hot */
+  const void* w_embed16;     /* bf16 [>= V1, E] copy of `embed` */
+  /* scheduled sampling of AttModel.forward (:119-131): with probability ss_prob per row the next
+   * input is the id drawn from softmax(z_t) (mode COOPCAP_SAMPLE_MULTINOMIAL) instead of
+   * forced[t]; logp stays the log-probability of forced[t] (the XE target). */
+  float ss_prob;
+  const float* ss_u;         /* [cap, B] injected uniforms or NULL -> Philox */
+  /* decoding_constraint (AttModel.py:437-442): the logit of the previously emitted id is -inf */
+  int no_repeat;
 } coopcap_speaker;
 
 /* att16, att_e16, p_att16 from att_feats (AttModel.py:110-114 / :315-319). */
@@ -246,7 +265,7 @@ int coopcap_logp_backward(const coopcap_speaker* ctx, const int64_t* tok, const 
 
 typedef struct coopcap_speaker_grads {
   /* input */
-  const void* dz16;     /* bf16 [n_steps*B, V1] */
+  const void* dz16;     /* bf16 [n_steps*B, V1] (partial-sampling passes: a workspace, written) */
   /* workspaces */
   float* d_out;         /* [max(cap,2)*B, R]  d(loss)/d(dropout(h_t)) from the logit layer (reused as scratch) */
   void* dscat16;        /* bf16 [cap*B, 5R+A] : d(gate pre-acts) | d(att_h) */
@@ -274,6 +293,18 @@ typedef struct coopcap_speaker_grads {
   float* g_w_logit;
   float* g_b_logit;
   float* g_w_alpha;     /* [A] */
+  /* partial-sampling modes only (COOPCAP_SAMPLE_PS_*): the gradient of v_t has two sources, the
+   * consumer of the emitted vectors (listener) and the next input x_{t+1} = relu(v_t . embed), so
+   * d(loss)/d(logits) is formed step by step inside the BPTT loop and dz16 is a WORKSPACE
+   * (bf16 [n_steps*B, V1]) instead of an input.  Upstream gradient, one of:
+   *   factored: ps_demb16 bf16 [n_steps*B, E] (d loss / d listener word embedding at caption
+   *             positions 1..n_steps) and ps_w_emb16 bf16 [>= V1, E]; ps_g fp32 [B, V1] scratch
+   *   dense   : ps_demb16 NULL; ps_g fp32 [n_steps*B, ps_ldg] = d loss / d v, modified in place */
+  const void* ps_demb16;
+  const void* ps_w_emb16;
+  float* ps_g;
+  int64_t ps_ldg;
+  void* ps_dpre16;      /* bf16 [n_steps*B, E] workspace: d(loss)/d(v_{t-1} . embed) */
 } coopcap_speaker_grads;
 
 /* BPTT through the decode loop and the prologue given d(loss)/d(logits). */
@@ -359,9 +390,29 @@ typedef struct coopcap_listener {
   int* arg_im;
   float* loss_rows;
   float* loss;
+  /* variants (0 / NULL = the run_joint.sh defaults) */
+  int emb_given;      /* 1: emb16 was filled by the caller (dense one-hot / soft caption vectors,
+                         VSEFCModel.py:102-104); tok is not read */
+  int pool_type;      /* 0 last (:128), 1 masked mean (:115-119), 2 masked max (:120-126) */
+  int use_abs;        /* vse_use_abs: |l2norm(.)| on both encoders (:50-52,137-139) */
+  int sum_violation;  /* 1: vse_max_violation = 0, mean over the negatives (:190-193) */
+  float* cap_pre;     /* [B, M] pooled state before l2norm (pool mean / max; 'last' uses h32[S]) */
+  int* pool_arg;      /* [B, M] arg-max step of the max pool */
 } coopcap_listener;
 
 int coopcap_listener_fwd(const coopcap_listener* ctx, coopcap_stream_t stream);
+
+/* Caption embedding of dense caption vectors (VSEFCModel.py:102-104, `seqs.dim() > 2`) for the
+ * partial-sampling joint step: emb16[0] = bf16(w_emb[bos_id]) on every row (the BOS one-hot that
+ * AlternatingJointModel.py:356-370 prepends), emb16[1 + t] = v_t . w_emb[:V1]  for t < n.
+ * soft16: bf16 [n, B, V1]; w_emb fp32 [V2, E]; w_emb16 bf16 [V2, E]; emb16: bf16 [n+1, B, E]. */
+int coopcap_caption_embed_dense(const void* soft16, const float* w_emb, const void* w_emb16, int n,
+                                int B, int V1, int E, int64_t bos_id, void* emb16,
+                                coopcap_stream_t stream);
+/* Its weight gradient: g_w_emb[:V1] = sum_t v_t^T . demb[1 + t], g_w_emb[bos_id] = sum_b demb[0, b]
+ * (positions beyond a row's length carry zero demb).  g_w_emb: fp32 [V2, E], other rows untouched. */
+int coopcap_caption_embed_dense_bwd(const void* soft16, const void* demb16, int n, int B, int V1,
+                                    int E, int64_t bos_id, float* g_w_emb, coopcap_stream_t stream);
 
 typedef struct coopcap_listener_grads {
   /* upstream gradient: d(total)/d(loss) scalar (device, [1]) or per-row vector [B]; exactly one */

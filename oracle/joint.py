@@ -43,7 +43,8 @@ def caption_masks(word_index):
 
 
 def st_joint_loss(Ps, Pl, fc_feats, att_feats, att_masks, noise: S.SpeakerNoise, cfg: JointCfg,
-                  forced_tokens: Optional[torch.Tensor] = None, keep_all_steps: bool = False):
+                  forced_tokens: Optional[torch.Tensor] = None, keep_all_steps: bool = False,
+                  hinge_replay: Optional[dict] = None):
     """Speaker turn in gumbel / multinomial / *_soft mode: st_and_ps_methods
     (AlternatingJointModel.py:343-376) with VSE weight forced to 0 (:516-518)."""
     V = cfg.vocab_size
@@ -60,7 +61,8 @@ def st_joint_loss(Ps, Pl, fc_feats, att_feats, att_masks, noise: S.SpeakerNoise,
     bos[:, 0, V + 1] = 1.0                                                           # :360-369
     seqs = torch.cat([bos, res.one_hots], 1)                                         # :370
     loss_vse = L.vse_forward(Pl, fc_feats, seqs, masks, False, cfg.only_one_retrieval,
-                             cfg.margin, cfg.max_violation, cfg.pool_type)           # :371-373
+                             cfg.margin, cfg.max_violation, cfg.pool_type,
+                             hinge_replay)                                           # :371-373
     loss = loss_vse * cfg.retrieval_reward_weight                                    # :374
     return loss, res, masks, loss_vse
 

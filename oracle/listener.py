@@ -73,16 +73,27 @@ def txt_enc(P: Params, seqs, masks, pool_type="last", use_abs=False):
 
 
 def contrastive_loss(im, s, margin=0.2, max_violation=True, whole_batch=False,
-                     only_one_retrieval="off"):
-    """ContrastiveLoss.forward                                          (VSEFCModel.py:167-207)"""
+                     only_one_retrieval="off", hinge_replay=None):
+    """ContrastiveLoss.forward                                          (VSEFCModel.py:167-207)
+
+    `hinge_replay` (test aid, like the token / maxout / ReLU replays of the speaker oracle): a dict
+    with int64 `arg_s` [B] / `arg_im` [B] replaces the max-violation arg-max (:191-193) by the given
+    hardest-negative indices, so a near-tie decided differently under bf16 operands does not
+    masquerade as a gradient error; the oracle's own score matrix is left in `hinge_replay["scores"]`
+    for the near-tie check."""
     scores = im @ s.t()                                                # cosine_sim, :143-146
+    if hinge_replay is not None:
+        hinge_replay["scores"] = scores.detach()
     diag = scores.diag().view(-1, 1)
     cost_s = (margin + scores - diag).clamp(min=0)                     # :176 caption retrieval
     cost_im = (margin + scores - diag.t()).clamp(min=0)                # :179 image retrieval
     eye = torch.eye(scores.size(0), dtype=torch.bool)
     cost_s = cost_s.masked_fill(eye, 0)                                # :182-188
     cost_im = cost_im.masked_fill(eye, 0)
-    if max_violation:
+    if max_violation and hinge_replay is not None and "arg_s" in hinge_replay:
+        cost_s = cost_s.gather(1, hinge_replay["arg_s"].view(-1, 1)).squeeze(1)
+        cost_im = cost_im.gather(0, hinge_replay["arg_im"].view(1, -1)).squeeze(0)
+    elif max_violation:
         cost_s = cost_s.max(1)[0]                                      # :191-193
         cost_im = cost_im.max(0)[0]
     else:
@@ -97,7 +108,7 @@ def contrastive_loss(im, s, margin=0.2, max_violation=True, whole_batch=False,
 
 
 def vse_forward(P: Params, fc_feats, seq, masks, whole_batch=False, only_one_retrieval="off",
-                margin=0.2, max_violation=True, pool_type="last"):
+                margin=0.2, max_violation=True, pool_type="last", hinge_replay=None):
     """VSEFCModel.forward                                               (VSEFCModel.py:230-241)"""
     return contrastive_loss(img_enc(P, fc_feats), txt_enc(P, seq, masks, pool_type), margin,
-                            max_violation, whole_batch, only_one_retrieval)
+                            max_violation, whole_batch, only_one_retrieval, hinge_replay)

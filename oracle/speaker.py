@@ -49,6 +49,7 @@ class SpeakerNoise:
     # not masquerade as a gradient error.  None -> the oracle decides itself (reference behaviour).
     relu_att: Optional[torch.Tensor] = None      # bool [B, L, R]: att_embed pre-activation > 0
     maxout_first: Optional[torch.Tensor] = None  # bool [steps, B, R]: u[:, :R] >= u[:, R:]
+    relu_embed: Optional[torch.Tensor] = None    # bool [steps, B, E]: (v . embed) > 0 (partial sampling)
     # filled by the oracle for diagnostics: margins of its own decisions
     margins: Optional[dict] = None
 
@@ -270,7 +271,13 @@ def sample(P: Params, att_feats, att_masks, *, mode: str, seq_length: int, vocab
                 vec = torch.cat([vec, vec.new_zeros(B, 1)], 1)        # :348-354,:373-378
         # next input                                                          # :395-399
         if ps_mode and t >= 1:
-            xt = _dropout(torch.relu(vec @ P["embed.0.weight"]), keep_e, drop_p)
+            pre = vec @ P["embed.0.weight"]
+            if noise.margins is not None:
+                noise.margins.setdefault("relu_embed", []).append(pre.detach())
+            if noise.relu_embed is not None and t < noise.relu_embed.size(0):
+                xt = _dropout(pre * noise.relu_embed[t].to(pre.dtype), keep_e, drop_p)   # replayed
+            else:
+                xt = _dropout(torch.relu(pre), keep_e, drop_p)
         else:
             xt = embed_tokens(P, it, keep_e, drop_p)
         if t >= 1:

@@ -48,6 +48,13 @@ def branch_replay(sp, att_masks, noise):
         relu = relu | (noise.drop_att == 0)
     out = copy.copy(noise)
     out.maxout_first, out.relu_att, out.margins = first, relu, {}
+    if "soft16" in sp.t:
+        # partial-sampling modes: the next input relu(v . embed) is a bf16 contraction here
+        E = sp.dims.E
+        on = (sp.t["xh16"][: n, :, :E].float() > 0).cpu()           # [steps, B, E]
+        if noise.drop_embed is not None:
+            on = on | (noise.drop_embed[: n] == 0)
+        out.relu_embed = on
     return out
 
 
@@ -75,4 +82,43 @@ def check_near_ties(replay_noise, att_masks, tol):
     stats["relu_total"] = int(valid.sum())
     if flipped.any():
         assert float(pre[flipped].abs().max()) <= tol * scale, "ReLU decision differs away from a tie"
+    if replay_noise.relu_embed is not None and "relu_embed" in mg:
+        pre = torch.stack(mg["relu_embed"], 0)                       # oracle steps 1..k
+        pre = pre[: replay_noise.relu_embed.size(0) - 1]             # the last step's input is never built here
+        dec = replay_noise.relu_embed[1: 1 + pre.size(0)]
+        valid = torch.ones_like(dec)
+        if replay_noise.drop_embed is not None:
+            valid = replay_noise.drop_embed[1: 1 + pre.size(0)] > 0
+        flipped = (dec != (pre > 0)) & valid
+        # per-row scale: soft rows have much smaller pre-activations than one-hot rows
+        scale = pre.abs().median(dim=2, keepdim=True)[0].expand_as(pre)
+        stats["embed_relu_flips"] = int(flipped.sum())
+        stats["embed_relu_total"] = int(valid.sum())
+        if flipped.any():
+            assert bool((pre[flipped].abs() <= tol * scale[flipped]).all()), \
+                "embed ReLU decision differs away from a tie"
     return stats
+
+
+def hinge_replay_of(lp):
+    """The listener's max-violation arg-max decisions (VSEFCModel.py:191-193) of a CUDA pass, in the
+    form oracle.listener.contrastive_loss replays."""
+    return {"arg_s": lp.t["arg_s"].cpu().long(), "arg_im": lp.t["arg_im"].cpu().long()}
+
+
+def check_hinge_near_ties(hinge_replay, tol=2e-3):
+    """The replayed hardest negatives may differ from the oracle's own arg-max only where the
+    oracle's score of the replayed negative is within `tol` of its own maximum."""
+    S = hinge_replay["scores"]
+    B = S.size(0)
+    S = S.masked_fill(torch.eye(B, dtype=torch.bool), -1e9)
+    flips = 0
+    for dim, key in ((1, "arg_s"), (0, "arg_im")):
+        best = S.max(dim)[0]
+        idx = hinge_replay[key]
+        got = S.gather(dim, idx.view(-1, 1) if dim == 1 else idx.view(1, -1)).reshape(-1)
+        own = idx == torch.arange(B)          # the kernel reports i itself when B == 1
+        gap = (best - got)[~own]
+        flips += int((gap > 0).sum())
+        assert bool((gap <= tol).all()), (key, gap.max())
+    return {"hinge_flips": flips, "hinge_total": 2 * B}

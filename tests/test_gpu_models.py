@@ -7,7 +7,8 @@ from oracle import joint as OJ
 from oracle import speaker as OS
 from oracle import synth
 from oracle.ref_loader import reference_opt
-from gpu_util import REAL, branch_replay, check_near_ties, pack_keep, u8
+from gpu_util import (REAL, branch_replay, check_hinge_near_ties, check_near_ties, hinge_replay_of,
+                      pack_keep, u8)
 
 pytestmark = pytest.mark.gpu
 
@@ -24,8 +25,10 @@ def _build(mode, B, L, seed, *, varlen, dropout, tau=1.0, eos_bias=7.5, **optkw)
     Ps = synth.speaker_params(d, seed=seed, eos_bias=eos_bias)
     Pl = synth.listener_params(d, seed=seed + 1)
     batch = synth.make_batch(d, B, L, seed + 2, varlen=varlen, min_regions=2)
-    noise = synth.make_noise(d, B, L, seed + 3, dropout=dropout, gumbel=(mode == "gumbel"),
-                             multinomial=(mode in ("multinomial", "reinforce")))
+    noise = synth.make_noise(d, B, L, seed + 3, dropout=dropout,
+                             gumbel=(mode in ("gumbel", "gumbel_softmax")),
+                             multinomial=(mode in ("multinomial", "reinforce", "multinomial_soft")),
+                             partial=(mode in ("gumbel_softmax", "multinomial_soft")))
     drop_p = 0.5 if dropout else 0.0
     opt = reference_opt(retrieval_reward=mode, gumbel_temp=tau, multinomial_temp=tau,
                         drop_prob_lm=drop_p, batch_size=B, **optkw)
@@ -40,17 +43,21 @@ def _build(mode, B, L, seed, *, varlen, dropout, tau=1.0, eos_bias=7.5, **optkw)
         rnd.keep_att = pack_keep(noise.drop_att, batch.att_masks)
         rnd.keep_embed = u8(noise.drop_embed)
         rnd.keep_core = u8(noise.drop_core)
-    if mode == "gumbel":
+    if mode in ("gumbel", "gumbel_softmax"):
         rnd.noise = noise.U.cuda().contiguous()
-    elif mode in ("multinomial", "reinforce"):
+    elif mode in ("multinomial", "reinforce", "multinomial_soft"):
         rnd.noise = noise.E.cuda().contiguous()
+    if noise.part_u is not None:
+        rnd.part_u = noise.part_u.cuda().contiguous()
     model.caption_generator.injected = rnd
     model.caption_generator.keep_passes = True
     cfg = OJ.JointCfg(drop_p=drop_p, retrieval_reward=mode, gumbel_temp=tau, multinomial_temp=tau,
                       retrieval_reward_weight=opt.retrieval_reward_weight,
                       vse_loss_weight=opt.vse_loss_weight,
                       caption_loss_weight=opt.caption_loss_weight,
-                      reinforce_baseline_type=opt.reinforce_baseline_type)
+                      reinforce_baseline_type=opt.reinforce_baseline_type,
+                      prob_gumbel_softmax=opt.prob_gumbel_softmax,
+                      prob_multinomial_soft=opt.prob_multinomial_soft)
     return model, Ps, Pl, batch, noise, cfg
 
 
@@ -63,6 +70,14 @@ def _oracle_grads(loss, Pso, Plo):
 
 def _check_grads(model, ref, tag):
     worst_l2, worst_cos = 0.0, 1.0
+    import os
+    if os.environ.get("COOPCAP_TEST_VERBOSE"):
+        for name, p in model.named_parameters():
+            r = ref[name].double().flatten()
+            g = torch.zeros_like(r) if p.grad is None else p.grad.detach().double().cpu().flatten()
+            if float(r.norm()) > 0:
+                print(f"  [{tag}] {name}: l2 {float((g - r).norm() / r.norm()):.3e} "
+                      f"cos {float((g @ r) / (g.norm() * r.norm() + 1e-300)):.6f} |ref| {float(r.norm()):.3e}")
     for name, p in model.named_parameters():
         r = ref[name].double().flatten()
         g = torch.zeros_like(r) if p.grad is None else p.grad.detach().double().cpu().flatten()
@@ -83,12 +98,13 @@ def _cuda_batch(batch):
             batch.att_feats.cuda(), None if batch.att_masks is None else batch.att_masks.cuda())
 
 
-def _replay_tokens(Ps, batch, noise, mode, drop_p, tau, sample_max=0):
+def _replay_tokens(Ps, batch, noise, mode, drop_p, tau, sample_max=0, prob=0.25):
     d = REAL
     free = OS.sample(Ps, batch.att_feats, batch.att_masks, mode=mode, seq_length=d.seq_length,
                      vocab_size=d.vocab_size, noise=noise, drop_p=drop_p, sample_max=sample_max,
                      use_one_hot=0 if mode == "reinforce" else 1, gumbel_temp=tau,
-                     multinomial_temp=tau, keep_all_steps=True)
+                     multinomial_temp=tau, prob_gumbel_softmax=prob, prob_multinomial_soft=prob,
+                     keep_all_steps=True)
     return torch.stack(free.tokens_raw, 1)
 
 
@@ -112,6 +128,86 @@ def test_joint_st_speaker_turn(mode, varlen, dropout, tau):
     _check_grads(model, ref, f"st-{mode}")
     out = model.loss()
     assert "vse_contrastive" in out
+
+
+@pytest.mark.parametrize("mode,varlen,dropout,tau,prob,seed", [
+    ("gumbel_softmax", True, True, 0.75, 0.25, 131),
+    ("multinomial_soft", False, True, 1.0, 0.5, 131),
+    ("multinomial_soft", True, False, 0.75, 0.25, 131),     # unnormalised y = exp(lp / tau)
+    ("gumbel_softmax", False, False, 1.0, 0.0, 131),        # prob 0: every row stays soft
+    # seed 131 of this case: every tensor <= 5e-3 except the attention-score parameters (ctx2att,
+    # h2att, alpha_net; gradient norms 100x below the rest, 12 rows x 3 steps of averaging) at 3.1e-2
+    ("multinomial_soft", True, False, 1.0, 0.25, 137),
+    ("multinomial_soft", False, True, 0.75, 0.25, 131),
+    ("gumbel_softmax", True, False, 0.75, 0.25, 131),
+])
+def test_joint_partial_sampling_speaker_turn(mode, varlen, dropout, tau, prob, seed):
+    """gumbel_softmax / multinomial_soft (gumbel_softmax.py:17-42, multinomial_soft.py:5-35): the
+    emitted vectors feed both the listener and the next input, so the gradient of the logits has
+    two sources."""
+    model, Ps, Pl, batch, noise, cfg = _build(mode, 12, 8, seed, varlen=varlen, dropout=dropout,
+                                              tau=tau, prob_gumbel_softmax=prob,
+                                              prob_multinomial_soft=prob)
+    forced = _replay_tokens(Ps, batch, noise, mode, cfg.drop_p, tau, prob=prob)
+    model.caption_generator.forced_tokens = forced.cuda()
+    model.vse.keep_passes = True
+    fc, labels, masks, data, att, am = _cuda_batch(batch)
+    loss = model(fc, labels, masks, data, att, am, is_alternating=True, alternating_turn="speaker")
+    loss.backward()
+    sp = model.caption_generator._passes[0]
+    rn = branch_replay(sp, batch.att_masks, noise)
+    # soft rows emit near-identical vectors (no noise in multinomial_soft), so their caption
+    # embeddings nearly tie as hardest negatives: replay the kernel's arg-max like the other
+    # non-smooth decisions and check it only differs from the oracle's at near-ties
+    hr = hinge_replay_of(model.vse._passes[0])
+    Pso = {k: v.clone().requires_grad_(True) for k, v in Ps.items()}
+    Plo = {k: v.clone().requires_grad_(True) for k, v in Pl.items()}
+    loss_ref, res, _, _ = OJ.st_joint_loss(Pso, Plo, batch.fc_feats, batch.att_feats,
+                                           batch.att_masks, rn, cfg, forced, hinge_replay=hr)
+    ref = _oracle_grads(loss_ref, Pso, Plo)
+    print(check_near_ties(rn, batch.att_masks, NEAR_TIE))
+    print(check_hinge_near_ties(hr))
+    # the emitted vectors themselves (bf16 storage): value parity on the steps the oracle ran
+    n = res.one_hots.size(1)
+    v = sp.t["soft16"][:n].float().transpose(0, 1).cpu()
+    ref_v = res.one_hots[:, :, : v.size(2)].detach()
+    assert float((v - ref_v).abs().max()) <= 1e-2, float((v - ref_v).abs().max())
+    sel = sp.t["ps_sel"][:n].t().cpu().bool()
+    assert bool((sel == (noise.part_u[:n].t() < prob)).all())
+    assert abs(float(loss) - float(loss_ref)) <= LOSS_TOL * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    _check_grads(model, ref, f"ps-{mode}")
+
+
+def test_partial_sampling_dense_boundary():
+    """speaker.sample(use_one_hot=1) in a partial-sampling mode returns (word_index, soft_vecs,
+    logprobs) (AttModel.py:448-452); vse(soft_vecs) embeds them with the dense contraction
+    (VSEFCModel.py:102-104).  Loss and gradients match the fused joint node."""
+    model, Ps, Pl, batch, noise, cfg = _build("gumbel_softmax", 8, 5, 171, varlen=False, dropout=True,
+                                              prob_gumbel_softmax=0.5)
+    forced = _replay_tokens(Ps, batch, noise, "gumbel_softmax", cfg.drop_p, 1.0, prob=0.5)
+    spk, lis = model.caption_generator, model.vse
+    spk.forced_tokens = forced.cuda()
+    fc, labels, masks, data, att, am = _cuda_batch(batch)
+    loss_f = model(fc, labels, masks, data, att, am, is_alternating=True, alternating_turn="speaker")
+    loss_f.backward()
+    g_fused = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    word_index, soft_vecs, logprobs = spk.sample(fc, att, am, {"sample_max": 0, "temperature": 1,
+                                                               "use_one_hot": 1})
+    B, V = word_index.size(0), spk.vocab_size
+    assert soft_vecs.shape == (B, word_index.size(1), V + 2)
+    _masks = torch.cat([torch.ones(B, 2, device="cuda"), (word_index > 0).float()[:, :-1]], 1)
+    bos = torch.zeros(B, 1, V + 2, device="cuda")
+    bos[:, 0, V + 1] = 1.0
+    _seqs = torch.cat([bos, soft_vecs], 1)
+    loss_d = lis(fc, att, _seqs, _masks) * model.retrieval_reward_weight
+    loss_d.backward()
+    assert abs(float(loss_d) - float(loss_f)) <= 1e-3 * abs(float(loss_f)), (float(loss_d), float(loss_f))
+    for n, p in model.named_parameters():
+        a, b = p.grad.double().flatten(), g_fused[n].double().flatten()
+        if float(b.norm()) == 0:
+            continue
+        assert float((a - b).norm() / b.norm()) <= 2e-2, n
 
 
 def test_mle_step():
