@@ -40,8 +40,9 @@ def build_case(meta: Dict):
     noise = synth.make_noise(
         dims, rows, regions, seed + 3, dropout=meta["dropout"],
         gumbel=mode in ("gumbel", "gumbel_softmax"),
-        multinomial=mode in ("multinomial", "multinomial_soft", "reinforce"),
-        partial=mode in ("gumbel_softmax", "multinomial_soft"))
+        multinomial=mode in ("multinomial", "multinomial_soft", "reinforce") or
+        meta.get("ss_prob", 0.0) > 0 or meta["kind"] == "decode",
+        partial=mode in ("gumbel_softmax", "multinomial_soft"), sched=meta.get("ss_prob", 0.0) > 0)
     noise2 = synth.make_noise(dims, rows, regions, seed + 4, dropout=meta["dropout"])
     kind = meta["kind"]
     cfg = OJ.JointCfg(
@@ -62,9 +63,20 @@ def run_oracle(meta: Dict, forced_tokens=None, keep_all_steps=False):
     Plo = {k: v.clone().requires_grad_(True) for k, v in Pl.items()}
     kind, mode = meta["kind"], meta["mode"]
     out = {}
+    if kind == "decode":
+        from . import speaker as OS
+        with torch.no_grad():
+            res = OS.sample(Ps, batch.att_feats, batch.att_masks, mode=mode,
+                            seq_length=dims.seq_length, vocab_size=dims.vocab_size, noise=noise,
+                            drop_p=cfg.drop_p, sample_max=meta["sample_max"], use_one_hot=0,
+                            temperature=meta["tau"],
+                            decoding_constraint=meta.get("decoding_constraint", 0))
+        return dict(seq=res.seq, logprobs=res.logprobs, grads={})
     if kind == "mle":
+        fed = []
         loss = OJ.mle_loss(Pso, batch.att_feats, batch.att_masks, batch.labels, batch.masks,
-                           noise, cfg)
+                           noise, cfg, ss_prob=meta.get("ss_prob", 0.0), fed_out=fed)
+        out["fed"] = torch.stack(fed, 1)
     elif kind == "listener_turn":
         loss, res, _ = OJ.listener_turn_loss(Pso, Plo, batch.fc_feats, batch.att_feats,
                                              batch.att_masks, noise, cfg, forced_tokens,

@@ -67,9 +67,11 @@ def st_joint_loss(Ps, Pl, fc_feats, att_feats, att_masks, noise: S.SpeakerNoise,
     return loss, res, masks, loss_vse
 
 
-def mle_loss(Ps, att_feats, att_masks, seq, masks, noise, cfg: JointCfg):
+def mle_loss(Ps, att_feats, att_masks, seq, masks, noise, cfg: JointCfg, ss_prob: float = 0.0,
+             forced_fed=None, fed_out=None):
     """ce_loss -> AttModel.forward                           (AlternatingJointModel.py:196-207)"""
-    return S.forward_xe(Ps, att_feats, att_masks, seq, masks, noise=noise, drop_p=cfg.drop_p)
+    return S.forward_xe(Ps, att_feats, att_masks, seq, masks, noise=noise, drop_p=cfg.drop_p,
+                        ss_prob=ss_prob, forced_fed=forced_fed, fed_out=fed_out)
 
 
 def vse_gt_loss(Pl, fc_feats, seq, masks, cfg: JointCfg):

@@ -36,6 +36,7 @@ class SpeakerNoise:
     U          uniforms [T, B, V+1] turned into Gumbel noise                       (gumbel.py:6-11)
     E          Exp(1) draws [T, B, V+1]; torch.multinomial(p,1) == argmax(p / E)   (multinomial.py:17)
     part_u     uniforms [T, B] for the partial-sampling variants                   (gumbel_softmax.py:31)
+    ss_u       uniforms [T, B] for scheduled sampling in AttModel.forward          (AttModel.py:119-120)
     Any entry may be None -> that source of randomness is off (dropout) or unused.
     """
     drop_att: Optional[torch.Tensor] = None
@@ -44,6 +45,7 @@ class SpeakerNoise:
     U: Optional[torch.Tensor] = None
     E: Optional[torch.Tensor] = None
     part_u: Optional[torch.Tensor] = None
+    ss_u: Optional[torch.Tensor] = None          # uniforms [T, B] of scheduled sampling (AttModel.py:119-120)
     # --- branch replay (test aid, like forced_tokens): decisions of the non-smooth ops taken from
     # the implementation under test, so that a near-tie flip (bf16 vs fp32 pre-activations) does
     # not masquerade as a gradient error.  None -> the oracle decides itself (reference behaviour).
@@ -206,13 +208,14 @@ def sample(P: Params, att_feats, att_masks, *, mode: str, seq_length: int, vocab
            noise: SpeakerNoise, drop_p: float = 0.0, sample_max: int = 1, use_one_hot: int = 0,
            temperature: float = 1.0, gumbel_temp: float = 1.0, multinomial_temp: float = 1.0,
            prob_gumbel_softmax: float = 1.0, prob_multinomial_soft: float = 1.0,
-           forced_tokens: Optional[torch.Tensor] = None, keep_all_steps: bool = False
-           ) -> SampleResult:
+           forced_tokens: Optional[torch.Tensor] = None, keep_all_steps: bool = False,
+           decoding_constraint: int = 0) -> SampleResult:
     """mode = retrieval_reward in {'reinforce','gumbel','multinomial','gumbel_softmax',
     'multinomial_soft'}.  `forced_tokens` [B, T] (optional, test aid) replaces the sampled id at
     each step so that a near-tie flip in one implementation cannot cascade; the id the oracle
     would have drawn is still recorded in `tokens_raw`.  `keep_all_steps` disables the early
-    `break` (the CUDA path always runs all steps and slices afterwards)."""
+    `break` (the CUDA path always runs all steps and slices afterwards).  `decoding_constraint`
+    (index outputs only): the previously emitted id gets logit -inf (:437-442)."""
     B = att_feats.size(0)
     V1 = vocab_size + 1
     att_e, p_att = prologue(P, att_feats, att_masks, noise, drop_p)           # :315-319
@@ -298,7 +301,10 @@ def sample(P: Params, att_feats, att_masks, *, mode: str, seq_length: int, vocab
             else noise.maxout_first[t]
         out, h, c, _ = core_step(P, xt, h, c, att_e, p_att, att_masks, keep_c, drop_p, mf,
                                  noise.margins)                                         # :436
-        logprobs = F.log_softmax(logits_of(P, out), dim=1)                    # :444
+        z = logits_of(P, out)
+        if decoding_constraint and len(seq) > 0:                              # :437-442
+            z = z + torch.zeros_like(z).scatter_(1, seq[-1][:, None], float("-inf"))
+        logprobs = F.log_softmax(z, dim=1)                                    # :444
         res.step_logprobs.append(logprobs)
         res.n_steps += 1
     if len(seq) == 0:
@@ -328,9 +334,13 @@ def language_model_criterion(logp, target, mask):
 
 
 def forward_xe(P: Params, att_feats, att_masks, seq, masks, *, noise: SpeakerNoise,
-               drop_p: float = 0.0, return_logprobs: bool = False):
-    """ss_prob = 0 path of AttModel.forward: step i feeds seq[:, i]; stops at the first i >= 1
-    whose whole column is 0 (:133); loss over seq[:,1:], masks[:,1:] (:144)."""
+               drop_p: float = 0.0, return_logprobs: bool = False, ss_prob: float = 0.0,
+               forced_fed: Optional[torch.Tensor] = None, fed_out: Optional[list] = None):
+    """AttModel.forward: step i feeds seq[:, i] -- or, with scheduled sampling (ss_prob > 0, training,
+    i >= 1; :118-131), on rows with ss_u[i-1] < ss_prob the id drawn from exp(outputs[i-1]) by
+    torch.multinomial (== argmax(p / E[i-1]), no gradient through it); stops at the first i >= 1
+    whose whole ground-truth column is 0 (:133); loss over seq[:,1:], masks[:,1:] (:144).
+    `forced_fed` [B, steps] (test aid) replaces the drawn ids; `fed_out` collects the fed ids."""
     B = att_feats.size(0)
     att_e, p_att = prologue(P, att_feats, att_masks, noise, drop_p)
     h = att_feats.new_zeros(B, P["core.h2h.weight"].size(1))
@@ -338,8 +348,17 @@ def forward_xe(P: Params, att_feats, att_masks, seq, masks, *, noise: SpeakerNoi
     outputs = []
     for i in range(seq.size(1) - 1):                                          # :116
         it = seq[:, i]
+        if i >= 1 and ss_prob > 0.0:                                          # :118-129
+            sel = noise.ss_u[i - 1] < ss_prob
+            if forced_fed is not None:      # (a draw made right before the :133 break is never fed)
+                drawn = forced_fed[:, i] if i < forced_fed.size(1) else seq[:, i]
+            else:
+                drawn = (torch.exp(outputs[-1].detach()) / noise.E[i - 1]).max(dim=1)[1]
+            it = torch.where(sel, drawn, seq[:, i])
         if i >= 1 and int(seq[:, i].sum()) == 0:                              # :133
             break
+        if fed_out is not None:
+            fed_out.append(it.clone())
         keep_e = None if noise.drop_embed is None else noise.drop_embed[i]
         keep_c = None if noise.drop_core is None else noise.drop_core[i]
         xt = embed_tokens(P, it, keep_e, drop_p)                              # :136

@@ -111,7 +111,7 @@ def make_batch(d: Dims, rows: int, regions: int, seed: int, varlen: bool = False
 
 def make_noise(d: Dims, rows: int, regions: int, seed: int, *, dropout: bool = True,
                gumbel: bool = False, multinomial: bool = False, partial: bool = False,
-               steps: Optional[int] = None) -> SpeakerNoise:
+               steps: Optional[int] = None, sched: bool = False) -> SpeakerNoise:
     g = torch.Generator().manual_seed(seed)
     T = d.seq_length
     steps = steps if steps is not None else T + 1
@@ -126,4 +126,6 @@ def make_noise(d: Dims, rows: int, regions: int, seed: int, *, dropout: bool = T
         n.E = torch.empty(T, rows, d.vocab_size + 1).exponential_(generator=g)
     if partial:
         n.part_u = torch.rand(T, rows, generator=g)
+    if sched:                      # drawn last: the other streams keep their values
+        n.ss_u = torch.rand(T + 1, rows, generator=g)
     return n

@@ -108,8 +108,9 @@ class Inject:
 
         def uniform_(tensor, *a, **k):
             n = inj.noises[max(inj.cur, 0)]
-            if n.part_u is not None and tensor.dim() == 1 and tensor.numel() == inj.rows:
-                tensor.copy_(n.part_u[inj.t_part])
+            u = n.part_u if n.part_u is not None else n.ss_u      # scheduled sampling (AttModel.py:119)
+            if u is not None and tensor.dim() == 1 and tensor.numel() == inj.rows:
+                tensor.copy_(u[inj.t_part])
                 inj.t_part += 1
                 return tensor
             return orig_uniform(tensor, *a, **k)
@@ -165,14 +166,16 @@ def compare(tag, a, b, rtol=2e-4, atol=2e-6):
 
 
 def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dropout=True,
-             baseline="gt", weight=0.01, seed=0, eos_bias=0.0, prob=0.25):
+             baseline="gt", weight=0.01, seed=0, eos_bias=0.0, prob=0.25, ss_prob=0.0,
+             sample_max=0, decoding_constraint=0):
     Ps = synth.speaker_params(dims, seed=seed, eos_bias=eos_bias)
     Pl = synth.listener_params(dims, seed=seed + 1)
     batch = synth.make_batch(dims, rows, regions, seed=seed + 2, varlen=varlen, min_regions=2)
     need_g = mode in ("gumbel", "gumbel_softmax")
-    need_m = mode in ("multinomial", "multinomial_soft", "reinforce")
+    need_m = mode in ("multinomial", "multinomial_soft", "reinforce") or ss_prob > 0 or kind == "decode"
     noise = synth.make_noise(dims, rows, regions, seed + 3, dropout=dropout, gumbel=need_g,
-                             multinomial=need_m, partial=mode.endswith("soft") or mode == "gumbel_softmax")
+                             multinomial=need_m, partial=mode.endswith("soft") or mode == "gumbel_softmax",
+                             sched=ss_prob > 0)
     noise2 = synth.make_noise(dims, rows, regions, seed + 4, dropout=dropout)
     drop_p = 0.5 if dropout else 0.0
     cfg = OJ.JointCfg(vocab_size=dims.vocab_size, seq_length=dims.seq_length, drop_p=drop_p,
@@ -197,7 +200,28 @@ def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dro
         return out
 
     model.caption_generator.sample = rec_sample
+    model.caption_generator.ss_prob = ss_prob
     out = {}
+    meta = dict(name=name, dims=asdict(dims), rows=rows, regions=regions, varlen=varlen, mode=mode,
+                kind=kind, tau=tau, dropout=dropout, baseline=baseline, weight=weight, seed=seed,
+                eos_bias=eos_bias, prob=prob, ss_prob=ss_prob, sample_max=sample_max,
+                decoding_constraint=decoding_constraint)
+    if kind == "decode":
+        # AttModel.sample with index outputs (eval_utils.py:187 style call), optional constraint
+        from oracle import cases as OC
+        with Inject(ref, [noise, noise2], rows, batch.att_masks), torch.no_grad():
+            seq, lp = orig_sample(batch.fc_feats, batch.att_feats, batch.att_masks,
+                                  {"sample_max": sample_max, "temperature": tau,
+                                   "decoding_constraint": decoding_constraint})
+        o = OC.run_oracle(meta)
+        compare(name + ".seq", o["seq"], seq)
+        compare(name + ".logprobs", o["logprobs"], lp)
+        blob = {"meta": np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8),
+                "out.seq": seq.numpy(), "out.logprobs": lp.numpy()}
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+        rep = int((seq[:, 1:] == seq[:, :-1])[seq[:, 1:] > 0].sum())
+        print(f"[golden] {name:34s} decode tokens={int(seq.numel())} repeats={rep} OK")
+        return
     with Inject(ref, [noise, noise2], rows, batch.att_masks):
         if kind == "mle":
             loss = model(batch.fc_feats, batch.labels, batch.masks, {}, batch.att_feats,
@@ -222,8 +246,13 @@ def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dro
     # ---- oracle on the same tensors ---------------------------------------------------------
     Pso, Plo = leaf(Ps), leaf(Pl)
     if kind == "mle":
+        fed = []
         o_loss = OJ.mle_loss(Pso, batch.att_feats, batch.att_masks, batch.labels, batch.masks,
-                             noise, cfg)
+                             noise, cfg, ss_prob=ss_prob, fed_out=fed)
+        out["fed"] = torch.stack(fed, 1)       # oracle's own record (the reference does not expose it)
+        if ss_prob > 0:
+            swapped = int((out["fed"][:, 1:] != batch.labels[:, 1: out["fed"].size(1)]).sum())
+            assert swapped > 0, "scheduled sampling never replaced an input: pick another seed"
     elif kind == "listener_turn":
         o_loss, res, _ = OJ.listener_turn_loss(Pso, Plo, batch.fc_feats, batch.att_feats,
                                                batch.att_masks, noise, cfg)
@@ -246,9 +275,6 @@ def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dro
     for k in ref_grads:
         compare(f"{name}.grad[{k}]", o_grads[k], ref_grads[k], rtol=5e-4, atol=1e-7)
 
-    meta = dict(name=name, dims=asdict(dims), rows=rows, regions=regions, varlen=varlen, mode=mode,
-                kind=kind, tau=tau, dropout=dropout, baseline=baseline, weight=weight, seed=seed,
-                eos_bias=eos_bias, prob=prob)
     blob = {"meta": np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)}
     for k, v in out.items():
         blob["out." + k] = v.numpy()
@@ -286,6 +312,14 @@ CASES = [
     ("tiny_listener_turn", synth.TINY, dict(rows=6, regions=5, varlen=False, mode="reinforce",
                                             kind="listener_turn", seed=90)),
     ("tiny_mle", synth.TINY, dict(rows=6, regions=5, varlen=True, mode="gumbel", kind="mle", seed=100)),
+    ("tiny_mle_sched_sampling", synth.TINY, dict(rows=6, regions=5, varlen=True, mode="gumbel", kind="mle",
+                                                 seed=110, ss_prob=0.5)),
+    ("tiny_decode_constraint_greedy", synth.TINY, dict(rows=6, regions=5, varlen=True, mode="reinforce",
+                                                       kind="decode", seed=120, sample_max=1,
+                                                       decoding_constraint=1, dropout=False)),
+    ("tiny_decode_constraint_sampled", synth.TINY, dict(rows=6, regions=5, varlen=False, mode="reinforce",
+                                                        kind="decode", seed=130, sample_max=0, tau=0.5,
+                                                        decoding_constraint=1)),
     ("real_gumbel_b4", synth.Dims(), dict(rows=4, regions=6, varlen=True, mode="gumbel",
                                           kind="speaker_turn", seed=200, eos_bias=6.0)),
     ("real_mle_b4", synth.Dims(), dict(rows=4, regions=6, varlen=False, mode="gumbel", kind="mle",

@@ -65,6 +65,44 @@ def test_greedy_decode_is_bit_exact_off_near_ties(B, L, varlen):
     assert exact >= B          # at least the first token of every row
 
 
+def test_decoding_constraint_bans_the_previous_word():
+    """AttModel.sample with opt['decoding_constraint'] = 1 (AttModel.py:437-442): the logit of the
+    previously emitted id is -inf.  Greedy ids bit-exact against the oracle off near-ties, no
+    immediate repeats, and the same weights without the constraint do repeat (so it is active)."""
+    d = REAL
+    B, L = 12, 5
+    m, Ps, _ = _models(B, 85, eos_bias=-8.0)
+    m.eval()
+    batch = synth.make_batch(d, B, L, 87, varlen=True, min_regions=1)
+    ref = OS.sample(Ps, batch.att_feats, batch.att_masks, mode="reinforce", seq_length=d.seq_length,
+                    vocab_size=d.vocab_size, noise=OS.SpeakerNoise(), drop_p=0.0, sample_max=1,
+                    keep_all_steps=True, decoding_constraint=1)
+    fc, att, am = batch.fc_feats.cuda(), batch.att_feats.cuda(), batch.att_masks.cuda()
+    with torch.no_grad():
+        seq, logp = m.sample(fc, att, am, {"sample_max": 1, "decoding_constraint": 1})
+        free, _ = m.sample(fc, att, am, {"sample_max": 1})
+    seq, logp, free = seq.cpu(), logp.cpu(), free.cpu()
+    rep = lambda s: int(((s[:, 1:] == s[:, :-1]) & (s[:, 1:] > 0)).sum())
+    assert rep(seq) == 0
+    assert rep(free) > 0, "the unconstrained decode has no repeats: the case does not exercise the ban"
+    ref_raw = torch.stack(ref.tokens_raw, 1)
+    exact = 0
+    for b in range(B):
+        for t in range(seq.shape[1]):
+            want = int(ref_raw[b, t])
+            if int(seq[b, t]) != want:
+                top2 = ref.step_logprobs[t][b].topk(2)[0]
+                assert float(top2[0] - top2[1]) < 5e-3, (b, t, float(top2[0] - top2[1]))
+                break
+            exact += 1
+            ref_lp = float(ref.step_logprobs[t][b, want])
+            assert abs(float(logp[b, t]) - ref_lp) <= 2e-2 * abs(ref_lp)
+            if want == 0:
+                break
+    print(f"constrained greedy decode: {exact} tokens bit-exact, {rep(free)} repeats without the ban")
+    assert exact >= 4 * B
+
+
 @pytest.mark.parametrize("only,whole_batch", [("off", False), ("image", False), ("caption", True),
                                               ("off", True)])
 def test_listener_variants(only, whole_batch):

@@ -227,6 +227,49 @@ def test_mle_step():
     assert abs(float(model.loss()["cap_xe"]) - float(loss_ref)) <= LOSS_TOL * abs(float(loss_ref))
 
 
+def test_mle_step_with_scheduled_sampling():
+    """AttModel.forward with ss_prob > 0 (AttModel.py:118-131): rows with u < ss_prob are fed the id
+    drawn from the previous step's distribution (torch.multinomial == exponential race on the
+    injected E) instead of the ground truth; the XE target stays the ground truth."""
+    model, Ps, Pl, batch, noise, cfg = _build("gumbel", 10, 6, 43, varlen=True, dropout=True,
+                                              caption_loss_weight=1.0, retrieval_reward_weight=0.0)
+    d = REAL
+    extra = synth.make_noise(d, 10, 6, 47, dropout=False, multinomial=True, sched=True)
+    noise.E, noise.ss_u = extra.E, extra.ss_u
+    spk = model.caption_generator
+    spk.ss_prob = 0.4
+    spk.injected.noise = noise.E.cuda().contiguous()
+    spk.injected.ss_u = noise.ss_u.cuda().contiguous()
+    fc, labels, masks, data, att, am = _cuda_batch(batch)
+    loss = model(fc, labels, masks, data, att, am)
+    loss.backward()
+    sp = spk._passes[0]
+    n = sp.n_steps
+    fed = sp.t["tok_fed"][:n].t().cpu()                                  # what the CUDA pass fed
+    swapped = int((fed[:, 1:] != batch.labels[:, 1:n]).sum())
+    assert swapped > 0
+    rn = branch_replay(sp, batch.att_masks, noise)
+    # the oracle's own draws (free run) agree with the kernel's; the graded run replays them
+    own = []
+    OJ.mle_loss(Ps, batch.att_feats, batch.att_masks, batch.labels, batch.masks, rn, cfg,
+                ss_prob=0.4, forced_fed=fed, fed_out=own)
+    free = []
+    with torch.no_grad():
+        OJ.mle_loss(Ps, batch.att_feats, batch.att_masks, batch.labels, batch.masks, noise, cfg,
+                    ss_prob=0.4, fed_out=free)
+    free = torch.stack(free, 1)
+    agree = float((free == fed[:, : free.size(1)]).float().mean())
+    print(f"scheduled sampling: {swapped} inputs replaced, free-run agreement {agree:.4f}")
+    assert agree >= 0.97           # a near-tie flip of one draw changes the rest of that row only
+    Pso = {k: v.clone().requires_grad_(True) for k, v in Ps.items()}
+    Plo = {k: v.clone().requires_grad_(True) for k, v in Pl.items()}
+    loss_ref = OJ.mle_loss(Pso, batch.att_feats, batch.att_masks, batch.labels, batch.masks, rn, cfg,
+                           ss_prob=0.4, forced_fed=fed)
+    ref = _oracle_grads(loss_ref, Pso, Plo)
+    assert abs(float(loss) - float(loss_ref)) <= LOSS_TOL * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    _check_grads(model, ref, "mle-ss")
+
+
 @pytest.mark.parametrize("baseline", ["gt", "greedy", "none"])
 def test_reinforce_speaker_turn(baseline):
     model, Ps, Pl, batch, noise, cfg = _build("reinforce", 10, 6, 51, varlen=False, dropout=False,
