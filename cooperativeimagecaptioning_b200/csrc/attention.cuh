@@ -1,14 +1,14 @@
 // Additive attention over packed region features (AttModel.py:465-489), forward / per-step
 // backward / deferred region-gradient accumulation.
 //
-// All three kernels are HBM-bound streams over the region tensors of one batch row per CTA:
-// chunks of 8 regions (8 x AR bf16 = 8 KB per tensor) are brought into shared memory by TMA bulk
-// copies (cp.async.bulk + mbarrier transaction counts) through a multi-stage ring, so the copy
-// engine keeps several KB per CTA in flight while the warps compute on the previous chunk.
+// All three kernels are streams over the packed region tensors:
 //   forward : one pass over (p_att, att_e) with an online softmax (running max / sum / weighted sum)
 //   backward: pass 1 over att_e (dw_l = <d_att_res, att_e_l>), softmax backward, pass 2 over p_att
 //             (d_att_h = alpha * sum_l de_l (1 - tanh^2))
-//   deferred: one pass over p_att for all steps at once (d_p_att, d_att_e, alpha / bias partials)
+//   deferred: one pass over p_att for all steps at once (d_p_att, d_att_e, alpha / bias partials),
+//             one CTA per row, 8-region chunks through a TMA bulk-copy ring
+// forward / backward run once per decode step: persistent CTAs, two warps per row, per-warp
+// cp.async rings (see the v4 note below).
 #pragma once
 #include "common.cuh"
 #include "speaker_kernels.cuh"
@@ -32,242 +32,361 @@ __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
 }
 
 // ------------------------------------------------------------------------------------------
-// forward
+// v4: one persistent CTA per SM, 16 warps, TWO WARPS PER ROW (each takes half of the row's
+// regions).  Every warp owns a private 3-stage cp.async ring (16-byte pieces per lane, 12 KB) and
+// refills a stage right after consuming it, so ~190 KB of region data stay in flight per SM with
+// no block-wide barrier anywhere; the two half-row states meet once through a 64-thread named
+// barrier.  (Measured on B200: per-warp cp.async.bulk copies of 2 KB are issue-rate bound at
+// 2.2 TB/s, 4 KB at 3.6 TB/s; plain 16-byte streams reach 4.4-4.6 TB/s on this 117 MB read.)
 // ------------------------------------------------------------------------------------------
-template <int AR, int STAGES>
-__global__ void __launch_bounds__(ATT_THREADS)
-attention_fwd2_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bfloat16* __restrict__ att_e16,
-                      const int* __restrict__ off, int Lfix, const float* __restrict__ s_row0,
-                      int64_t lds, int att_h_col, const float* __restrict__ w_alpha,
-                      __nv_bfloat16* __restrict__ att_res16, float* __restrict__ att_w) {
-  static_assert(AR == 2 * ATT_THREADS, "thread -> 2 columns mapping");
-  constexpr int EPL = AR / 32;                    // score elements per lane (16)
-  constexpr int CHUNK_BYTES = ATT_CH * AR * 2;    // one tensor, one chunk
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* stages = smem;                                             // [STAGES][2][CHUNK_BYTES]
-  float* s_e = reinterpret_cast<float*>(smem + STAGES * 2 * CHUNK_BYTES);   // [Lb] scores
-  const int b = blockIdx.x;
-  const int r0 = off ? off[b] : b * Lfix;
-  const int Lb = off ? off[b + 1] - r0 : Lfix;
-  float* s_ce = s_e + ((Lb + 7) & ~7);                                // [ATT_CH]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ce + ATT_CH);        // [STAGES]
+constexpr int ATT4_WARPS = 16;
+constexpr int ATT4_ROWS = ATT4_WARPS / 2;
+constexpr int ATT4_THREADS = ATT4_WARPS * 32;
+constexpr int ATT4_STAGES = 3;
+constexpr int ATT4_STAGE_BYTES = 4096;
+constexpr int ATT4_SMEM = ATT4_WARPS * ATT4_STAGES * ATT4_STAGE_BYTES + ATT4_WARPS * ATT4_STAGES * 8 +
+                          ATT4_WARPS * 8;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void pair_barrier(int pair) {
+  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+
+// Row -> warp mapping shared by both v4 kernels.  Rows are dealt by rank: `order` lists the rows
+// by decreasing region count (NULL = identity), rank i goes to CTA i % grid, pair slot
+// (i / grid) % 8, so every SM gets the same mix of long and short rows.  Pair slot k is served by
+// warps k and 15 - k: with the slots of one CTA sorted by length this also equalises the four
+// warp schedulers (warp % 4).
+struct Att4Map {
+  int pair, half;
+  __device__ __forceinline__ Att4Map(int warp) : pair(warp < 8 ? warp : 15 - warp), half(warp >> 3) {}
+};
+
+template <int AR>
+__global__ void __launch_bounds__(ATT4_THREADS, 1)
+attention_fwd4_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bfloat16* __restrict__ att_e16,
+                      const int* __restrict__ off, int Lfix, const int* __restrict__ order,
+                      const float* __restrict__ s_row0, int64_t lds, int att_h_col,
+                      const float* __restrict__ w_alpha, __nv_bfloat16* __restrict__ att_res16,
+                      float* att_w, int B, int dbg_skip) {
+  static_assert(AR == 512, "lane -> 2 x 8 columns mapping; one region row = 1 KB");
+  constexpr int EPL = AR / 32;
+  constexpr int ROWB = AR * 2;                    // bytes of one region row
+  extern __shared__ __align__(128) uint8_t smem4[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nch = (Lb + ATT_CH - 1) / ATT_CH;
-  const __nv_bfloat16* pg = p_att16 + int64_t(r0) * AR;
-  const __nv_bfloat16* eg = att_e16 + int64_t(r0) * AR;
-
+  const Att4Map map(warp);
+  const int half = map.half;
+  const int partner = 15 - warp;
+  uint8_t* ring = smem4 + warp * (ATT4_STAGES * ATT4_STAGE_BYTES);
   pdl_launch_dependents();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
-    fence_barrier_init();
-  }
-  __syncthreads();
-  pdl_wait();
-  auto issue = [&](int c) {
-    const int st = c % STAGES;
-    const int rows = min(ATT_CH, Lb - c * ATT_CH);
-    const uint32_t bytes = uint32_t(rows) * AR * 2;
-    mbar_expect_tx(&bars[st], 2 * bytes);
-    bulk_load_1d(stages + (st * 2 + 0) * CHUNK_BYTES, pg + int64_t(c) * ATT_CH * AR, bytes, &bars[st]);
-    bulk_load_1d(stages + (st * 2 + 1) * CHUNK_BYTES, eg + int64_t(c) * ATT_CH * AR, bytes, &bars[st]);
-  };
-  if (threadIdx.x == 0)
-    for (int c = 0; c < min(STAGES, nch); ++c) issue(c);
-
-  // per-lane slices of att_h and alpha for the score phase: columns lane*8.. and AR/2 + lane*8..
   float ah[EPL], al[EPL];
-  {
-    const float* att_h = s_row0 + int64_t(b) * lds + att_h_col;
 #pragma unroll
-    for (int h = 0; h < EPL / 8; ++h)
+  for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int col = h * 256 + lane * 8 + j;
-        ah[h * 8 + j] = att_h[col];
-        al[h * 8 + j] = __ldg(w_alpha + col);
+    for (int j = 0; j < 8; ++j) al[h * 8 + j] = __ldg(w_alpha + h * 256 + lane * 8 + j);
+  pdl_wait();
+  uint32_t it = 0;                                // ring items consumed so far (stage index)
+  for (int rank = blockIdx.x + gridDim.x * map.pair; rank < B; rank += gridDim.x * ATT4_ROWS) {
+    const int b = order ? order[rank] : rank;
+    const int r0 = off ? off[b] : b * Lfix;
+    const int Lb = off ? off[b + 1] - r0 : Lfix;
+    const int n0 = (Lb + 1) >> 1;
+    const int a0 = half ? n0 : 0;                 // this warp: regions [a0, a0 + n)
+    const int n = half ? Lb - n0 : n0;
+    const int npair = (n + 1) >> 1;
+    const __nv_bfloat16* pg = p_att16 + int64_t(r0 + a0) * AR;
+    const __nv_bfloat16* eg = att_e16 + int64_t(r0 + a0) * AR;
+    // one ring item = a pair of regions: [p0 p1 e0 e1], 1 KB each; every lane copies 16-byte pieces
+    // (cp.async, L1 bypass) and EVERY call commits a group, so the wait depth below is static
+    auto issue = [&](int i) {
+      if (i < npair) {
+        uint8_t* dst = ring + ((it + i) % ATT4_STAGES) * ATT4_STAGE_BYTES;
+        const int pieces = min(2, n - 2 * i) * (ROWB / 512);      // 512-byte warp pieces per tensor
+        const uint8_t* ps = reinterpret_cast<const uint8_t*>(pg + int64_t(2 * i) * AR) + lane * 16;
+        const uint8_t* es = reinterpret_cast<const uint8_t*>(eg + int64_t(2 * i) * AR) + lane * 16;
+#pragma unroll
+        for (int k = 0; k < 2 * (ROWB / 512); ++k)
+          if (k < pieces) {
+            cp_async16(dst + k * 512 + lane * 16, ps + k * 512);
+            cp_async16(dst + 2 * ROWB + k * 512 + lane * 16, es + k * 512);
+          }
       }
-  }
-  float m = -INFINITY, sum = 0.f, acc0 = 0.f, acc1 = 0.f;
-  for (int c = 0; c < nch; ++c) {
-    const int st = c % STAGES;
-    mbar_wait(&bars[st], (c / STAGES) & 1);
-    const uint8_t* ps = stages + (st * 2 + 0) * CHUNK_BYTES;
-    const uint8_t* es = stages + (st * 2 + 1) * CHUNK_BYTES;
-    const int rows = min(ATT_CH, Lb - c * ATT_CH);
-    // scores: warp w -> region c*8 + w
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < ATT4_STAGES; ++i) issue(i);
     {
-      float e = -INFINITY;
-      if (warp < rows) {
-        float a = 0.f;
+      const float* att_h = s_row0 + int64_t(b) * lds + att_h_col;
 #pragma unroll
-        for (int h = 0; h < EPL / 8; ++h) {
-          const uint4 u = *reinterpret_cast<const uint4*>(ps + warp * (AR * 2) + (h * 256 + lane * 8) * 2);
-          float f[8];
-          bf16x8_to_float(u, f);
+      for (int h = 0; h < 2; ++h) {
+        const float4 x = *reinterpret_cast<const float4*>(att_h + h * 256 + lane * 8);
+        const float4 y = *reinterpret_cast<const float4*>(att_h + h * 256 + lane * 8 + 4);
+        ah[h * 8 + 0] = x.x; ah[h * 8 + 1] = x.y; ah[h * 8 + 2] = x.z; ah[h * 8 + 3] = x.w;
+        ah[h * 8 + 4] = y.x; ah[h * 8 + 5] = y.y; ah[h * 8 + 6] = y.z; ah[h * 8 + 7] = y.w;
+      }
+    }
+    float m = -INFINITY, sum = 0.f, acc[EPL];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) a += al[h * 8 + j] * tanh_fast(f[j] + ah[h * 8 + j]);
+    for (int j = 0; j < EPL; ++j) acc[j] = 0.f;
+    float* wrow = att_w + r0 + a0;                // raw scores first, normalised in place below
+    for (int i = 0; i < npair; ++i) {
+      const int st = (it + i) % ATT4_STAGES;
+      cp_async_wait<ATT4_STAGES - 1>();           // this lane's pieces of item i have landed
+      __syncwarp();                               // ... and so have the other lanes'
+      const bool two = 2 * i + 1 < n;
+      const uint8_t* ps = ring + st * ATT4_STAGE_BYTES;
+      const uint8_t* es = ps + 2 * ROWB;
+      const int o1 = two ? ROWB : 0;              // a single-region stage re-reads region 0 (weight 0)
+      if (dbg_skip) {                             // TUNING PROBE: copies only, no math
+        sum += float(ps[lane]);
+        __syncwarp();
+        issue(i + ATT4_STAGES);
+        continue;
+      }
+      float sc0 = 0.f, sc1 = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint4 u0 = *reinterpret_cast<const uint4*>(ps + (h * 256 + lane * 8) * 2);
+        const uint4 u1 = *reinterpret_cast<const uint4*>(ps + o1 + (h * 256 + lane * 8) * 2);
+        float f0[8], f1[8];
+        bf16x8_to_float(u0, f0);
+        bf16x8_to_float(u1, f1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sc0 += al[h * 8 + j] * tanh_fast(f0[j] + ah[h * 8 + j]);
+          sc1 += al[h * 8 + j] * tanh_fast(f1[j] + ah[h * 8 + j]);
         }
-        e = warp_sum(a);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sc0 += __shfl_xor_sync(0xffffffffu, sc0, o);
+        sc1 += __shfl_xor_sync(0xffffffffu, sc1, o);
       }
       if (lane == 0) {
-        s_ce[warp] = e;
-        if (warp < rows) s_e[c * ATT_CH + warp] = e;
+        wrow[2 * i] = sc0;
+        if (two) wrow[2 * i + 1] = sc1;
+      }
+      const float nm = fmaxf(m, two ? fmaxf(sc0, sc1) : sc0);
+      const float scale = __expf(m - nm);         // exp(-inf) = 0 on the first pair
+      const float w0 = __expf(sc0 - nm), w1 = two ? __expf(sc1 - nm) : 0.f;
+      m = nm;
+      sum = sum * scale + w0 + w1;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint4 u0 = *reinterpret_cast<const uint4*>(es + (h * 256 + lane * 8) * 2);
+        const uint4 u1 = *reinterpret_cast<const uint4*>(es + o1 + (h * 256 + lane * 8) * 2);
+        float f0[8], f1[8];
+        bf16x8_to_float(u0, f0);
+        bf16x8_to_float(u1, f1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[h * 8 + j] = acc[h * 8 + j] * scale + w0 * f0[j] + w1 * f1[j];
+      }
+      __syncwarp();                               // every lane is done with this stage
+      issue(i + ATT4_STAGES);
+    }
+    it += npair;
+    cp_async_wait<0>();
+    // the ring is drained: its first 2 KB + 8 B carry this warp's partial state to the partner
+    float* part = reinterpret_cast<float*>(ring);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float* d = part + h * 256 + lane * 8;
+      *reinterpret_cast<float4*>(d) = make_float4(acc[h * 8], acc[h * 8 + 1], acc[h * 8 + 2], acc[h * 8 + 3]);
+      *reinterpret_cast<float4*>(d + 4) =
+          make_float4(acc[h * 8 + 4], acc[h * 8 + 5], acc[h * 8 + 6], acc[h * 8 + 7]);
+    }
+    if (lane == 0) { part[AR] = m; part[AR + 1] = sum; }
+    pair_barrier(map.pair);
+    const float* other = reinterpret_cast<const float*>(smem4 + partner * (ATT4_STAGES * ATT4_STAGE_BYTES));
+    const float m2 = other[AR], s2 = other[AR + 1];
+    const float M = fmaxf(m, m2);                 // the first half always holds >= 1 region
+    const float f1 = __expf(m - M), f2 = __expf(m2 - M);
+    const float inv = 1.f / (sum * f1 + s2 * f2);
+    {
+      const int c0 = half * 256 + lane * 8;       // this warp writes 256 of the 512 columns
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (f1 * part[c0 + j] + f2 * other[c0 + j]) * inv;
+      *reinterpret_cast<uint4*>(att_res16 + int64_t(b) * AR + c0) = float8_to_bf16x8(o);
+    }
+    for (int l = lane; l < n; l += 32) wrow[l] = __expf(wrow[l] - M) * inv;
+    // the partner must be done with this warp's partials before the next row's copies land on them
+    if (rank + gridDim.x * ATT4_ROWS < B) pair_barrier(map.pair);
+  }
+}
+
+template <int AR>
+__global__ void __launch_bounds__(ATT4_THREADS, 1)
+attention_bwd4_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bfloat16* __restrict__ att_e16,
+                      const int* __restrict__ off, int Lfix, const int* __restrict__ order,
+                      const float* __restrict__ s_row0, int64_t lds, int att_h_col,
+                      const float* __restrict__ w_alpha, const float* __restrict__ d_att_res,
+                      const float* __restrict__ att_w, float* de_out, __nv_bfloat16* __restrict__ dscat,
+                      int B) {
+  static_assert(AR == 512, "lane -> 2 x 8 columns mapping; one region row = 1 KB");
+  constexpr int EPL = AR / 32;
+  constexpr int ROWB = AR * 2;
+  extern __shared__ __align__(128) uint8_t smem4[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Att4Map map(warp);
+  const int half = map.half;
+  const int partner = 15 - warp;
+  uint8_t* ring = smem4 + warp * (ATT4_STAGES * ATT4_STAGE_BYTES);
+  float* s_dot = reinterpret_cast<float*>(smem4 + ATT4_WARPS * ATT4_STAGES * ATT4_STAGE_BYTES +
+                                          ATT4_WARPS * ATT4_STAGES * 8);
+  pdl_launch_dependents();
+  pdl_wait();
+  uint32_t it = 0;
+  for (int rank = blockIdx.x + gridDim.x * map.pair; rank < B; rank += gridDim.x * ATT4_ROWS) {
+    const int b = order ? order[rank] : rank;
+    const int r0 = off ? off[b] : b * Lfix;
+    const int Lb = off ? off[b + 1] - r0 : Lfix;
+    const int n0 = (Lb + 1) >> 1;
+    const int a0 = half ? n0 : 0;
+    const int n = half ? Lb - n0 : n0;
+    const int ng = (n + 3) >> 2;                  // groups of 4 regions; item i < ng: att_e, else p_att
+    const __nv_bfloat16* pg = p_att16 + int64_t(r0 + a0) * AR;
+    const __nv_bfloat16* eg = att_e16 + int64_t(r0 + a0) * AR;
+    // one ring item = 4 regions of one tensor (4 KB); every call commits a group (static wait depth)
+    auto issue = [&](int i) {
+      if (i < 2 * ng) {
+        const int c = i < ng ? i : i - ng;
+        uint8_t* dst = ring + ((it + i) % ATT4_STAGES) * ATT4_STAGE_BYTES;
+        const int pieces = min(4, n - 4 * c) * (ROWB / 512);
+        const uint8_t* src =
+            reinterpret_cast<const uint8_t*>((i < ng ? eg : pg) + int64_t(4 * c) * AR) + lane * 16;
+#pragma unroll
+        for (int k = 0; k < 4 * (ROWB / 512); ++k)
+          if (k < pieces) cp_async16(dst + k * 512 + lane * 16, src + k * 512);
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < ATT4_STAGES; ++i) issue(i);
+    const float* wrow = att_w + r0 + a0;
+    float* drow = de_out + r0 + a0;               // dw first, de in place below
+    // pass 1: dw_l = <d_att_res, att_e_l>, dot = sum_l w_l dw_l
+    float dot = 0.f;
+    {
+      float dr[EPL];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float* src = d_att_res + int64_t(b) * AR + h * 256 + lane * 8;
+        const float4 x = *reinterpret_cast<const float4*>(src);
+        const float4 y = *reinterpret_cast<const float4*>(src + 4);
+        dr[h * 8 + 0] = x.x; dr[h * 8 + 1] = x.y; dr[h * 8 + 2] = x.z; dr[h * 8 + 3] = x.w;
+        dr[h * 8 + 4] = y.x; dr[h * 8 + 5] = y.y; dr[h * 8 + 6] = y.z; dr[h * 8 + 7] = y.w;
+      }
+      for (int c = 0; c < ng; ++c) {
+        const int st = (it + c) % ATT4_STAGES;
+        cp_async_wait<ATT4_STAGES - 1>();
+        __syncwarp();
+        const uint8_t* es = ring + st * ATT4_STAGE_BYTES;
+        const int rows = min(4, n - 4 * c);
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < rows) {                          // warp-uniform
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float f[8];
+              bf16x8_to_float(*reinterpret_cast<const uint4*>(es + q * ROWB + (h * 256 + lane * 8) * 2), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) a[q] += dr[h * 8 + j] * f[j];
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < rows) dot += wrow[4 * c + q] * a[q];
+        const float mine = lane == 0 ? a[0] : lane == 1 ? a[1] : lane == 2 ? a[2] : a[3];
+        if (lane < rows) drow[4 * c + lane] = mine;
+        __syncwarp();
+        issue(c + ATT4_STAGES);
       }
     }
-    __syncthreads();
-    // online softmax update; thread -> columns 2*tid, 2*tid+1
+    if (lane == 0) s_dot[warp] = dot;
+    pair_barrier(map.pair);
+    const float dotw = dot + s_dot[partner];
+    // pass 2: de_l = w_l (dw_l - dotw);  d_att_h[j] = alpha_j sum_l de_l (1 - tanh^2(p_att[l,j] + att_h[j]))
+    float ah[EPL], acc[EPL];
     {
-      float ce[ATT_CH];
-      float cm = m;
+      const float* att_h = s_row0 + int64_t(b) * lds + att_h_col;
 #pragma unroll
-      for (int w = 0; w < ATT_CH; ++w) { ce[w] = s_ce[w]; cm = fmaxf(cm, ce[w]); }
-      const float scale = __expf(m - cm);      // exp(-inf) = 0 on the first chunk
-      m = cm;
-      sum *= scale; acc0 *= scale; acc1 *= scale;
+      for (int h = 0; h < 2; ++h) {
+        const float4 x = *reinterpret_cast<const float4*>(att_h + h * 256 + lane * 8);
+        const float4 y = *reinterpret_cast<const float4*>(att_h + h * 256 + lane * 8 + 4);
+        ah[h * 8 + 0] = x.x; ah[h * 8 + 1] = x.y; ah[h * 8 + 2] = x.z; ah[h * 8 + 3] = x.w;
+        ah[h * 8 + 4] = y.x; ah[h * 8 + 5] = y.y; ah[h * 8 + 6] = y.z; ah[h * 8 + 7] = y.w;
+      }
+    }
 #pragma unroll
-      for (int w = 0; w < ATT_CH; ++w) {
-        if (w < rows) {
-          const float pw = __expf(ce[w] - m);
-          const float2 v = bf2_to_f2(*reinterpret_cast<const uint32_t*>(es + w * (AR * 2) + threadIdx.x * 4));
-          sum += pw;
-          acc0 += pw * v.x;
-          acc1 += pw * v.y;
+    for (int j = 0; j < EPL; ++j) acc[j] = 0.f;
+    for (int c = 0; c < ng; ++c) {
+      const int st = (it + ng + c) % ATT4_STAGES;
+      cp_async_wait<ATT4_STAGES - 1>();
+      __syncwarp();
+      const uint8_t* ps = ring + st * ATT4_STAGE_BYTES;
+      const int rows = min(4, n - 4 * c);
+      float de[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) de[q] = (q < rows) ? wrow[4 * c + q] * (drow[4 * c + q] - dotw) : 0.f;
+      __syncwarp();                               // all lanes have read dw before it becomes de
+      {
+        const float mine = lane == 0 ? de[0] : lane == 1 ? de[1] : lane == 2 ? de[2] : de[3];
+        if (lane < rows) drow[4 * c + lane] = mine;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q < rows) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float f[8];
+            bf16x8_to_float(*reinterpret_cast<const uint4*>(ps + q * ROWB + (h * 256 + lane * 8) * 2), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float t = tanh_fast(f[j] + ah[h * 8 + j]);
+              acc[h * 8 + j] += de[q] * (1.f - t * t);
+            }
+          }
         }
       }
+      __syncwarp();
+      issue(ng + c + ATT4_STAGES);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && c + STAGES < nch) issue(c + STAGES);
-  }
-  const float inv = 1.f / sum;
-  {
-    __nv_bfloat162 o = __floats2bfloat162_rn(acc0 * inv, acc1 * inv);
-    *reinterpret_cast<__nv_bfloat162*>(att_res16 + int64_t(b) * AR + 2 * threadIdx.x) = o;
-  }
-  for (int l = threadIdx.x; l < Lb; l += ATT_THREADS) att_w[r0 + l] = __expf(s_e[l] - m) * inv;
-}
-
-template <int AR, int STAGES>
-size_t attention_fwd2_smem(int L) {
-  return size_t(STAGES) * 2 * ATT_CH * AR * 2 + sizeof(float) * (((L + 7) & ~7) + ATT_CH) +
-         sizeof(uint64_t) * STAGES + 16;
-}
-
-// ------------------------------------------------------------------------------------------
-// per-step backward (inside the BPTT chain): d(scores) and d(att_h)
-// ------------------------------------------------------------------------------------------
-template <int AR, int STAGES>
-__global__ void __launch_bounds__(ATT_THREADS)
-attention_bwd2_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bfloat16* __restrict__ att_e16,
-                      const int* __restrict__ off, int Lfix, const float* __restrict__ s_row0,
-                      int64_t lds, int att_h_col, const float* __restrict__ w_alpha,
-                      const float* __restrict__ d_att_res, const float* __restrict__ att_w,
-                      float* __restrict__ de_out, __nv_bfloat16* __restrict__ dscat) {
-  static_assert(AR == 2 * ATT_THREADS, "thread -> 2 columns mapping");
-  constexpr int EPL = AR / 32;
-  constexpr int CHUNK_BYTES = ATT_CH * AR * 2;
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* stages = smem;                                              // [STAGES][CHUNK_BYTES]
-  float* s_de = reinterpret_cast<float*>(smem + STAGES * CHUNK_BYTES); // [Lb] dw -> de
-  const int b = blockIdx.x;
-  const int r0 = off ? off[b] : b * Lfix;
-  const int Lb = off ? off[b + 1] - r0 : Lfix;
-  float* s_red = s_de + ((Lb + 7) & ~7);                               // [8]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 8);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nch = (Lb + ATT_CH - 1) / ATT_CH;
-  const __nv_bfloat16* pg = p_att16 + int64_t(r0) * AR;
-  const __nv_bfloat16* eg = att_e16 + int64_t(r0) * AR;
-  pdl_launch_dependents();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
-    fence_barrier_init();
-  }
-  __syncthreads();
-  pdl_wait();
-  // item i in [0, 2*nch): att_e chunks first, then p_att chunks
-  auto issue = [&](int i) {
-    const int st = i % STAGES;
-    const int c = i < nch ? i : i - nch;
-    const int rows = min(ATT_CH, Lb - c * ATT_CH);
-    const uint32_t bytes = uint32_t(rows) * AR * 2;
-    mbar_expect_tx(&bars[st], bytes);
-    bulk_load_1d(stages + st * CHUNK_BYTES, (i < nch ? eg : pg) + int64_t(c) * ATT_CH * AR, bytes,
-                 &bars[st]);
-  };
-  if (threadIdx.x == 0)
-    for (int i = 0; i < min(STAGES, 2 * nch); ++i) issue(i);
-  // pass 1: dw_l = <d_att_res, att_e_l>; lane slices of d_att_res in registers
-  float dr[EPL];
+    it += 2 * ng;
+    cp_async_wait<0>();
+    float* part = reinterpret_cast<float*>(ring);
 #pragma unroll
-  for (int h = 0; h < EPL / 8; ++h)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dr[h * 8 + j] = d_att_res[int64_t(b) * AR + h * 256 + lane * 8 + j];
-  for (int c = 0; c < nch; ++c) {
-    const int st = c % STAGES;
-    mbar_wait(&bars[st], (c / STAGES) & 1);
-    const uint8_t* es = stages + st * CHUNK_BYTES;
-    const int rows = min(ATT_CH, Lb - c * ATT_CH);
-    if (warp < rows) {
-      float a = 0.f;
-#pragma unroll
-      for (int h = 0; h < EPL / 8; ++h) {
-        const uint4 u = *reinterpret_cast<const uint4*>(es + warp * (AR * 2) + (h * 256 + lane * 8) * 2);
-        float f[8];
-        bf16x8_to_float(u, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a += dr[h * 8 + j] * f[j];
-      }
-      a = warp_sum(a);
-      if (lane == 0) s_de[c * ATT_CH + warp] = a;
+    for (int h = 0; h < 2; ++h) {
+      float* d = part + h * 256 + lane * 8;
+      *reinterpret_cast<float4*>(d) = make_float4(acc[h * 8], acc[h * 8 + 1], acc[h * 8 + 2], acc[h * 8 + 3]);
+      *reinterpret_cast<float4*>(d + 4) =
+          make_float4(acc[h * 8 + 4], acc[h * 8 + 5], acc[h * 8 + 6], acc[h * 8 + 7]);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && c + STAGES < 2 * nch) issue(c + STAGES);
-  }
-  // softmax backward: de_l = w_l (dw_l - sum_l' w_l' dw_l')
-  float dotw = 0.f;
-  for (int l = threadIdx.x; l < Lb; l += ATT_THREADS) dotw += att_w[r0 + l] * s_de[l];
-  dotw = block_sum_256(dotw, s_red);
-  __syncthreads();
-  for (int l = threadIdx.x; l < Lb; l += ATT_THREADS) {
-    const float de = att_w[r0 + l] * (s_de[l] - dotw);
-    s_de[l] = de;
-    de_out[r0 + l] = de;
-  }
-  __syncthreads();
-  // pass 2: d_att_h[j] = alpha_j sum_l de_l (1 - tanh^2(p_att[l,j] + att_h[j])); thread -> 2 columns
-  const float* att_h = s_row0 + int64_t(b) * lds + att_h_col;
-  const float ah0 = att_h[2 * threadIdx.x], ah1 = att_h[2 * threadIdx.x + 1];
-  float acc0 = 0.f, acc1 = 0.f;
-  for (int c = 0; c < nch; ++c) {
-    const int i = nch + c;
-    const int st = i % STAGES;
-    mbar_wait(&bars[st], (i / STAGES) & 1);
-    const uint8_t* ps = stages + st * CHUNK_BYTES;
-    const int rows = min(ATT_CH, Lb - c * ATT_CH);
+    pair_barrier(map.pair);
+    {
+      const float* other = reinterpret_cast<const float*>(smem4 + partner * (ATT4_STAGES * ATT4_STAGE_BYTES));
+      const int c0 = half * 256 + lane * 8;
+      float o[8];
 #pragma unroll
-    for (int w = 0; w < ATT_CH; ++w) {
-      if (w < rows) {
-        const float de = s_de[c * ATT_CH + w];
-        const float2 v = bf2_to_f2(*reinterpret_cast<const uint32_t*>(ps + w * (AR * 2) + threadIdx.x * 4));
-        const float t0 = tanh_fast(v.x + ah0), t1 = tanh_fast(v.y + ah1);
-        acc0 += de * (1.f - t0 * t0);
-        acc1 += de * (1.f - t1 * t1);
-      }
+      for (int j = 0; j < 8; ++j) o[j] = (part[c0 + j] + other[c0 + j]) * __ldg(w_alpha + c0 + j);
+      *reinterpret_cast<uint4*>(dscat + int64_t(b) * lds + att_h_col + c0) = float8_to_bf16x8(o);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && i + STAGES < 2 * nch) issue(i + STAGES);
+    if (rank + gridDim.x * ATT4_ROWS < B) pair_barrier(map.pair);
   }
-  {
-    const float a0 = __ldg(w_alpha + 2 * threadIdx.x), a1 = __ldg(w_alpha + 2 * threadIdx.x + 1);
-    __nv_bfloat162 o = __floats2bfloat162_rn(acc0 * a0, acc1 * a1);
-    *reinterpret_cast<__nv_bfloat162*>(dscat + int64_t(b) * lds + att_h_col + 2 * threadIdx.x) = o;
-  }
-}
-
-template <int AR, int STAGES>
-size_t attention_bwd2_smem(int L) {
-  return size_t(STAGES) * ATT_CH * AR * 2 + sizeof(float) * (((L + 7) & ~7) + 8) +
-         sizeof(uint64_t) * STAGES + 16;
 }
 
 // ------------------------------------------------------------------------------------------

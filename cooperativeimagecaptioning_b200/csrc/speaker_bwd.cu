@@ -1,6 +1,7 @@
 // Speaker (Att2in2) backward: logit gradients of the straight-through samplers and of log-prob
 // losses, BPTT through the decode loop, deferred accumulation of the region-tensor gradients and
 // all weight gradients.  Maths: SURVEY.md Appendix A.2/A.3/A.5; buffers: include/coopcap.h.
+#include <algorithm>
 #include "../../include/coopcap.h"
 #include "common.cuh"
 #include "gemm.cuh"
@@ -598,19 +599,19 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
       if ((rc = gemm_run(0, 0, 1, ds_t + 3 * R, NS, c->w_a2c16, R, B, R, 2 * R, 1, 0, e, s))) return rc;
     }
     if (A == 512 && R == 512) {
-      constexpr int ST = 4;
-      const size_t sm2 = attention_bwd2_smem<512, ST>(c->L);
-      static size_t sm2_set = 0;
-      if (sm2 > sm2_set) {
-        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd2_kernel<512, ST>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2)));
-        sm2_set = sm2;
+      static bool set4 = false;
+      if (!set4) {
+        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd4_kernel<512>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM));
+        set4 = true;
       }
-      CC_CHECK_CUDA(launch_pdl(attention_bwd2_kernel<512, ST>, dim3(B), dim3(ATT_THREADS), sm2, s,
+      CC_CHECK_CUDA(launch_pdl(attention_bwd4_kernel<512>, dim3(std::min(num_sms(), B)),
+                               dim3(ATT4_THREADS), size_t(ATT4_SMEM), s,
                                reinterpret_cast<const bf16*>(c->p_att16),
-                               reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L, s_t,
+                               reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L,
+                               c->att_order, s_t,
                                int64_t(NS), 5 * R, c->w_alpha, dres_t, c->att_w + int64_t(t) * NL,
-                               g->de + int64_t(t) * NL, ds_t));
+                               g->de + int64_t(t) * NL, ds_t, B));
     } else {
       attention_bwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
           reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),

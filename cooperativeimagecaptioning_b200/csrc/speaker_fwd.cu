@@ -2,6 +2,7 @@
 // and the decode loop (gate GEMM -> additive attention -> a2c GEMM -> maxout-LSTM pointwise ->
 // logit GEMM -> sampling + next-input gather).  See include/coopcap.h for the buffer layout and
 // the reference lines each piece replaces.
+#include <algorithm>
 #include "../../include/coopcap.h"
 #include "common.cuh"
 #include "gemm.cuh"
@@ -346,8 +347,9 @@ struct OnlineLse2 {
 // One CTA per row, one streaming pass over the logits (one global read, few registers -> high
 // occupancy): per 4 elements one Philox call, the perturbed scores, an online (max, sum) for
 // log-sum-exp and for the relaxed sample y, and the running argmax.
+template <int MODE, bool INJ>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
-sample_kernel(float* __restrict__ z, int V1, int mode, float inv_tau,
+sample_kernel(const float* __restrict__ z, int V1, float inv_tau,
               const float* __restrict__ noise, uint64_t seed, uint64_t nstream,
               const int64_t* __restrict__ forced, const uint8_t* __restrict__ unf_prev,
               int64_t* __restrict__ tok_raw, int64_t* __restrict__ tok_out,
@@ -356,9 +358,9 @@ sample_kernel(float* __restrict__ z, int V1, int mode, float inv_tau,
               // next-step input
               const float* __restrict__ embed, int E, const uint8_t* __restrict__ keep_embed_next,
               uint64_t estream, float drop_p, bf16* __restrict__ xh_next, int64_t ld_xh,
-              // scheduled sampling (AttModel.py:119-131) and decoding_constraint (:437-442)
-              float ss_prob, const float* __restrict__ ss_u, uint64_t ss_stream,
-              const int64_t* __restrict__ prev_out) {
+              // scheduled sampling (AttModel.py:119-131)
+              float ss_prob, const float* __restrict__ ss_u, uint64_t ss_stream) {
+  constexpr int mode = MODE;
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_m1[8], s_s1[8], s_m2[8], s_s2[8], s_bv[8];
@@ -366,16 +368,15 @@ sample_kernel(float* __restrict__ z, int V1, int mode, float inv_tau,
   __shared__ int64_t s_fed;
   constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   const int b = blockIdx.x;
-  float* zr = z + int64_t(b) * V1;
-  const float* nr = noise ? noise + int64_t(b) * V1 : nullptr;
-  const bool fast = (noise == nullptr);
-  const bool gum = (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_PS_GUMBEL);
-  const bool race = (mode == COOPCAP_SAMPLE_MULTINOMIAL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL ||
-                     mode == COOPCAP_SAMPLE_PS_MULTINOMIAL);
-  const bool st = gum || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL || mode == COOPCAP_SAMPLE_PS_MULTINOMIAL;
-  const bool use_noise = gum || race;
+  const float* zr = z + int64_t(b) * V1;
+  const float* nr = INJ ? noise + int64_t(b) * V1 : nullptr;
+  constexpr bool fast = !INJ;
+  constexpr bool gum = (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_PS_GUMBEL);
+  constexpr bool race = (mode == COOPCAP_SAMPLE_MULTINOMIAL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL ||
+                         mode == COOPCAP_SAMPLE_PS_MULTINOMIAL);
+  constexpr bool st = gum || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL || mode == COOPCAP_SAMPLE_PS_MULTINOMIAL;
+  constexpr bool use_noise = gum || race;
   const int nv4 = V1 / 4;
-  const int banned = prev_out ? int(prev_out[b]) : -1;   // decoding_constraint: logit := -inf
   OnlineLse2 l1, l2;
   l1.init();
   l2.init();
@@ -384,11 +385,7 @@ sample_kernel(float* __restrict__ z, int V1, int mode, float inv_tau,
 #pragma unroll 2
   for (int v4 = threadIdx.x; v4 < nv4; v4 += SAMPLE_THREADS) {
     const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
-    float x4[4] = {zv.x, zv.y, zv.z, zv.w};
-    if ((banned >> 2) == v4) {          // banned = -1 never matches
-      x4[banned & 3] = -INFINITY;
-      zr[banned] = -INFINITY;           // the saved logits are what backward differentiates
-    }
+    const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
     float u4[4] = {0.f, 0.f, 0.f, 0.f};
     if (use_noise) noise4(nr, v4, seed, nstream, uint64_t(b) * nv4 + v4, u4);
     float a4[4], y4[4], xs[4];
@@ -398,7 +395,7 @@ sample_kernel(float* __restrict__ z, int V1, int mode, float inv_tau,
       a4[q] = x4[q];
       y4[q] = 0.f;
       if (st) { y4[q] = st_score(mode, x4[q], u4[q], inv_tau, fast); a4[q] = y4[q]; y4[q] *= LOG2E; }
-      if (race) a4[q] = x4[q] * inv_tau + neg_log_exp1(u4[q], nr != nullptr);
+      if (race) a4[q] = x4[q] * inv_tau + neg_log_exp1(u4[q], INJ);
     }
     l1.add4(xs);
     if (st) l2.add4(y4);
@@ -461,6 +458,33 @@ sample_kernel(float* __restrict__ z, int V1, int mode, float inv_tau,
     embed_row(embed, s_fed, E, keep_embed_next ? keep_embed_next + int64_t(b) * E : nullptr, seed,
               estream, int64_t(b) * E, drop_p, xh_next + int64_t(b) * ld_xh);
   }
+}
+
+// decoding_constraint (AttModel.py:437-442): the logit of the previously emitted id becomes -inf
+// in the saved logits (what the sampler reads and what backward differentiates)
+__global__ void ban_prev_kernel(float* __restrict__ z, int V1, const int64_t* __restrict__ prev_out,
+                                int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) z[int64_t(b) * V1 + prev_out[b]] = -INFINITY;
+}
+
+template <typename... Args>
+static cudaError_t launch_sampler(int mode, bool inj, int B, cudaStream_t s, Args... args) {
+#define CC_SAMPLER_CASE(M)                                                                          \
+  case M:                                                                                          \
+    return inj ? launch_pdl(sample_kernel<M, true>, dim3(B), dim3(SAMPLE_THREADS), 0, s, args...)  \
+               : launch_pdl(sample_kernel<M, false>, dim3(B), dim3(SAMPLE_THREADS), 0, s, args...)
+  switch (mode) {
+    CC_SAMPLER_CASE(COOPCAP_SAMPLE_GREEDY);
+    CC_SAMPLER_CASE(COOPCAP_SAMPLE_MULTINOMIAL);
+    CC_SAMPLER_CASE(COOPCAP_SAMPLE_ST_GUMBEL);
+    CC_SAMPLER_CASE(COOPCAP_SAMPLE_ST_MULTINOMIAL);
+    CC_SAMPLER_CASE(COOPCAP_SAMPLE_NONE);
+    CC_SAMPLER_CASE(COOPCAP_SAMPLE_PS_GUMBEL);
+    CC_SAMPLER_CASE(COOPCAP_SAMPLE_PS_MULTINOMIAL);
+    default: return cudaErrorInvalidValue;
+  }
+#undef CC_SAMPLER_CASE
 }
 
 // Partial-sampling modes: the vector a step emits (gumbel_softmax.py:28-40, multinomial_soft.py:21-33).
@@ -623,19 +647,20 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     rc = gemm_run(0, 0, 0, xh16 + int64_t(t) * B * XH, XH, c->w_cat16, XH, B, NS, XH, 1, 0, e1, s);
     if (rc) return rc;
     if (A == 512 && R == 512) {
-      constexpr int ST = 3;
-      const size_t sm2 = attention_fwd2_smem<512, ST>(c->L);
-      static size_t sm2_set = 0;
-      if (sm2 > sm2_set) {
-        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd2_kernel<512, ST>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm2)));
-        sm2_set = sm2;
+      static bool set4 = false;
+      if (!set4) {
+        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd4_kernel<512>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM));
+        set4 = true;
       }
-      CC_CHECK_CUDA(launch_pdl(attention_fwd2_kernel<512, ST>, dim3(B), dim3(ATT_THREADS), sm2, s,
+      CC_CHECK_CUDA(launch_pdl(attention_fwd4_kernel<512>, dim3(std::min(num_sms(), B)),
+                               dim3(ATT4_THREADS), size_t(ATT4_SMEM), s,
                                reinterpret_cast<const bf16*>(c->p_att16),
-                               reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L, s_t,
+                               reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L,
+                               c->att_order, s_t,
                                int64_t(NS), 5 * R, c->w_alpha, att_res16 + int64_t(t) * B * R,
-                               c->att_w + int64_t(t) * c->NL));
+                               c->att_w + int64_t(t) * c->NL, B,
+                               0));
     } else {
       attention_fwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
           reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
@@ -666,8 +691,12 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     if (rc) return rc;
     const bool ps = (c->mode == COOPCAP_SAMPLE_PS_GUMBEL || c->mode == COOPCAP_SAMPLE_PS_MULTINOMIAL);
     bf16* x_next = (t + 1 < c->n_steps) ? xh16 + int64_t(t + 1) * B * XH : nullptr;
-    CC_CHECK_CUDA(launch_pdl(
-        sample_kernel, dim3(B), dim3(SAMPLE_THREADS), 0, s, z_t, V1, c->mode, c->inv_tau,
+    if (c->no_repeat && t > 0) {
+      ban_prev_kernel<<<(B + 255) / 256, 256, 0, s>>>(z_t, V1, c->tok_out + int64_t(t - 1) * B, B);
+      CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 0.0);
+    }
+    CC_CHECK_CUDA(launch_sampler(
+        c->mode, c->noise != nullptr, B, s, z_t, V1, c->inv_tau,
         c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed, uint64_t(SITE_NOISE + t),
         c->forced ? c->forced + int64_t(t) * B : nullptr,
         t > 0 ? c->unfinished + int64_t(t - 1) * B : nullptr, c->tok_raw + int64_t(t) * B,
@@ -676,8 +705,7 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
         c->unfinished + int64_t(t) * B, c->embed, E,
         c->keep_embed ? c->keep_embed + int64_t(t + 1) * B * E : nullptr,
         uint64_t(SITE_DROP_EMBED + t + 1), c->drop_p, ps ? nullptr : x_next, int64_t(XH),
-        c->ss_prob, c->ss_u ? c->ss_u + int64_t(t) * B : nullptr, uint64_t(SITE_SCHED + t),
-        (c->no_repeat && t > 0) ? c->tok_out + int64_t(t - 1) * B : nullptr));
+        c->ss_prob, c->ss_u ? c->ss_u + int64_t(t) * B : nullptr, uint64_t(SITE_SCHED + t)));
     // algorithmic bytes: logits (+ injected noise) read once
     CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 4.0 * B * V1 * (c->noise ? 2.0 : 1.0));
     if (ps) {

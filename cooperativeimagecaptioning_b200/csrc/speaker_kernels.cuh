@@ -5,6 +5,7 @@
 // HBM-bound kernels: bf16 storage for the region tensors (att_e, p_att), 16-byte vector loads,
 // one CTA per batch row for attention (warp per region, online softmax), warp-shuffle reductions.
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace coopcap {

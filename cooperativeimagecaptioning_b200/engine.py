@@ -220,6 +220,11 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     c.B, c.L, c.D, c.R, c.E, c.A, c.V1 = B, L, d.D, d.R, d.E, d.A, d.V1
     c.NL, c.cap, c.n_steps = NL, cap, n_steps
     c.att_feats, c.att_off = (None if att16 is not None else _p(att_feats)), _p(att_off)
+    # longest rows first: the attention kernels deal rows to SMs by rank (load balance only)
+    att_order = None
+    if att_off is not None and B > 1:
+        att_order = torch.argsort(att_off[1:] - att_off[:-1], descending=True).to(torch.int32)
+    c.att_order = _p(att_order)
     c.att_prepacked = int(att16 is not None)
     c.embed = _p(_f32c(P["embed.0.weight"].detach()))
     c.b_att_embed = _p(_f32c(P["att_embed.0.bias"].detach()))
@@ -267,7 +272,7 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     for n, tsr in T.items():
         setattr(c, n, _p(tsr))
     sp = SpeakerPass(ctx=c, dims=d, B=B, L=L, NL=NL, cap=cap, n_steps=n_steps, t=T,
-                     keep=[att_feats, att_off, forced, start_tokens, rnd, packed, P, w_embed16])
+                     keep=[att_feats, att_off, att_order, forced, start_tokens, rnd, packed, P, w_embed16])
     lib = _lib.load()
     check(lib.coopcap_speaker_prologue_fwd(C.byref(c), _stream()))
     check(lib.coopcap_speaker_decode_fwd(C.byref(c), _stream()))

@@ -167,6 +167,8 @@ typedef struct coopcap_speaker {
   /* inputs */
   const float* att_feats; /* [B, L, D] */
   const int* att_off;     /* [B+1] packed-row offsets, or NULL */
+  const int* att_order;   /* [B] row ids by decreasing region count, or NULL (identity): only a
+                             schedule hint, the attention kernels deal rows to SMs in this order */
   int att_prepacked;      /* 1: att16 already holds the packed bf16 regions (att_feats unused) */
   /* parameters */
   const float* embed;     /* [V+2, E] fp32 */
