@@ -510,3 +510,9 @@ int gemm_run(int kind, int a_major, int b_major, const void* A, int64_t lda, con
              cudaStream_t s);
 
 }  // namespace coopcap
+
+struct coopcap_gemm_args;
+namespace coopcap {
+// Full argument-struct entry (tcgen05 or the SIMT cross-check backend), defined in gemm_api.cu.
+int gemm_store(const coopcap_gemm_args* a, cudaStream_t s);
+}  // namespace coopcap

@@ -83,7 +83,7 @@ __global__ void gru_fwd_kernel(const float* __restrict__ gi, const float* __rest
 
 // y = x / (||x||_2 + 1e-7), one CTA (256 threads) per row          (VSEFCModel.py:12-17)
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int M,
-                                  int passthrough) {
+                                  int passthrough, int use_abs) {
   __shared__ float red[8];
   const float* xr = x + int64_t(blockIdx.x) * M;
   float* yr = y + int64_t(blockIdx.x) * M;
@@ -91,20 +91,23 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict
   for (int i = threadIdx.x; i < M; i += 256) ss += xr[i] * xr[i];
   ss = block_sum_256(ss, red);
   const float inv = passthrough ? 1.f : 1.f / (sqrtf(ss) + 1e-7f);
-  for (int i = threadIdx.x; i < M; i += 256) yr[i] = xr[i] * inv;
+  // use_abs: |.| after the normalisation (VSEFCModel.py:50-52,137-139)
+  for (int i = threadIdx.x; i < M; i += 256) yr[i] = use_abs ? fabsf(xr[i] * inv) : xr[i] * inv;
 }
 
 // dx = dy / (n + eps) - x (dy . x) / (n (n + eps)^2); optional fp32 and bf16 outputs
 __global__ void l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                   float* __restrict__ dx, bf16* __restrict__ dx16, int M,
-                                  int passthrough) {
+                                  int passthrough, int use_abs) {
   __shared__ float red[8];
   const float* xr = x + int64_t(blockIdx.x) * M;
   const float* dr = dy + int64_t(blockIdx.x) * M;
+  // use_abs: the upstream gradient first passes |.|, i.e. takes the sign of the normalised value
+  auto dyv = [&](int i) { return (use_abs && xr[i] < 0.f) ? -dr[i] : dr[i]; };
   float ss = 0.f, dot = 0.f;
   for (int i = threadIdx.x; i < M; i += 256) {
     ss += xr[i] * xr[i];
-    dot += xr[i] * dr[i];
+    dot += xr[i] * dyv(i);
   }
   ss = block_sum_256(ss, red);
   dot = block_sum_256(dot, red);
@@ -112,7 +115,7 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ x, const float* __re
   const float a = passthrough ? 1.f : 1.f / ne;
   const float c = (passthrough || n == 0.f) ? 0.f : dot / (n * ne * ne);
   for (int i = threadIdx.x; i < M; i += 256) {
-    const float v = dr[i] * a - xr[i] * c;
+    const float v = dyv(i) * a - xr[i] * c;
     if (dx) dx[int64_t(blockIdx.x) * M + i] = v;
     if (dx16) dx16[int64_t(blockIdx.x) * M + i] = __float2bfloat16_rn(v);
   }
@@ -180,6 +183,103 @@ __global__ void hinge_cols_kernel(const float* __restrict__ S, int B, float marg
   }
 }
 
+// vse_max_violation = 0 (VSEFCModel.py:190-193 else-branch): mean over the row / column of the
+// hinge matrix with its diagonal zeroed, i.e. (1/B) sum over the negatives
+__global__ void hinge_sum_rows_kernel(const float* __restrict__ S, int B, float margin,
+                                      float* __restrict__ cost_s) {
+  __shared__ float red[8];
+  const int i = blockIdx.x;
+  const float* row = S + int64_t(i) * B;
+  const float d = row[i];
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < B; j += 256)
+    if (j != i) acc += fmaxf(margin + row[j] - d, 0.f);
+  acc = block_sum_256(acc, red);
+  if (threadIdx.x == 0) cost_s[i] = acc / float(B);
+}
+__global__ void hinge_sum_cols_kernel(const float* __restrict__ S, int B, float margin,
+                                      float* __restrict__ cost_im) {
+  __shared__ float sv[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (j < B) {
+    const float d = S[int64_t(j) * B + j];
+    for (int i = threadIdx.y; i < B; i += 8)
+      if (i != j) acc += fmaxf(margin + S[int64_t(i) * B + j] - d, 0.f);
+  }
+  sv[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < B) {
+    for (int w = 1; w < 8; ++w) acc += sv[w][threadIdx.x];
+    cost_im[j] = acc / float(B);
+  }
+}
+// its backward: dS[i,j] (i != j) = g_i [m + S_ij - S_ii > 0] / B + g_j [m + S_ij - S_jj > 0] / B,
+// dS[i,i] = -(sum of row i's first terms) - (sum of column i's second terms); one CTA per row i
+// writes the off-diagonal entries and the row part of the diagonal, a second pass adds the column part
+__global__ void hinge_sum_ds_kernel(const float* __restrict__ S, int B, float margin,
+                                    const float* __restrict__ g_loss, const float* __restrict__ g_rows,
+                                    int only, float* __restrict__ dS) {
+  __shared__ float red[8];
+  const int i = blockIdx.x;
+  const float gi = g_loss ? g_loss[0] : g_rows[i];
+  const float dii = S[int64_t(i) * B + i];
+  const float invB = 1.f / float(B);
+  float rowpart = 0.f;
+  for (int j = threadIdx.x; j < B; j += 256) {
+    if (j == i) continue;
+    const float sij = S[int64_t(i) * B + j];
+    const float gj = g_loss ? g_loss[0] : g_rows[j];
+    float v = 0.f;
+    if (only != 1 && margin + sij - dii > 0.f) { v += gi * invB; rowpart += gi * invB; }
+    if (only != 2 && margin + sij - S[int64_t(j) * B + j] > 0.f) v += gj * invB;
+    dS[int64_t(i) * B + j] = v;
+  }
+  rowpart = block_sum_256(rowpart, red);
+  if (threadIdx.x == 0) dS[int64_t(i) * B + i] = -rowpart;
+}
+__global__ void hinge_sum_ds_diag_kernel(const float* __restrict__ S, int B, float margin,
+                                         const float* __restrict__ g_loss,
+                                         const float* __restrict__ g_rows, int only,
+                                         float* __restrict__ dS) {
+  __shared__ float red[8];
+  const int j = blockIdx.x;
+  float colpart = 0.f;
+  if (only != 2) {
+    const float gj = g_loss ? g_loss[0] : g_rows[j];
+    const float djj = S[int64_t(j) * B + j];
+    for (int i = threadIdx.x; i < B; i += 256)
+      if (i != j && margin + S[int64_t(i) * B + j] - djj > 0.f) colpart += gj / float(B);
+  }
+  colpart = block_sum_256(colpart, red);
+  if (threadIdx.x == 0) dS[int64_t(j) * B + j] -= colpart;
+}
+
+// vse_pool_type mean / max over the valid steps (VSEFCModel.py:115-126); h32[t + 1] is the state
+// after step t
+__global__ void pool_kernel(const float* __restrict__ h32, const int* __restrict__ len, int S, int B,
+                            int M, int pool_type, float* __restrict__ cap_pre,
+                            int* __restrict__ pool_arg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * M) return;
+  const int b = idx / M;
+  const int n = min(len[b], S);
+  if (pool_type == 1) {
+    float acc = 0.f;
+    for (int t = 0; t < n; ++t) acc += h32[int64_t(t + 1) * B * M + idx];
+    cap_pre[idx] = acc / float(n);
+  } else {
+    float bv = -1e10f;     // the reference's fill value for masked steps
+    int bt = 0;
+    for (int t = 0; t < n; ++t) {
+      const float v = h32[int64_t(t + 1) * B * M + idx];
+      if (v > bv) { bv = v; bt = t; }
+    }
+    cap_pre[idx] = bv;
+    pool_arg[idx] = bt;
+  }
+}
+
 // loss_rows = cost_s (+) cost_im according to only_one_retrieval; loss = sum (deterministic order)
 __global__ void hinge_finish_kernel(const float* __restrict__ cost_s, const float* __restrict__ cost_im,
                                     int B, int only, float* __restrict__ loss_rows,
@@ -233,7 +333,9 @@ __global__ void hinge_bwd_kernel(const float* __restrict__ im, const float* __re
 // d(loss)/d(h_{t-1}) (the recurrent part, d_gh . W_hh, is accumulated by the following GEMM).
 __global__ void gru_bwd_kernel(float* __restrict__ dh, const float* __restrict__ gates,
                                const float* __restrict__ h_prev, const int* __restrict__ len, int t,
-                               bf16* __restrict__ d_gi16, bf16* __restrict__ d_gh16, int B, int M) {
+                               bf16* __restrict__ d_gi16, bf16* __restrict__ d_gh16, int B, int M,
+                               int pool_type, const float* __restrict__ d_pool,
+                               const int* __restrict__ pool_arg) {
   pdl_launch_dependents();
   pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -251,7 +353,10 @@ __global__ void gru_bwd_kernel(float* __restrict__ dh, const float* __restrict__
   const float* g = gates + int64_t(b) * 4 * M;
   const float r = g[j], z = g[M + j], n = g[2 * M + j], ghn = g[3 * M + j];
   const float hp = h_prev[idx];
-  const float d = dh[idx];
+  float d = dh[idx];
+  // pooled variants: h_t also feeds the pool directly
+  if (pool_type == 1) d += d_pool[idx] / float(len[b]);
+  else if (pool_type == 2 && pool_arg[idx] == t) d += d_pool[idx];
   const float dn = d * (1.f - z);
   const float dz = d * (hp - n);
   const float dnp = dn * (1.f - n * n);
@@ -285,6 +390,9 @@ static int check_dims(const coopcap_listener* c) {
   CC_REQUIRE(c != nullptr, "listener: null context");
   CC_REQUIRE(c->B > 0 && c->S > 0, "listener: empty batch B=%d S=%d", c->B, c->S);
   CC_REQUIRE(c->F % 8 == 0 && c->M % 8 == 0 && c->E % 8 == 0, "listener: F,M,E must be multiples of 8");
+  CC_REQUIRE(c->pool_type >= 0 && c->pool_type <= 2, "listener: pool_type %d", c->pool_type);
+  CC_REQUIRE(c->pool_type == 0 || (c->cap_pre && (c->pool_type == 1 || c->pool_arg)),
+             "listener: pool mean / max need cap_pre (and pool_arg)");
   return CC_OK;
 }
 
@@ -300,7 +408,7 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
     e.alpha = 1.f; e.bias = c->b_img; e.C = c->img_pre; e.ldc = M;
     if ((rc = gemm_run(0, 0, 0, c->fc16, F, c->w_img16, F, B, M, F, 1, 0, e, s))) return rc;
   }
-  l2norm_fwd_kernel<<<B, 256, 0, s>>>(c->img_pre, c->im, M, c->no_imgnorm);
+  l2norm_fwd_kernel<<<B, 256, 0, s>>>(c->img_pre, c->im, M, c->no_imgnorm, c->use_abs);
   CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   // caption branch                                                    (VSEFCModel.py:83-140)
   if (!c->emb_given) {
@@ -326,7 +434,14 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
                              c->h32 + int64_t(t + 1) * B * M, h16 + int64_t(t + 1) * B * M, B, M));
     CC_LAUNCH_CHECK_K(PROF_GRU, s, 0.0, 0.0);
   }
-  l2norm_fwd_kernel<<<B, 256, 0, s>>>(c->h32 + int64_t(S) * B * M, c->cap, M, 0);
+  const float* pooled = c->h32 + int64_t(S) * B * M;     // 'last': the masked update carries it
+  if (c->pool_type != 0) {
+    pool_kernel<<<(B * M + 255) / 256, 256, 0, s>>>(c->h32, c->len, S, B, M, c->pool_type, c->cap_pre,
+                                                    c->pool_arg);
+    CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
+    pooled = c->cap_pre;
+  }
+  l2norm_fwd_kernel<<<B, 256, 0, s>>>(pooled, c->cap, M, 0, c->use_abs);
   CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   // scores (tf32 operands: the hinge compares score differences against a 0.2 margin)
   {
@@ -334,11 +449,18 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
     e.alpha = 1.f; e.C = c->scores; e.ldc = B;
     if ((rc = gemm_run(1, 0, 0, c->im, M, c->cap, M, B, B, M, 1, 0, e, s))) return rc;
   }
-  hinge_rows_kernel<<<B, 256, 0, s>>>(c->scores, B, c->margin, c->cost_s, c->arg_s);
-  CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
-  hinge_cols_kernel<<<(B + 31) / 32, dim3(32, 8), 0, s>>>(c->scores, B, c->margin, c->cost_im,
-                                                           c->arg_im);
-  CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
+  if (c->sum_violation) {
+    hinge_sum_rows_kernel<<<B, 256, 0, s>>>(c->scores, B, c->margin, c->cost_s);
+    CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
+    hinge_sum_cols_kernel<<<(B + 31) / 32, dim3(32, 8), 0, s>>>(c->scores, B, c->margin, c->cost_im);
+    CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
+  } else {
+    hinge_rows_kernel<<<B, 256, 0, s>>>(c->scores, B, c->margin, c->cost_s, c->arg_s);
+    CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
+    hinge_cols_kernel<<<(B + 31) / 32, dim3(32, 8), 0, s>>>(c->scores, B, c->margin, c->cost_im,
+                                                             c->arg_im);
+    CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
+  }
   hinge_finish_kernel<<<1, 256, 0, s>>>(c->cost_s, c->cost_im, B, c->only_one_retrieval,
                                         c->loss_rows, c->loss);
   CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
@@ -355,26 +477,55 @@ int listener_bwd(const coopcap_listener* c, const coopcap_listener_grads* g, cud
   bf16* h16 = reinterpret_cast<bf16*>(c->h16);
   bf16* d_gi16 = reinterpret_cast<bf16*>(g->d_gi16);
   bf16* d_gh16 = reinterpret_cast<bf16*>(g->d_gh16);
-  CC_CHECK_CUDA(cudaMemsetAsync(g->d_im, 0, sizeof(float) * B * M, s));
-  CC_CHECK_CUDA(cudaMemsetAsync(g->d_cap, 0, sizeof(float) * B * M, s));
-  hinge_bwd_kernel<<<B, 256, 0, s>>>(c->im, c->cap, c->cost_s, c->cost_im, c->arg_s, c->arg_im,
-                                     g->g_loss, g->g_rows, c->only_one_retrieval, M, g->d_im,
-                                     g->d_cap);
-  CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
+  if (c->sum_violation) {
+    // dense d(scores), then d_im = dS . cap and d_cap = dS^T . im (fp32 SIMT: B x B x M, non-default)
+    CC_REQUIRE(g->d_scores != nullptr, "listener_bwd: the sum-violation hinge needs d_scores");
+    hinge_sum_ds_kernel<<<B, 256, 0, s>>>(c->scores, B, c->margin, g->g_loss, g->g_rows,
+                                          c->only_one_retrieval, g->d_scores);
+    CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
+    hinge_sum_ds_diag_kernel<<<B, 256, 0, s>>>(c->scores, B, c->margin, g->g_loss, g->g_rows,
+                                               c->only_one_retrieval, g->d_scores);
+    CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
+    coopcap_gemm_args a = {};
+    a.kind = 1; a.backend = 1; a.alpha = 1.f;
+    a.M = B; a.N = M; a.K = B;
+    a.A = g->d_scores; a.lda = B; a.a_major = 0; a.B = c->cap; a.ldb = M; a.b_major = 1;
+    a.C = g->d_im; a.ldc = M;
+    if ((rc = gemm_store(&a, s))) return rc;
+    a.a_major = 1; a.B = c->im; a.C = g->d_cap;
+    if ((rc = gemm_store(&a, s))) return rc;
+  } else {
+    CC_CHECK_CUDA(cudaMemsetAsync(g->d_im, 0, sizeof(float) * B * M, s));
+    CC_CHECK_CUDA(cudaMemsetAsync(g->d_cap, 0, sizeof(float) * B * M, s));
+    hinge_bwd_kernel<<<B, 256, 0, s>>>(c->im, c->cap, c->cost_s, c->cost_im, c->arg_s, c->arg_im,
+                                       g->g_loss, g->g_rows, c->only_one_retrieval, M, g->d_im,
+                                       g->d_cap);
+    CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
+  }
   if (g->need_param_grads) {
     l2norm_bwd_kernel<<<B, 256, 0, s>>>(c->img_pre, g->d_im, nullptr,
-                                        reinterpret_cast<bf16*>(g->d_img_pre16), M, c->no_imgnorm);
+                                        reinterpret_cast<bf16*>(g->d_img_pre16), M, c->no_imgnorm,
+                                        c->use_abs);
     CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
     if ((rc = wgrad(g->d_img_pre16, M, c->fc16, F, M, F, B, g->g_w_img, F, s))) return rc;
     if ((rc = colsum_bf16(g->d_img_pre16, B, M, M, g->g_b_img, s))) return rc;
   }
-  l2norm_bwd_kernel<<<B, 256, 0, s>>>(c->h32 + int64_t(S) * B * M, g->d_cap, g->dh, nullptr, M, 0);
+  if (c->pool_type == 0) {
+    l2norm_bwd_kernel<<<B, 256, 0, s>>>(c->h32 + int64_t(S) * B * M, g->d_cap, g->dh, nullptr, M, 0,
+                                        c->use_abs);
+  } else {
+    // the pooled state feeds every valid step (mean) / its arg-max step (max): gru_bwd_kernel adds it
+    CC_REQUIRE(g->d_pool != nullptr, "listener_bwd: pool mean / max need d_pool");
+    l2norm_bwd_kernel<<<B, 256, 0, s>>>(c->cap_pre, g->d_cap, g->d_pool, nullptr, M, 0, c->use_abs);
+    CC_CHECK_CUDA(cudaMemsetAsync(g->dh, 0, sizeof(float) * B * M, s));
+  }
   CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   for (int t = S - 1; t >= 0; --t) {
     const int n = B * M;
     CC_CHECK_CUDA(launch_pdl(gru_bwd_kernel, dim3((n + 255) / 256), dim3(256), 0, s, g->dh,
                              c->gates + int64_t(t) * B * 4 * M, c->h32 + int64_t(t) * B * M, c->len, t,
-                             d_gi16 + int64_t(t) * B * 3 * M, d_gh16 + int64_t(t) * B * 3 * M, B, M));
+                             d_gi16 + int64_t(t) * B * 3 * M, d_gh16 + int64_t(t) * B * 3 * M, B, M,
+                             c->pool_type, g->d_pool, c->pool_arg));
     CC_LAUNCH_CHECK_K(PROF_GRU, s, 0.0, 0.0);
     if (t > 0) {
       // dh += d_gh . W_hh        ([B,3M] x [3M,M]; W_hh stored [K, N])

@@ -468,8 +468,12 @@ class ListenerPass:
 ONLY = {"off": 0, "image": 1, "caption": 2}
 
 
+POOL = {"last": 0, "": 0, "mean": 1, "max": 2}
+
+
 def listener_forward(P, packed, fc_feats, tok_sb, lens, *, margin=0.2, only_one_retrieval="off",
-                     no_imgnorm=False, emb16: Optional[torch.Tensor] = None) -> ListenerPass:
+                     no_imgnorm=False, emb16: Optional[torch.Tensor] = None, pool_type="last",
+                     use_abs=False, max_violation=True) -> ListenerPass:
     """tok_sb int64 [S, B] time-major ids, lens int32 [B].  Results in .t['loss'] ([1]) and
     .t['loss_rows'] ([B]).  `emb16` bf16 [S, B, E]: caption embeddings computed by the caller
     (dense caption vectors); tok_sb is then None."""
@@ -501,6 +505,11 @@ def listener_forward(P, packed, fc_feats, tok_sb, lens, *, margin=0.2, only_one_
     c.margin, c.only_one_retrieval, c.no_imgnorm = float(margin), ONLY[only_one_retrieval], int(no_imgnorm)
     c.fc_feats, c.tok, c.len = _p(fc_feats), _p(tok_sb), _p(lens)
     c.emb_given = int(emb16 is not None)
+    # non-default listener options (VSEFCModel.py:115-126 pooling, :50-52/:137-139 abs, :190-193 hinge)
+    c.pool_type, c.use_abs, c.sum_violation = POOL[pool_type], int(bool(use_abs)), int(not max_violation)
+    if c.pool_type:
+        T["cap_pre"] = torch.empty(B, d.M, **f32)
+        T["pool_arg"] = torch.empty(B, d.M, dtype=torch.int32, device=dev)
     c.w_emb = _p(_f32c(P["txt_enc.embed.weight"].detach()))
     c.b_img = _p(_f32c(P["img_enc.fc.bias"].detach()))
     c.b_ih = _p(_f32c(P["txt_enc.rnn.bias_ih_l0"].detach()))
@@ -524,6 +533,10 @@ def listener_backward(lp: ListenerPass, P, *, g_loss=None, g_rows=None, need_par
               dh=torch.empty(B, d.M, **f32), d_img_pre16=torch.empty(B, d.M, **bf),
               d_gi16=torch.empty(S, B, 3 * d.M, **bf), d_gh16=torch.empty(S, B, 3 * d.M, **bf),
               demb16=torch.empty(S, B, d.E, **bf))
+    if lp.ctx.pool_type:
+        ws["d_pool"] = torch.empty(B, d.M, **f32)
+    if lp.ctx.sum_violation:
+        ws["d_scores"] = torch.empty(B, B, **f32)
     g = _lib.ListenerGrads()
     if g_loss is not None:
         g_loss = _f32c(g_loss.reshape(1))

@@ -258,7 +258,8 @@ class AlternatingJointModel(nn.Module):
         lp = EN.listener_forward(Pl, lis._packed.get(Pl), fc_feats.detach().float().contiguous(),
                                  None if is_ps else tok_sb, sp.t["cap_len"], margin=lis.margin,
                                  only_one_retrieval=self.only_one_retrieval,
-                                 no_imgnorm=bool(lis.img_enc.no_imgnorm), emb16=emb16)  # :371-373
+                                 no_imgnorm=bool(lis.img_enc.no_imgnorm), emb16=emb16,
+                                 **lis._variant())                                      # :371-373
         if lis.keep_passes:
             lp.pinned = True
             lis._passes.append(lp)

@@ -119,12 +119,11 @@ class VSEFCModel(nn.Module):
             raise NotImplementedError("only the contrastive listener loss is on the hot path")
         if opt.vse_rnn_type.lower() != "gru" or opt.vse_num_layers != 1:
             raise NotImplementedError("the listener is a 1-layer GRU (run_joint.sh defaults)")
-        if getattr(opt, "vse_pool_type", "last") not in ("last", ""):
-            raise NotImplementedError("only vse_pool_type='last' is on the B200 path")
-        if not getattr(opt, "vse_max_violation", 1):
-            raise NotImplementedError("only the max-violation hinge is on the B200 path")
-        if getattr(opt, "vse_use_abs", 0):
-            raise NotImplementedError("vse_use_abs is outside the hot path")
+        self.pool_type = getattr(opt, "vse_pool_type", "last") or "last"          # :70,:115-127
+        if self.pool_type not in EN.POOL:
+            raise ValueError(f"unknown vse_pool_type {self.pool_type!r}")
+        self.max_violation = bool(getattr(opt, "vse_max_violation", 1))           # :163,:190-193
+        self.use_abs = bool(getattr(opt, "vse_use_abs", 0))                        # :31,:69
         self.img_enc = EncoderImage(opt)
         self.txt_enc = EncoderText(opt)
         self.contrastive_loss = ContrastiveLoss(opt)
@@ -143,6 +142,9 @@ class VSEFCModel(nn.Module):
             "txt_enc.rnn.weight_ih_l0": r.weight_ih_l0, "txt_enc.rnn.weight_hh_l0": r.weight_hh_l0,
             "txt_enc.rnn.bias_ih_l0": r.bias_ih_l0, "txt_enc.rnn.bias_hh_l0": r.bias_hh_l0,
         }
+
+    def _variant(self) -> dict:
+        return dict(pool_type=self.pool_type, use_abs=self.use_abs, max_violation=self.max_violation)
 
     def _forward_ids(self, fc_feats, tok_sb, lens, whole_batch, only_one_retrieval, dense_seq=None):
         """tok_sb int64 [S, B] time-major, lens int32 [B]; or dense_seq float [B, S, V+2]."""
@@ -165,7 +167,8 @@ class VSEFCModel(nn.Module):
                      out16=emb16.view(S * B, d.E))
         lp = EN.listener_forward(P, packed, fc_feats.detach().float().contiguous(), tok_sb, lens,
                                  margin=self.margin, only_one_retrieval=only_one_retrieval,
-                                 no_imgnorm=bool(self.img_enc.no_imgnorm), emb16=emb16)
+                                 no_imgnorm=bool(self.img_enc.no_imgnorm), emb16=emb16,
+                                 **self._variant())
         lp.dense_x16 = x16
         if self.keep_passes:
             lp.pinned = True

@@ -437,6 +437,9 @@ typedef struct coopcap_listener_grads {
   float* g_w_hh;
   float* g_b_ih;
   float* g_b_hh;
+  /* variants */
+  float* d_pool;        /* [B, M] workspace: d(loss)/d(pooled state), pool mean / max only */
+  float* d_scores;      /* [B, B] workspace: d(loss)/d(scores), sum-violation hinge only */
 } coopcap_listener_grads;
 
 int coopcap_listener_bwd(const coopcap_listener* ctx, const coopcap_listener_grads* gr,

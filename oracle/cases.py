@@ -72,7 +72,16 @@ def run_oracle(meta: Dict, forced_tokens=None, keep_all_steps=False):
                             temperature=meta["tau"],
                             decoding_constraint=meta.get("decoding_constraint", 0))
         return dict(seq=res.seq, logprobs=res.logprobs, grads={})
-    if kind == "mle":
+    if kind == "vse":
+        from . import listener as OL
+        v = meta["vse"]
+        loss = OL.vse_forward(Plo, batch.fc_feats, batch.labels, batch.masks, v["whole_batch"],
+                              v["only"], 0.2, bool(v["max_violation"]), v["pool_type"],
+                              use_abs=bool(v["use_abs"]))
+        out["loss_rows"] = loss.detach()
+        if v["whole_batch"]:
+            loss = (loss * torch.linspace(0.5, 1.5, loss.numel())).sum()
+    elif kind == "mle":
         fed = []
         loss = OJ.mle_loss(Pso, batch.att_feats, batch.att_masks, batch.labels, batch.masks,
                            noise, cfg, ss_prob=meta.get("ss_prob", 0.0), fed_out=fed)

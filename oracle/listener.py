@@ -19,13 +19,24 @@ def l2norm(X):
     return X / (torch.norm(X, dim=1, keepdim=True) + 1e-7)
 
 
-def img_enc(P: Params, fc_feats, no_imgnorm=False, use_abs=False):
+def _abs(x, replay, key):
+    """torch.abs; with `replay` (test aid) the sign decisions come from replay[key + "_sign"] (+-1,
+    taken from the implementation under test) and the oracle's own values are left in
+    replay[key + "_val"] for the near-zero check."""
+    if replay is None:
+        return x.abs()
+    replay[key + "_val"] = x.detach()
+    sign = replay.get(key + "_sign")
+    return x.abs() if sign is None else x * sign
+
+
+def img_enc(P: Params, fc_feats, no_imgnorm=False, use_abs=False, replay=None):
     """EncoderImage.forward                                             (VSEFCModel.py:40-54)"""
     f = torch.nn.functional.linear(fc_feats, P["img_enc.fc.weight"], P["img_enc.fc.bias"])
     if not no_imgnorm:
         f = l2norm(f)
     if use_abs:
-        f = f.abs()
+        f = _abs(f, replay, "im")
     return f
 
 
@@ -40,7 +51,7 @@ def gru_step(P: Params, x, h):
     return (1 - z) * n + z * h
 
 
-def txt_enc(P: Params, seqs, masks, pool_type="last", use_abs=False):
+def txt_enc(P: Params, seqs, masks, pool_type="last", use_abs=False, replay=None):
     """EncoderText.forward                                              (VSEFCModel.py:83-140)
     lengths = sum(mask > 0) (:84); embedding by lookup or dense one-hot matmul (:102-106);
     a packed GRU only advances rows with t < len (:108-112) -- restated as a masked update, which
@@ -63,12 +74,18 @@ def txt_enc(P: Params, seqs, masks, pool_type="last", use_abs=False):
         out = (torch.stack(outs, 1) * m[:, :, None]).sum(1) / masks.float().sum(1, keepdim=True)
     elif pool_type == "max":
         m = masks[:, :tmax].float()
-        out = (torch.stack(outs, 1) * m[:, :, None] + (m == 0)[:, :, None].float() * -1e10).max(1)[0]
+        filled = torch.stack(outs, 1) * m[:, :, None] + (m == 0)[:, :, None].float() * -1e10
+        if replay is not None:
+            replay["pool_vals"] = filled.detach()                      # [B, tmax, H]
+        if replay is not None and "pool_arg" in replay:                # replayed arg-max step
+            out = filled.gather(1, replay["pool_arg"][:, None, :]).squeeze(1)
+        else:
+            out = filled.max(1)[0]
     else:
         out = h                                                        # gather at len-1 (:128)
     out = l2norm(out)
     if use_abs:
-        out = out.abs()
+        out = _abs(out, replay, "cap")
     return out
 
 
@@ -108,7 +125,11 @@ def contrastive_loss(im, s, margin=0.2, max_violation=True, whole_batch=False,
 
 
 def vse_forward(P: Params, fc_feats, seq, masks, whole_batch=False, only_one_retrieval="off",
-                margin=0.2, max_violation=True, pool_type="last", hinge_replay=None):
-    """VSEFCModel.forward                                               (VSEFCModel.py:230-241)"""
-    return contrastive_loss(img_enc(P, fc_feats), txt_enc(P, seq, masks, pool_type), margin,
+                margin=0.2, max_violation=True, pool_type="last", hinge_replay=None, use_abs=False,
+                no_imgnorm=False, enc_replay=None):
+    """VSEFCModel.forward                                               (VSEFCModel.py:230-241)
+    `enc_replay` (test aid): decisions of the encoders' non-smooth options -- sign of |.| and the
+    max-pool arg-max step -- taken from the implementation under test (see _abs / txt_enc)."""
+    return contrastive_loss(img_enc(P, fc_feats, no_imgnorm, use_abs, enc_replay),
+                            txt_enc(P, seq, masks, pool_type, use_abs, enc_replay), margin,
                             max_violation, whole_batch, only_one_retrieval, hinge_replay)

@@ -167,7 +167,7 @@ def compare(tag, a, b, rtol=2e-4, atol=2e-6):
 
 def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dropout=True,
              baseline="gt", weight=0.01, seed=0, eos_bias=0.0, prob=0.25, ss_prob=0.0,
-             sample_max=0, decoding_constraint=0):
+             sample_max=0, decoding_constraint=0, vse=None):
     Ps = synth.speaker_params(dims, seed=seed, eos_bias=eos_bias)
     Pl = synth.listener_params(dims, seed=seed + 1)
     batch = synth.make_batch(dims, rows, regions, seed=seed + 2, varlen=varlen, min_regions=2)
@@ -205,7 +205,31 @@ def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dro
     meta = dict(name=name, dims=asdict(dims), rows=rows, regions=regions, varlen=varlen, mode=mode,
                 kind=kind, tau=tau, dropout=dropout, baseline=baseline, weight=weight, seed=seed,
                 eos_bias=eos_bias, prob=prob, ss_prob=ss_prob, sample_max=sample_max,
-                decoding_constraint=decoding_constraint)
+                decoding_constraint=decoding_constraint, vse=vse)
+    if kind == "vse":
+        # VSEFCModel.forward alone, non-default listener options (vse_pool_type / vse_use_abs /
+        # vse_max_violation), loss and parameter gradients
+        from oracle import cases as OC
+        vopt = ref_loader.reference_opt(**asdict(dims), batch_size=rows, vse_pool_type=vse["pool_type"],
+                                        vse_use_abs=vse["use_abs"], vse_max_violation=vse["max_violation"])
+        vmodel = ref.VSEFCModel(vopt)
+        vmodel.load_state_dict({k: v.clone() for k, v in Pl.items()}, strict=True)
+        vmodel.train()
+        lr = vmodel(batch.fc_feats, None, batch.labels, batch.masks, vse["whole_batch"], vse["only"])
+        total = (lr * torch.linspace(0.5, 1.5, lr.numel())).sum() if vse["whole_batch"] else lr
+        total.backward()
+        o = OC.run_oracle(meta)
+        compare(name + ".loss_rows", o["loss_rows"], lr.detach())
+        compare(name + ".loss", o["loss"], total.detach())
+        blob = {"meta": np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8),
+                "out.loss_rows": lr.detach().numpy(), "out.loss": total.detach().numpy()}
+        for k, p in vmodel.named_parameters():
+            g = torch.zeros_like(p) if p.grad is None else p.grad
+            compare(f"{name}.grad[{k}]", o["grads"]["vse." + k], g, rtol=5e-4, atol=1e-7)
+            blob["grad.vse." + k] = g.numpy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+        print(f"[golden] {name:34s} vse loss={float(total):+.6f} OK")
+        return
     if kind == "decode":
         # AttModel.sample with index outputs (eval_utils.py:187 style call), optional constraint
         from oracle import cases as OC
@@ -320,6 +344,16 @@ CASES = [
     ("tiny_decode_constraint_sampled", synth.TINY, dict(rows=6, regions=5, varlen=False, mode="reinforce",
                                                         kind="decode", seed=130, sample_max=0, tau=0.5,
                                                         decoding_constraint=1)),
+    ("tiny_vse_mean_abs", synth.TINY, dict(rows=7, regions=3, varlen=False, mode="gumbel", kind="vse", seed=140,
+                                           vse=dict(pool_type="mean", use_abs=1, max_violation=1,
+                                                    whole_batch=False, only="off"))),
+    ("tiny_vse_max_sumviolation", synth.TINY, dict(rows=7, regions=3, varlen=False, mode="gumbel", kind="vse",
+                                                   seed=150, vse=dict(pool_type="max", use_abs=0, max_violation=0,
+                                                                      whole_batch=True, only="off"))),
+    ("tiny_vse_last_sumviolation_image", synth.TINY, dict(rows=6, regions=3, varlen=False, mode="gumbel",
+                                                          kind="vse", seed=160,
+                                                          vse=dict(pool_type="last", use_abs=0, max_violation=0,
+                                                                   whole_batch=False, only="image"))),
     ("real_gumbel_b4", synth.Dims(), dict(rows=4, regions=6, varlen=True, mode="gumbel",
                                           kind="speaker_turn", seed=200, eos_bias=6.0)),
     ("real_mle_b4", synth.Dims(), dict(rows=4, regions=6, varlen=False, mode="gumbel", kind="mle",

@@ -69,4 +69,10 @@ def test_out_of_scope_options_raise():
     with pytest.raises(NotImplementedError):
         models.setup(reference_opt(use_bn=1), "att2in2", "caption_model")
     with pytest.raises(NotImplementedError):
-        models.setup(reference_opt(vse_pool_type="mean"), "fc", "vse_model")
+        models.setup(reference_opt(vse_loss_type="pair"), "fc", "vse_model")
+    with pytest.raises(ValueError):
+        models.setup(reference_opt(vse_pool_type="median"), "fc", "vse_model")
+    # the listener's pooling / abs / hinge options are on the path
+    vse = models.setup(reference_opt(vse_pool_type="mean", vse_use_abs=1, vse_max_violation=0), "fc",
+                       "vse_model")
+    assert vse._variant() == dict(pool_type="mean", use_abs=True, max_violation=False)

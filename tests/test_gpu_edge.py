@@ -65,6 +65,78 @@ def test_greedy_decode_is_bit_exact_off_near_ties(B, L, varlen):
     assert exact >= B          # at least the first token of every row
 
 
+@pytest.mark.parametrize("pool,use_abs,max_violation,whole_batch,only", [
+    ("mean", 1, 1, False, "off"),
+    ("max", 0, 0, True, "off"),
+    ("last", 0, 0, False, "image"),
+    ("max", 1, 1, True, "caption"),
+    ("mean", 0, 0, False, "off"),
+])
+def test_listener_option_variants(pool, use_abs, max_violation, whole_batch, only):
+    """vse_pool_type mean / max (VSEFCModel.py:115-126), vse_use_abs (:50-52,:137-139) and
+    vse_max_violation = 0 (mean over the negatives, :190-193): loss and parameter gradients.
+    The options' non-smooth decisions (sign of |.|, max-pool arg-max step, hardest negative) are
+    replayed from the CUDA pass and may differ from the oracle's own only at near-ties."""
+    d = REAL
+    B = 9
+    m, _, Pl = _models(B, 95, vse_pool_type=pool, vse_use_abs=use_abs, vse_max_violation=max_violation)
+    m.vse.keep_passes = True
+    batch = synth.make_batch(d, B, 4, 97)
+    out = m.vse(batch.fc_feats.cuda(), None, batch.labels.cuda(), batch.masks.cuda(), whole_batch,
+                only_one_retrieval=only)
+    lp = m.vse._passes[0]
+    enc, hr = {}, None
+    if use_abs:
+        enc["im_sign"] = torch.where(lp.t["img_pre"].cpu() < 0, -1.0, 1.0)
+        pre = lp.t["cap_pre"] if pool != "last" else lp.t["h32"][-1]
+        enc["cap_sign"] = torch.where(pre.cpu() < 0, -1.0, 1.0)
+    if pool == "max":
+        enc["pool_arg"] = lp.t["pool_arg"].cpu().long()
+    if max_violation:
+        hr = {"arg_s": lp.t["arg_s"].cpu().long(), "arg_im": lp.t["arg_im"].cpu().long()}
+    Plo = {k: v.clone().requires_grad_(True) for k, v in Pl.items()}
+    ref = OL.vse_forward(Plo, batch.fc_feats, batch.labels, batch.masks, whole_batch, only, 0.2,
+                         bool(max_violation), pool, use_abs=bool(use_abs), hinge_replay=hr,
+                         enc_replay=enc)
+    # replayed decisions differ from the oracle's own only at near-ties
+    flips = {}
+    for key in ("im", "cap"):
+        if key + "_sign" in enc:
+            v = enc[key + "_val"]
+            bad = (v < 0) != (enc[key + "_sign"] < 0)
+            flips[key] = int(bad.sum())
+            assert not bool(bad.any()) or float(v[bad].abs().max()) <= 5e-2 * float(v.abs().median())
+    if pool == "max":
+        vals = enc["pool_vals"]
+        own = vals.max(1)[0]
+        got = vals.gather(1, enc["pool_arg"][:, None, :]).squeeze(1)
+        flips["pool"] = int((own != got).sum())
+        assert float((own - got).abs().max()) <= 5e-2 * float(own.abs().median())
+    if hr is not None:
+        from gpu_util import check_hinge_near_ties
+        flips.update(check_hinge_near_ties(hr))
+    print(f"listener variant {pool}/{use_abs}/{max_violation}: decision flips {flips}")
+    w = torch.linspace(0.5, 1.5, B)
+    ref_scalar = (ref * w).sum() if whole_batch else ref
+    gref = torch.autograd.grad(ref_scalar, list(Plo.values()), allow_unused=True)
+    assert out.shape == ref.shape
+    assert torch.allclose(out.detach().cpu(), ref.detach(), rtol=2e-2, atol=2e-3), (out, ref)
+    ((out * w.cuda()).sum() if whole_batch else out).backward()
+    for (k, _), g in zip(Plo.items(), gref):
+        p = dict(m.vse.named_parameters())[k]
+        got = torch.zeros(p.numel(), dtype=torch.double) if p.grad is None else \
+            p.grad.cpu().double().flatten()
+        r = torch.zeros_like(got) if g is None else g.double().flatten()
+        if float(r.norm()) == 0:
+            assert float(got.norm()) == 0, k
+            continue
+        # 9 rows: the bias gradients are column sums of bf16-rounded per-row terms that largely
+        # cancel (most of all under the dense sum-violation hinge)
+        tol = 8e-2 if k.endswith("bias") or "bias_" in k else 3e-2
+        err = float((got - r).norm() / r.norm())
+        assert err <= tol, (k, err)
+
+
 def test_decoding_constraint_bans_the_previous_word():
     """AttModel.sample with opt['decoding_constraint'] = 1 (AttModel.py:437-442): the logit of the
     previously emitted id is -inf.  Greedy ids bit-exact against the oracle off near-ties, no
