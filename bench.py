@@ -49,6 +49,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
     ap.add_argument("--no-decode", action="store_true", help="skip the decode tokens/s side metric")
     ap.add_argument("--upload-ctas", type=int, default=64, help="CTAs of the zero-copy upload kernel")
+    ap.add_argument("--upload", default="zero_copy", choices=["host_pack", "zero_copy"],
+                    help="e2e staging: host threads pack bf16 + one DMA copy, or the zero-copy kernel")
+    ap.add_argument("--pack-threads", type=int, default=0,
+                    help="worker threads of the host-side packer (0 = hardware threads - 1)")
     ap.add_argument("--clock-samples", type=int, default=3, help="NVML samples inside the timed region; 0 = off")
     return ap.parse_args()
 
@@ -360,7 +364,7 @@ def main():
     value = args.rows * world * args.steps / (ms_max * 1e-3)
 
     # ---------------- end to end from pinned host buffers (`e2e`) ----------------
-    e2e_value, e2e_ms, h2d, e2e_allocs = None, None, 0, None
+    e2e_value, e2e_ms, h2d, e2e_allocs, e2e_host = None, None, 0, None, {}
     if not args.no_e2e:
         # double-buffered: batch i+1 is uploaded on a copy stream while batch i computes; the loss of
         # every step is read back to pinned host memory (async, drained at the end of the region)
@@ -369,18 +373,52 @@ def main():
         h2d = 0
         resident = None
 
-        from cooperativeimagecaptioning_b200.data import record_stream, upload_batch
+        from cooperativeimagecaptioning_b200.data import HostPacker, record_stream, upload_batch
 
-        def upload(i):
-            # the repo's own load_data: only the valid regions of att_feats cross PCIe
+        packer = HostPacker(dev, threads=args.pack_threads) if args.upload == "host_pack" else None
+        e2e_host = {}
+
+        def stage(i):
+            # host side of the repo's load_data for batch i: worker threads pack the valid regions
+            # to bf16 in a pinned staging buffer while the main thread keeps enqueueing
             h = hb[i % 2]
-            fc, att, am, lab, msk = upload_batch(h["fc"], h["att"], h["att_masks"], h["labels"],
-                                                 h["masks"], dev, stream=copy_stream, ctas=args.upload_ctas)
+            return packer.start(h["fc"], h["att"], h["att_masks"], h["labels"], h["masks"])
+
+        def upload(i, job=None):
+            h = hb[i % 2]
+            if packer is not None:
+                fc, att, am, lab, msk = packer.finish(job, stream=copy_stream)       # one DMA copy
+            else:
+                # zero-copy kernel: only the valid regions of att_feats cross PCIe (fp32)
+                fc, att, am, lab, msk = upload_batch(h["fc"], h["att"], h["att_masks"], h["labels"],
+                                                     h["masks"], dev, stream=copy_stream,
+                                                     ctas=args.upload_ctas)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
             return dict(fc=fc, att=att, att_masks=am, labels=lab, masks=msk), ev
 
         def e2e_loop(n, record):
+            if packer is not None:
+                tm = [0.0, 0.0, 0.0]
+                jobs = [stage(0)] + ([stage(1)] if n > 1 else [])      # packing runs two batches ahead
+                for i in range(n):
+                    h0 = time.perf_counter()
+                    d, ev = upload(i, jobs.pop(0))
+                    h1 = time.perf_counter()
+                    if i + 2 < n:
+                        jobs.append(stage(i + 2))    # packs while steps i, i+1 are being enqueued
+                    h2 = time.perf_counter()
+                    torch.cuda.current_stream().wait_event(ev)
+                    loss = train_step(d)
+                    record_stream(d.values(), torch.cuda.current_stream())
+                    if record:
+                        loss_host[i].copy_(loss.detach().reshape(()), non_blocking=True)
+                    h3 = time.perf_counter()
+                    tm[0] += h1 - h0; tm[1] += h2 - h1; tm[2] += h3 - h2
+                if record:
+                    e2e_host.update(wait_pack_and_dma_enqueue_ms=1e3 * tm[0] / n, stage_ms=1e3 * tm[1] / n,
+                                    step_enqueue_ms=1e3 * tm[2] / n)
+                return
             nxt = upload(0)
             for i in range(n):
                 d, ev = nxt
@@ -402,7 +440,7 @@ def main():
         e2e_loop(args.steps, True)
         t1.record()
         e2e_allocs = torch.cuda.memory_stats()["num_device_alloc"] - a0
-        h2d = upload_batch.last_bytes
+        h2d = packer.last_bytes if packer is not None else upload_batch.last_bytes
         barrier()
         t = torch.tensor([t0.elapsed_time(t1)], device=dev)
         if world > 1:
@@ -529,8 +567,14 @@ def main():
             e2e=None if e2e_value is None else dict(
                      value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
                      ms_per_step=e2e_ms / args.steps, device_allocs_in_region=e2e_allocs,
-                     note="public API (AlternatingJointModel.forward + backward + optimizer.step) "
-                          "from pinned host buffers, valid regions only (data.upload_batch), upload double-buffered on a copy stream"),
+                     upload=args.upload, host_ms_per_step=e2e_host or None,
+                     note="public API (AlternatingJointModel.forward + backward + optimizer.step) from pinned "
+                          "fp32 host buffers every step; " +
+                          ("data.HostPacker: library worker threads pack the valid regions to bf16 in a pinned "
+                           "staging buffer (inside the timed region), one DMA copy on a copy stream"
+                           if args.upload == "host_pack" else
+                           "data.upload_batch: zero-copy kernel reads the valid fp32 regions over PCIe on a "
+                           "copy stream") + "; loss of every step read back to pinned memory"),
             gpu_launches=int(launches), host_enqueue_ms_per_step=host_enqueue_ms,
             value_loop_debug=loop_debug,
             ms_per_step_by_rank=[m / args.steps for m in ms_ranks],

@@ -78,6 +78,86 @@ def upload_batch(fc_feats: torch.Tensor, att_feats: torch.Tensor, att_masks: Opt
 upload_batch.last_bytes = 0
 
 
+class HostPacker:
+    """Pipelined upload of batches: worker threads of libcoopcap pack the valid regions of the
+    host `att_feats` into a pinned bf16 staging buffer (`coopcap_host_pack_start`) while the caller
+    keeps enqueueing the current step; `finish` then moves the packed operand with one DMA copy.
+    Compared with `upload_batch(zero_copy=True)` half the bytes cross PCIe (bf16 instead of fp32)
+    and no SM is taken from the compute stream.  Same rounding as the device-side pack, so the
+    operand is bit-identical.
+
+        job = packer.start(fc, att, att_masks, labels, masks)      # returns immediately
+        ...                                                         # enqueue other work
+        batch = packer.finish(job, stream=copy_stream)              # CUDA tensors, async on `stream`
+    """
+
+    def __init__(self, device, nbuf: int = 3, threads: int = 0):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.CoopcapError("HostPacker targets a CUDA device (there is no CPU path)")
+        self.threads = int(threads)
+        self._slots = [dict(buf=None, ev=None) for _ in range(max(2, nbuf))]
+        self._next = 0
+        self.last_bytes = 0
+
+    def start(self, fc_feats, att_feats, att_masks, labels, masks):
+        lib = _lib.load()
+        B, L, D = att_feats.shape
+        if att_feats.dtype != torch.float32 or att_feats.device.type != "cpu":
+            raise _lib.CoopcapError("HostPacker.start takes fp32 host tensors")
+        att_feats = att_feats.contiguous()
+        off = None
+        NL = B * L
+        if att_masks is not None:
+            lens = (att_masks > 0).sum(1).to(torch.int32)
+            off = torch.zeros(B + 1, dtype=torch.int32)
+            off[1:] = torch.cumsum(lens, 0)
+            NL = int(off[-1])
+        slot = self._slots[self._next]
+        self._next = (self._next + 1) % len(self._slots)
+        if slot["ev"] is not None:
+            slot["ev"].synchronize()          # the DMA that last read this staging buffer is done
+        if slot["buf"] is None or slot["buf"].numel() < NL * D:
+            slot["buf"] = torch.empty(B * L * D, dtype=torch.bfloat16).pin_memory()
+        job = lib.coopcap_host_pack_start(
+            C.c_void_p(att_feats.data_ptr()), C.c_void_p(off.data_ptr()) if off is not None else None,
+            B, L, D, C.c_void_p(slot["buf"].data_ptr()), self.threads)
+        check(job if job < 0 else 0)
+        return dict(job=job, slot=slot, off=off, NL=NL, shape=(B, L, D), fc=fc_feats, labels=labels,
+                    masks=masks, att_masks=att_masks, src=att_feats)
+
+    def finish(self, j, stream=None):
+        lib = _lib.load()
+        check(lib.coopcap_host_pack_wait(j["job"]))
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        B, L, D = j["shape"]
+        NL = j["NL"]
+        nb = lambda t: t.numel() * t.element_size()
+        with torch.cuda.stream(st):
+            fc = j["fc"].to(self.device, non_blocking=True)
+            lab = j["labels"].to(self.device, non_blocking=True)
+            msk = j["masks"].to(self.device, non_blocking=True)
+            att16 = torch.empty(NL, D, dtype=torch.bfloat16, device=self.device)
+            att16.copy_(j["slot"]["buf"][: NL * D].view(NL, D), non_blocking=True)
+            moved = nb(j["fc"]) + nb(j["labels"]) + nb(j["masks"]) + NL * D * 2
+            if j["att_masks"] is not None:
+                am = j["att_masks"].to(self.device, non_blocking=True)
+                off_d = j["off"].to(self.device, non_blocking=True)
+                moved += nb(j["att_masks"]) + 4 * (B + 1)
+            else:
+                # fixed region count: an all-ones mask carries the packed operand
+                am = torch.ones(B, L, device=self.device)
+                off_d = torch.arange(0, (B + 1) * L, L, dtype=torch.int32, device=self.device)
+            am._coopcap_off = (off_d, NL)
+            am._coopcap_att16 = att16
+            att = torch.zeros(1, 1, 1, device=self.device).expand(B, L, D)      # shape carrier only
+            ev = torch.cuda.Event()
+            ev.record(st)
+        j["slot"]["ev"] = ev
+        self.last_bytes = moved
+        return fc, att, am, lab, msk
+
+
 def record_stream(batch, stream):
     """Tell the caching allocator that `stream` uses the tensors of an uploaded batch (they were
     allocated on the upload stream), including the packed side buffers."""

@@ -471,6 +471,17 @@ int coopcap_h2d_ragged_rows(void* dst, const void* src_host, const int* lens_hos
 int coopcap_pack_att_from_host(const float* att_feats_pinned, const int* att_off, int B, int L, int D,
                                int NL, void* att16, int ctas, coopcap_stream_t stream);
 
+/* Host-side variant: worker threads of the library pack the valid regions of a HOST tensor
+ * att_feats [B, L, D] fp32 into a (pinned) HOST staging buffer att16_host [NL, D] bf16 -- same
+ * round-to-nearest-even as the device pack, so the operand is bit-identical -- which the caller
+ * then moves with one DMA copy: a quarter of the padded fp32 bytes cross PCIe and no SM is used.
+ * att_off_host is a HOST array [B+1] (or NULL: all L valid); nthreads <= 0 picks hardware threads - 1.
+ * coopcap_host_pack_start returns a job id >= 0 immediately (or a negative error code); the buffers
+ * must stay valid until coopcap_host_pack_wait(job) has returned. */
+int coopcap_host_pack_start(const float* att_feats, const int* att_off_host, int B, int L, int D,
+                            void* att16_host, int nthreads);
+int coopcap_host_pack_wait(int job);
+
 /* ---- instrumentation ---------------------------------------------------------------------------
  * coopcap_launch_count: kernels launched by this library since load (all streams).
  * coopcap_prof_enable(1, stream): start an event timeline on `stream` (one event after every

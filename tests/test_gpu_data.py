@@ -37,3 +37,40 @@ def test_upload_batch_matches_plain_copy(zero_copy):
     assert torch.equal(a.t["tok_out"], b.t["tok_out"])      # hence identical greedy captions
     assert torch.equal(lab.cpu(), batch.labels) and torch.equal(msk.cpu(), batch.masks)
     assert upload_batch.last_bytes < batch.att_feats.numel() * 4 + 10 ** 6
+
+
+@pytest.mark.parametrize("varlen", [True, False])
+def test_host_packer_matches_plain_copy(varlen):
+    """data.HostPacker: bf16 packing by the library's worker threads + one DMA copy gives the
+    kernels the bit-identical operand; several batches in flight reuse the staging slots."""
+    import cooperativeimagecaptioning_b200.models as models
+    from cooperativeimagecaptioning_b200.data import HostPacker
+    d = REAL
+    B, L = 12, 9
+    spk = models.setup(reference_opt(), "att2in2", "caption_model").cuda().eval()
+    spk.keep_passes = True
+    packer = HostPacker("cuda", nbuf=2, threads=3)
+    side = torch.cuda.Stream()
+    pin = lambda t: None if t is None else t.contiguous().pin_memory()
+    batches = [synth.make_batch(d, B, L, 7 + i, varlen=varlen, min_regions=2) for i in range(3)]
+    jobs = [packer.start(pin(b.fc_feats), pin(b.att_feats), pin(b.att_masks), pin(b.labels), pin(b.masks))
+            for b in batches[:2]]
+    with torch.no_grad():
+        for i, b in enumerate(batches):
+            fc, att, am, lab, msk = packer.finish(jobs[i], stream=side)
+            if i + 2 < len(batches):       # third batch recycles the first staging slot
+                nb = batches[i + 2]
+                jobs.append(packer.start(pin(nb.fc_feats), pin(nb.att_feats), pin(nb.att_masks),
+                                         pin(nb.labels), pin(nb.masks)))
+            torch.cuda.current_stream().wait_stream(side)
+            spk.sample(fc, att, am, {"sample_max": 1})
+            spk.sample(b.fc_feats.cuda(), b.att_feats.cuda(),
+                       None if b.att_masks is None else b.att_masks.cuda(), {"sample_max": 1})
+            assert torch.equal(lab.cpu(), b.labels) and torch.equal(msk.cpu(), b.masks)
+    torch.cuda.synchronize()
+    for i in range(len(batches)):
+        a, r = spk._passes[2 * i], spk._passes[2 * i + 1]
+        assert a.NL == r.NL
+        assert torch.equal(a.t["att16"], r.t["att16"])
+        assert torch.equal(a.t["tok_out"], r.t["tok_out"])
+    assert packer.last_bytes < batches[-1].att_feats.numel() * 2 + 10 ** 6
