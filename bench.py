@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
     ap.add_argument("--no-decode", action="store_true", help="skip the decode tokens/s side metric")
     ap.add_argument("--upload-ctas", type=int, default=64, help="CTAs of the zero-copy upload kernel")
-    ap.add_argument("--upload", default="zero_copy", choices=["host_pack", "zero_copy"],
+    ap.add_argument("--upload", default="zero_copy", choices=["host_pack", "zero_copy", "dma_rows"],
                     help="e2e staging: host threads pack bf16 + one DMA copy, or the zero-copy kernel")
     ap.add_argument("--pack-threads", type=int, default=0,
                     help="worker threads of the host-side packer (0 = hardware threads - 1)")
@@ -392,7 +392,8 @@ def main():
                 # zero-copy kernel: only the valid regions of att_feats cross PCIe (fp32)
                 fc, att, am, lab, msk = upload_batch(h["fc"], h["att"], h["att_masks"], h["labels"],
                                                      h["masks"], dev, stream=copy_stream,
-                                                     ctas=args.upload_ctas)
+                                                     ctas=args.upload_ctas,
+                                                     zero_copy=(args.upload == "zero_copy"))
             ev = torch.cuda.Event()
             ev.record(copy_stream)
             return dict(fc=fc, att=att, att_masks=am, labels=lab, masks=msk), ev

@@ -224,7 +224,13 @@ struct EpiStore {
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-template <int KIND, int BN, int AMAJ, int BMAJ, class Epi>
+// LEAN = true: the epilogue is only alpha * acc + bias -> fp32 C through TMA store / reduce-add, as a
+// rolled loop over the 32-column chunks.  The generic epilogue (relu, dropout, masks, bf16 /
+// transposed outputs, three store modes) unrolls to ~200 KB of SASS per instantiation; the ~100
+// per-step GEMMs of the decode loop run ONE tile per CTA, so every instruction they execute is an
+// instruction-cache miss (ncu: stall_no_instruction 8.0 per issued instruction on the generic
+// kernel).  The lean variant keeps their code to a few KB.
+template <int KIND, int BN, int AMAJ, int BMAJ, class Epi, bool LEAN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)   // 10 warps are allocated as 12: 168 regs/thread
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int split_k,
@@ -375,6 +381,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (kb0 >= kb1) continue;
       const int row = m_blk * GEMM_BM + q * 32 + lane;
       const int n0 = n_blk * BN;
+      if constexpr (LEAN) {
+        constexpr int NCL = BN / 32 / 2;
+        const int row0 = m_blk * GEMM_BM + q * 32;
+        const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+        uint8_t* wstage = epi_stage + (warp - 2) * Cfg::EPI_BUFS * 4096;
+        float bias_lane = (ep.bias && n0 + half * 32 + lane < N) ? __ldg(ep.bias + n0 + half * 32 + lane) : 0.f;
+        mbar_wait(&tfull_bar[as], aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int i = 0; i < NCL; ++i) {
+          const int col0 = n0 + (half + 2 * i) * 32;
+          float v[32];
+          tmem_ld32(t_addr + (half + 2 * i) * 32, v);
+          // next chunk's bias while the accumulator columns are in flight
+          const int coln = col0 + 64 + lane;
+          const float bias_next = (ep.bias && i + 1 < NCL && coln < N) ? __ldg(ep.bias + coln) : 0.f;
+          tmem_ld_wait();
+          if (i + 1 == NCL) {
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[as]);
+          }
+          if (col0 < N && row0 < M) {            // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * ep.alpha + __shfl_sync(0xffffffffu, bias_lane, j);
+            uint8_t* buf = wstage + (Cfg::EPI_BUFS == 2 ? ebuf * 4096 : 0);
+            ebuf ^= 1;
+            if (lane == 0) bulk_wait_read<Cfg::EPI_BUFS - 1>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (ep.mode == 0) tma_store_2d(&tmC, buf, col0, row0);
+              else tma_reduce_add_2d(&tmC, buf, col0, row0);
+              bulk_commit();
+            }
+          }
+          bias_lane = bias_next;
+        }
+        if (++as == 2) { as = 0; aph ^= 1; }
+        continue;
+      }
       float bias_pf[BN / 64];
 #pragma unroll
       for (int i = 0; i < BN / 64; ++i) bias_pf[i] = epi.prefetch_bias(ep, n0 + (half + 2 * i) * 32, N, lane);
@@ -483,12 +534,16 @@ int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int M
     if (rc) return rc;
     ep.tma_store = 1;
   }
-  auto kern = gemm_tc_kernel<KIND, BN, AMAJ, BMAJ, Epi>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // plain "alpha * acc + bias -> fp32 C by TMA" problems take the small-code kernel
+  const bool lean = ep.tma_store && !ep.relu && !ep.row_scale && !ep.seg_lens && !ep.keep &&
+                    !ep.philox_dropout && !ep.dbg;
+  auto kern = lean ? gemm_tc_kernel<KIND, BN, AMAJ, BMAJ, Epi, true>
+                   : gemm_tc_kernel<KIND, BN, AMAJ, BMAJ, Epi, false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[lean]) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set[lean] = true;
   }
   const int num_m = (M + GEMM_BM - 1) / GEMM_BM, num_n = (N + BN - 1) / BN;
   const int nkb = (K + Cfg::BK - 1) / Cfg::BK;
