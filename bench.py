@@ -489,12 +489,12 @@ def main():
                         launches_per_step=pln[top] / psteps, ms_per_step=pms[top] / psteps)
         # DRAM traffic of the same kernel class from the committed ncu capture (per launch)
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_launch_summary.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r01_final_ncu_launch_summary.json")) as f:
                 summ = json.load(f)
             cls = summ["by_class"].get(KIND_NAMES[top])
             if roof is not None and cls:
                 roof["traffic"] = cls["dram_MB"] * 1e6 / cls["launches"]
-                roof["traffic_unit"] = "bytes per launch (dram read+write, ncu, profiles/r01_ncu_launch_summary.json)"
+                roof["traffic_unit"] = "bytes per launch (dram read+write, ncu, profiles/r01_final_ncu_launch_summary.json)"
                 roof["algorithmic_per_launch"] = (pfl[top] if pfl[top] > 0 else pby[top]) / max(pln[top], 1)
         except (OSError, KeyError, ValueError):
             pass
