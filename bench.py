@@ -316,14 +316,15 @@ def main():
         prev = cur
     for i in range(args.warmup):
         train_step(resident[i % 2])
-    barrier()
     sample_at = set()
     if clocks:
         n = args.clock_samples
         sample_at = {max(1, (k + 1) * args.steps // (n + 1)) for k in range(n)}
-    if clocks:
         clocks.nvml_edge()                     # GPU busy with the warm-up steps still draining
-        torch.cuda.synchronize()
+    # every rank enters the timed region together: the NVML query above (rank 0 only, 10-200 ms on
+    # these hosts) used to sit between the barrier and the first timed step, so the other ranks'
+    # regions contained it (they waited for rank 0 in the first all-reduce): +1.1 ms/step at N = 2
+    barrier()
     l0 = lib.coopcap_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st0 = torch.cuda.memory_stats()
