@@ -42,10 +42,68 @@ __global__ void colsum_kernel(const T* __restrict__ src, int64_t rows, int cols,
   }
 }
 
+// bf16 source with 16-byte aligned rows: every thread owns 8 adjacent columns (one 16-byte load per
+// row, a warp reads 512 contiguous bytes), four rows in flight per thread
+__global__ void __launch_bounds__(256)
+colsum_bf16x8_kernel(const bf16* __restrict__ src, int64_t rows, int cols, int64_t ld,
+                     float* __restrict__ out, int64_t rows_per_block) {
+  __shared__ float sm[8][32][9];
+  const int c0 = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int64_t r0 = int64_t(blockIdx.y) * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < cols) {
+    int64_t r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const uint4*>(src + (r + 8 * q) * ld + c0));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float f[8];
+        bf16x8_to_float(v[q], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    for (; r < r1; r += 8) {
+      float f[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(src + r * ld + c0)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[threadIdx.y][threadIdx.x][j] = acc[j];
+  __syncthreads();
+  // 256 threads reduce the 8 row-slices of the block's 256 columns
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  const int col = blockIdx.x * 256 + t;
+  if (col < cols) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += sm[i][t >> 3][t & 7];
+    atomicAdd(out + col, tot);
+  }
+}
+
 template <typename T>
 static int colsum_impl(const T* src, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t s) {
   CC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
   if (rows <= 0) return CC_OK;
+  if constexpr (sizeof(T) == 2) {
+    if (cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const int col_blocks = (cols + 255) / 256;
+      int64_t row_blocks = (int64_t(num_sms()) * 4 + col_blocks - 1) / col_blocks;
+      if (row_blocks > (rows + 63) / 64) row_blocks = (rows + 63) / 64;
+      if (row_blocks < 1) row_blocks = 1;
+      const int64_t rpb = (rows + row_blocks - 1) / row_blocks;
+      colsum_bf16x8_kernel<<<dim3(col_blocks, (unsigned)row_blocks), dim3(32, 8), 0, s>>>(
+          reinterpret_cast<const bf16*>(src), rows, cols, ld, out, rpb);
+      CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
+      return CC_OK;
+    }
+  }
   const int col_blocks = (cols + 31) / 32;
   int64_t row_blocks = (int64_t(num_sms()) * 4 + col_blocks - 1) / col_blocks;
   if (row_blocks > (rows + 63) / 64) row_blocks = (rows + 63) / 64;
