@@ -338,37 +338,65 @@ __global__ void gru_bwd_kernel(float* __restrict__ dh, const float* __restrict__
                                const int* __restrict__ pool_arg) {
   pdl_launch_dependents();
   pdl_wait();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * M) return;
-  const int b = idx / M, j = idx % M;
+  // 4 hidden units per thread: 16-byte loads, 8-byte bf16 stores
+  const int idx4 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = M / 4;
+  if (idx4 >= B * per_row) return;
+  const int b = idx4 / per_row, j = (idx4 % per_row) * 4;
+  const int64_t idx = int64_t(b) * M + j;
   const bool active = t < len[b];
   bf16* gi = d_gi16 + int64_t(b) * 3 * M;
   bf16* gh = d_gh16 + int64_t(b) * 3 * M;
   if (!active) {
-    const bf16 zero = __float2bfloat16_rn(0.f);
-    gi[j] = zero; gi[M + j] = zero; gi[2 * M + j] = zero;
-    gh[j] = zero; gh[M + j] = zero; gh[2 * M + j] = zero;
+    store_bf16x4(gi + j, 0.f, 0.f, 0.f, 0.f); store_bf16x4(gi + M + j, 0.f, 0.f, 0.f, 0.f);
+    store_bf16x4(gi + 2 * M + j, 0.f, 0.f, 0.f, 0.f);
+    store_bf16x4(gh + j, 0.f, 0.f, 0.f, 0.f); store_bf16x4(gh + M + j, 0.f, 0.f, 0.f, 0.f);
+    store_bf16x4(gh + 2 * M + j, 0.f, 0.f, 0.f, 0.f);
     return;  // dh passes through unchanged
   }
+  auto ld4 = [](const float* p, float (&o)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  };
   const float* g = gates + int64_t(b) * 4 * M;
-  const float r = g[j], z = g[M + j], n = g[2 * M + j], ghn = g[3 * M + j];
-  const float hp = h_prev[idx];
-  float d = dh[idx];
+  float r[4], z[4], n[4], ghn[4], hp[4], d[4];
+  ld4(g + j, r); ld4(g + M + j, z); ld4(g + 2 * M + j, n); ld4(g + 3 * M + j, ghn);
+  ld4(h_prev + idx, hp); ld4(dh + idx, d);
   // pooled variants: h_t also feeds the pool directly
-  if (pool_type == 1) d += d_pool[idx] / float(len[b]);
-  else if (pool_type == 2 && pool_arg[idx] == t) d += d_pool[idx];
-  const float dn = d * (1.f - z);
-  const float dz = d * (hp - n);
-  const float dnp = dn * (1.f - n * n);
-  const float dzp = dz * z * (1.f - z);
-  const float drp = dnp * ghn * r * (1.f - r);
-  gi[j] = __float2bfloat16_rn(drp);
-  gi[M + j] = __float2bfloat16_rn(dzp);
-  gi[2 * M + j] = __float2bfloat16_rn(dnp);
-  gh[j] = __float2bfloat16_rn(drp);
-  gh[M + j] = __float2bfloat16_rn(dzp);
-  gh[2 * M + j] = __float2bfloat16_rn(dnp * r);
-  dh[idx] = d * z;
+  if (pool_type == 1) {
+    float dp[4];
+    ld4(d_pool + idx, dp);
+    const float inv = 1.f / float(len[b]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) d[q] += dp[q] * inv;
+  } else if (pool_type == 2) {
+    float dp[4];
+    ld4(d_pool + idx, dp);
+    const int4 pa = *reinterpret_cast<const int4*>(pool_arg + idx);
+    const int a4[4] = {pa.x, pa.y, pa.z, pa.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (a4[q] == t) d[q] += dp[q];
+  }
+  float o_r[4], o_z[4], o_n[4], o_nr[4], o_dh[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float dn = d[q] * (1.f - z[q]);
+    const float dz = d[q] * (hp[q] - n[q]);
+    const float dnp = dn * (1.f - n[q] * n[q]);
+    o_z[q] = dz * z[q] * (1.f - z[q]);
+    o_r[q] = dnp * ghn[q] * r[q] * (1.f - r[q]);
+    o_n[q] = dnp;
+    o_nr[q] = dnp * r[q];
+    o_dh[q] = d[q] * z[q];
+  }
+  store_bf16x4(gi + j, o_r[0], o_r[1], o_r[2], o_r[3]);
+  store_bf16x4(gi + M + j, o_z[0], o_z[1], o_z[2], o_z[3]);
+  store_bf16x4(gi + 2 * M + j, o_n[0], o_n[1], o_n[2], o_n[3]);
+  store_bf16x4(gh + j, o_r[0], o_r[1], o_r[2], o_r[3]);
+  store_bf16x4(gh + M + j, o_z[0], o_z[1], o_z[2], o_z[3]);
+  store_bf16x4(gh + 2 * M + j, o_nr[0], o_nr[1], o_nr[2], o_nr[3]);
+  *reinterpret_cast<float4*>(dh + idx) = make_float4(o_dh[0], o_dh[1], o_dh[2], o_dh[3]);
 }
 
 // g_w_emb[tok[s,b], :] += demb[s, b, :] for s < len[b]            (sparse embedding wgrad)
@@ -521,7 +549,7 @@ int listener_bwd(const coopcap_listener* c, const coopcap_listener_grads* g, cud
   }
   CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   for (int t = S - 1; t >= 0; --t) {
-    const int n = B * M;
+    const int n = B * (M / 4);
     CC_CHECK_CUDA(launch_pdl(gru_bwd_kernel, dim3((n + 255) / 256), dim3(256), 0, s, g->dh,
                              c->gates + int64_t(t) * B * 4 * M, c->h32 + int64_t(t) * B * M, c->len, t,
                              d_gi16 + int64_t(t) * B * 3 * M, d_gh16 + int64_t(t) * B * 3 * M, B, M,

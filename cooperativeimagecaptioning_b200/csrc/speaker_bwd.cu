@@ -255,34 +255,69 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ d_out, const bf16* __r
                                 bf16* __restrict__ dscat, float drop_p, int B, int R) {
   pdl_launch_dependents();
   pdl_wait();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * R) return;
-  const int b = idx / R, j = idx % R;
-  float dh = d_out[idx];
-  if (drop_p > 0.f)
-    dh = (__bfloat162float(out16[idx]) != 0.f) ? dh * (1.f / (1.f - drop_p)) : 0.f;
-  if (dh_next) dh += dh_next[int64_t(b) * ld_dh + j];
+  // 4 hidden units per thread: 16-byte loads, 8-byte bf16 stores
+  const int idx4 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = R / 4;
+  if (idx4 >= B * per_row) return;
+  const int b = idx4 / per_row, j = (idx4 % per_row) * 4;
+  const int64_t idx = int64_t(b) * R + j;
+  auto ld4 = [](const float* p, float (&o)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  };
+  float dh[4], si[4], sf[4], so[4], s1[4], s2[4], u1[4], u2[4], cc[4], cp[4], dci[4] = {0.f, 0.f, 0.f, 0.f};
+  ld4(d_out + idx, dh);
   const float* sr = s + int64_t(b) * lds;
-  const float ig = 1.f / (1.f + expf(-sr[j]));
-  const float fg = 1.f / (1.f + expf(-sr[R + j]));
-  const float og = 1.f / (1.f + expf(-sr[2 * R + j]));
-  const float a1 = sr[3 * R + j] + u[int64_t(b) * 2 * R + j];
-  const float a2 = sr[4 * R + j] + u[int64_t(b) * 2 * R + R + j];
-  const float g = fmaxf(a1, a2);
-  const float tc = tanhf(c_cur[idx]);
-  float dc = (dc_in ? dc_in[idx] : 0.f) + dh * og * (1.f - tc * tc);
-  const float d_o = dh * tc;
-  const float d_f = dc * c_prev[idx];
-  const float d_i = dc * g;
-  const float d_g = dc * ig;
-  dc_out[idx] = dc * fg;
+  ld4(sr + j, si); ld4(sr + R + j, sf); ld4(sr + 2 * R + j, so); ld4(sr + 3 * R + j, s1);
+  ld4(sr + 4 * R + j, s2);
+  ld4(u + int64_t(b) * 2 * R + j, u1); ld4(u + int64_t(b) * 2 * R + R + j, u2);
+  ld4(c_cur + idx, cc); ld4(c_prev + idx, cp);
+  if (dc_in) ld4(dc_in + idx, dci);
+  if (drop_p > 0.f) {
+    const uint2 o = *reinterpret_cast<const uint2*>(out16 + idx);
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&o.x);
+    const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&o.y);
+    const float k[4] = {__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi)};
+    const float sc = 1.f / (1.f - drop_p);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dh[q] = (k[q] != 0.f) ? dh[q] * sc : 0.f;
+  }
+  if (dh_next) {
+    float n[4];
+    ld4(dh_next + int64_t(b) * ld_dh + j, n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dh[q] += n[q];
+  }
+  float o_dc[4], o_i[4], o_f[4], o_o[4], o_g1[4], o_g2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float ig = 1.f / (1.f + expf(-si[q]));
+    const float fg = 1.f / (1.f + expf(-sf[q]));
+    const float og = 1.f / (1.f + expf(-so[q]));
+    const float a1 = s1[q] + u1[q];
+    const float a2 = s2[q] + u2[q];
+    const float g = fmaxf(a1, a2);
+    const float tc = tanhf(cc[q]);
+    const float dc = dci[q] + dh[q] * og * (1.f - tc * tc);
+    const float d_o = dh[q] * tc;
+    const float d_f = dc * cp[q];
+    const float d_i = dc * g;
+    const float d_g = dc * ig;
+    o_dc[q] = dc * fg;
+    o_i[q] = d_i * ig * (1.f - ig);
+    o_f[q] = d_f * fg * (1.f - fg);
+    o_o[q] = d_o * og * (1.f - og);
+    const bool first = a1 >= a2;
+    o_g1[q] = first ? d_g : 0.f;
+    o_g2[q] = first ? 0.f : d_g;
+  }
+  *reinterpret_cast<float4*>(dc_out + idx) = make_float4(o_dc[0], o_dc[1], o_dc[2], o_dc[3]);
   bf16* dr = dscat + int64_t(b) * lds;
-  dr[j] = __float2bfloat16_rn(d_i * ig * (1.f - ig));
-  dr[R + j] = __float2bfloat16_rn(d_f * fg * (1.f - fg));
-  dr[2 * R + j] = __float2bfloat16_rn(d_o * og * (1.f - og));
-  const bool first = a1 >= a2;
-  dr[3 * R + j] = __float2bfloat16_rn(first ? d_g : 0.f);
-  dr[4 * R + j] = __float2bfloat16_rn(first ? 0.f : d_g);
+  store_bf16x4(dr + j, o_i[0], o_i[1], o_i[2], o_i[3]);
+  store_bf16x4(dr + R + j, o_f[0], o_f[1], o_f[2], o_f[3]);
+  store_bf16x4(dr + 2 * R + j, o_o[0], o_o[1], o_o[2], o_o[3]);
+  store_bf16x4(dr + 3 * R + j, o_g1[0], o_g1[1], o_g1[2], o_g1[3]);
+  store_bf16x4(dr + 4 * R + j, o_g2[0], o_g2[1], o_g2[2], o_g2[3]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -641,7 +676,7 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
       if ((rc = gemm_run(0, 0, 1, dz_t, V1, c->w_logit16, R, B, R, V1, 1, 0, e, s))) return rc;
     }
     {
-      const int nthr = B * R;
+      const int nthr = B * (R / 4);
       CC_CHECK_CUDA(launch_pdl(
           lstm_bwd_kernel, dim3((nthr + 255) / 256), dim3(256), 0, s, g->d_out + int64_t(t) * B * R,
           out16 + int64_t(t) * B * R, dh_next, int64_t(XH), dc_in, dc_out, s_t, int64_t(NS),

@@ -552,8 +552,10 @@ __global__ void caption_summary_kernel(const int64_t* __restrict__ tok_out, int 
   if (threadIdx.x == 0) s_max = 0;
   __syncthreads();
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    int k = 0;
-    while (k < n_steps && tok_out[int64_t(k) * B + b] > 0) ++k;
+    // first step with a non-positive id; the loads are independent (no early exit), so they overlap
+    int k = n_steps;
+    for (int t = n_steps - 1; t >= 0; --t)
+      if (tok_out[int64_t(t) * B + b] <= 0) k = t;
     cap_len[b] = k;
     atomicMax(&s_max, k);
   }
@@ -734,7 +736,7 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     }
   }
   if (c->n_out && c->cap_len) {
-    caption_summary_kernel<<<1, 256, 0, s>>>(c->tok_out, B, c->n_steps, c->n_out, c->cap_len);
+    caption_summary_kernel<<<1, 1024, 0, s>>>(c->tok_out, B, c->n_steps, c->n_out, c->cap_len);
     CC_LAUNCH_CHECK_K(PROF_MISC, s, 0.0, 0.0);
   }
   return CC_OK;
