@@ -72,8 +72,8 @@ __device__ __forceinline__ int find_row(const int* __restrict__ off, int B, int 
 // (8 independent loads in flight at D = 2048 -- this kernel also runs as the zero-copy PCIe
 // reader), then converts and stores.  128 threads / <= 64 registers per CTA so that a resident
 // pack CTA still leaves room for a 320-thread GEMM CTA on the same SM (the upload overlaps compute).
-constexpr int PACK_ROWS = 1;
 constexpr int PACK_THREADS = 128;
+template <int PACK_ROWS>
 __global__ void __launch_bounds__(PACK_THREADS)
 pack_att_kernel(const float* __restrict__ att, const int* __restrict__ off, int B, int L, int D,
                 int NL, bf16* __restrict__ out) {
@@ -597,7 +597,7 @@ int speaker_prologue_fwd(const coopcap_speaker* c, cudaStream_t s) {
   if (rc) return rc;
   if (!c->att_prepacked) {
     CC_REQUIRE(c->att_feats != nullptr, "speaker: att_feats is null and att16 is not pre-packed");
-    pack_att_kernel<<<(c->NL + PACK_ROWS - 1) / PACK_ROWS, PACK_THREADS, 0, s>>>(c->att_feats, c->att_off, c->B, c->L, c->D, c->NL,
+    pack_att_kernel<1><<<c->NL, PACK_THREADS, 0, s>>>(c->att_feats, c->att_off, c->B, c->L, c->D, c->NL,
                                           reinterpret_cast<bf16*>(c->att16));
     CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 6.0 * c->NL * c->D);
   }
@@ -777,10 +777,22 @@ int coopcap_pack_att_from_host(const float* att_feats_pinned, const int* att_off
   // the host buffer must be pinned + mapped (UVA): ask the runtime for its device alias
   CC_CHECK_CUDA(cudaHostGetDevicePointer(&dptr, const_cast<float*>(att_feats_pinned), 0));
   if (ctas <= 0) ctas = 64;
-  if (ctas > (NL + PACK_ROWS - 1) / PACK_ROWS) ctas = (NL + PACK_ROWS - 1) / PACK_ROWS;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  pack_att_kernel<<<ctas, PACK_THREADS, 0, s>>>(reinterpret_cast<const float*>(dptr), att_off, B, L, D, NL,
-                                       reinterpret_cast<bf16*>(att16));
+  // rows in flight per CTA (tuning knob COOPCAP_PACK_ROWS = 1, 2 or 4).  Measured inside the
+  // end-to-end step (upload overlapping compute), 64 CTAs: 1 row 10.5 ms/step, 2 rows 12.3, 4 rows
+  // 12.8; 128 CTAs are worse at every setting -- more requests in flight do not help this path.
+  static const int rows_per_item = [] {
+    const char* e = getenv("COOPCAP_PACK_ROWS");
+    const int v = e ? atoi(e) : 1;
+    return (v == 1 || v == 2 || v == 4) ? v : 1;
+  }();
+  const int items = (NL + rows_per_item - 1) / rows_per_item;
+  if (ctas > items) ctas = items;
+  const float* src = reinterpret_cast<const float*>(dptr);
+  bf16* dst = reinterpret_cast<bf16*>(att16);
+  if (rows_per_item == 1) pack_att_kernel<1><<<ctas, PACK_THREADS, 0, s>>>(src, att_off, B, L, D, NL, dst);
+  else if (rows_per_item == 2) pack_att_kernel<2><<<ctas, PACK_THREADS, 0, s>>>(src, att_off, B, L, D, NL, dst);
+  else pack_att_kernel<4><<<ctas, PACK_THREADS, 0, s>>>(src, att_off, B, L, D, NL, dst);
   CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 4.0 * NL * D);
   return CC_OK;
 }
