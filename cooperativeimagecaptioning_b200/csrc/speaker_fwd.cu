@@ -689,7 +689,8 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     float* z_t = c->z_all + int64_t(t) * B * V1;
     EpiStoreParams e3 = {};
     e3.alpha = 1.f; e3.bias = c->b_logit; e3.C = z_t; e3.ldc = V1;
-    rc = gemm_run(0, 0, 0, out16 + int64_t(t) * B * R, R, c->w_logit16, R, B, V1, R, 1, 0, e3, s);
+    rc = gemm_run(0, 0, 0, out16 + int64_t(t) * B * R, R, c->w_logit16, R, B, V1, R, 1,
+                  B >= 512 ? 256 : 0, e3, s);   // measured: 22.6 us at BN = 256 vs 24.6 us for the cost model's pick
     if (rc) return rc;
     const bool ps = (c->mode == COOPCAP_SAMPLE_PS_GUMBEL || c->mode == COOPCAP_SAMPLE_PS_MULTINOMIAL);
     bf16* x_next = (t + 1 < c->n_steps) ? xh16 + int64_t(t + 1) * B * XH : nullptr;
