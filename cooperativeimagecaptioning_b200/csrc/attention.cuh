@@ -405,11 +405,13 @@ attention_deferred2_kernel(const __nv_bfloat16* __restrict__ p_att16, const int*
                            const float* __restrict__ d_att_res, const float* __restrict__ att_w,
                            const float* __restrict__ de, int NL, int n_steps, int B,
                            float* __restrict__ d_att_e, __nv_bfloat16* __restrict__ d_p_att16,
-                           float* __restrict__ galpha_part, float* __restrict__ gbias_part) {
+                           float* __restrict__ galpha_part, float* __restrict__ gbias_part,
+                           const int* __restrict__ order) {
   static_assert(AR == 2 * ATT_THREADS, "thread -> 2 columns mapping");
   constexpr int CHUNK_BYTES = ATT_CH * AR * 2;
   extern __shared__ __align__(128) uint8_t smem[];
-  const int b = blockIdx.x;
+  // CTAs are dispatched in blockIdx order: longest rows first keeps the tail of the grid short
+  const int b = order ? order[blockIdx.x] : blockIdx.x;
   const int r0 = off ? off[b] : b * Lfix;
   const int Lb = off ? off[b + 1] - r0 : Lfix;
   const int Lp = (Lb + 7) & ~7;

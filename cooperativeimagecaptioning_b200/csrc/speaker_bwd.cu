@@ -769,7 +769,7 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
       attention_deferred2_kernel<512, ST><<<B, ATT_THREADS, smem, s>>>(
           reinterpret_cast<const bf16*>(c->p_att16), c->att_off, c->L, c->s_all, NS, 5 * R,
           int64_t(B) * NS, c->w_alpha, g->d_att_res, c->att_w, g->de, NL, n, B, g->d_att_e,
-          reinterpret_cast<bf16*>(g->d_p_att16), galpha_part, gbias_part);
+          reinterpret_cast<bf16*>(g->d_p_att16), galpha_part, gbias_part, c->att_order);
     } else {
       const int Lp = (c->L + 3) & ~3;
       const int groups = ATT_THREADS / (A / 8);
