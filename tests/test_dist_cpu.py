@@ -25,18 +25,31 @@ def _worker(rank, world, port, out):
         net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
         w0 = [p.detach().clone() for p in net.parameters()]
         opt = OPT.FlatAdam(net.parameters(), lr=1e-3, grad_clip=0.1)
-        # parameters and gradients are views of the flat buckets
+        # parameters are views of the flat bucket; gradients join theirs in gather_grads()
         for p, o in zip(opt.params, opt.offsets):
             assert p.data_ptr() == opt.flat_param.data_ptr() + 4 * o
-            assert p.grad.data_ptr() == opt.flat_grad.data_ptr() + 4 * o
+            assert p.grad is None
             assert o % 4 == 0
         for p, w in zip(net.parameters(), w0):
             assert torch.equal(p, w)
-        # rank-local "shard" loss -> rank-local gradients accumulate INTO the bucket
+        # rank-local "shard" loss -> rank-local gradients, gathered into the bucket
         opt.zero_grad()
         g = torch.Generator().manual_seed(100 + rank)
         x = torch.randn(4, 7, generator=g)
         net(x).square().sum().backward()
+        want = [p.grad.clone() for p in net.parameters()]
+        opt.gather_grads()
+        for p, o, w in zip(opt.params, opt.offsets, want):
+            assert p.grad.data_ptr() == opt.flat_grad.data_ptr() + 4 * o and torch.equal(p.grad, w)
+        # a parameter without a gradient contributes zeros, a second backward accumulates
+        opt.zero_grad()
+        net[1](torch.randn(2, 5, generator=g)).sum().backward()
+        net[1](torch.randn(2, 5, generator=g)).sum().backward()
+        opt.gather_grads()
+        assert float(net[0].weight.grad.abs().sum()) == 0.0 and float(net[1].bias.grad[0]) == 4.0
+        opt.zero_grad()
+        net(x).square().sum().backward()
+        opt.gather_grads()
         local = opt.flat_grad.clone()
         n = opt.all_reduce()
         assert n == world
