@@ -267,6 +267,7 @@ def main():
         model.caption_generator.logit.bias[0] = -1e4      # no early EOS: all 16 steps execute
     optim = OPT.define_optimizer(model, opt)   # one flat bucket over both agents (26.13 M fp32)
 
+    from cooperativeimagecaptioning_b200.data import row_order
     hb = [host_batch(args.rows, args.max_regions, args.min_regions, 1234 + 5 + 97 * rank + i, pin=True)
           for i in range(2)]
     B, L = args.rows, args.max_regions
@@ -277,6 +278,7 @@ def main():
         off = torch.zeros(B + 1, dtype=torch.int32)
         off[1:] = torch.cumsum(h["lens"], 0).to(torch.int32)
         d["att_masks"]._coopcap_off = (off.to(dev, non_blocking=non_blocking), int(off[-1]))
+        d["att_masks"]._coopcap_order = row_order(h["lens"]).to(dev, non_blocking=non_blocking)
         return d
 
     def train_step(d):

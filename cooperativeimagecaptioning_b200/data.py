@@ -18,6 +18,13 @@ from . import _lib
 from ._lib import check
 
 
+def row_order(lens: torch.Tensor) -> torch.Tensor:
+    """Row ids by decreasing region count (int32, pinned): the attention kernels deal rows to SMs in
+    this order; computing it here saves a device-side sort at the head of every pass."""
+    o = torch.argsort(lens, descending=True, stable=True).to(torch.int32)
+    return o.pin_memory() if torch.cuda.is_available() else o
+
+
 def upload_batch(fc_feats: torch.Tensor, att_feats: torch.Tensor, att_masks: Optional[torch.Tensor],
                  labels: torch.Tensor, masks: torch.Tensor, device, *, stream=None,
                  zero_copy: bool = True, ctas: int = 64):
@@ -57,6 +64,7 @@ def upload_batch(fc_feats: torch.Tensor, att_feats: torch.Tensor, att_masks: Opt
             off_d = off.to(device, non_blocking=True)
             am = att_masks.to(device, non_blocking=True)
             am._coopcap_off = (off_d, NL)
+            am._coopcap_order = row_order(lens).to(device, non_blocking=True)
             if zero_copy and att_feats.is_pinned() and att_feats.dtype == torch.float32:
                 att16 = torch.empty(NL, D, dtype=torch.bfloat16, device=device)
                 check(lib.coopcap_pack_att_from_host(
@@ -143,6 +151,7 @@ class HostPacker:
             if j["att_masks"] is not None:
                 am = j["att_masks"].to(self.device, non_blocking=True)
                 off_d = j["off"].to(self.device, non_blocking=True)
+                am._coopcap_order = row_order(j["off"][1:] - j["off"][:-1]).to(self.device, non_blocking=True)
                 moved += nb(j["att_masks"]) + 4 * (B + 1)
             else:
                 # fixed region count: an all-ones mask carries the packed operand
@@ -168,6 +177,9 @@ def record_stream(batch, stream):
         off = getattr(t, "_coopcap_off", None)
         if off is not None:
             off[0].record_stream(stream)
+        order = getattr(t, "_coopcap_order", None)
+        if order is not None:
+            order.record_stream(stream)
         a16 = getattr(t, "_coopcap_att16", None)
         if a16 is not None:
             a16.record_stream(stream)

@@ -180,7 +180,7 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
                     start_tokens: Optional[torch.Tensor] = None,
                     att16: Optional[torch.Tensor] = None, ps_prob: float = 0.0,
                     w_embed16: Optional[torch.Tensor] = None, ss_prob: float = 0.0,
-                    no_repeat: bool = False) -> SpeakerPass:
+                    no_repeat: bool = False, att_order: Optional[torch.Tensor] = None) -> SpeakerPass:
     """Prologue + n_steps decode steps.  `forced` int64 [n_steps, B] (time-major);
     `start_tokens` int64 [B] overrides the scalar start id per row."""
     _need_cuda(att_feats, att_off, forced, start_tokens)
@@ -221,8 +221,7 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     c.NL, c.cap, c.n_steps = NL, cap, n_steps
     c.att_feats, c.att_off = (None if att16 is not None else _p(att_feats)), _p(att_off)
     # longest rows first: the attention kernels deal rows to SMs by rank (load balance only)
-    att_order = None
-    if att_off is not None and B > 1:
+    if att_order is None and att_off is not None and B > 1:
         att_order = torch.argsort(att_off[1:] - att_off[:-1], descending=True).to(torch.int32)
     c.att_order = _p(att_order)
     c.att_prepacked = int(att16 is not None)

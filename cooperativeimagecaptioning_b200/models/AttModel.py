@@ -220,9 +220,11 @@ class AttModel(nn.Module):
                 # precondition of the reference (Appendix D): padded width == longest row
                 att_masks = att_masks[:, :L]
             off, NL = EN.region_offsets(att_masks, B, L)
+        # rows by decreasing region count (schedule hint), if the loader side already knows it
+        order = getattr(att_masks, "_coopcap_order", None) if att_masks is not None else None
         sp = EN.speaker_forward(P, packed, att_feats, off, NL, n_steps=n_steps, mode=mode,
                                 inv_tau=inv_tau, start_token=start_token, rnd=self._random(),
-                                forced=forced, start_tokens=start_tokens, att16=att16,
+                                forced=forced, start_tokens=start_tokens, att16=att16, att_order=order,
                                 ps_prob=ps_prob, ss_prob=ss_prob, no_repeat=no_repeat,
                                 w_embed16=self._packed.get_embed16(P) if mode in EN.PS_MODES else None)
         if self.keep_passes:
