@@ -271,7 +271,8 @@ class AlternatingJointModel(nn.Module):
         else:
             loss_vse = lp.t["loss"][0].clone()
         lis._loss["contrastive"] = loss_vse.detach()
-        loss = loss + loss_vse * self.retrieval_reward_weight                           # :374
+        term = loss_vse * self.retrieval_reward_weight                                  # :374
+        loss = term if (isinstance(loss, float) and loss == 0.0) else loss + term
         return loss, sp.t["tok_out"], sp.t["logp"], sp.t["cap_len"], tok_sb
 
     # ------------------------------------------------------------------ forward (:433-555)
@@ -281,10 +282,15 @@ class AlternatingJointModel(nn.Module):
             if self.cider_optimization:
                 raise NotImplementedError("CIDEr self-critical terms are outside the hot path "
                                           "(SURVEY.md §2 row 8): run with cider_optimization=0")
-            loss_cap = self.ce_loss(fc_feats, att_feats, att_masks, seq, masks)
-            loss_vse = self.vse_loss(fc_feats, att_feats, seq, masks,
-                                     only_one_retrieval=self.only_one_retrieval)
-            loss = self.caption_loss_weight * loss_cap + self.vse_loss_weight * loss_vse
+            # (:449-454) caption_loss_weight * loss_cap + vse_loss_weight * loss_vse; a term whose
+            # weight is 0 is skipped instead of being materialised as a zero tensor, so the speaker
+            # turn does not queue half a dozen one-element kernels between decode and listener
+            loss = 0.0
+            if self.caption_loss_weight > 0:
+                loss = self.caption_loss_weight * self.ce_loss(fc_feats, att_feats, att_masks, seq, masks)
+            if self.vse_loss_weight > 0:
+                loss = loss + self.vse_loss_weight * self.vse_loss(
+                    fc_feats, att_feats, seq, masks, only_one_retrieval=self.only_one_retrieval)
             if self.retrieval_reward_weight > 0:
                 if self.retrieval_reward == "reinforce":
                     loss, gen_result, sample_logprobs, _masks, gen_result, gen_masks, _seqs, \
@@ -304,7 +310,7 @@ class AlternatingJointModel(nn.Module):
                 else:
                     loss, *_ = self.st_and_ps_methods(fc_feats, att_feats, att_masks, seq, masks,
                                                       data, loss)
-            return loss
+            return loss if torch.is_tensor(loss) else self._zero(fc_feats)
         if alternating_turn == "speaker":                                               # :508-526
             if self.retrieval_reward == "reinforce":
                 self.changeModelUpdateStatus({"vseModel": False, "captionModel": True})
