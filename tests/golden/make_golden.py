@@ -358,6 +358,14 @@ CASES = [
                                           kind="speaker_turn", seed=200, eos_bias=6.0)),
     ("real_mle_b4", synth.Dims(), dict(rows=4, regions=6, varlen=False, mode="gumbel", kind="mle",
                                        seed=210)),
+    ("real_reinforce_gt_b4", synth.Dims(), dict(rows=4, regions=6, varlen=True, mode="reinforce",
+                                                kind="speaker_turn", baseline="gt", weight=0.8, seed=220,
+                                                eos_bias=6.0)),
+    ("real_multinomial_soft_b4", synth.Dims(), dict(rows=4, regions=6, varlen=False, mode="multinomial_soft",
+                                                    kind="speaker_turn", seed=230, eos_bias=6.0, prob=0.5,
+                                                    tau=0.75)),
+    ("real_listener_turn_b4", synth.Dims(), dict(rows=4, regions=6, varlen=True, mode="reinforce",
+                                                 kind="listener_turn", seed=240, eos_bias=6.0)),
 ]
 
 
