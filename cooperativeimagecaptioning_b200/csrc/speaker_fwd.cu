@@ -67,10 +67,10 @@ __device__ __forceinline__ int find_row(const int* __restrict__ off, int B, int 
   return lo;
 }
 
-// Cast + pack: packed row r (valid region l of batch row b) <- att[b, l, :].  Work item = 2
-// consecutive packed rows; every thread first issues all of its 16-byte loads for the item
-// (8 independent loads in flight at D = 2048 -- this kernel also runs as the zero-copy PCIe
-// reader), then converts and stores.  128 threads / <= 64 registers per CTA so that a resident
+// Cast + pack: packed row r (valid region l of batch row b) <- att[b, l, :].  Work item =
+// PACK_ROWS consecutive packed rows; every thread first issues all of its 16-byte loads for the
+// item (4 per row at D = 2048 -- this kernel also runs as the zero-copy PCIe reader), then
+// converts and stores.  128 threads / <= 64 registers per CTA (PACK_ROWS <= 2) so that a resident
 // pack CTA still leaves room for a 320-thread GEMM CTA on the same SM (the upload overlaps compute).
 constexpr int PACK_THREADS = 128;
 template <int PACK_ROWS>
