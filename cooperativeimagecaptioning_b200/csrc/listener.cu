@@ -11,6 +11,8 @@ namespace coopcap {
 using bf16 = __nv_bfloat16;
 
 int cast_block(const float* src, int64_t rows, int cols, void* dst, int64_t ld_dst, cudaStream_t s);
+int cast_blocks(int n, const float* const* src, const int64_t* rows, const int* cols, void* const* dst,
+                const int64_t* ld_dst, cudaStream_t s);
 int colsum_bf16(const void* src, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t s);
 int wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, float* C,
           int64_t ldc, cudaStream_t s);
@@ -596,12 +598,12 @@ int coopcap_listener_pack_weights(const coopcap_listener_pack* p, coopcap_stream
   using namespace coopcap;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CC_REQUIRE(p != nullptr, "listener_pack: null");
-  int rc;
-  if ((rc = cast_block(p->w_img, p->M, p->F, p->w_img16, p->F, s))) return rc;
-  if ((rc = cast_block(p->w_ih, 3 * p->M, p->E, p->w_ih16, p->E, s))) return rc;
-  if ((rc = cast_block(p->w_hh, 3 * p->M, p->M, p->w_hh16, p->M, s))) return rc;
-  if (p->w_emb16 && (rc = cast_block(p->w_emb, p->V2, p->E, p->w_emb16, p->E, s))) return rc;
-  return CC_OK;
+  const float* src[4] = {p->w_img, p->w_ih, p->w_hh, p->w_emb};
+  const int64_t rows[4] = {p->M, 3 * p->M, 3 * p->M, p->V2};
+  const int cols[4] = {p->F, p->E, p->M, p->E};
+  void* dst[4] = {p->w_img16, p->w_ih16, p->w_hh16, p->w_emb16};
+  const int64_t ld[4] = {p->F, p->E, p->M, p->E};
+  return cast_blocks(p->w_emb16 ? 4 : 3, src, rows, cols, dst, ld, s);
 }
 
 // emb16[row, :] = bf16(w_emb[id, :]) for `rows` rows (the prepended BOS position)

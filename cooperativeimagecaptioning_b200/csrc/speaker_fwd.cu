@@ -54,6 +54,68 @@ __global__ void bias_cat_kernel(const float* __restrict__ b_i2h, const float* __
   else if (i < n5r + A) out[i] = b_h2att[i - n5r];
 }
 
+// Several fp32 -> bf16 block casts in ONE launch (the weight re-pack after every optimizer step is
+// eleven small casts: as separate launches their latency, not their 157 MB, set the cost).
+// Sources are dense [rows, cols] fp32 with cols % 8 == 0; destinations bf16 with row pitch ld_dst.
+constexpr int CAST_MULTI_MAX = 12;
+struct CastJobs {
+  const float* src[CAST_MULTI_MAX];
+  bf16* dst[CAST_MULTI_MAX];
+  int cols[CAST_MULTI_MAX];
+  int64_t ld_dst[CAST_MULTI_MAX];
+  int64_t first[CAST_MULTI_MAX + 1];      // prefix sums of the jobs' 8-element groups
+  int n;
+};
+__global__ void __launch_bounds__(256) cast_multi_kernel(const CastJobs J) {
+  const int64_t total = J.first[J.n];
+  for (int64_t g = int64_t(blockIdx.x) * 256 + threadIdx.x; g < total; g += int64_t(gridDim.x) * 256) {
+    int k = 0;
+    while (k + 1 < J.n && g >= J.first[k + 1]) ++k;
+    const int64_t e = (g - J.first[k]) * 8;            // flat element index inside job k
+    const int cols = J.cols[k];
+    const int64_t row = e / cols;
+    const int col = int(e - row * cols);
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(J.src[k] + e));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(J.src[k] + e + 4));
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    *reinterpret_cast<uint4*>(J.dst[k] + row * J.ld_dst[k] + col) = float8_to_bf16x8(f);
+  }
+}
+struct CastBatch {
+  CastJobs J = {};
+  bool ok = true;
+  void add(const float* src, int64_t rows, int cols, void* dst, int64_t ld_dst) {
+    if (J.n >= CAST_MULTI_MAX || cols % 8 != 0 || ld_dst % 8 != 0 ||
+        (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) {
+      ok = false;
+      return;
+    }
+    const int k = J.n++;
+    J.src[k] = src; J.dst[k] = reinterpret_cast<bf16*>(dst); J.cols[k] = cols; J.ld_dst[k] = ld_dst;
+    J.first[k + 1] = J.first[k] + rows * cols / 8;
+  }
+  int run(cudaStream_t s) {
+    if (J.n == 0) return CC_OK;
+    const int64_t groups = J.first[J.n];
+    int64_t grid = (groups + 255) / 256;
+    const int64_t cap = int64_t(num_sms()) * 16;
+    if (grid > cap) grid = cap;
+    cast_multi_kernel<<<unsigned(grid), 256, 0, s>>>(J);
+    CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
+    return CC_OK;
+  }
+};
+int cast_blocks(int n, const float* const* src, const int64_t* rows, const int* cols, void* const* dst,
+                const int64_t* ld_dst, cudaStream_t s) {
+  CastBatch b;
+  for (int i = 0; i < n; ++i) b.add(src[i], rows[i], cols[i], dst[i], ld_dst[i]);
+  if (b.ok) return b.run(s);
+  int rc;
+  for (int i = 0; i < n; ++i)
+    if ((rc = cast_block(src[i], rows[i], cols[i], dst[i], ld_dst[i], s))) return rc;
+  return CC_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // prologue: cast + pack valid regions
 // ------------------------------------------------------------------------------------------
@@ -754,15 +816,17 @@ int coopcap_speaker_pack_weights(const coopcap_speaker_pack* p, coopcap_stream_t
   const int R = p->R, E = p->E, A = p->A, D = p->D, XH = E + R;
   bf16* wc = reinterpret_cast<bf16*>(p->w_cat16);
   int rc;
-  if ((rc = cast_block(p->w_att_embed, R, D, p->w_att_embed16, D, s))) return rc;
-  if ((rc = cast_block(p->w_ctx2att, A, R, p->w_ctx2att16, R, s))) return rc;
-  if ((rc = cast_block(p->w_i2h, 5 * R, E, wc, XH, s))) return rc;
-  if ((rc = cast_block(p->w_h2h, 5 * R, R, wc + E, XH, s))) return rc;
   CC_CHECK_CUDA(cudaMemset2DAsync(wc + int64_t(5 * R) * XH, XH * sizeof(bf16), 0, E * sizeof(bf16),
                                   A, s));
-  if ((rc = cast_block(p->w_h2att, A, R, wc + int64_t(5 * R) * XH + E, XH, s))) return rc;
-  if ((rc = cast_block(p->w_a2c, 2 * R, R, p->w_a2c16, R, s))) return rc;
-  if ((rc = cast_block(p->w_logit, p->V1, R, p->w_logit16, R, s))) return rc;
+  {
+    const float* src[7] = {p->w_att_embed, p->w_ctx2att, p->w_i2h, p->w_h2h, p->w_h2att, p->w_a2c, p->w_logit};
+    const int64_t rows[7] = {R, A, 5 * R, 5 * R, A, 2 * R, p->V1};
+    const int cols[7] = {D, R, E, R, R, R, R};
+    void* dst[7] = {p->w_att_embed16, p->w_ctx2att16, wc, wc + E, wc + int64_t(5 * R) * XH + E,
+                    p->w_a2c16, p->w_logit16};
+    const int64_t ld[7] = {D, R, XH, XH, XH, R, R};
+    if ((rc = cast_blocks(7, src, rows, cols, dst, ld, s))) return rc;
+  }
   const int n = 5 * R + A;
   bias_cat_kernel<<<(n + 255) / 256, 256, 0, s>>>(p->b_i2h, p->b_h2h, p->b_h2att, 5 * R, A, p->b_cat);
   CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
