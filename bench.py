@@ -197,12 +197,21 @@ def cpu_joint_step_rate(rows, lmax, lmin, steps, warmup):
     cfg = OJ.JointCfg(drop_p=0.5, retrieval_reward="gumbel", retrieval_reward_weight=0.01)
     Pso = {k: v.clone().requires_grad_(True) for k, v in Ps.items()}
     Plo = {k: v.clone().requires_grad_(True) for k, v in Pl.items()}
+    params = list(Pso.values()) + list(Plo.values())
+    # the same step as the GPU arm: zero grads -> forward -> backward -> clamp(0.1) + Adam on both
+    # agents (optimizer.py:25-27,224-242; misc/utils.py:65-69)
+    adam = torch.optim.Adam(params, lr=5e-4)
     times = []
     for i in range(warmup + steps):
         noise = synth.make_noise(d, rows, lmax, 77 + i, dropout=True, gumbel=True)
         t0 = time.perf_counter()
+        adam.zero_grad()
         loss, _, _, _ = OJ.st_joint_loss(Pso, Plo, hb["fc"], hb["att"], hb["att_masks"], noise, cfg)
-        torch.autograd.grad(loss, list(Pso.values()) + list(Plo.values()), allow_unused=True)
+        loss.backward()
+        for p in params:
+            if p.grad is not None:
+                p.grad.clamp_(-0.1, 0.1)
+        adam.step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -215,14 +224,18 @@ def run_reference(args, rank, world):
     rate, sec, threads = cpu_joint_step_rate(args.cpu_rows, args.max_regions, args.min_regions,
                                              max(1, args.steps), max(1, min(args.warmup, 2)))
     sample = (f"{args.cpu_rows} rows x {args.min_regions}-{args.max_regions} regions, Gumbel joint "
-              f"step fwd+bwd (noise generation outside the timed region), fp32")
+              f"step fwd+bwd+clamp+Adam (noise generation outside the timed region), fp32")
     line = dict(
         impl="reference", metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus,
         steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)), ms_per_step=sec * 1e3,
         higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload="gumbel_joint_step_varlen", rows_per_gpu=args.rows,
+        config=dict(workload="gumbel_joint_step_varlen (BASELINE.json configs[4])",
+                    rows_per_gpu=args.rows, global_rows=args.rows,
                     regions=f"{args.min_regions}-{args.max_regions}", vocab=9487, seq_len=16,
-                    note="CPU restatement (oracle/) of the reference path on a bounded sample"),
+                    speaker="att2in2 rnn512", listener="vsefc gru1024", gumbel_temp=1.0,
+                    dropout=0.5, optimizer="clamp(0.1)+Adam, both agents", parallelism="host cores",
+                    note="CPU restatement (oracle/) of the reference path on a bounded sample of the "
+                         "workload (--cpu-rows rows per step)"),
         cpu_baseline=dict(value=rate, unit=UNIT, cores=threads, kind="port", sample=sample),
         e2e=dict(value=rate, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         gpu_launches=0)
@@ -553,7 +566,7 @@ def main():
         rate, sec, threads = cpu_joint_step_rate(args.cpu_rows, args.max_regions, args.min_regions, 4, 1)
         cpu = dict(value=rate, unit=UNIT, cores=threads, kind="port",
                    sample=f"{args.cpu_rows} rows x {args.min_regions}-{args.max_regions} regions, "
-                          f"Gumbel joint step fwd+bwd, fp32, {sec:.2f} s/step, 1 warm-up + 4 timed")
+                          f"Gumbel joint step fwd+bwd+clamp+Adam, fp32, {sec:.2f} s/step, 1 warm-up + 4 timed")
 
     if rank == 0:
         line = dict(
