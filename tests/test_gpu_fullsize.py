@@ -176,3 +176,49 @@ def test_backward_is_linear_in_the_upstream_gradient_and_step_is_finite():
         assert bool(torch.isfinite(p).all()), n
         if n in g1 and float(g1[n].abs().max()) > 0:
             assert not torch.equal(p, before[n]), n
+
+
+def test_batch_larger_than_the_attention_grid_equals_its_halves():
+    """1300 rows > 148 SMs x 8 row slots: every warp pair of the persistent attention kernels serves
+    more than one row (ring / barrier state carried across rows).  Rows are independent, so the
+    greedy decode of the whole batch must equal the decode of its two halves bit for bit (650 rows
+    take the one-row-per-pair path the oracle tests cover), and the MLE gradient of the whole batch
+    must equal the token-count-weighted mean of the halves' gradients."""
+    B, h = 1300, 650
+    spk = _speaker(seed=2, eos_bias=-1.0, drop_prob_lm=0.0)
+    fc, att, am, lens = _batch(B, 2, 12, 29)
+    spk.eval()
+    with torch.no_grad():
+        seq, lp = spk.sample(fc, att, am, {"sample_max": 1})
+        parts = [spk.sample(fc[s], att[s], am[s], {"sample_max": 1}) for s in (slice(0, h), slice(h, B))]
+    assert seq.shape[1] >= 2
+    for (sq, l), s in zip(parts, (slice(0, h), slice(h, B))):
+        n = sq.shape[1]
+        assert torch.equal(seq[s, :n], sq) and torch.equal(lp[s, :n], l)
+        assert not bool(seq[s, n:].any())            # the half's captions had all ended by then
+    # teacher-forced XE, forward + backward
+    g = torch.Generator().manual_seed(31)
+    clen = torch.randint(3, 11, (B,), generator=g)
+    labels = torch.zeros(B, 18, dtype=torch.long)
+    words = torch.randint(1, 9488, (B, 16), generator=g)
+    labels[:, 1:17] = torch.where(torch.arange(16)[None, :] < clen[:, None], words, torch.zeros_like(words))
+    masks = (torch.arange(18)[None, :] < (clen + 2)[:, None]).float()
+    labels, masks = labels.cuda(), masks.cuda()
+    spk.train()
+
+    def grads(s):
+        spk.zero_grad(set_to_none=True)
+        loss = spk(fc[s], att[s], am[s], labels[s], masks[s])
+        loss.backward()
+        return float(loss.detach()), {n: p.grad.double().clone() for n, p in spk.named_parameters() if p.grad is not None}
+
+    l_all, g_all = grads(slice(0, B))
+    (l1, g1), (l2, g2) = grads(slice(0, h)), grads(slice(h, B))
+    n1, n2 = float(masks[:h, 1:].sum()), float(masks[h:, 1:].sum())
+    assert abs(l_all - (n1 * l1 + n2 * l2) / (n1 + n2)) <= 1e-4 * abs(l_all)
+    for n in g_all:
+        want = (n1 * g1[n] + n2 * g2[n]) / (n1 + n2)
+        if float(want.norm()) == 0:
+            continue
+        err = float((g_all[n] - want).norm() / want.norm())
+        assert err <= 5e-3, (n, err)
