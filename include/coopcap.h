@@ -471,7 +471,8 @@ int coopcap_h2d_ragged_rows(void* dst, const void* src_host, const int* lens_hos
 int coopcap_pack_att_from_host(const float* att_feats_pinned, const int* att_off, int B, int L, int D,
                                int NL, void* att16, int ctas, coopcap_stream_t stream);
 
-/* Host-side variant: worker threads of the library pack the valid regions of a HOST tensor
+/* Host-side variant of the batch staging (reference: `load_data` / `utils.var_wrapper(...).cuda()`,
+ * train.py:162-178, misc/utils.py:72-87): worker threads of the library pack the valid regions of a HOST tensor
  * att_feats [B, L, D] fp32 into a (pinned) HOST staging buffer att16_host [NL, D] bf16 -- same
  * round-to-nearest-even as the device pack, so the operand is bit-identical -- which the caller
  * then moves with one DMA copy: a quarter of the padded fp32 bytes cross PCIe and no SM is used.
