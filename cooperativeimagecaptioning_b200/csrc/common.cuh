@@ -73,6 +73,11 @@ void prof_mark(int kind, cudaStream_t stream, double flops, double bytes);
 
 int num_sms();
 
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device.  The attribute is per
+// (device, function); the cache is keyed the same way, so a process that drives several GPUs (or
+// switches devices between calls) sets it on each of them.  Returns CC_OK or a negative code.
+int ensure_dyn_smem(const void* func, int bytes);
+
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
@@ -314,8 +319,13 @@ struct Philox {
     }
     return make_uint4(c0, c1, c2, c3);
   }
-  // uniform in [0,1) with 24 bits, matching torch.rand's float granularity
-  __host__ __device__ static inline float u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }
+  // uniform on the open interval: (k + 1/2) * 2^-23, k in [0, 2^23), i.e. [2^-24, 1 - 2^-24], every
+  // value exact in fp32.  Neither end is reachable, so -log(u) and -log(1 - u) (the Gumbel and
+  // exponential-race transforms) are finite and non-zero for every draw: with a closed lower end
+  // u == 0 made the race score +inf once per 2^24 logits and that token won whatever its logit.
+  __host__ __device__ static inline float u01(uint32_t x) {
+    return (float(x >> 9) + 0.5f) * (1.0f / 8388608.0f);
+  }
 };
 
 }  // namespace coopcap

@@ -539,12 +539,7 @@ int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int M
                     !ep.philox_dropout && !ep.dbg;
   auto kern = lean ? gemm_tc_kernel<KIND, BN, AMAJ, BMAJ, Epi, true>
                    : gemm_tc_kernel<KIND, BN, AMAJ, BMAJ, Epi, false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[lean]) {
-    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
-    attr_set[lean] = true;
-  }
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES))) return rc;
   const int num_m = (M + GEMM_BM - 1) / GEMM_BM, num_n = (N + BN - 1) / BN;
   const int nkb = (K + Cfg::BK - 1) / Cfg::BK;
   if (split_k > nkb) split_k = nkb;

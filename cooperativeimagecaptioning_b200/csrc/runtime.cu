@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/coopcap.h"
@@ -63,6 +64,25 @@ int num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+int ensure_dyn_smem(const void* func, int bytes) {
+  if (bytes <= 48 * 1024) return CC_OK;           // within the default limit: nothing to opt in to
+  static std::mutex mu;
+  static std::vector<std::pair<std::pair<int, const void*>, int>> seen;   // ((device, func), bytes)
+  int dev = 0;
+  CC_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto& e : seen)
+    if (e.first.first == dev && e.first.second == func) {
+      if (e.second >= bytes) return CC_OK;
+      CC_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      e.second = bytes;
+      return CC_OK;
+    }
+  CC_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  seen.push_back({{dev, func}, bytes});
+  return CC_OK;
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {

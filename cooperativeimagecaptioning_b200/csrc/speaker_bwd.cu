@@ -540,12 +540,7 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
              c->mode);
   const int B = c->B, V1 = c->V1, E = c->E;
   const size_t smem = sizeof(float) * V1;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    CC_CHECK_CUDA(cudaFuncSetAttribute(st_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(smem)));
-    smem_set = smem;
-  }
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel), int(smem)))) return rc;
   // several steps per launch: M = chunk * B rows give properly sized GEMM tiles instead of
   // n_steps launches at the latency floor (g_ws holds `g_chunk_steps` steps)
   const int chunk = demb16 ? (g_chunk_steps < 1 ? 1 : g_chunk_steps) : c->n_steps;
@@ -614,21 +609,11 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
   bf16* ps_dpre16 = reinterpret_cast<bf16*>(g->ps_dpre16);
   if (ps) {
     const size_t smem = sizeof(float) * V1;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-      CC_CHECK_CUDA(cudaFuncSetAttribute(st_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         int(smem)));
-      smem_set = smem;
-    }
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel), int(smem)))) return rc;
   }
 
   const size_t att_smem = attention_smem_bytes(A, R, c->L);
-  static size_t att_smem_set = 0;
-  if (att_smem > 48 * 1024 && att_smem > att_smem_set) {
-    CC_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(att_smem)));
-    att_smem_set = att_smem;
-  }
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_bwd_kernel), int(att_smem)))) return rc;
   // BPTT.  d[x|h] = dscat . w_cat has only 8 x 8 output tiles for K = 5R+A: it runs split along K
   // with TMA reduce-add into a zeroed buffer so that the whole machine works on it.
   const int dxh_split = (int64_t(B) * XH <= int64_t(128) * 128 * 74 && NS >= 2048) ? 2 : 1;
@@ -692,12 +677,7 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
       if ((rc = gemm_run(0, 0, 1, ds_t + 3 * R, NS, c->w_a2c16, R, B, R, 2 * R, 1, 0, e, s))) return rc;
     }
     if (A == 512 && R == 512) {
-      static bool set4 = false;
-      if (!set4) {
-        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd4_kernel<512>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM));
-        set4 = true;
-      }
+      if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_bwd4_kernel<512>), ATT4_SMEM))) return rc;
       CC_CHECK_CUDA(launch_pdl(attention_bwd4_kernel<512>, dim3(std::min(num_sms(), B)),
                                dim3(ATT4_THREADS), size_t(ATT4_SMEM), s,
                                reinterpret_cast<const bf16*>(c->p_att16),
@@ -760,12 +740,7 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
       constexpr int ST = 3;
       const size_t smem = attention_deferred2_smem<512, ST>(c->L, n);
       CC_REQUIRE(smem <= 227 * 1024, "deferred attention backward needs %zu B of shared memory", smem);
-      static size_t set = 0;
-      if (smem > set) {
-        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_deferred2_kernel<512, ST>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        set = smem;
-      }
+      if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_deferred2_kernel<512, ST>), int(smem)))) return rc;
       attention_deferred2_kernel<512, ST><<<B, ATT_THREADS, smem, s>>>(
           reinterpret_cast<const bf16*>(c->p_att16), c->att_off, c->L, c->s_all, NS, 5 * R,
           int64_t(B) * NS, c->w_alpha, g->d_att_res, c->att_w, g->de, NL, n, B, g->d_att_e,
@@ -775,12 +750,7 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
       const int groups = ATT_THREADS / (A / 8);
       const size_t smem = sizeof(float) * (size_t(n) * (A + R) + 2 * size_t(n) * Lp + size_t(groups) * A);
       CC_REQUIRE(smem <= 227 * 1024, "deferred attention backward needs %zu B of shared memory", smem);
-      static size_t set = 0;
-      if (smem > 48 * 1024 && smem > set) {
-        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_deferred_bwd_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        set = smem;
-      }
+      if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_deferred_bwd_kernel), int(smem)))) return rc;
       attention_deferred_bwd_kernel<<<B, ATT_THREADS, smem, s>>>(
           reinterpret_cast<const bf16*>(c->p_att16), c->att_off, c->L, c->s_all, NS, 5 * R,
           int64_t(B) * NS, c->w_alpha, g->d_att_res, c->att_w, g->de, NL, n, B, g->d_att_e,
@@ -815,8 +785,8 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
 // flat fp32 bucket: g *= grad_scale; clamp; Adam  (optimizer.py:233-242, misc/utils.py:65-69)
 __global__ void clamp_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                   float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                  float grad_scale, float clip, float lr, float b1, float b2, float eps,
-                                  float wd, float bc1, float bc2_sqrt) {
+                                  float grad_scale, float clip, float step_size, float b1, float b2,
+                                  float eps, float wd, float bc2_sqrt) {
   const int64_t n4 = n / 4;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4;
        i += int64_t(gridDim.x) * blockDim.x) {
@@ -831,10 +801,10 @@ __global__ void clamp_adam_kernel(float* __restrict__ p, const float* __restrict
       float x = gg[q] * grad_scale;
       if (clip > 0.f) x = fminf(fmaxf(x, -clip), clip);
       x += wd * pp[q];
-      mm[q] = b1 * mm[q] + (1.f - b1) * x;
+      mm[q] = fmaf(1.f - b1, x - mm[q], mm[q]);      // torch: exp_avg.lerp_(grad, 1 - beta1)
       vq[q] = b2 * vq[q] + (1.f - b2) * x * x;
       const float denom = sqrtf(vq[q]) / bc2_sqrt + eps;
-      pp[q] -= (lr / bc1) * (mm[q] / denom);
+      pp[q] -= step_size * (mm[q] / denom);
     }
     reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
     reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
@@ -846,10 +816,10 @@ __global__ void clamp_adam_kernel(float* __restrict__ p, const float* __restrict
       float x = g[i] * grad_scale;
       if (clip > 0.f) x = fminf(fmaxf(x, -clip), clip);
       x += wd * p[i];
-      const float mq = b1 * m[i] + (1.f - b1) * x;
+      const float mq = fmaf(1.f - b1, x - m[i], m[i]);
       const float vq = b2 * v[i] + (1.f - b2) * x * x;
       m[i] = mq; v[i] = vq;
-      p[i] -= (lr / bc1) * (mq / (sqrtf(vq) / bc2_sqrt + eps));
+      p[i] -= step_size * (mq / (sqrtf(vq) / bc2_sqrt + eps));
     }
   }
 }
@@ -897,14 +867,15 @@ int coopcap_clamp_adam(float* param, const float* grad, float* exp_avg, float* e
   CC_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
              "clamp_adam: buffers must be 16-byte aligned");
-  const float bc1 = 1.f - powf(beta1, float(step));
-  const float bc2 = 1.f - powf(beta2, float(step));
+  // bias corrections in double, as torch.optim.Adam computes them on the host (1 - beta ** step)
+  const double bc1 = 1.0 - pow(double(beta1), double(step));
+  const double bc2 = 1.0 - pow(double(beta2), double(step));
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks > int64_t(num_sms()) * 8) blocks = int64_t(num_sms()) * 8;
   if (blocks < 1) blocks = 1;
   clamp_adam_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      param, grad, exp_avg, exp_avg_sq, n, grad_scale, clip, lr, beta1, beta2, eps, weight_decay,
-      bc1, sqrtf(bc2));
+      param, grad, exp_avg, exp_avg_sq, n, grad_scale, clip, float(double(lr) / bc1), beta1, beta2, eps,
+      weight_decay, float(sqrt(bc2)));
   CC_LAUNCH_CHECK_K(PROF_ADAM, reinterpret_cast<cudaStream_t>(stream), 0.0, 28.0 * double(n));
   return CC_OK;
 }

@@ -496,8 +496,13 @@ sample_kernel(const float* __restrict__ z, int V1, float inv_tau,
       if (s_bv[w] > bv || (s_bv[w] == bv && s_bi[w] < bi)) { bv = s_bv[w]; bi = s_bi[w]; }
     }
     const float lse = (l1.m + log2f(l1.s)) * LN2;
+    // a row of NaN logits (diverged training) wins no comparison: emit EOS, its NaN log-prob tells
+    // the host; ids handed in by the caller are range-checked before they index anything
+    if (unsigned(bi) >= unsigned(V1)) bi = 0;
     const int64_t raw = (mode == COOPCAP_SAMPLE_NONE) ? 0 : int64_t(bi);
-    const int64_t tgt = forced ? forced[b] : raw;
+    int64_t tgt = forced ? forced[b] : raw;
+    const bool tgt_ok = uint64_t(tgt) < uint64_t(V1);
+    if (!tgt_ok) tgt = 0;
     int64_t fed = tgt;
     if (ss_prob > 0.f) {               // scheduled sampling: feed the drawn id instead of the target
       const float u = ss_u ? ss_u[b] : Philox::u01(Philox::gen(seed, ss_stream, uint64_t(b)).x);
@@ -508,7 +513,7 @@ sample_kernel(const float* __restrict__ z, int V1, float inv_tau,
     tok_raw[b] = raw;
     tok_out[b] = un ? fed : 0;                       // :409
     tok_fed_next[b] = fed;
-    logp[b] = zr[tgt] - lse;
+    logp[b] = tgt_ok ? zr[tgt] - lse : __int_as_float(0x7fc00000);
     lse_o[b] = lse;
     if (mode == COOPCAP_SAMPLE_PS_MULTINOMIAL) {
       // y = exp(log_softmax(z) / tau), unnormalised for tau != 1  (multinomial_soft.py:12-15)
@@ -533,7 +538,7 @@ sample_kernel(const float* __restrict__ z, int V1, float inv_tau,
 __global__ void ban_prev_kernel(float* __restrict__ z, int V1, const int64_t* __restrict__ prev_out,
                                 int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) z[int64_t(b) * V1 + prev_out[b]] = -INFINITY;
+  if (b < B && uint64_t(prev_out[b]) < uint64_t(V1)) z[int64_t(b) * V1 + prev_out[b]] = -INFINITY;
 }
 
 template <typename... Args>
@@ -699,12 +704,7 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
   bf16* att_res16 = reinterpret_cast<bf16*>(c->att_res16);
   bf16* out16 = reinterpret_cast<bf16*>(c->out16);
   const size_t att_smem = attention_smem_bytes(A, R, c->L);
-  static size_t att_smem_set = 0;
-  if (att_smem > 48 * 1024 && att_smem > att_smem_set) {
-    CC_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(att_smem)));
-    att_smem_set = att_smem;
-  }
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_fwd_kernel), int(att_smem)))) return rc;
   start_step_kernel<<<B, 128, 0, s>>>(c->embed, c->start_token, c->start_tokens, B, E, R, c->keep_embed, c->seed,
                                       c->drop_p, xh16, c->c_all, c->tok_fed);
   CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 0.0);
@@ -717,12 +717,7 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     rc = gemm_run(0, 0, 0, xh16 + int64_t(t) * B * XH, XH, c->w_cat16, XH, B, NS, XH, 1, 0, e1, s);
     if (rc) return rc;
     if (A == 512 && R == 512) {
-      static bool set4 = false;
-      if (!set4) {
-        CC_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd4_kernel<512>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM));
-        set4 = true;
-      }
+      if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_fwd4_kernel<512>), ATT4_SMEM))) return rc;
       CC_CHECK_CUDA(launch_pdl(attention_fwd4_kernel<512>, dim3(std::min(num_sms(), B)),
                                dim3(ATT4_THREADS), size_t(ATT4_SMEM), s,
                                reinterpret_cast<const bf16*>(c->p_att16),

@@ -24,9 +24,20 @@ from .. import engine as EN
 _call_counter = itertools.count(1)
 
 
+def _rank() -> int:
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
 def _next_seed() -> int:
-    """Philox seed for one pass: torch's seed (so torch.manual_seed controls it) + a call counter."""
-    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_call_counter)) & (2 ** 63 - 1)
+    """Philox seed for one pass: torch's seed (so torch.manual_seed controls it), a call counter
+    and the data-parallel rank.  Every rank calls torch.manual_seed(s) with the same s to start
+    from identical weights; without the rank in the key all of them would then draw the same
+    dropout masks and Gumbel noise for their (different) rows, and the averaged gradient would not
+    be the mean of N independent single-process steps (per-rank RNG streams)."""
+    s = torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_call_counter)
+    s ^= (_rank() + 1) * 0xD1B54A32D192ED03
+    return s & (2 ** 63 - 1)
 
 
 class Attention(nn.Module):

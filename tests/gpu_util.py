@@ -69,8 +69,10 @@ def check_near_ties(replay_noise, att_masks, tol):
     scale = float(m.abs().median())
     stats["maxout_flips"] = int(flipped.sum())
     stats["maxout_total"] = flipped.numel()
+    stats["maxout_worst"] = float(m[flipped].abs().max()) / scale if flipped.any() else 0.0
     if flipped.any():
-        assert float(m[flipped].abs().max()) <= tol * scale, "maxout decision differs away from a tie"
+        assert float(m[flipped].abs().max()) <= tol * scale, \
+            f"maxout decision differs away from a tie ({stats['maxout_worst']:.3e} of the median margin)"
     pre = mg["relu_att"]
     dec = replay_noise.relu_att
     valid = torch.ones_like(dec) if att_masks is None else (att_masks[:, :dec.size(1)] > 0)[:, :, None].expand_as(dec)
@@ -80,8 +82,10 @@ def check_near_ties(replay_noise, att_masks, tol):
     scale = float(pre.abs().median())
     stats["relu_flips"] = int(flipped.sum())
     stats["relu_total"] = int(valid.sum())
+    stats["relu_worst"] = float(pre[flipped].abs().max()) / scale if flipped.any() else 0.0
     if flipped.any():
-        assert float(pre[flipped].abs().max()) <= tol * scale, "ReLU decision differs away from a tie"
+        assert float(pre[flipped].abs().max()) <= tol * scale, \
+            f"ReLU decision differs away from a tie ({stats['relu_worst']:.3e} of the median margin)"
     if replay_noise.relu_embed is not None and "relu_embed" in mg:
         pre = torch.stack(mg["relu_embed"], 0)                       # oracle steps 1..k
         pre = pre[: replay_noise.relu_embed.size(0) - 1]             # the last step's input is never built here
@@ -112,7 +116,7 @@ def check_hinge_near_ties(hinge_replay, tol=2e-3):
     S = hinge_replay["scores"]
     B = S.size(0)
     S = S.masked_fill(torch.eye(B, dtype=torch.bool), -1e9)
-    flips = 0
+    flips, worst = 0, 0.0
     for dim, key in ((1, "arg_s"), (0, "arg_im")):
         best = S.max(dim)[0]
         idx = hinge_replay[key]
@@ -120,5 +124,32 @@ def check_hinge_near_ties(hinge_replay, tol=2e-3):
         own = idx == torch.arange(B)          # the kernel reports i itself when B == 1
         gap = (best - got)[~own]
         flips += int((gap > 0).sum())
+        worst = max(worst, float(gap.max()) if gap.numel() else 0.0)
         assert bool((gap <= tol).all()), (key, gap.max())
-    return {"hinge_flips": flips, "hinge_total": 2 * B}
+    return {"hinge_flips": flips, "hinge_total": 2 * B, "hinge_worst_gap": worst}
+
+
+def grad_report(named_grads, ref, skip_zero=1e-11):
+    """Per-tensor relative L2 error and cosine of the CUDA gradients against oracle gradients
+    `ref` ({name: tensor}); `named_grads` is {name: tensor or None}."""
+    out = {}
+    for name, g in named_grads.items():
+        r = ref[name].double().flatten()
+        g = torch.zeros_like(r) if g is None else g.detach().double().cpu().flatten()
+        if name.endswith("alpha_net.bias") or float(r.abs().max()) < skip_zero:
+            continue
+        out[name] = dict(l2=float((g - r).norm() / r.norm()),
+                         cos=float((g @ r) / (g.norm() * r.norm() + 1e-300)),
+                         ref_norm=float(r.norm()))
+    return out
+
+
+def write_report(name, payload):
+    """Drop a JSON record under gpurun_out/ (merged back by gpurun; copied to profiles/ by hand)."""
+    import json
+    import os
+    root = os.environ.get("GRAFT_REPO_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "gpurun_out", "parity")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, name + ".json"), "w") as f:
+        json.dump(payload, f, indent=1, sort_keys=True)

@@ -64,7 +64,28 @@ def _worker(rank, world, port, out):
             pass
         # checkpoint layout is torch.optim-shaped
         sd = opt.state_dict()
-        assert set(sd) == {"state", "param_groups"} and len(sd["state"]) == 4
+        assert set(sd) == {"state", "param_groups"} and len(sd["state"]) == 0   # no step yet
+        opt.step_count = 1
+        assert len(opt.state_dict()["state"]) == 4
+        # a parameter shared by two optimizers (--share_embed): the second owner copies the
+        # gradient the first one already summed over the ranks and must not sum it again
+        shared = torch.nn.Parameter(torch.zeros(6))
+        a_own, b_own = torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(5))
+        A = OPT.FlatAdam([shared, a_own], lr=1e-3)
+        Bo = OPT.FlatAdam([b_own, shared], lr=1e-3)
+        assert Bo.foreign == [False, True]
+        for reduce_a_first in (True, False):
+            A.zero_grad()
+            Bo.zero_grad()
+            ((shared.sum() + a_own.sum() + b_own.sum()) * float(rank + 1)).backward()
+            if reduce_a_first:                      # gumbel: both agents step (optimizer.py:233-237)
+                A.all_reduce()
+            Bo.all_reduce()                         # reinforce listener turn: only this one steps
+            total = float(sum(r + 1 for r in range(world)))
+            assert torch.equal(Bo.flat_grad[Bo.offsets[1]:Bo.offsets[1] + 6], torch.full((6,), total))
+            assert torch.equal(Bo.flat_grad[:5], torch.full((5,), total))
+            if reduce_a_first:
+                assert torch.equal(A.flat_grad[:6], torch.full((6,), total))
         out.put((rank, float(opt.flat_grad.abs().sum())))
     finally:
         dist.destroy_process_group()

@@ -1,0 +1,229 @@
+"""GPU: CUDA path vs. the CPU oracle AT THE SIZES BASELINE.json names (VERDICT r1 "weak" 2, 3):
+
+* config 1  -- Gumbel joint step, 50 rows = 10 images x 5 (features repeat-interleaved), 36 regions,
+               no masks, `opt.batch_size = 50`                          (SURVEY §8(d) parity anchor)
+* config 2  -- speaker MLE step, 250 rows = 50 images x 5, 36 regions
+* config 4  -- one rank's shard of the REINFORCE job (160 rows, `gt` baseline, run_joint.sh
+               example 2 weights -D 0.8 -v 0.1): speaker turn and listener turn
+* config 5  -- Gumbel joint step at 256 rows with 10-100 regions per image (the oracle does the
+               1024-row job in seconds too, but its dense one-hot autograd graph needs ~12 GB)
+
+Token ids are forced from the oracle's free run (the north star's near-tie exemption covers ids);
+every case reports the per-tensor gradient error TWICE: against the oracle that decides the other
+non-smooth ops itself ("free": maxout branch, att_embed ReLU, hinge arg-max), and against the
+oracle that replays the CUDA pass's decisions ("replay").  The difference between the two is the
+price of bf16 pre-activations at near-ties; the flip counts and the worst flipped margin are
+recorded with them.  Records go to gpurun_out/parity/*.json (committed under profiles/).
+"""
+import pytest
+import torch
+
+from oracle import joint as OJ
+from oracle import speaker as OS
+from oracle import synth
+from oracle.ref_loader import reference_opt
+from gpu_util import (REAL, branch_replay, check_hinge_near_ties, check_near_ties, grad_report,
+                      hinge_replay_of, pack_keep, u8, write_report)
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 2e-2          # north star, bf16 operands
+GRAD_L2_REPLAY = 2e-2    # per parameter tensor, decisions replayed
+GRAD_COS_REPLAY = 0.9995
+# without replay a flipped unit moves its gradient to another weight row: relative L2 error
+# ~ sqrt(flipped fraction); measured flip fractions are <= 0.2 % -> a few per cent
+GRAD_L2_FREE = 8e-2
+GRAD_COS_FREE = 0.995
+NEAR_TIE = 2e-2          # a decision may differ only if |margin| < 2 % of the median margin
+HINGE_TIE = 2e-3
+
+
+def _case(mode, rows, regions, seed, *, varlen, repeat=1, tau=1.0, min_regions=10, eos_bias=7.5,
+          **optkw):
+    import cooperativeimagecaptioning_b200.models as models
+    from cooperativeimagecaptioning_b200 import engine as EN
+    d = REAL
+    Ps = synth.speaker_params(d, seed=seed, eos_bias=eos_bias)
+    Pl = synth.listener_params(d, seed=seed + 1)
+    batch = synth.make_batch(d, rows, regions, seed + 2, varlen=varlen, min_regions=min_regions,
+                             repeat=repeat)
+    noise = synth.make_noise(d, rows, regions, seed + 3, dropout=True, gumbel=(mode == "gumbel"),
+                             multinomial=(mode == "reinforce"))
+    opt = reference_opt(retrieval_reward=mode, gumbel_temp=tau, multinomial_temp=tau,
+                        drop_prob_lm=0.5, batch_size=rows, **optkw)
+    model = models.AlternatingJointModel(opt)
+    sd = {"caption_generator." + k: v for k, v in Ps.items()}
+    sd.update({"vse." + k: v for k, v in Pl.items()})
+    model.load_state_dict(sd)
+    model.cuda().train()
+    rnd = EN.SpeakerRandom(seed=1, drop_p=0.5, keep_att=pack_keep(noise.drop_att, batch.att_masks),
+                           keep_embed=u8(noise.drop_embed), keep_core=u8(noise.drop_core))
+    if mode == "gumbel":
+        rnd.noise = noise.U.cuda().contiguous()
+    elif mode == "reinforce":
+        rnd.noise = noise.E.cuda().contiguous()
+    model.caption_generator.injected = rnd
+    model.caption_generator.keep_passes = True
+    model.vse.keep_passes = True
+    cfg = OJ.JointCfg(drop_p=0.5, retrieval_reward=mode, gumbel_temp=tau, multinomial_temp=tau,
+                      retrieval_reward_weight=opt.retrieval_reward_weight,
+                      vse_loss_weight=opt.vse_loss_weight,
+                      caption_loss_weight=opt.caption_loss_weight,
+                      reinforce_baseline_type=opt.reinforce_baseline_type)
+    return model, Ps, Pl, batch, noise, cfg
+
+
+def _cuda(batch):
+    return (batch.fc_feats.cuda(), batch.labels.cuda(), batch.masks.cuda(), None,
+            batch.att_feats.cuda(), None if batch.att_masks is None else batch.att_masks.cuda())
+
+
+def _leaf(P):
+    return {k: v.clone().requires_grad_(True) for k, v in P.items()}
+
+
+def _oracle_grads(loss, Pso, Plo):
+    ts = list(Pso.values()) + list(Plo.values())
+    names = ["caption_generator." + k for k in Pso] + ["vse." + k for k in Plo]
+    gs = torch.autograd.grad(loss, ts, allow_unused=True)
+    return {n: (torch.zeros_like(t) if g is None else g) for n, t, g in zip(names, ts, gs)}
+
+
+def _forced(Ps, batch, noise, mode, tau=1.0):
+    d = REAL
+    with torch.no_grad():
+        free = OS.sample(Ps, batch.att_feats, batch.att_masks, mode=mode, seq_length=d.seq_length,
+                         vocab_size=d.vocab_size, noise=noise, drop_p=0.5, sample_max=0,
+                         use_one_hot=0 if mode == "reinforce" else 1, gumbel_temp=tau,
+                         multinomial_temp=tau, keep_all_steps=True)
+    return torch.stack(free.tokens_raw, 1)
+
+
+def _grade(tag, model, loss, runs, stats, extra=None):
+    """runs = {"free": (loss_ref, grads_ref), "replay": (...)}; asserts the tolerances and writes
+    the record."""
+    named = {n: p.grad for n, p in model.named_parameters()}
+    rec = dict(case=tag, loss=float(loss), near_ties=stats, tolerances=dict(
+        loss=LOSS_TOL, grad_l2_replay=GRAD_L2_REPLAY, grad_l2_free=GRAD_L2_FREE, near_tie=NEAR_TIE))
+    if extra:
+        rec.update(extra)
+    failures = []
+    for kind, (loss_ref, ref) in runs.items():
+        rep = grad_report(named, ref)
+        worst = max(rep.items(), key=lambda kv: kv[1]["l2"])
+        rec[kind] = dict(loss_ref=float(loss_ref),
+                         loss_rel_err=abs(float(loss) - float(loss_ref)) / max(abs(float(loss_ref)), 1e-12),
+                         worst_tensor=worst[0], worst_l2=worst[1]["l2"],
+                         worst_cos=min(v["cos"] for v in rep.values()), per_tensor=rep)
+        l2_tol, cos_tol = (GRAD_L2_REPLAY, GRAD_COS_REPLAY) if kind == "replay" else (GRAD_L2_FREE, GRAD_COS_FREE)
+        if rec[kind]["loss_rel_err"] > LOSS_TOL:
+            failures.append(f"{kind}: loss {float(loss)} vs {float(loss_ref)}")
+        for name, v in rep.items():
+            if v["l2"] > l2_tol or v["cos"] < cos_tol:
+                failures.append(f"{kind}: {name} l2 {v['l2']:.3e} cos {v['cos']:.6f}")
+        print(f"[{tag}/{kind}] loss rel err {rec[kind]['loss_rel_err']:.2e}; worst grad l2 "
+              f"{worst[1]['l2']:.3e} ({worst[0]}), worst cos {rec[kind]['worst_cos']:.6f}")
+    write_report(tag, rec)
+    assert not failures, failures
+
+
+def _st_joint(tag, rows, regions, seed, *, varlen, repeat, tau):
+    model, Ps, Pl, batch, noise, cfg = _case("gumbel", rows, regions, seed, varlen=varlen,
+                                             repeat=repeat, tau=tau)
+    forced = _forced(Ps, batch, noise, "gumbel", tau)
+    model.caption_generator.forced_tokens = forced.cuda()
+    fc, labels, masks, data, att, am = _cuda(batch)
+    loss = model(fc, labels, masks, data, att, am, is_alternating=True, alternating_turn="speaker")
+    loss.backward()
+    sp = model.caption_generator._passes[0]
+    rn = branch_replay(sp, batch.att_masks, noise)
+    hr = hinge_replay_of(model.vse._passes[0])
+    runs = {}
+    for kind, nz, h in (("replay", rn, hr), ("free", noise, None)):
+        Pso, Plo = _leaf(Ps), _leaf(Pl)
+        loss_ref, res, _, _ = OJ.st_joint_loss(Pso, Plo, batch.fc_feats, batch.att_feats,
+                                               batch.att_masks, nz, cfg, forced, hinge_replay=h)
+        runs[kind] = (loss_ref.detach(), _oracle_grads(loss_ref, Pso, Plo))
+        del loss_ref, res
+    stats = check_near_ties(rn, batch.att_masks, NEAR_TIE)
+    stats.update(check_hinge_near_ties(hr, HINGE_TIE))
+    # ids: the CUDA pass's own arg-max (tok_raw) against the oracle's free run, step by step
+    raw = sp.t["tok_raw"][: sp.n_steps].t().cpu()
+    n = min(raw.size(1), forced.size(1))
+    stats["token_flips"] = int((raw[:, :n] != forced[:, :n]).sum())
+    stats["token_total"] = int(raw[:, :n].numel())
+    _grade(tag, model, loss.detach(), runs, stats, dict(rows=rows, regions=regions, varlen=varlen))
+    assert stats["token_flips"] <= max(2, stats["token_total"] // 2000), stats
+
+
+def test_config1_gumbel_joint_50_rows_36_regions():
+    _st_joint("config1_gumbel_50x36", 50, 36, 1235, varlen=False, repeat=5, tau=1.0)
+
+
+def test_config5_gumbel_joint_256_rows_varlen():
+    _st_joint("config5_gumbel_256_varlen", 256, 100, 1239, varlen=True, repeat=1, tau=1.0)
+
+
+def test_config2_mle_250_rows():
+    model, Ps, Pl, batch, noise, cfg = _case("gumbel", 250, 36, 1236, varlen=False, repeat=5,
+                                             caption_loss_weight=1.0, retrieval_reward_weight=0.0)
+    fc, labels, masks, data, att, am = _cuda(batch)
+    loss = model(fc, labels, masks, data, att, am)
+    loss.backward()
+    rn = branch_replay(model.caption_generator._passes[0], batch.att_masks, noise)
+    runs = {}
+    for kind, nz in (("replay", rn), ("free", noise)):
+        Pso, Plo = _leaf(Ps), _leaf(Pl)
+        loss_ref = OJ.mle_loss(Pso, batch.att_feats, batch.att_masks, batch.labels, batch.masks, nz, cfg)
+        runs[kind] = (loss_ref.detach(), _oracle_grads(loss_ref, Pso, Plo))
+    stats = check_near_ties(rn, batch.att_masks, NEAR_TIE)
+    _grade("config2_mle_250x36", model, loss.detach(), runs, stats, dict(rows=250, regions=36))
+
+
+def test_config4_reinforce_gt_160_row_shard_speaker_and_listener_turn():
+    kw = dict(retrieval_reward_weight=0.8, vse_loss_weight=0.1, reinforce_baseline_type="gt",
+              is_alternating=1)
+    # ---- speaker turn
+    model, Ps, Pl, batch, noise, cfg = _case("reinforce", 160, 36, 1238, varlen=False, repeat=5, **kw)
+    forced = _forced(Ps, batch, noise, "reinforce")
+    cfg.vse_loss_weight = 0.0                      # the speaker turn zeroes the VSE weight (:516-518)
+    spk = model.caption_generator
+    spk.forced_tokens = forced.cuda()
+    fc, labels, masks, data, att, am = _cuda(batch)
+    loss = model(fc, labels, masks, data, att, am, is_alternating=True, alternating_turn="speaker")
+    loss.backward()
+    rn = branch_replay(spk._passes[0], batch.att_masks, noise)
+    runs = {}
+    for kind, nz in (("replay", rn), ("free", noise)):
+        Pso, Plo = _leaf(Ps), _leaf(Pl)
+        loss_ref, res, r, b = OJ.reinforce_speaker_loss(
+            Pso, Plo, batch.fc_feats, batch.att_feats, batch.att_masks, batch.labels, batch.masks,
+            nz, cfg, forced_tokens=forced)
+        runs[kind] = (loss_ref.detach(), _oracle_grads(loss_ref, Pso, Plo))
+    stats = check_near_ties(rn, batch.att_masks, NEAR_TIE)
+    _grade("config4_reinforce_gt_160_speaker_turn", model, loss.detach(), runs, stats,
+           dict(rows=160, regions=36))
+    assert all(p.grad is None for p in model.vse.parameters())       # frozen listener
+    # ---- listener turn (fresh model: the speaker turn toggled requires_grad)
+    model, Ps, Pl, batch, noise, cfg = _case("reinforce", 160, 36, 1238, varlen=False, repeat=5, **kw)
+    model.caption_generator.forced_tokens = forced.cuda()
+    loss = model(fc, labels, masks, data, att, am, is_alternating=True, alternating_turn="listener")
+    loss.backward()
+    hr = hinge_replay_of(model.vse._passes[0])
+    runs = {}
+    for kind, h in (("replay", hr), ("free", None)):
+        Pso, Plo = _leaf(Ps), _leaf(Pl)
+        with torch.no_grad():
+            res = OS.sample(Ps, batch.att_feats, batch.att_masks, mode="reinforce",
+                            seq_length=REAL.seq_length, vocab_size=REAL.vocab_size, noise=noise,
+                            drop_p=0.5, sample_max=0, temperature=1.0, forced_tokens=forced)
+        _masks = OJ.caption_masks(res.seq)
+        _seqs = torch.cat([torch.full((160, 1), REAL.vocab_size + 1, dtype=torch.long), res.seq], 1)
+        from oracle import listener as OL
+        loss_ref = cfg.vse_loss_weight * OL.vse_forward(Plo, batch.fc_feats, _seqs, _masks, False,
+                                                        "off", cfg.margin, True, "last", h)
+        runs[kind] = (loss_ref.detach(), _oracle_grads(loss_ref, Pso, Plo))
+    stats = check_hinge_near_ties(hr, HINGE_TIE)
+    _grade("config4_reinforce_gt_160_listener_turn", model, loss.detach(), runs, stats,
+           dict(rows=160, regions=36))
+    assert all(p.grad is None for p in model.caption_generator.parameters())
