@@ -22,11 +22,18 @@ import sys
 import tempfile
 import time
 
-import numpy as np
-import torch
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+# The reference arm times the reference's own code on the HOST cores.  Its modules branch on
+# torch.cuda.is_available() (models/AttModel.py:297,348; AlternatingJointModel.py:358; ...), so the
+# process that runs it must not see a GPU: hide the devices before torch initialises.
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"] \
+        or "--impl=reference" in sys.argv:
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 METRIC = "joint_gumbel_train_images_per_sec"
 UNIT = "images/s"
@@ -84,7 +91,9 @@ def make_opt(rows):
         batch_size=rows, vse_loss_weight=0.0, caption_loss_weight=0.0, retrieval_reward_weight=0.01,
         reinforce_baseline_type="gt", only_one_retrieval="off", cider_optimization=0,
         use_gen_cider_scores=0, is_alternating=1, alternating_turn=["speaker"], start_from=None,
-        initialize_retrieval=None, id="bench", grad_clip=0.1, learning_rate=5e-4, weight_decay=0.0)
+        initialize_retrieval=None, id="bench", grad_clip=0.1, learning_rate=5e-4, weight_decay=0.0,
+        continue_from_existing_models=False, speaker_stage_2_model_path=None,
+        speaker_stage_2_optimizer_path=None, checkpoint_path=None)
 
 
 def host_batch(rows, lmax, lmin, seed, pin):
@@ -218,25 +227,77 @@ def cpu_joint_step_rate(rows, lmax, lmin, steps, warmup):
     return rows / float(np.mean(times)), float(np.mean(times)), torch.get_num_threads()
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_joint_step_rate(rows, lmax, lmin, steps, warmup):
+    """Rows/s of the REAL reference (baseline/_ref: /root/reference's models/, misc/utils.py and
+    optimizer.py made importable on torch 2.x by oracle/make_ref.py, rules R1-R5) running its own
+    training-loop body (train.py:512-528: zeroing_optimizer -> AlternatingJointModel.forward ->
+    backward -> update_optimizer = clip_gradient + Adam for both agents) on the host cores."""
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import warnings
+    warnings.filterwarnings("ignore")
+    import models as ref_models                     # the reference's package, not ours
+    import optimizer as ref_optimizer
+    assert os.path.realpath(ref_models.__file__).startswith(os.path.realpath(REF_DIR))
+    torch.set_num_threads(os.cpu_count() or 1)
+    opt = make_opt(rows)
+    torch.manual_seed(0)
+    model = ref_models.AlternatingJointModel(opt)
+    with torch.no_grad():
+        model.caption_generator.logit.bias[0] = -1e4     # no early EOS, as in the GPU arm
+    model.train()
+    optimizer_dict = {"speaker": {"speaker": ref_optimizer.define_optimizer(model.caption_generator, opt),
+                                  "listener": ref_optimizer.define_optimizer(model.vse, opt)}}
+    hb = host_batch(rows, lmax, lmin, 1234 + 5, pin=False)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        ref_optimizer.zeroing_optimizer(opt, optimizer_dict, None)
+        loss = model(hb["fc"], hb["labels"], hb["masks"], None, hb["att"], hb["att_masks"],
+                     is_alternating=True, alternating_turn="speaker")
+        loss.backward()
+        ref_optimizer.update_optimizer(optimizer_dict, None, opt)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    assert bool(torch.isfinite(loss.detach()).all())
+    return rows / float(np.mean(times)), float(np.mean(times)), torch.get_num_threads()
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    rate, sec, threads = cpu_joint_step_rate(args.cpu_rows, args.max_regions, args.min_regions,
-                                             max(1, args.steps), max(1, min(args.warmup, 2)))
-    sample = (f"{args.cpu_rows} rows x {args.min_regions}-{args.max_regions} regions, Gumbel joint "
-              f"step fwd+bwd+clamp+Adam (noise generation outside the timed region), fp32")
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+    have_ref = os.path.isfile(os.path.join(REF_DIR, "models", "AlternatingJointModel.py"))
+    if have_ref:
+        kind = "reference"
+        rate, sec, threads = reference_joint_step_rate(args.cpu_rows, args.max_regions, args.min_regions,
+                                                       steps, warmup)
+        what = ("the reference's own modules (baseline/_ref, patched for torch 2.x by oracle/make_ref.py) "
+                "driven by its own train-loop body on the host cores")
+    else:
+        kind = "port"
+        rate, sec, threads = cpu_joint_step_rate(args.cpu_rows, args.max_regions, args.min_regions,
+                                                 steps, warmup)
+        what = "CPU restatement (oracle/) of the reference path: baseline/_ref is not present in this tree"
+    sample = (f"{args.cpu_rows} rows x {args.min_regions}-{args.max_regions} regions per step, Gumbel joint "
+              f"step fwd+bwd+clamp+Adam (both agents), fp32, {sec:.2f} s/step")
     line = dict(
         impl="reference", metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus,
-        steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)), ms_per_step=sec * 1e3,
+        steps=steps, warmup=warmup, ms_per_step=sec * 1e3,
         higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(workload="gumbel_joint_step_varlen (BASELINE.json configs[4])",
-                    rows_per_gpu=args.rows, global_rows=args.rows,
+                    rows_per_gpu=args.cpu_rows, global_rows=args.cpu_rows,
+                    rows_per_gpu_of_the_gpu_arm=args.rows,
                     regions=f"{args.min_regions}-{args.max_regions}", vocab=9487, seq_len=16,
                     speaker="att2in2 rnn512", listener="vsefc gru1024", gumbel_temp=1.0,
                     dropout=0.5, optimizer="clamp(0.1)+Adam, both agents", parallelism="host cores",
-                    note="CPU restatement (oracle/) of the reference path on a bounded sample of the "
-                         "workload (--cpu-rows rows per step)"),
-        cpu_baseline=dict(value=rate, unit=UNIT, cores=threads, kind="port", sample=sample),
+                    note=what + "; a bounded sample of the workload (--cpu-rows rows per step, the "
+                         "rate is rows/s so it compares with the GPU arm's)"),
+        cpu_baseline=dict(value=rate, unit=UNIT, cores=threads, kind=kind, sample=sample),
         e2e=dict(value=rate, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         gpu_launches=0)
     print(json.dumps(line), flush=True)

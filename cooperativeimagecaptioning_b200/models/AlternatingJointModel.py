@@ -130,21 +130,28 @@ class AlternatingJointModel(nn.Module):
         self._loss = {}
         self._load_checkpoints(opt, iteration)
 
-    # checkpoint loading (:131-177): same file names, tolerant state-dict loader
+    # checkpoint loading (:131-177): same file names and precedence, tolerant state-dict loader
     def _load_checkpoints(self, opt, iteration):
-        from . import load_state_dict
-        start = vars(opt).get("start_from", None)
-        if start is not None and os.path.isdir(start):
-            name = "alternatingModel.pth" if iteration is None else f"alternatingModel-{iteration}.pth"
-            path = os.path.join(start, name)
-            if not os.path.isfile(path):
-                path = os.path.join(start, "model.pth" if iteration is None else f"model-{iteration}.pth")
-            if os.path.isfile(path):
+        from . import load, load_state_dict
+        if getattr(opt, "is_alternating", 0):
+            if getattr(opt, "continue_from_existing_models", False):
+                # a previous alternating snapshot wins; else the speaker pre-trained in stage 2
+                start = vars(opt).get("start_from", None)
+                path = os.path.join(start, "alternatingModel.pth") if start is not None else None
+                if path is not None and os.path.isfile(path):
+                    if iteration:
+                        path = os.path.join(start, "alternatingModel-" + str(iteration) + ".pth")
+                    print("Loaded alternating model from {}".format(path))
+                else:
+                    path = opt.speaker_stage_2_model_path
+                    print(f'Loaded pre-trained "speaker" model, after stage 2 from {path}')
                 load_state_dict(self, torch.load(path, map_location="cpu"))
-        init = vars(opt).get("initialize_retrieval", None)
-        if init is not None and os.path.isfile(str(init)):
+            return
+        load(self, opt, iteration)
+        init = getattr(opt, "initialize_retrieval", None)
+        if init is not None:
             sd = torch.load(init, map_location="cpu")
-            load_state_dict(self, {k: v for k, v in sd.items() if k.startswith("vse.")})
+            load_state_dict(self, {k: v for k, v in sd.items() if "vse." in k})
 
     # ------------------------------------------------------------------ flags (:180-194)
     def getLossFlags(self):
