@@ -21,7 +21,7 @@ class CoopcapError(RuntimeError):
 
 
 _SCALARS = {
-    "int": C.c_int, "float": C.c_float, "int64_t": C.c_int64, "uint64_t": C.c_uint64,
+    "int": C.c_int, "float": C.c_float, "double": C.c_double, "int64_t": C.c_int64, "uint64_t": C.c_uint64,
     "coopcap_stream_t": C.c_void_p, "long long": C.c_longlong,
 }
 

@@ -785,8 +785,9 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
 // flat fp32 bucket: g *= grad_scale; clamp; Adam  (optimizer.py:233-242, misc/utils.py:65-69)
 __global__ void clamp_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                   float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                  float grad_scale, float clip, float step_size, float b1, float b2,
-                                  float eps, float wd, float bc2_sqrt) {
+                                  float grad_scale, float clip, float step_size, float b1c, float b2,
+                                  float b2c, float eps, float wd, float bc2_sqrt) {
+  // b1c = 1 - beta1, b2c = 1 - beta2, rounded from double like torch's scalar arguments
   const int64_t n4 = n / 4;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4;
        i += int64_t(gridDim.x) * blockDim.x) {
@@ -801,8 +802,8 @@ __global__ void clamp_adam_kernel(float* __restrict__ p, const float* __restrict
       float x = gg[q] * grad_scale;
       if (clip > 0.f) x = fminf(fmaxf(x, -clip), clip);
       x += wd * pp[q];
-      mm[q] = fmaf(1.f - b1, x - mm[q], mm[q]);      // torch: exp_avg.lerp_(grad, 1 - beta1)
-      vq[q] = b2 * vq[q] + (1.f - b2) * x * x;
+      mm[q] = fmaf(b1c, x - mm[q], mm[q]);           // torch: exp_avg.lerp_(grad, 1 - beta1)
+      vq[q] = fmaf(b2c * x, x, b2 * vq[q]);          // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
       const float denom = sqrtf(vq[q]) / bc2_sqrt + eps;
       pp[q] -= step_size * (mm[q] / denom);
     }
@@ -816,8 +817,8 @@ __global__ void clamp_adam_kernel(float* __restrict__ p, const float* __restrict
       float x = g[i] * grad_scale;
       if (clip > 0.f) x = fminf(fmaxf(x, -clip), clip);
       x += wd * p[i];
-      const float mq = fmaf(1.f - b1, x - m[i], m[i]);
-      const float vq = b2 * v[i] + (1.f - b2) * x * x;
+      const float mq = fmaf(b1c, x - m[i], m[i]);
+      const float vq = fmaf(b2c * x, x, b2 * v[i]);
       m[i] = mq; v[i] = vq;
       p[i] -= step_size * (mq / (sqrtf(vq) / bc2_sqrt + eps));
     }
@@ -859,8 +860,8 @@ int coopcap_speaker_decode_bwd(const coopcap_speaker* ctx, const coopcap_speaker
 }
 
 int coopcap_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                       float grad_scale, float clip, float lr, float beta1, float beta2, float eps,
-                       float weight_decay, int step, coopcap_stream_t stream) {
+                       double grad_scale, double clip, double lr, double beta1, double beta2,
+                       double eps, double weight_decay, int step, coopcap_stream_t stream) {
   using namespace coopcap;
   if (n <= 0) return CC_OK;
   CC_REQUIRE(step >= 1, "clamp_adam: step must be >= 1");
@@ -868,14 +869,15 @@ int coopcap_clamp_adam(float* param, const float* grad, float* exp_avg, float* e
                reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
              "clamp_adam: buffers must be 16-byte aligned");
   // bias corrections in double, as torch.optim.Adam computes them on the host (1 - beta ** step)
-  const double bc1 = 1.0 - pow(double(beta1), double(step));
-  const double bc2 = 1.0 - pow(double(beta2), double(step));
+  const double bc1 = 1.0 - pow(beta1, double(step));
+  const double bc2 = 1.0 - pow(beta2, double(step));
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks > int64_t(num_sms()) * 8) blocks = int64_t(num_sms()) * 8;
   if (blocks < 1) blocks = 1;
   clamp_adam_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      param, grad, exp_avg, exp_avg_sq, n, grad_scale, clip, float(double(lr) / bc1), beta1, beta2, eps,
-      weight_decay, float(sqrt(bc2)));
+      param, grad, exp_avg, exp_avg_sq, n, float(grad_scale), float(clip), float(lr / bc1),
+      float(1.0 - beta1), float(beta2), float(1.0 - beta2), float(eps), float(weight_decay),
+      float(sqrt(bc2)));
   CC_LAUNCH_CHECK_K(PROF_ADAM, reinterpret_cast<cudaStream_t>(stream), 0.0, 28.0 * double(n));
   return CC_OK;
 }

@@ -143,7 +143,9 @@ class AlternatingJointModel(nn.Module):
                         path = os.path.join(start, "alternatingModel-" + str(iteration) + ".pth")
                     print("Loaded alternating model from {}".format(path))
                 else:
-                    path = opt.speaker_stage_2_model_path
+                    path = getattr(opt, "speaker_stage_2_model_path", None)
+                    if path is None:        # nothing to resume from (the reference would fail here)
+                        return
                     print(f'Loaded pre-trained "speaker" model, after stage 2 from {path}')
                 load_state_dict(self, torch.load(path, map_location="cpu"))
             return

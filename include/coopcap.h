@@ -448,10 +448,13 @@ int coopcap_listener_bwd(const coopcap_listener* ctx, const coopcap_listener_gra
 /* ---- optimizer (optimizer.py:233-242 + misc/utils.py:65-69 + torch.optim.Adam) ---------------
  * One pass over a flat fp32 bucket: g *= grad_scale (1/world_size after the all-reduce);
  * g = clamp(g, -clip, clip); Adam(lr, beta1, beta2, eps, weight_decay) with bias correction for
- * `step` (1-based).  clip <= 0 disables clamping. */
+ * `step` (1-based).  clip <= 0 disables clamping.  The hyper-parameters are doubles, as in
+ * torch.optim.Adam, whose scalar factors (1 - beta, lr / (1 - beta1^step), sqrt(1 - beta2^step)) are
+ * formed in double on the host and only then rounded to fp32: the update is bit-comparable. */
 int coopcap_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
-                       int64_t n, float grad_scale, float clip, float lr, float beta1, float beta2,
-                       float eps, float weight_decay, int step, coopcap_stream_t stream);
+                       int64_t n, double grad_scale, double clip, double lr, double beta1,
+                       double beta2, double eps, double weight_decay, int step,
+                       coopcap_stream_t stream);
 
 /* ---- host -> device staging (train.py:162-178 `load_data` / misc/utils.py:72-87 `var_wrapper`) ----
  * The loader zero-pads att_feats to the longest image of the batch (dataloader.py:220-229); only

@@ -79,7 +79,7 @@ def check_near_ties(replay_noise, att_masks, tol):
     if replay_noise.drop_att is not None:
         valid = valid & (replay_noise.drop_att > 0)
     flipped = (dec != (pre > 0)) & valid
-    scale = float(pre.abs().median())
+    scale = float(pre[valid].abs().median())      # padded regions hold the bias only: not a margin
     stats["relu_flips"] = int(flipped.sum())
     stats["relu_total"] = int(valid.sum())
     stats["relu_worst"] = float(pre[flipped].abs().max()) / scale if flipped.any() else 0.0

@@ -123,6 +123,9 @@ def _grade(tag, model, loss, runs, stats, extra=None):
                 failures.append(f"{kind}: {name} l2 {v['l2']:.3e} cos {v['cos']:.6f}")
         print(f"[{tag}/{kind}] loss rel err {rec[kind]['loss_rel_err']:.2e}; worst grad l2 "
               f"{worst[1]['l2']:.3e} ({worst[0]}), worst cos {rec[kind]['worst_cos']:.6f}")
+    for key, tol in (("maxout_worst", NEAR_TIE), ("relu_worst", NEAR_TIE), ("hinge_worst_gap", HINGE_TIE)):
+        if stats.get(key, 0.0) > tol:
+            failures.append(f"{key} {stats[key]:.3e} > {tol}: a decision differs away from a tie")
     write_report(tag, rec)
     assert not failures, failures
 
@@ -145,8 +148,8 @@ def _st_joint(tag, rows, regions, seed, *, varlen, repeat, tau):
                                                batch.att_masks, nz, cfg, forced, hinge_replay=h)
         runs[kind] = (loss_ref.detach(), _oracle_grads(loss_ref, Pso, Plo))
         del loss_ref, res
-    stats = check_near_ties(rn, batch.att_masks, NEAR_TIE)
-    stats.update(check_hinge_near_ties(hr, HINGE_TIE))
+    stats = check_near_ties(rn, batch.att_masks, 1e9)      # graded in _grade, after the record is written
+    stats.update(check_hinge_near_ties(hr, 1e9))
     # ids: the CUDA pass's own arg-max (tok_raw) against the oracle's free run, step by step
     raw = sp.t["tok_raw"][: sp.n_steps].t().cpu()
     n = min(raw.size(1), forced.size(1))
@@ -176,7 +179,7 @@ def test_config2_mle_250_rows():
         Pso, Plo = _leaf(Ps), _leaf(Pl)
         loss_ref = OJ.mle_loss(Pso, batch.att_feats, batch.att_masks, batch.labels, batch.masks, nz, cfg)
         runs[kind] = (loss_ref.detach(), _oracle_grads(loss_ref, Pso, Plo))
-    stats = check_near_ties(rn, batch.att_masks, NEAR_TIE)
+    stats = check_near_ties(rn, batch.att_masks, 1e9)
     _grade("config2_mle_250x36", model, loss.detach(), runs, stats, dict(rows=250, regions=36))
 
 
@@ -200,7 +203,7 @@ def test_config4_reinforce_gt_160_row_shard_speaker_and_listener_turn():
             Pso, Plo, batch.fc_feats, batch.att_feats, batch.att_masks, batch.labels, batch.masks,
             nz, cfg, forced_tokens=forced)
         runs[kind] = (loss_ref.detach(), _oracle_grads(loss_ref, Pso, Plo))
-    stats = check_near_ties(rn, batch.att_masks, NEAR_TIE)
+    stats = check_near_ties(rn, batch.att_masks, 1e9)
     _grade("config4_reinforce_gt_160_speaker_turn", model, loss.detach(), runs, stats,
            dict(rows=160, regions=36))
     assert all(p.grad is None for p in model.vse.parameters())       # frozen listener
@@ -223,7 +226,7 @@ def test_config4_reinforce_gt_160_row_shard_speaker_and_listener_turn():
         loss_ref = cfg.vse_loss_weight * OL.vse_forward(Plo, batch.fc_feats, _seqs, _masks, False,
                                                         "off", cfg.margin, True, "last", h)
         runs[kind] = (loss_ref.detach(), _oracle_grads(loss_ref, Pso, Plo))
-    stats = check_hinge_near_ties(hr, HINGE_TIE)
+    stats = check_hinge_near_ties(hr, 1e9)
     _grade("config4_reinforce_gt_160_listener_turn", model, loss.detach(), runs, stats,
            dict(rows=160, regions=36))
     assert all(p.grad is None for p in model.caption_generator.parameters())

@@ -58,6 +58,7 @@ def test_decode_matches_oracle(mode, varlen, dropout, tau):
     lse = sp.t["lse"].cpu()
     raw = sp.t["tok_raw"].cpu()
     worst = 0.0
+    worst_gap = 0.0
     flips = 0
     for t in range(T):
         lp_ref = ref.step_logprobs[t]
@@ -75,8 +76,14 @@ def test_decode_matches_oracle(mode, varlen, dropout, tau):
         gap = (top2[:, 0] - top2[:, 1])
         bad = (raw[t] != ref.tokens_raw[t])
         flips += int(bad.sum())
-        assert bool((gap[bad] < 5e-2).all()), f"step {t}: token differs away from a near-tie"
-    print(f"[{mode}] worst rel logprob err {worst:.3e}, near-tie flips {flips}/{T * forced_bt.shape[0]}")
+        # a flip is legitimate only where the oracle's top-2 gap is within what the bf16 logits can
+        # move it: two candidates, each off by at most the step's measured log-prob error
+        tie = 2.0 * float((lp - lp_ref).abs().max()) / tau
+        worst_gap = max(worst_gap, float(gap[bad].max()) if bool(bad.any()) else 0.0)
+        assert bool((gap[bad] <= tie).all()), \
+            f"step {t}: token differs away from a near-tie (gap {float(gap[bad].max()):.3e} > {tie:.3e})"
+    print(f"[{mode}] worst rel logprob err {worst:.3e}, near-tie flips {flips}/{T * forced_bt.shape[0]}, "
+          f"largest flipped gap {worst_gap:.3e}")
     assert worst <= BF16_TOL
     lp_tok = sp.t["logp"].cpu().t()                    # [B, T]
     ref_lp = torch.stack([ref.step_logprobs[t].gather(1, forced_bt[:, t:t + 1]).squeeze(1)
