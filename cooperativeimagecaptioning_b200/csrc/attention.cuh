@@ -76,7 +76,7 @@ attention_fwd4_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bflo
                       const int* __restrict__ off, int Lfix, const int* __restrict__ order,
                       const float* __restrict__ s_row0, int64_t lds, int att_h_col,
                       const float* __restrict__ w_alpha, __nv_bfloat16* __restrict__ att_res16,
-                      float* att_w, int B, int dbg_skip) {
+                      float* att_w, int B) {
   static_assert(AR == 512, "lane -> 2 x 8 columns mapping; one region row = 1 KB");
   constexpr int EPL = AR / 32;
   constexpr int ROWB = AR * 2;                    // bytes of one region row
@@ -145,12 +145,6 @@ attention_fwd4_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bflo
       const uint8_t* ps = ring + st * ATT4_STAGE_BYTES;
       const uint8_t* es = ps + 2 * ROWB;
       const int o1 = two ? ROWB : 0;              // a single-region stage re-reads region 0 (weight 0)
-      if (dbg_skip) {                             // TUNING PROBE: copies only, no math
-        sum += float(ps[lane]);
-        __syncwarp();
-        issue(i + ATT4_STAGES);
-        continue;
-      }
       float sc0 = 0.f, sc1 = 0.f;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {

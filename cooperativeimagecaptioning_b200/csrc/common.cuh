@@ -268,6 +268,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// same, 16 columns (half the registers: used where the epilogue math needs the rest)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -299,32 +311,40 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // ---------------------------------------------------------------------------------------------
 struct Philox {
   static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-  __host__ __device__ static inline uint4 gen(uint64_t seed, uint64_t stream, uint64_t ctr) {
+  // ROUNDS = 10 is the conservative default (cuRAND's); 7 is the smallest round count of
+  // Philox4x32 that passes BigCrush (Salmon et al., SC'11, table 2) and is what the per-logit noise
+  // site uses: there the generator is ~1/4 of the sampling epilogue's instructions.
+  template <int ROUNDS>
+  __host__ __device__ static inline uint4 gen_r(uint64_t seed, uint64_t stream, uint64_t ctr) {
     uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
     uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32);
     uint32_t c2 = static_cast<uint32_t>(stream), c3 = static_cast<uint32_t>(stream >> 32);
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
-#ifdef __CUDA_ARCH__
-      uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-      uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-#else
-      uint64_t p0 = uint64_t(M0) * c0, p1 = uint64_t(M1) * c2;
-      uint32_t hi0 = uint32_t(p0 >> 32), lo0 = uint32_t(p0);
-      uint32_t hi1 = uint32_t(p1 >> 32), lo1 = uint32_t(p1);
-#endif
-      uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    for (int r = 0; r < ROUNDS; ++r) {
+      // one 32x32->64 multiply per product (IMAD.WIDE), not a hi/lo pair
+      const uint64_t p0 = uint64_t(M0) * c0, p1 = uint64_t(M1) * c2;
+      const uint32_t hi0 = uint32_t(p0 >> 32), lo0 = uint32_t(p0);
+      const uint32_t hi1 = uint32_t(p1 >> 32), lo1 = uint32_t(p1);
+      const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
       c0 = n0; c1 = n1; c2 = n2; c3 = n3;
       k0 += W0; k1 += W1;
     }
     return make_uint4(c0, c1, c2, c3);
+  }
+  __host__ __device__ static inline uint4 gen(uint64_t seed, uint64_t stream, uint64_t ctr) {
+    return gen_r<10>(seed, stream, ctr);
   }
   // uniform on the open interval: (k + 1/2) * 2^-23, k in [0, 2^23), i.e. [2^-24, 1 - 2^-24], every
   // value exact in fp32.  Neither end is reachable, so -log(u) and -log(1 - u) (the Gumbel and
   // exponential-race transforms) are finite and non-zero for every draw: with a closed lower end
   // u == 0 made the race score +inf once per 2^24 logits and that token won whatever its logit.
   __host__ __device__ static inline float u01(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    // mantissa trick: [1, 2) from the top 23 bits, then shift to (0, 1): 2 instructions, same value
+    return __uint_as_float(0x3f800000u | (x >> 9)) - 0.99999994f;     // 1 - 2^-24
+#else
     return (float(x >> 9) + 0.5f) * (1.0f / 8388608.0f);
+#endif
   }
 };
 

@@ -67,16 +67,7 @@ struct EpiStoreParams {
   float drop_p;
   uint64_t seed, stream;
   int tma_store;         // set by the launcher: fp32 C is written / reduced by TMA from swizzled smem
-  unsigned long long* dbg;  // optional globaltimer stamps of CTA 0 (tuning aid), else null
 };
-
-__device__ __forceinline__ void dbg_stamp(unsigned long long* dbg, int slot) {
-  if (dbg && blockIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    dbg[slot] = t;
-  }
-}
 
 struct EpiStore {
   using Params = EpiStoreParams;
@@ -222,6 +213,96 @@ struct EpiStore {
 };
 
 // ------------------------------------------------------------------------------------------
+// main-loop roles, shared by every kernel built on this pipeline (gemm_tc_kernel and the fused
+// logit + sampling kernel of logit_sample.cuh).  Tiles are dealt round-robin, m fastest:
+//   t = blockIdx.x + i * gridDim.x ;  m_blk = t % num_m ;  n_blk = (t / num_m) % num_n ;  ks = ...
+// ------------------------------------------------------------------------------------------
+// one elected thread: TMA loads of the A / B k-blocks into the smem ring
+template <class Cfg, int BN, int AMAJ, int BMAJ>
+__device__ __forceinline__ void gemm_producer_role(const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                                   uint8_t* sA, uint8_t* sB, uint64_t* full_bar,
+                                                   uint64_t* empty_bar, int num_m, int num_n,
+                                                   int num_tiles, int nkb, int kb_per_split) {
+  constexpr int STAGES = Cfg::STAGES;
+  int st = 0;
+  uint32_t ph = 0;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int m_blk = t % num_m;
+    const int rest = t / num_m;
+    const int n_blk = rest % num_n;
+    const int ks = rest / num_n;
+    const int kb0 = ks * kb_per_split;
+    const int kb1 = min(nkb, kb0 + kb_per_split);
+    const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&empty_bar[st], ph ^ 1);
+      mbar_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
+      uint8_t* a_dst = sA + st * Cfg::A_BYTES;
+      uint8_t* b_dst = sB + st * Cfg::B_BYTES;
+      const int k0 = kb * Cfg::BK;
+      if constexpr (AMAJ == 0) {
+        tma_load_2d(a_dst, tmA, &full_bar[st], k0, m0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < GEMM_BM / Cfg::MN_ATOM; ++j)
+          tma_load_2d(a_dst + j * (Cfg::BK * 128), tmA, &full_bar[st], m0 + j * Cfg::MN_ATOM, k0);
+      }
+      if constexpr (BMAJ == 0) {
+        tma_load_2d(b_dst, tmB, &full_bar[st], k0, n0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BN / Cfg::MN_ATOM; ++j)
+          tma_load_2d(b_dst + j * (Cfg::BK * 128), tmB, &full_bar[st], n0 + j * Cfg::MN_ATOM, k0);
+      }
+      if (++st == STAGES) { st = 0; ph ^= 1; }
+    }
+  }
+}
+
+// one elected thread: tcgen05.mma over the ring into the double-buffered TMEM accumulator
+template <int KIND, class Cfg, int BN, int AMAJ, int BMAJ>
+__device__ __forceinline__ void gemm_mma_role(uint8_t* sA, uint8_t* sB, uint64_t* full_bar,
+                                              uint64_t* empty_bar, uint64_t* tfull_bar,
+                                              uint64_t* tempty_bar, uint32_t tmem_base, int num_m,
+                                              int num_n, int num_tiles, int nkb, int kb_per_split) {
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr uint32_t idesc = make_idesc<KIND>(GEMM_BM, BN, AMAJ, BMAJ);
+  int st = 0;
+  uint32_t ph = 0;
+  int as = 0;
+  uint32_t aph = 0;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int ks = (t / num_m) / num_n;
+    const int kb0 = ks * kb_per_split;
+    const int kb1 = min(nkb, kb0 + kb_per_split);
+    if (kb0 >= kb1) continue;
+    mbar_wait(&tempty_bar[as], aph ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + as * BN;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&full_bar[st], ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(sA + st * Cfg::A_BYTES);
+      const uint32_t b_addr = smem_u32(sB + st * Cfg::B_BYTES);
+#pragma unroll
+      for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
+        const uint64_t da = (AMAJ == 0)
+                                ? make_smem_desc(a_addr + k * 32, 16, 1024)
+                                : make_smem_desc(a_addr + k * Cfg::UK * 128, Cfg::BK * 128, 1024);
+        const uint64_t db = (BMAJ == 0)
+                                ? make_smem_desc(b_addr + k * 32, 16, 1024)
+                                : make_smem_desc(b_addr + k * Cfg::UK * 128, Cfg::BK * 128, 1024);
+        umma_ss<KIND>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&empty_bar[st]);
+      if (++st == STAGES) { st = 0; ph ^= 1; }
+    }
+    umma_commit(&tfull_bar[as]);
+    if (++as == 2) { as = 0; aph ^= 1; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
 // LEAN = true: the epilogue is only alpha * acc + bias -> fp32 C through TMA store / reduce-add, as a
@@ -273,7 +354,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (threadIdx.x == 0) dbg_stamp(ep.dbg, 0);
   pdl_launch_dependents();
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
@@ -282,87 +362,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   // setup above overlapped the previous kernel's tail; from here on global memory is touched
   pdl_wait();
-  if (threadIdx.x == 0) dbg_stamp(ep.dbg, 1);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int st = 0;
-      uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = t % num_m;
-        const int rest = t / num_m;
-        const int n_blk = rest % num_n;
-        const int ks = rest / num_n;
-        const int kb0 = ks * kb_per_split;
-        const int kb1 = min(nkb, kb0 + kb_per_split);
-        const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[st], ph ^ 1);
-          mbar_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
-          uint8_t* a_dst = sA + st * Cfg::A_BYTES;
-          uint8_t* b_dst = sB + st * Cfg::B_BYTES;
-          const int k0 = kb * Cfg::BK;
-          if constexpr (AMAJ == 0) {
-            tma_load_2d(a_dst, &tmA, &full_bar[st], k0, m0);
-          } else {
-#pragma unroll
-            for (int j = 0; j < GEMM_BM / Cfg::MN_ATOM; ++j)
-              tma_load_2d(a_dst + j * (Cfg::BK * 128), &tmA, &full_bar[st],
-                          m0 + j * Cfg::MN_ATOM, k0);
-          }
-          if constexpr (BMAJ == 0) {
-            tma_load_2d(b_dst, &tmB, &full_bar[st], k0, n0);
-          } else {
-#pragma unroll
-            for (int j = 0; j < BN / Cfg::MN_ATOM; ++j)
-              tma_load_2d(b_dst + j * (Cfg::BK * 128), &tmB, &full_bar[st],
-                          n0 + j * Cfg::MN_ATOM, k0);
-          }
-          if (++st == STAGES) { st = 0; ph ^= 1; }
-        }
-        if (t / gridDim.x < 6) dbg_stamp(ep.dbg, 8 + int(t / gridDim.x));       // loads of tile i issued
-      }
-    }
+    if (lane == 0)
+      gemm_producer_role<Cfg, BN, AMAJ, BMAJ>(&tmA, &tmB, sA, sB, full_bar, empty_bar, num_m, num_n,
+                                              num_tiles, nkb, kb_per_split);
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<KIND>(GEMM_BM, BN, AMAJ, BMAJ);
-      int st = 0;
-      uint32_t ph = 0;
-      int as = 0;
-      uint32_t aph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int ks = (t / num_m) / num_n;
-        const int kb0 = ks * kb_per_split;
-        const int kb1 = min(nkb, kb0 + kb_per_split);
-        if (kb0 >= kb1) continue;
-        mbar_wait(&tempty_bar[as], aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[st], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + st * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + st * Cfg::B_BYTES);
-#pragma unroll
-          for (int k = 0; k < Cfg::BK / Cfg::UK; ++k) {
-            const uint64_t da = (AMAJ == 0)
-                                    ? make_smem_desc(a_addr + k * 32, 16, 1024)
-                                    : make_smem_desc(a_addr + k * Cfg::UK * 128, Cfg::BK * 128, 1024);
-            const uint64_t db = (BMAJ == 0)
-                                    ? make_smem_desc(b_addr + k * 32, 16, 1024)
-                                    : make_smem_desc(b_addr + k * Cfg::UK * 128, Cfg::BK * 128, 1024);
-            umma_ss<KIND>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[st]);
-          if (++st == STAGES) { st = 0; ph ^= 1; }
-        }
-        umma_commit(&tfull_bar[as]);
-        if (t / gridDim.x < 6) dbg_stamp(ep.dbg, 16 + int(t / gridDim.x));      // MMAs of tile i issued
-        if (++as == 2) { as = 0; aph ^= 1; }
-      }
-    }
+    if (lane == 0)
+      gemm_mma_role<KIND, Cfg, BN, AMAJ, BMAJ>(sA, sB, full_bar, empty_bar, tfull_bar, tempty_bar,
+                                               tmem_base, num_m, num_n, num_tiles, nkb, kb_per_split);
   } else {
     // ===================== epilogue (warps 2..9: two warps per TMEM lane quarter) =====================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
@@ -431,7 +439,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = 0; i < BN / 64; ++i) bias_pf[i] = epi.prefetch_bias(ep, n0 + (half + 2 * i) * 32, N, lane);
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      if (warp == 2 && lane == 0 && t / gridDim.x < 6) dbg_stamp(ep.dbg, 24 + int(t / gridDim.x));  // accumulator ready
       epi.begin(ep, row, n0, M, N, ks);
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
       uint8_t* wstage = epi_stage + (warp - 2) * Cfg::EPI_BUFS * 4096;
@@ -481,15 +488,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       epi.end(ep, row, n0, M, N, n_blk);
-      if (warp == 2 && lane == 0 && t / gridDim.x < 6) dbg_stamp(ep.dbg, 32 + int(t / gridDim.x));  // epilogue of tile i issued
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   }
   if (warp >= 2 && lane == 0 && ep.tma_store) bulk_wait_all();
-  if (warp == 2 && lane == 0) dbg_stamp(ep.dbg, 2);     // stores drained
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) dbg_stamp(ep.dbg, 3);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -536,7 +540,7 @@ int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int M
   }
   // plain "alpha * acc + bias -> fp32 C by TMA" problems take the small-code kernel
   const bool lean = ep.tma_store && !ep.relu && !ep.row_scale && !ep.seg_lens && !ep.keep &&
-                    !ep.philox_dropout && !ep.dbg;
+                    !ep.philox_dropout;
   auto kern = lean ? gemm_tc_kernel<KIND, BN, AMAJ, BMAJ, Epi, true>
                    : gemm_tc_kernel<KIND, BN, AMAJ, BMAJ, Epi, false>;
   if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES))) return rc;

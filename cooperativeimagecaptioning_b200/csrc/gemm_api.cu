@@ -132,7 +132,6 @@ int gemm_store(const coopcap_gemm_args* a, cudaStream_t s) {
   ep.alpha = a->alpha;
   ep.relu = a->relu;
   ep.mode = a->mode;
-  ep.dbg = reinterpret_cast<unsigned long long*>(a->dbg);
   if (a->backend == 1) {
     dim3 blk(32, 8), grd((a->N + 31) / 32, (a->M + 7) / 8);
     if (a->kind == 0)

@@ -146,7 +146,7 @@ int wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, 
 //   (max, sum) and the regenerated / injected noise;  dz = y (g - <y,g>) / tau on unfinished rows.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t ldg, int V1, int mode,
+st_bwd_kernel(const __half* __restrict__ z, const float* __restrict__ g, int64_t ldg, int V1, int mode,
               float inv_tau, const float* __restrict__ noise, uint64_t seed, uint64_t nstream0,
               int B, const float* __restrict__ ymax, const float* __restrict__ ysum,
               const uint8_t* __restrict__ unf, bf16* __restrict__ dz,
@@ -164,15 +164,15 @@ st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t 
     for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) store_bf16x4(dr + 4 * v4, 0.f, 0.f, 0.f, 0.f);
     return;
   }
-  const float* zr = z + row * V1;
+  const __half* zr = z + row * V1;
   const float* gr = g + row * ldg;
   const float* nr = noise ? noise + row * V1 : nullptr;
   const float m = ymax[row], inv_s = 1.f / ysum[row];
   const bool fast = (noise == nullptr);
   float dot = 0.f;
   for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
-    const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
-    const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
+    float x4[4];
+    f16x4_to_float(zr + 4 * v4, x4);
     const float g4[4] = {gr[4 * v4], gr[4 * v4 + 1], gr[4 * v4 + 2], gr[4 * v4 + 3]};
     float u4[4] = {0.f, 0.f, 0.f, 0.f};
     if (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_PS_GUMBEL)
@@ -191,9 +191,10 @@ st_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, int64_t 
     const float l = lse[row];
     for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
       const float4 yv = *reinterpret_cast<const float4*>(s_y + 4 * v4);
-      const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
-      const float p0 = ex2_ftz((zv.x - l) * 1.4426950408889634f), p1 = ex2_ftz((zv.y - l) * 1.4426950408889634f);
-      const float p2 = ex2_ftz((zv.z - l) * 1.4426950408889634f), p3 = ex2_ftz((zv.w - l) * 1.4426950408889634f);
+      float zq[4];
+      f16x4_to_float(zr + 4 * v4, zq);
+      const float p0 = ex2_ftz((zq[0] - l) * 1.4426950408889634f), p1 = ex2_ftz((zq[1] - l) * 1.4426950408889634f);
+      const float p2 = ex2_ftz((zq[2] - l) * 1.4426950408889634f), p3 = ex2_ftz((zq[3] - l) * 1.4426950408889634f);
       store_bf16x4(dr + 4 * v4, inv_tau * (yv.x * gr[4 * v4] - p0 * dot),
                    inv_tau * (yv.y * gr[4 * v4 + 1] - p1 * dot),
                    inv_tau * (yv.z * gr[4 * v4 + 2] - p2 * dot),
@@ -220,7 +221,7 @@ __global__ void ps_dpre_kernel(const float* __restrict__ d_xh, const bf16* __res
 
 // dz = coef * (onehot(tok) - softmax(z))   (REINFORCE / XE), one CTA per (step, row)
 __global__ void __launch_bounds__(256)
-logp_bwd_kernel(const float* __restrict__ z, int V1, const float* __restrict__ lse,
+logp_bwd_kernel(const __half* __restrict__ z, int V1, const float* __restrict__ lse,
                 const int64_t* __restrict__ tok, const float* __restrict__ coef,
                 bf16* __restrict__ dz) {
   const int64_t row = blockIdx.x;
@@ -230,12 +231,12 @@ logp_bwd_kernel(const float* __restrict__ z, int V1, const float* __restrict__ l
     for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) store_bf16x4(dr + 4 * v4, 0.f, 0.f, 0.f, 0.f);
     return;
   }
-  const float* zr = z + row * V1;
+  const __half* zr = z + row * V1;
   const float l = lse[row];
   const int t = int(tok[row]);
   for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
-    const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
-    const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
+    float x4[4];
+    f16x4_to_float(zr + 4 * v4, x4);
     float o[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -559,13 +560,14 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
       g_t = g_ws + int64_t(t0) * B * ldg;   // dense upstream gradient, all steps
     }
     CC_CHECK_CUDA(launch_pdl(
-        st_bwd_kernel, dim3((unsigned)rows), dim3(256), smem, s, c->z_all + int64_t(t0) * B * V1, g_t,
+        st_bwd_kernel, dim3((unsigned)rows), dim3(256), smem, s,
+        reinterpret_cast<const __half*>(c->z16_all) + int64_t(t0) * B * V1, g_t,
         ldg, V1, c->mode, c->inv_tau, c->noise ? c->noise + int64_t(t0) * B * V1 : nullptr, c->seed,
         uint64_t(SITE_NOISE + t0), B, c->y_max + int64_t(t0) * B, c->y_sum + int64_t(t0) * B,
         c->unfinished + int64_t(t0) * B, reinterpret_cast<bf16*>(dz16) + int64_t(t0) * B * V1,
         c->lse + int64_t(t0) * B));
     // logits + upstream gradient (+ injected noise) read, bf16 dz written
-    CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(rows) * V1 * (4.0 + 4.0 + 2.0 + (c->noise ? 4.0 : 0.0)));
+    CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(rows) * V1 * (2.0 + 4.0 + 2.0 + (c->noise ? 4.0 : 0.0)));
   }
   return CC_OK;
 }
@@ -574,7 +576,7 @@ int logp_backward(const coopcap_speaker* c, const int64_t* tok, const float* coe
                   cudaStream_t s) {
   int rc = check_dims(c);
   if (rc) return rc;
-  logp_bwd_kernel<<<c->n_steps * c->B, 256, 0, s>>>(c->z_all, c->V1, c->lse, tok, coef,
+  logp_bwd_kernel<<<c->n_steps * c->B, 256, 0, s>>>(reinterpret_cast<const __half*>(c->z16_all), c->V1, c->lse, tok, coef,
                                                     reinterpret_cast<bf16*>(dz16));
   CC_LAUNCH_CHECK_K(PROF_LOGP_BWD, s, 0.0, 0.0);
   return CC_OK;
@@ -648,14 +650,14 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
       bf16* dz_t = const_cast<bf16*>(dz16) + int64_t(t) * B * V1;
       CC_CHECK_CUDA(launch_pdl(
           st_bwd_kernel, dim3((unsigned)B), dim3(256), sizeof(float) * V1, s,
-          static_cast<const float*>(c->z_all + int64_t(t) * B * V1), static_cast<const float*>(g_t),
+          reinterpret_cast<const __half*>(c->z16_all) + int64_t(t) * B * V1, static_cast<const float*>(g_t),
           ldg, V1, c->mode, c->inv_tau,
           c->noise ? c->noise + int64_t(t) * B * V1 : static_cast<const float*>(nullptr), c->seed,
           uint64_t(SITE_NOISE + t), B, static_cast<const float*>(c->y_max + int64_t(t) * B),
           static_cast<const float*>(c->y_sum + int64_t(t) * B),
           static_cast<const uint8_t*>(c->unfinished + int64_t(t) * B), dz_t,
           static_cast<const float*>(c->lse + int64_t(t) * B)));
-      CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(B) * V1 * 10.0);
+      CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(B) * V1 * 8.0);
       EpiStoreParams e = {};
       e.alpha = 1.f; e.C = g->d_out + int64_t(t) * B * R; e.ldc = R;
       if ((rc = gemm_run(0, 0, 1, dz_t, V1, c->w_logit16, R, B, R, V1, 1, 0, e, s))) return rc;

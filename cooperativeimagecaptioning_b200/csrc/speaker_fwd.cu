@@ -1,6 +1,6 @@
 // Speaker (Att2in2) forward: weight packing, prologue (att_embed / ctx2att over packed regions),
 // and the decode loop (gate GEMM -> additive attention -> a2c GEMM -> maxout-LSTM pointwise ->
-// logit GEMM -> sampling + next-input gather).  See include/coopcap.h for the buffer layout and
+// logit GEMM with the sampler in its epilogue -> per-row finish + next-input gather).  See include/coopcap.h for the buffer layout and
 // the reference lines each piece replaces.
 #include <algorithm>
 #include "../../include/coopcap.h"
@@ -8,6 +8,7 @@
 #include "gemm.cuh"
 #include "speaker_kernels.cuh"
 #include "attention.cuh"
+#include "logit_sample.cuh"
 
 namespace coopcap {
 
@@ -190,31 +191,6 @@ pack_att_kernel(const float* __restrict__ att, const int* __restrict__ off, int 
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// embedding of the fed token: x = dropout(relu(embed[tok]))            (AttModel.py:74-76)
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void embed_row(const float* __restrict__ embed, int64_t tok, int E,
-                                          const uint8_t* keep_row, uint64_t seed, uint64_t stream,
-                                          int64_t elem_base, float drop_p, bf16* __restrict__ dst) {
-  const float sc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const float4* src = reinterpret_cast<const float4*>(embed + tok * E);
-  for (int i = threadIdx.x; i < E / 4; i += blockDim.x) {
-    float4 v = __ldg(src + i);
-    float x[4] = {fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)};
-    if (drop_p > 0.f) {
-      bool k[4];
-      keep4(keep_row, keep_row ? i : (elem_base >> 2) + i, seed, stream, drop_p, k);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) x[j] = k[j] ? x[j] * sc : 0.f;
-    }
-    __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b2 = __floats2bfloat162_rn(x[2], x[3]);
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&a);
-    o.y = *reinterpret_cast<uint32_t*>(&b2);
-    reinterpret_cast<uint2*>(dst)[i] = o;
-  }
-}
-
 // step 0: feed the start token, zero h_{-1} and c_{-1}
 __global__ void start_step_kernel(const float* __restrict__ embed, int64_t start_scalar,
                                   const int64_t* __restrict__ start_rows, int B, int E, int R,
@@ -384,188 +360,12 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ s, int64_t lds, const 
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// sampling: one CTA per row, one pass over the logits (online log-sum-exp), then the fed token's
-// embedding is written as the next step's input.
-//   greedy        : id = argmax z                                        (AttModel.py:327-329)
-//   multinomial   : id = argmax exp(lp/T)/E == argmax (z/T - log E)       (:332-343)
-//   ST gumbel     : id = argmax (z+G), y = softmax((z+G)/tau)              (gumbel.py:6-30)
-//   ST multinomial: id = argmax (z/tau - log E), y = softmax(z/tau)        (multinomial.py:4-27)
-// ------------------------------------------------------------------------------------------
-constexpr int SAMPLE_THREADS = 256;
-
-// running (max, sum of exp) pair; exponentials in base 2 on pre-scaled inputs
-struct OnlineLse2 {
-  float m, s;   // m in log2 units
-  __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
-  __device__ __forceinline__ void add4(const float (&x2)[4]) {      // x2 = x * log2(e)
-    const float nm = fmaxf(fmaxf(fmaxf(x2[0], x2[1]), fmaxf(x2[2], x2[3])), m);
-    s = s * ex2_ftz(m - nm) + ex2_ftz(x2[0] - nm) + ex2_ftz(x2[1] - nm) + ex2_ftz(x2[2] - nm) +
-        ex2_ftz(x2[3] - nm);
-    m = nm;
-  }
-  __device__ __forceinline__ void merge(float m2, float s2) {
-    const float nm = fmaxf(m, m2);
-    if (nm == -INFINITY) return;
-    s = s * ex2_ftz(m - nm) + s2 * ex2_ftz(m2 - nm);
-    m = nm;
-  }
-};
-
-// One CTA per row, one streaming pass over the logits (one global read, few registers -> high
-// occupancy): per 4 elements one Philox call, the perturbed scores, an online (max, sum) for
-// log-sum-exp and for the relaxed sample y, and the running argmax.
-template <int MODE, bool INJ>
-__global__ void __launch_bounds__(SAMPLE_THREADS)
-sample_kernel(const float* __restrict__ z, int V1, float inv_tau,
-              const float* __restrict__ noise, uint64_t seed, uint64_t nstream,
-              const int64_t* __restrict__ forced, const uint8_t* __restrict__ unf_prev,
-              int64_t* __restrict__ tok_raw, int64_t* __restrict__ tok_out,
-              int64_t* __restrict__ tok_fed_next, float* __restrict__ logp, float* __restrict__ lse_o,
-              float* __restrict__ ymax_o, float* __restrict__ ysum_o, uint8_t* __restrict__ unf,
-              // next-step input
-              const float* __restrict__ embed, int E, const uint8_t* __restrict__ keep_embed_next,
-              uint64_t estream, float drop_p, bf16* __restrict__ xh_next, int64_t ld_xh,
-              // scheduled sampling (AttModel.py:119-131)
-              float ss_prob, const float* __restrict__ ss_u, uint64_t ss_stream) {
-  constexpr int mode = MODE;
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ float s_m1[8], s_s1[8], s_m2[8], s_s2[8], s_bv[8];
-  __shared__ int s_bi[8];
-  __shared__ int64_t s_fed;
-  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-  const int b = blockIdx.x;
-  const float* zr = z + int64_t(b) * V1;
-  const float* nr = INJ ? noise + int64_t(b) * V1 : nullptr;
-  constexpr bool fast = !INJ;
-  constexpr bool gum = (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_PS_GUMBEL);
-  constexpr bool race = (mode == COOPCAP_SAMPLE_MULTINOMIAL || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL ||
-                         mode == COOPCAP_SAMPLE_PS_MULTINOMIAL);
-  constexpr bool st = gum || mode == COOPCAP_SAMPLE_ST_MULTINOMIAL || mode == COOPCAP_SAMPLE_PS_MULTINOMIAL;
-  constexpr bool use_noise = gum || race;
-  const int nv4 = V1 / 4;
-  OnlineLse2 l1, l2;
-  l1.init();
-  l2.init();
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-#pragma unroll 2
-  for (int v4 = threadIdx.x; v4 < nv4; v4 += SAMPLE_THREADS) {
-    const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
-    const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
-    float u4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (use_noise) noise4(nr, v4, seed, nstream, uint64_t(b) * nv4 + v4, u4);
-    float a4[4], y4[4], xs[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      xs[q] = x4[q] * LOG2E;
-      a4[q] = x4[q];
-      y4[q] = 0.f;
-      if (st) { y4[q] = st_score(mode, x4[q], u4[q], inv_tau, fast); a4[q] = y4[q]; y4[q] *= LOG2E; }
-      if (race) a4[q] = x4[q] * inv_tau + neg_log_exp1(u4[q], INJ);
-    }
-    l1.add4(xs);
-    if (st) l2.add4(y4);
-    if (mode != COOPCAP_SAMPLE_NONE) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (a4[q] > bv) { bv = a4[q]; bi = 4 * v4 + q; }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float m1 = __shfl_xor_sync(0xffffffffu, l1.m, o), s1 = __shfl_xor_sync(0xffffffffu, l1.s, o);
-    l1.merge(m1, s1);
-    const float m2 = __shfl_xor_sync(0xffffffffu, l2.m, o), s2 = __shfl_xor_sync(0xffffffffu, l2.s, o);
-    l2.merge(m2, s2);
-    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-    s_m1[warp] = l1.m; s_s1[warp] = l1.s; s_m2[warp] = l2.m; s_s2[warp] = l2.s;
-    s_bv[warp] = bv; s_bi[warp] = bi;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < SAMPLE_THREADS / 32; ++w) {
-      l1.merge(s_m1[w], s_s1[w]);
-      l2.merge(s_m2[w], s_s2[w]);
-      if (s_bv[w] > bv || (s_bv[w] == bv && s_bi[w] < bi)) { bv = s_bv[w]; bi = s_bi[w]; }
-    }
-    const float lse = (l1.m + log2f(l1.s)) * LN2;
-    // a row of NaN logits (diverged training) wins no comparison: emit EOS, its NaN log-prob tells
-    // the host; ids handed in by the caller are range-checked before they index anything
-    if (unsigned(bi) >= unsigned(V1)) bi = 0;
-    const int64_t raw = (mode == COOPCAP_SAMPLE_NONE) ? 0 : int64_t(bi);
-    int64_t tgt = forced ? forced[b] : raw;
-    const bool tgt_ok = uint64_t(tgt) < uint64_t(V1);
-    if (!tgt_ok) tgt = 0;
-    int64_t fed = tgt;
-    if (ss_prob > 0.f) {               // scheduled sampling: feed the drawn id instead of the target
-      const float u = ss_u ? ss_u[b] : Philox::u01(Philox::gen(seed, ss_stream, uint64_t(b)).x);
-      if (u < ss_prob) fed = raw;
-    }
-    const bool up = unf_prev ? (unf_prev[b] != 0) : true;
-    const bool un = up && (fed > 0);                 // AttModel.py:403-406
-    tok_raw[b] = raw;
-    tok_out[b] = un ? fed : 0;                       // :409
-    tok_fed_next[b] = fed;
-    logp[b] = tgt_ok ? zr[tgt] - lse : __int_as_float(0x7fc00000);
-    lse_o[b] = lse;
-    if (mode == COOPCAP_SAMPLE_PS_MULTINOMIAL) {
-      // y = exp(log_softmax(z) / tau), unnormalised for tau != 1  (multinomial_soft.py:12-15)
-      ymax_o[b] = lse * inv_tau;
-      ysum_o[b] = 1.f;
-    } else {
-      ymax_o[b] = l2.m * LN2;                        // back to natural-log units (st_bwd_kernel)
-      ysum_o[b] = l2.s;
-    }
-    unf[b] = un ? 1 : 0;
-    s_fed = fed;
-  }
-  __syncthreads();
-  if (xh_next) {
-    embed_row(embed, s_fed, E, keep_embed_next ? keep_embed_next + int64_t(b) * E : nullptr, seed,
-              estream, int64_t(b) * E, drop_p, xh_next + int64_t(b) * ld_xh);
-  }
-}
-
-// decoding_constraint (AttModel.py:437-442): the logit of the previously emitted id becomes -inf
-// in the saved logits (what the sampler reads and what backward differentiates)
-__global__ void ban_prev_kernel(float* __restrict__ z, int V1, const int64_t* __restrict__ prev_out,
-                                int B) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B && uint64_t(prev_out[b]) < uint64_t(V1)) z[int64_t(b) * V1 + prev_out[b]] = -INFINITY;
-}
-
-template <typename... Args>
-static cudaError_t launch_sampler(int mode, bool inj, int B, cudaStream_t s, Args... args) {
-#define CC_SAMPLER_CASE(M)                                                                          \
-  case M:                                                                                          \
-    return inj ? launch_pdl(sample_kernel<M, true>, dim3(B), dim3(SAMPLE_THREADS), 0, s, args...)  \
-               : launch_pdl(sample_kernel<M, false>, dim3(B), dim3(SAMPLE_THREADS), 0, s, args...)
-  switch (mode) {
-    CC_SAMPLER_CASE(COOPCAP_SAMPLE_GREEDY);
-    CC_SAMPLER_CASE(COOPCAP_SAMPLE_MULTINOMIAL);
-    CC_SAMPLER_CASE(COOPCAP_SAMPLE_ST_GUMBEL);
-    CC_SAMPLER_CASE(COOPCAP_SAMPLE_ST_MULTINOMIAL);
-    CC_SAMPLER_CASE(COOPCAP_SAMPLE_NONE);
-    CC_SAMPLER_CASE(COOPCAP_SAMPLE_PS_GUMBEL);
-    CC_SAMPLER_CASE(COOPCAP_SAMPLE_PS_MULTINOMIAL);
-    default: return cudaErrorInvalidValue;
-  }
-#undef CC_SAMPLER_CASE
-}
-
 // Partial-sampling modes: the vector a step emits (gumbel_softmax.py:28-40, multinomial_soft.py:21-33).
 // One CTA per row; y is rebuilt from the logits, the regenerated / injected noise and the saved
 // (max, sum) exactly like the straight-through backward does.  Rows with part_u < ps_prob emit
 // one_hot(id), the others y.
 __global__ void __launch_bounds__(256)
-ps_vec_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
+ps_vec_kernel(const __half* __restrict__ z, int V1, int mode, float inv_tau,
               const float* __restrict__ noise, uint64_t seed, uint64_t nstream,
               const float* __restrict__ ymax, const float* __restrict__ ysum,
               const int64_t* __restrict__ tok_fed_next, float ps_prob,
@@ -574,7 +374,7 @@ ps_vec_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x;
-  const float* zr = z + int64_t(b) * V1;
+  const __half* zr = z + int64_t(b) * V1;
   const float* nr = noise ? noise + int64_t(b) * V1 : nullptr;
   bf16* dr = soft16 + int64_t(b) * V1;
   const bool fast = (noise == nullptr);
@@ -594,8 +394,8 @@ ps_vec_kernel(const float* __restrict__ z, int V1, int mode, float inv_tau,
   }
   const float m = ymax[b], inv_s = 1.f / ysum[b];
   for (int v4 = threadIdx.x; v4 < nv4; v4 += 256) {
-    const float4 zv = *reinterpret_cast<const float4*>(zr + 4 * v4);
-    const float x4[4] = {zv.x, zv.y, zv.z, zv.w};
+    float x4[4];
+    f16x4_to_float(zr + 4 * v4, x4);
     float u4[4] = {0.f, 0.f, 0.f, 0.f};
     if (mode == COOPCAP_SAMPLE_PS_GUMBEL) noise4(nr, v4, seed, nstream, uint64_t(b) * nv4 + v4, u4);
     float y[4];
@@ -665,6 +465,85 @@ size_t attention_smem_bytes(int A, int R, int L) {
   return sizeof(float) * (2 * A + 8 + ((L + 3) & ~3) + groups * R);
 }
 
+// ------------------------------------------------------------------------------------------
+// one decode step's vocabulary layer: logits + sampling in the GEMM epilogue, then the per-row
+// finish (logit_sample.cuh)
+// ------------------------------------------------------------------------------------------
+template <int MODE, bool INJ>
+static int launch_logit_sample(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+                               const LogitSampleParams& p, cudaStream_t s) {
+  auto kern = logit_sample_kernel<MODE, INJ>;
+  int rc;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), LsCfg::SMEM_BYTES))) return rc;
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + LS_BN - 1) / LS_BN);
+  const int grid = std::min(num_sms(), tiles);
+  CC_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(LS_THREADS), size_t(LsCfg::SMEM_BYTES), s, tmA, tmB, M,
+                           N, K, p));
+  return CC_OK;
+}
+
+static int logit_sample_step(const coopcap_speaker* c, int t, const bf16* out16_t, __half* z_t,
+                             bf16* x_next, cudaStream_t s) {
+  const int B = c->B, R = c->R, E = c->E, V1 = c->V1, XH = E + R;
+  CC_REQUIRE(c->z16_all && c->ls_part && c->z_tgt, "speaker: z16_all / ls_part / z_tgt workspace missing");
+  CC_REQUIRE(V1 % 8 == 0, "speaker: V1 must be a multiple of 8 (fp16 logit rows are written 16 bytes at a time)");
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = encode_tmap_2d(&tmA, out16_t, 2, B, R, R, GEMM_BM, LsCfg::BK))) return rc;
+  if ((rc = encode_tmap_2d(&tmB, c->w_logit16, 2, V1, R, R, LS_BN, LsCfg::BK))) return rc;
+  LogitSampleParams p = {};
+  p.bias = c->b_logit;
+  p.noise = c->noise ? c->noise + int64_t(t) * B * V1 : nullptr;
+  p.forced = c->forced ? c->forced + int64_t(t) * B : nullptr;
+  p.ban = (c->no_repeat && t > 0) ? c->tok_out + int64_t(t - 1) * B : nullptr;    // AttModel.py:437-442
+  p.z16 = z_t;
+  p.part = c->ls_part;
+  p.z_tgt = c->z_tgt;
+  p.seed = c->seed;
+  p.nstream = uint64_t(SITE_NOISE + t);
+  p.inv_tau = c->inv_tau;
+  const bool inj = c->noise != nullptr;
+  switch (c->mode) {
+    case COOPCAP_SAMPLE_GREEDY:
+      rc = launch_logit_sample<COOPCAP_SAMPLE_GREEDY, false>(tmA, tmB, B, V1, R, p, s); break;
+    case COOPCAP_SAMPLE_NONE:
+      rc = launch_logit_sample<COOPCAP_SAMPLE_NONE, false>(tmA, tmB, B, V1, R, p, s); break;
+    case COOPCAP_SAMPLE_MULTINOMIAL:
+      rc = inj ? launch_logit_sample<COOPCAP_SAMPLE_MULTINOMIAL, true>(tmA, tmB, B, V1, R, p, s)
+               : launch_logit_sample<COOPCAP_SAMPLE_MULTINOMIAL, false>(tmA, tmB, B, V1, R, p, s);
+      break;
+    case COOPCAP_SAMPLE_ST_GUMBEL:
+    case COOPCAP_SAMPLE_PS_GUMBEL:        // same epilogue: y = softmax((z + G) / tau), id = argmax
+      rc = inj ? launch_logit_sample<COOPCAP_SAMPLE_ST_GUMBEL, true>(tmA, tmB, B, V1, R, p, s)
+               : launch_logit_sample<COOPCAP_SAMPLE_ST_GUMBEL, false>(tmA, tmB, B, V1, R, p, s);
+      break;
+    case COOPCAP_SAMPLE_ST_MULTINOMIAL:
+    case COOPCAP_SAMPLE_PS_MULTINOMIAL:   // same epilogue: softmax(z / tau) sums, id from the race
+      rc = inj ? launch_logit_sample<COOPCAP_SAMPLE_ST_MULTINOMIAL, true>(tmA, tmB, B, V1, R, p, s)
+               : launch_logit_sample<COOPCAP_SAMPLE_ST_MULTINOMIAL, false>(tmA, tmB, B, V1, R, p, s);
+      break;
+    default:
+      set_last_error("speaker: unknown sampling mode %d", c->mode);
+      return CC_ERR_ARG;
+  }
+  if (rc) return rc;
+  // dense contraction; algorithmic bytes of the fused sampler: the fp16 logits written once
+  prof_mark(PROF_GEMM, s, 2.0 * double(B) * V1 * R, 2.0 * (double(B) * R + double(V1) * R) + 2.0 * double(B) * V1);
+  const int nrec = LS_RECS_PER_TILE * ((V1 + LS_BN - 1) / LS_BN);
+  CC_CHECK_CUDA(launch_pdl(
+      sample_finish_kernel, dim3(B), dim3(FIN_THREADS), 0, s, static_cast<const float*>(c->ls_part), nrec,
+      static_cast<const float*>(c->z_tgt), c->mode, c->inv_tau, V1, p.forced,
+      static_cast<const uint8_t*>(t > 0 ? c->unfinished + int64_t(t - 1) * B : nullptr),
+      c->tok_raw + int64_t(t) * B, c->tok_out + int64_t(t) * B, c->tok_fed + int64_t(t + 1) * B,
+      c->logp + int64_t(t) * B, c->lse + int64_t(t) * B, c->y_max + int64_t(t) * B,
+      c->y_sum + int64_t(t) * B, c->unfinished + int64_t(t) * B, c->embed, E,
+      static_cast<const uint8_t*>(c->keep_embed ? c->keep_embed + int64_t(t + 1) * B * E : nullptr),
+      c->seed, uint64_t(SITE_DROP_EMBED + t + 1), c->drop_p, x_next, int64_t(XH), c->ss_prob,
+      static_cast<const float*>(c->ss_u ? c->ss_u + int64_t(t) * B : nullptr), uint64_t(SITE_SCHED + t)));
+  CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 32.0 * double(B) * nrec);
+  return CC_OK;
+}
+
 int speaker_prologue_fwd(const coopcap_speaker* c, cudaStream_t s) {
   int rc = check_dims(c);
   if (rc) return rc;
@@ -724,8 +603,7 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
                                reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L,
                                c->att_order, s_t,
                                int64_t(NS), 5 * R, c->w_alpha, att_res16 + int64_t(t) * B * R,
-                               c->att_w + int64_t(t) * c->NL, B,
-                               0));
+                               c->att_w + int64_t(t) * c->NL, B));
     } else {
       attention_fwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
           reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
@@ -749,31 +627,10 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
           uint64_t(SITE_DROP_CORE + t), c->drop_p, B, R));
       CC_LAUNCH_CHECK_K(PROF_LSTM, s, 0.0, 0.0);
     }
-    float* z_t = c->z_all + int64_t(t) * B * V1;
-    EpiStoreParams e3 = {};
-    e3.alpha = 1.f; e3.bias = c->b_logit; e3.C = z_t; e3.ldc = V1;
-    rc = gemm_run(0, 0, 0, out16 + int64_t(t) * B * R, R, c->w_logit16, R, B, V1, R, 1,
-                  B >= 512 ? 256 : 0, e3, s);   // measured: 22.6 us at BN = 256 vs 24.6 us for the cost model's pick
-    if (rc) return rc;
+    __half* z_t = reinterpret_cast<__half*>(c->z16_all) + int64_t(t) * B * V1;
     const bool ps = (c->mode == COOPCAP_SAMPLE_PS_GUMBEL || c->mode == COOPCAP_SAMPLE_PS_MULTINOMIAL);
     bf16* x_next = (t + 1 < c->n_steps) ? xh16 + int64_t(t + 1) * B * XH : nullptr;
-    if (c->no_repeat && t > 0) {
-      ban_prev_kernel<<<(B + 255) / 256, 256, 0, s>>>(z_t, V1, c->tok_out + int64_t(t - 1) * B, B);
-      CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 0.0);
-    }
-    CC_CHECK_CUDA(launch_sampler(
-        c->mode, c->noise != nullptr, B, s, z_t, V1, c->inv_tau,
-        c->noise ? c->noise + int64_t(t) * B * V1 : nullptr, c->seed, uint64_t(SITE_NOISE + t),
-        c->forced ? c->forced + int64_t(t) * B : nullptr,
-        t > 0 ? c->unfinished + int64_t(t - 1) * B : nullptr, c->tok_raw + int64_t(t) * B,
-        c->tok_out + int64_t(t) * B, c->tok_fed + int64_t(t + 1) * B, c->logp + int64_t(t) * B,
-        c->lse + int64_t(t) * B, c->y_max + int64_t(t) * B, c->y_sum + int64_t(t) * B,
-        c->unfinished + int64_t(t) * B, c->embed, E,
-        c->keep_embed ? c->keep_embed + int64_t(t + 1) * B * E : nullptr,
-        uint64_t(SITE_DROP_EMBED + t + 1), c->drop_p, ps ? nullptr : x_next, int64_t(XH),
-        c->ss_prob, c->ss_u ? c->ss_u + int64_t(t) * B : nullptr, uint64_t(SITE_SCHED + t)));
-    // algorithmic bytes: logits (+ injected noise) read once
-    CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 4.0 * B * V1 * (c->noise ? 2.0 : 1.0));
+    if ((rc = logit_sample_step(c, t, out16 + int64_t(t) * B * R, z_t, ps ? nullptr : x_next, s))) return rc;
     if (ps) {
       bf16* v_t = reinterpret_cast<bf16*>(c->soft16) + int64_t(t) * B * V1;
       CC_CHECK_CUDA(launch_pdl(

@@ -5,6 +5,7 @@
 // HBM-bound kernels: bf16 storage for the region tensors (att_e, p_att), 16-byte vector loads,
 // one CTA per batch row for attention (warp per region, online softmax), warp-shuffle reductions.
 #pragma once
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -19,6 +20,8 @@ enum : uint64_t {
   SITE_PARTIAL = 5ull << 32,    // partial-sampling row selection
   SITE_SCHED = 6ull << 32,      // scheduled-sampling row selection
 };
+
+constexpr int NOISE_ROUNDS = 7;   // Philox rounds of the per-logit noise site (see common.cuh)
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -85,7 +88,7 @@ __device__ __forceinline__ float lg2_ftz(float x) {
 // log1p series takes over (branch-free select)
 __device__ __forceinline__ float neg_log_fast(float u) {
   const float d = 1.f - u;
-  const float series = d * (1.f + d * (0.5f + d * (0.33333334f + d * 0.25f)));
+  const float series = d * fmaf(d, fmaf(d, 0.33333334f, 0.5f), 1.f);   // d < 1/16: rel. error < d^3/4
   const float direct = -0.69314718f * lg2_ftz(u);
   return d < 0.0625f ? series : direct;
 }
@@ -109,7 +112,7 @@ __device__ __forceinline__ void noise4(const float* inj_row, int v4, uint64_t se
     const float4 t = *reinterpret_cast<const float4*>(inj_row + 4 * v4);
     u[0] = t.x; u[1] = t.y; u[2] = t.z; u[3] = t.w;
   } else {
-    const uint4 r = Philox::gen(seed, stream, ctr);
+    const uint4 r = Philox::gen_r<NOISE_ROUNDS>(seed, stream, ctr);
     u[0] = Philox::u01(r.x); u[1] = Philox::u01(r.y); u[2] = Philox::u01(r.z); u[3] = Philox::u01(r.w);
   }
 }
@@ -117,6 +120,48 @@ __device__ __forceinline__ void noise4(const float* inj_row, int v4, uint64_t se
 __device__ __forceinline__ float st_score(int mode, float x, float u, float inv_tau, bool fast) {
   return (mode == 2 /*ST_GUMBEL*/ || mode == 5 /*PS_GUMBEL*/) ? (x + gumbel_of(u, fast)) * inv_tau
                                                               : x * inv_tau;
+}
+
+// ------------------------------------------------------------------------------------------
+// embedding of the fed token: x = dropout(relu(embed[tok]))            (AttModel.py:74-76)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void embed_row(const float* __restrict__ embed, int64_t tok, int E,
+                                          const uint8_t* keep_row, uint64_t seed, uint64_t stream,
+                                          int64_t elem_base, float drop_p, __nv_bfloat16* __restrict__ dst) {
+  const float sc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const float4* src = reinterpret_cast<const float4*>(embed + tok * E);
+  for (int i = threadIdx.x; i < E / 4; i += blockDim.x) {
+    float4 v = __ldg(src + i);
+    float x[4] = {fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)};
+    if (drop_p > 0.f) {
+      bool k[4];
+      keep4(keep_row, keep_row ? i : (elem_base >> 2) + i, seed, stream, drop_p, k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = k[j] ? x[j] * sc : 0.f;
+    }
+    __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b2 = __floats2bfloat162_rn(x[2], x[3]);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b2);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+}
+
+// fp16 logits (z16_all): 8 / 4 consecutive values as floats
+__device__ __forceinline__ void f16x8_to_float(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void f16x4_to_float(const __half* p, float (&f)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
 }
 
 // block-wide reductions for 256-thread CTAs (8 warps)

@@ -204,7 +204,11 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
         s_all=torch.empty(cap, B, NS, **f32), u_all=torch.empty(cap, B, 2 * d.R, **f32),
         c_all=torch.empty(cap + 1, B, d.R, **f32), att_res16=torch.empty(cap, B, d.R, **bf),
         att_w=torch.empty(cap, NL, **f32), out16=torch.empty(cap, B, d.R, **bf),
-        z_all=torch.empty(cap, B, d.V1, **f32), tok_raw=torch.empty(cap, B, **i64),
+        # logits are kept in fp16 for the backward pass only; the sampler runs on the fp32
+        # accumulators inside the logit GEMM (csrc/logit_sample.cuh)
+        z16_all=torch.empty(cap, B, d.V1, dtype=torch.float16, device=dev),
+        ls_part=torch.empty(B, 4 * ((d.V1 + 255) // 256), 8, **f32), z_tgt=torch.empty(B, **f32),
+        tok_raw=torch.empty(cap, B, **i64),
         tok_out=torch.empty(cap, B, **i64), tok_fed=torch.empty(cap + 1, B, **i64),
         logp=torch.empty(cap, B, **f32), lse=torch.empty(cap, B, **f32),
         y_max=torch.empty(cap, B, **f32), y_sum=torch.empty(cap, B, **f32),
@@ -345,7 +349,7 @@ def speaker_backward(sp: SpeakerPass, dz16: Optional[torch.Tensor], P: Dict[str,
     factored (`ps_demb16` bf16 [n_steps, B, E] + `ps_w_emb16`) or dense (`ps_g_dense` fp32
     [n_steps, B, ld >= V1], modified in place)."""
     d = sp.dims
-    dev = sp.t["z_all"].device
+    dev = sp.t["z16_all"].device
     is_ps = sp.ctx.mode in PS_MODES
     if is_ps:
         assert dz16 is None and ((ps_demb16 is None) != (ps_g_dense is None))

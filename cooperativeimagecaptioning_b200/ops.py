@@ -35,7 +35,7 @@ def device_info():
 
 
 def gemm(A, B, M, N, K, *, a_major=0, b_major=0, alpha=1.0, bias=None, row_scale=None, relu=False,
-         mode=0, out=None, out16=None, out_t16=None, split_k=1, tile_n=0, backend=0, dbg=None):
+         mode=0, out=None, out16=None, out_t16=None, split_k=1, tile_n=0, backend=0):
     """C[M,N] = alpha * A·Bᵀ (+bias)(relu)(*row_scale). A/B bf16 (kind 0) or fp32 (kind 1, tf32).
 
     a_major/b_major 0: operand stored [rows, K]; 1: stored [K, rows]. Operands are 2-D views with
@@ -68,7 +68,6 @@ def gemm(A, B, M, N, K, *, a_major=0, b_major=0, alpha=1.0, bias=None, row_scale
         assert out_t16.dtype == torch.bfloat16
         a.Ct16, a.ldct = out_t16.data_ptr(), out_t16.stride(0)
     a.split_k, a.tile_n, a.backend = split_k, tile_n, backend
-    a.dbg = None if dbg is None else dbg.data_ptr()
     check(_lib.load().coopcap_gemm(C.byref(a), _stream()))
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define COOPCAP_VERSION 100
+#define COOPCAP_VERSION 200
 
 #define COOPCAP_OK 0
 #define COOPCAP_ERR_CUDA (-1)
@@ -75,7 +75,6 @@ typedef struct coopcap_gemm_args {
   int split_k; /* >= 1 */
   int tile_n;  /* 0 = auto, else 64 / 128 / 192 / 256 */
   int backend; /* 0 tcgen05, 1 SIMT cross-check */
-  void* dbg;   /* NULL, or device uint64[64]: CTA 0 writes globaltimer stamps of its pipeline (tuning aid) */
 } coopcap_gemm_args;
 
 int coopcap_gemm(const coopcap_gemm_args* args, coopcap_stream_t stream);
@@ -105,7 +104,11 @@ int coopcap_cast_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_s
  *   att_res16  bf16 [cap, B, R]         attention output per step
  *   att_w      fp32 [cap, NL]           attention weights per step (packed like the regions)
  *   out16      bf16 [cap, B, R]         dropout(h_t) (operand of the logit GEMM)
- *   z_all      fp32 [cap, B, V1]        vocabulary logits per step
+ *   z16_all    fp16 [cap, B, V1]        vocabulary logits per step.  The sampler runs on the fp32
+ *                                       accumulators inside the logit GEMM's epilogue (logit_sample.cuh);
+ *                                       this half-precision copy is what backward rebuilds y from
+ *   ls_part    fp32 [B, 4*ceil(V1/256), 8]  per-(row, 64-column group) partials of one step's epilogue
+ *   z_tgt      fp32 [B]                 raw logit of the forced id of one step
  *   tok_raw    int64 [cap, B]           id drawn from z_t (before forcing / finished-row masking)
  *   tok_out    int64 [cap, B]           id after forcing and finished-row masking (AttModel.py:409)
  *   tok_fed    int64 [cap+1, B]         id embedded as the input of step t (tok_fed[0] = start)
@@ -207,7 +210,9 @@ typedef struct coopcap_speaker {
   void* att_res16;
   float* att_w;
   void* out16;
-  float* z_all;
+  void* z16_all;
+  float* ls_part;
+  float* z_tgt;
   int64_t* tok_raw;
   int64_t* tok_out;
   int64_t* tok_fed;
@@ -243,7 +248,8 @@ typedef struct coopcap_speaker {
 /* att16, att_e16, p_att16 from att_feats (AttModel.py:110-114 / :315-319). */
 int coopcap_speaker_prologue_fwd(const coopcap_speaker* ctx, coopcap_stream_t stream);
 /* n_steps decode steps: embed -> gates/att_h GEMM -> attention -> a2c GEMM -> LSTM pointwise ->
- * logit GEMM -> sampling (+ next-input gather).  No host synchronisation. */
+ * logit GEMM with the sampler in its epilogue -> per-row finish (+ next-input gather).  No host
+ * synchronisation. */
 int coopcap_speaker_decode_fwd(const coopcap_speaker* ctx, coopcap_stream_t stream);
 
 /* d(loss)/d(logits) of the straight-through samplers for all n_steps:

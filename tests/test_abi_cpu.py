@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.FUNCTIONS), declared ^ set(_lib.FUNCTIONS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.coopcap_version() == 100
+    assert lib.coopcap_version() == 200
     for sname, sid in _lib._SIZEOF_IDS.items():
         assert C.sizeof(_lib.STRUCTS[sname]) == lib.coopcap_sizeof(sid)
     assert lib.coopcap_sizeof(99) == -1

