@@ -56,8 +56,12 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
     ap.add_argument("--no-decode", action="store_true", help="skip the decode tokens/s side metric")
     ap.add_argument("--upload-ctas", type=int, default=64, help="CTAs of the zero-copy upload kernel")
-    ap.add_argument("--upload", default="zero_copy", choices=["host_pack", "zero_copy", "dma_rows"],
-                    help="e2e staging: host threads pack bf16 + one DMA copy, or the zero-copy kernel")
+    ap.add_argument("--upload", default="store", choices=["store", "host_pack", "zero_copy", "dma_rows"],
+                    help="e2e staging: device-resident feature store + index batches (default), or a "
+                         "loader-shaped fp32 host batch per step (zero-copy kernel / host pack + DMA / per-row DMA)")
+    ap.add_argument("--no-host-features", action="store_true",
+                    help="skip the extra N = 1 line `e2e_host_features` (the e2e step fed with loader-shaped fp32 "
+                         "host feature batches through the zero-copy upload instead of the feature store)")
     ap.add_argument("--pack-threads", type=int, default=0,
                     help="worker threads of the host-side packer (0 = hardware threads - 1)")
     ap.add_argument("--clock-samples", type=int, default=3, help="NVML samples inside the timed region; 0 = off")
@@ -441,36 +445,48 @@ def main():
     value = args.rows * world * args.steps / (ms_max * 1e-3)
 
     # ---------------- end to end from pinned host buffers (`e2e`) ----------------
-    e2e_value, e2e_ms, h2d, e2e_allocs, e2e_host = None, None, 0, None, {}
-    if not args.no_e2e:
-        # double-buffered: batch i+1 is uploaded on a copy stream while batch i computes; the loss of
-        # every step is read back to pinned host memory (async, drained at the end of the region)
+    from cooperativeimagecaptioning_b200.data import FeatureStore, HostPacker, record_stream, upload_batch
+    resident = None
+
+    def run_e2e(mode):
+        """One e2e measurement.  Double-buffered: batch i+1 is staged on a copy stream while batch i
+        computes; the loss of every step is read back to pinned host memory (async, drained at the
+        end of the region).  mode 'store': the feature set lives in HBM (data.FeatureStore, built
+        once outside the region); a step ships image indices + captions from pinned memory and a
+        gather kernel assembles the packed operand.  Other modes ship a loader-shaped fp32 feature
+        batch every step."""
         copy_stream = torch.cuda.Stream()
         loss_host = torch.zeros(args.steps, pin_memory=True)
-        h2d = 0
-        resident = None
-
-        from cooperativeimagecaptioning_b200.data import HostPacker, record_stream, upload_batch
-
-        packer = HostPacker(dev, threads=args.pack_threads) if args.upload == "host_pack" else None
-        e2e_host = {}
+        packer = HostPacker(dev, threads=args.pack_threads) if mode == "host_pack" else None
+        host_tm = {}
+        store, idx = None, None
+        if mode == "store":
+            # the two synthetic host batches form a 2 x rows image pool; every step draws `rows`
+            # images from it (indices pre-drawn, pinned)
+            store = FeatureStore.from_padded(dev, torch.cat([h["fc"] for h in hb]),
+                                             torch.cat([h["att"] for h in hb]),
+                                             torch.cat([h["att_masks"] for h in hb]))
+            g = torch.Generator().manual_seed(4321 + rank)
+            idx = [torch.randperm(store.n_img, generator=g)[:args.rows].contiguous().pin_memory()
+                   for _ in range(8)]
 
         def stage(i):
-            # host side of the repo's load_data for batch i: worker threads pack the valid regions
-            # to bf16 in a pinned staging buffer while the main thread keeps enqueueing
             h = hb[i % 2]
             return packer.start(h["fc"], h["att"], h["att_masks"], h["labels"], h["masks"])
 
         def upload(i, job=None):
             h = hb[i % 2]
-            if packer is not None:
+            if store is not None:
+                fc, att, am, lab, msk = store.load_batch(idx[i % len(idx)], h["labels"], h["masks"],
+                                                         stream=copy_stream)
+            elif packer is not None:
                 fc, att, am, lab, msk = packer.finish(job, stream=copy_stream)       # one DMA copy
             else:
                 # zero-copy kernel: only the valid regions of att_feats cross PCIe (fp32)
                 fc, att, am, lab, msk = upload_batch(h["fc"], h["att"], h["att_masks"], h["labels"],
                                                      h["masks"], dev, stream=copy_stream,
                                                      ctas=args.upload_ctas,
-                                                     zero_copy=(args.upload == "zero_copy"))
+                                                     zero_copy=(mode == "zero_copy"))
             ev = torch.cuda.Event()
             ev.record(copy_stream)
             return dict(fc=fc, att=att, att_masks=am, labels=lab, masks=msk), ev
@@ -494,19 +510,25 @@ def main():
                     h3 = time.perf_counter()
                     tm[0] += h1 - h0; tm[1] += h2 - h1; tm[2] += h3 - h2
                 if record:
-                    e2e_host.update(wait_pack_and_dma_enqueue_ms=1e3 * tm[0] / n, stage_ms=1e3 * tm[1] / n,
-                                    step_enqueue_ms=1e3 * tm[2] / n)
+                    host_tm.update(wait_pack_and_dma_enqueue_ms=1e3 * tm[0] / n, stage_ms=1e3 * tm[1] / n,
+                                   step_enqueue_ms=1e3 * tm[2] / n)
                 return
+            tm = [0.0, 0.0]
             nxt = upload(0)
             for i in range(n):
                 d, ev = nxt
+                h0 = time.perf_counter()
                 if i + 1 < n:
                     nxt = upload(i + 1)
+                h1 = time.perf_counter()
                 torch.cuda.current_stream().wait_event(ev)
                 loss = train_step(d)
                 record_stream(d.values(), torch.cuda.current_stream())
                 if record:
                     loss_host[i].copy_(loss.detach().reshape(()), non_blocking=True)
+                tm[0] += h1 - h0; tm[1] += time.perf_counter() - h1
+            if record:
+                host_tm.update(stage_enqueue_ms=1e3 * tm[0] / n, step_enqueue_ms=1e3 * tm[1] / n)
 
         # warm-up: the upload buffers live in the copy stream's allocator pool and are recycled
         # through record_stream, which needs a few rounds to reach its steady state
@@ -517,14 +539,36 @@ def main():
         t0.record()
         e2e_loop(args.steps, True)
         t1.record()
-        e2e_allocs = torch.cuda.memory_stats()["num_device_alloc"] - a0
-        h2d = packer.last_bytes if packer is not None else upload_batch.last_bytes
+        allocs = torch.cuda.memory_stats()["num_device_alloc"] - a0
+        moved = store.last_bytes if store is not None else \
+            (packer.last_bytes if packer is not None else upload_batch.last_bytes)
         barrier()
         t = torch.tensor([t0.elapsed_time(t1)], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t)
-        e2e_value = args.rows * world * args.steps / (e2e_ms * 1e-3)
+        ms_e = float(t)
+        assert bool(torch.isfinite(loss_host).all())
+        notes = {
+            "store": "data.FeatureStore: the feature set is resident in HBM as packed bf16 rows (built once, "
+                     "outside the region); every step ships the batch's image indices and caption tensors from "
+                     "pinned host memory and coopcap_store_gather assembles the packed operand on a copy stream",
+            "host_pack": "data.HostPacker: library worker threads pack the valid regions of a loader-shaped fp32 "
+                         "host batch to bf16 in a pinned staging buffer (inside the timed region), one DMA copy",
+            "zero_copy": "data.upload_batch: a zero-copy kernel reads the valid fp32 regions of a loader-shaped "
+                         "pinned host batch over PCIe on a copy stream",
+            "dma_rows": "data.upload_batch: one DMA copy per row of a loader-shaped pinned fp32 host batch"}
+        return dict(value=args.rows * world * args.steps / (ms_e * 1e-3), unit=UNIT,
+                    h2d_bytes_per_step=int(moved), d2h_bytes_per_step=4, ms_per_step=ms_e / args.steps,
+                    device_allocs_in_region=allocs, upload=mode, host_ms_per_step=host_tm or None,
+                    store_bytes=store.bytes() if store is not None else None,
+                    note="public API (AlternatingJointModel.forward + backward + optimizer.step) fed from pinned "
+                         "host buffers every step; " + notes[mode] + "; loss of every step read back to pinned memory")
+
+    e2e, e2e_host_features = None, None
+    if not args.no_e2e:
+        e2e = run_e2e(args.upload)
+        if not args.no_host_features and args.upload == "store" and world == 1:
+            e2e_host_features = run_e2e("zero_copy")
 
     # ---------------- per-kernel timeline (roofline of the dominant kernel) ----------------
     roof, breakdown = None, None
@@ -642,17 +686,7 @@ def main():
                         parallelism=f"dp{world}",
                         l2="inputs (839 MB att feats + 622 MB logits per step) exceed the 126 MB L2",
                         accumulate="fp32 accumulation, bf16 tensor-core operands, fp32 master weights"),
-            e2e=None if e2e_value is None else dict(
-                     value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
-                     ms_per_step=e2e_ms / args.steps, device_allocs_in_region=e2e_allocs,
-                     upload=args.upload, host_ms_per_step=e2e_host or None,
-                     note="public API (AlternatingJointModel.forward + backward + optimizer.step) from pinned "
-                          "fp32 host buffers every step; " +
-                          ("data.HostPacker: library worker threads pack the valid regions to bf16 in a pinned "
-                           "staging buffer (inside the timed region), one DMA copy on a copy stream"
-                           if args.upload == "host_pack" else
-                           "data.upload_batch: zero-copy kernel reads the valid fp32 regions over PCIe on a "
-                           "copy stream") + "; loss of every step read back to pinned memory"),
+            e2e=e2e, e2e_host_features=e2e_host_features,
             gpu_launches=int(launches), host_enqueue_ms_per_step=host_enqueue_ms,
             value_loop_debug=loop_debug,
             ms_per_step_by_rank=[m / args.steps for m in ms_ranks],

@@ -1,6 +1,9 @@
 """Host -> device staging of one batch: the B200 counterpart of the reference's `load_data`
 (train.py:162-178) / `utils.var_wrapper(...).cuda()` (misc/utils.py:72-87).
 
+Two ways in: `FeatureStore` keeps the whole feature set in HBM and a step ships only image indices
+(the fast path); `upload_batch` / `HostPacker` move one loader-shaped batch of host features.
+
 The reference copies the zero-padded `att_feats [rows, Lmax, 2048]` fp32 tensor whole.  Here only
 the valid regions of every row cross PCIe (`coopcap_h2d_ragged_rows`), and the packed-region
 offsets the kernels need are derived from the host-side mask, so no device synchronisation is
@@ -164,6 +167,112 @@ class HostPacker:
             ev.record(st)
         j["slot"]["ev"] = ev
         self.last_bytes = moved
+        return fc, att, am, lab, msk
+
+
+class FeatureStore:
+    """All images' features resident in HBM; a step ships image indices instead of features.
+
+    The reference's loader fetches every image's bottom-up features from disk by index, pads them
+    and `load_data` copies 839 MB of fp32 per 1024-row step to the GPU (dataloader.py:137-160,
+    220-229; train.py:162-178).  COCO's whole bottom-up set is ~28 GB as packed bf16 rows, so it
+    fits one B200 several times over: build the store once, then
+
+        fc, att, att_masks, labels, masks = store.load_batch(ix, labels, masks, stream=copy_stream)
+
+    is the drop-in for `load_data`: `ix` (int64, the loader's per-row image index) plus the
+    caption tensors cross PCIe (a few hundred KB), `coopcap_store_gather` assembles the packed
+    bf16 operand on the device.  The returned tuple is what AlternatingJointModel.forward takes
+    (`att` is a shape carrier; the packed operand rides on `att_masks`, as with upload_batch)."""
+
+    def __init__(self, device, fc_feats: torch.Tensor, att16: torch.Tensor, off: torch.Tensor):
+        """fc_feats fp32 [N, F], att16 bf16 [total_regions, D] and off int64 [N+1], all on `device`
+        (use the `from_padded` / `append` builders)."""
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.CoopcapError("FeatureStore lives on a CUDA device (there is no CPU path)")
+        assert fc_feats.dtype == torch.float32 and att16.dtype == torch.bfloat16 and off.dtype == torch.int64
+        self.fc, self.att16, self.off = fc_feats.contiguous(), att16.contiguous(), off.contiguous()
+        self.n_img = self.fc.shape[0]
+        self.lens_host = (off[1:] - off[:-1]).to("cpu", torch.int32)       # region counts, host copy
+        self.last_bytes = 0
+        self._slots, self._next = [], 0       # pinned staging for the per-batch offsets / row order
+
+    def _slot(self, B):
+        """Round-robin pinned staging (page-locking memory per call would cost more than the step)."""
+        if not self._slots or self._slots[0]["off"].numel() < B + 1:
+            self._slots = [dict(off=torch.empty(B + 1, dtype=torch.int32).pin_memory(),
+                                order=torch.empty(B, dtype=torch.int32).pin_memory(), ev=None)
+                           for _ in range(4)]
+        sl = self._slots[self._next]
+        self._next = (self._next + 1) % len(self._slots)
+        if sl["ev"] is not None:
+            sl["ev"].synchronize()            # the copy that last read this slot (4 batches ago) is done
+        return sl
+
+    @classmethod
+    def from_padded(cls, device, fc_feats: torch.Tensor, att_feats: torch.Tensor,
+                    att_masks: Optional[torch.Tensor], chunk: int = 256) -> "FeatureStore":
+        """Build from loader-shaped host tensors fc [N, F], att [N, L, D] (zero-padded), att_masks
+        [N, L] or None.  One-off setup: uploads `chunk` images at a time."""
+        device = torch.device(device)
+        N, L, D = att_feats.shape
+        lens = torch.full((N,), L, dtype=torch.int64) if att_masks is None \
+            else (att_masks > 0).sum(1).to(torch.int64)
+        off = torch.zeros(N + 1, dtype=torch.int64)
+        off[1:] = torch.cumsum(lens, 0)
+        att16 = torch.empty(int(off[-1]), D, dtype=torch.bfloat16, device=device)
+        for i0 in range(0, N, chunk):
+            blk = att_feats[i0:i0 + chunk].to(device)
+            keep = (torch.arange(L, device=device)[None, :] < lens[i0:i0 + chunk].to(device)[:, None])
+            att16[int(off[i0]):int(off[min(i0 + chunk, N)])] = blk[keep].to(torch.bfloat16)
+        return cls(device, fc_feats.to(device, torch.float32), att16, off.to(device))
+
+    def bytes(self) -> int:
+        return self.att16.numel() * 2 + self.fc.numel() * 4 + self.off.numel() * 8
+
+    def load_batch(self, ix: torch.Tensor, labels: torch.Tensor, masks: torch.Tensor, *, stream=None):
+        """ix int64 [B] (host, ideally pinned): image index of every batch row; labels / masks are
+        the loader's caption tensors (host).  Asynchronous on `stream`; no device synchronisation."""
+        if ix.device.type != "cpu" or ix.dtype != torch.int64:
+            raise _lib.CoopcapError("FeatureStore.load_batch takes a host int64 index tensor")
+        B = ix.numel()
+        if B == 0 or int(ix.min()) < 0 or int(ix.max()) >= self.n_img:
+            raise _lib.CoopcapError(f"image index out of range [0, {self.n_img})")
+        lens = self.lens_host[ix]                                  # host gather of B integers
+        sl = self._slot(B)
+        off, order = sl["off"][: B + 1], sl["order"][:B]
+        off[0] = 0
+        torch.cumsum(lens, 0, out=off[1:])
+        NL, L = int(off[-1]), int(lens.max())
+        order.copy_(torch.argsort(lens, descending=True, stable=True))
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        D, F = self.att16.shape[1], self.fc.shape[1]
+        nb = lambda t: t.numel() * t.element_size()
+        with torch.cuda.stream(st):
+            ix_d = ix.to(self.device, non_blocking=True)
+            off_d = off.to(self.device, non_blocking=True)
+            order_d = order.to(self.device, non_blocking=True)
+            lab = labels.to(self.device, non_blocking=True)
+            msk = masks.to(self.device, non_blocking=True)
+            att16 = torch.empty(NL, D, dtype=torch.bfloat16, device=self.device)
+            fc = torch.empty(B, F, dtype=torch.float32, device=self.device)
+            check(_lib.load().coopcap_store_gather(
+                C.c_void_p(self.att16.data_ptr()), C.c_void_p(self.off.data_ptr()),
+                C.c_void_p(self.fc.data_ptr()), self.n_img, C.c_void_p(ix_d.data_ptr()), B, D, F,
+                C.c_void_p(off_d.data_ptr()), C.c_void_p(att16.data_ptr()), C.c_void_p(fc.data_ptr()),
+                C.c_void_p(st.cuda_stream)))
+            # att_masks as the reference's loader shapes it: 1 on the valid regions, width = longest row
+            lens_d = (off_d[1:] - off_d[:-1])
+            am = (torch.arange(L, device=self.device, dtype=torch.int32)[None, :] < lens_d[:, None]).float()
+            am._coopcap_off = (off_d, NL)
+            am._coopcap_order = order_d
+            am._coopcap_att16 = att16
+            am._coopcap_src = (ix_d,)
+            att = torch.zeros(1, 1, 1, device=self.device).expand(B, L, D)      # shape carrier only
+            sl["ev"] = torch.cuda.Event()
+            sl["ev"].record(st)
+        self.last_bytes = nb(ix) + nb(off) + nb(order) + nb(labels) + nb(masks)
         return fc, att, am, lab, msk
 
 

@@ -492,6 +492,19 @@ int coopcap_host_pack_start(const float* att_feats, const int* att_off_host, int
                             void* att16_host, int nthreads);
 int coopcap_host_pack_wait(int job);
 
+/* ---- device-resident feature store (dataloader.py:137-160,220-229 + train.py:162-178) ------------
+ * The reference's loader reads an image's region features by image index, zero-pads the batch and
+ * `load_data` copies it to the GPU every step.  With the whole feature set resident in HBM as
+ * packed bf16 rows (store_att16 [total_regions, D], image i owns rows store_off[i]..store_off[i+1]),
+ * a step ships only indices: this call gathers the images ix[0..B) into the packed operand
+ * att16_out [NL, D] (row b's regions at att_off[b]..att_off[b+1], the layout of
+ * coopcap_speaker.att16 with att_prepacked = 1) and, when fc_out != NULL, their fc vectors
+ * store_fc [n_img, F] fp32 into fc_out [B, F].  ix, store_off, att_off are DEVICE arrays; att_off
+ * must be the running sum of the gathered images' region counts (the host knows them). */
+int coopcap_store_gather(const void* store_att16, const int64_t* store_off, const float* store_fc,
+                         int64_t n_img, const int64_t* ix, int B, int D, int F, const int* att_off,
+                         void* att16_out, float* fc_out, coopcap_stream_t stream);
+
 /* ---- instrumentation ---------------------------------------------------------------------------
  * coopcap_launch_count: kernels launched by this library since load (all streams).
  * coopcap_prof_enable(1, stream): start an event timeline on `stream` (one event after every

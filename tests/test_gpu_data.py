@@ -74,3 +74,48 @@ def test_host_packer_matches_plain_copy(varlen):
         assert torch.equal(a.t["att16"], r.t["att16"])
         assert torch.equal(a.t["tok_out"], r.t["tok_out"])
     assert packer.last_bytes < batches[-1].att_feats.numel() * 2 + 10 ** 6
+
+
+@pytest.mark.parametrize("varlen", [True, False])
+def test_feature_store_batches_equal_plain_copies(varlen):
+    """data.FeatureStore: with every image's features resident in HBM a step ships only image
+    indices; the gathered packed operand, fc vectors, masks and offsets must be exactly what a plain
+    `.cuda()` of the loader's padded batch (same images, same order, repeats included) gives."""
+    import cooperativeimagecaptioning_b200.models as models
+    from cooperativeimagecaptioning_b200.data import FeatureStore, record_stream
+    d = REAL
+    N, L, B = 40, 11, 23
+    pool = synth.make_batch(d, N, L, 91, varlen=varlen, min_regions=2)
+    store = FeatureStore.from_padded("cuda", pool.fc_feats, pool.att_feats, pool.att_masks, chunk=16)
+    assert store.n_img == N and store.att16.shape[0] == (int((pool.att_masks > 0).sum()) if varlen else N * L)
+    g = torch.Generator().manual_seed(5)
+    ix = torch.randint(0, N, (B,), generator=g)
+    ix[3] = ix[7]                                   # seq_per_img style repeats are fine
+    cap = synth.make_batch(d, B, L, 92)             # captions of the batch rows
+    spk = models.setup(reference_opt(), "att2in2", "caption_model").cuda().eval()
+    spk.keep_passes = True
+    side = torch.cuda.Stream()
+    with torch.no_grad():
+        fc, att, am, lab, msk = store.load_batch(ix.pin_memory(), cap.labels.pin_memory(),
+                                                 cap.masks.pin_memory(), stream=side)
+        torch.cuda.current_stream().wait_stream(side)
+        record_stream((fc, att, am, lab, msk), torch.cuda.current_stream())
+        spk.sample(fc, att, am, {"sample_max": 1})
+        # the same rows through the reference-shaped path: padded features + masks, width = longest row
+        ref_m = None if pool.att_masks is None else pool.att_masks[ix]
+        Lb = L if ref_m is None else int(ref_m.sum(1).max())
+        ref_att = pool.att_feats[ix][:, :Lb].contiguous()
+        ref_m = torch.ones(B, Lb) if ref_m is None else ref_m[:, :Lb].contiguous()
+        spk.sample(pool.fc_feats[ix].cuda(), ref_att.cuda(), ref_m.cuda(), {"sample_max": 1})
+    torch.cuda.synchronize()
+    a, b = spk._passes
+    assert a.NL == b.NL and att.shape == ref_att.shape
+    assert torch.equal(a.t["att16"], b.t["att16"])          # packed bf16 regions: bit-identical
+    assert torch.equal(a.t["tok_out"], b.t["tok_out"])      # hence identical greedy captions
+    assert torch.equal(fc.cpu(), pool.fc_feats[ix]) and torch.equal(am.cpu(), ref_m)
+    assert torch.equal(lab.cpu(), cap.labels) and torch.equal(msk.cpu(), cap.masks)
+    # what crossed PCIe: indices + captions, not features
+    assert store.last_bytes < 64 * B + cap.labels.numel() * 8 + cap.masks.numel() * 4
+    from cooperativeimagecaptioning_b200._lib import CoopcapError
+    with pytest.raises(CoopcapError):
+        store.load_batch(torch.tensor([N]), cap.labels[:1], cap.masks[:1])
