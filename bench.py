@@ -533,6 +533,11 @@ def main():
         # warm-up: the upload buffers live in the copy stream's allocator pool and are recycled
         # through record_stream, which needs a few rounds to reach its steady state
         e2e_loop(max(8, args.warmup), False)
+        for _ in range(3):          # ... and must not be growing any more (a cudaMalloc stalls the step)
+            a_before = torch.cuda.memory_stats()["num_device_alloc"]
+            e2e_loop(8, False)
+            if torch.cuda.memory_stats()["num_device_alloc"] == a_before:
+                break
         barrier()
         a0 = torch.cuda.memory_stats()["num_device_alloc"]
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

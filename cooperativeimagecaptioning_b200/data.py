@@ -246,29 +246,46 @@ class FeatureStore:
         torch.cumsum(lens, 0, out=off[1:])
         NL, L = int(off[-1]), int(lens.max())
         order.copy_(torch.argsort(lens, descending=True, stable=True))
-        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        home = torch.cuda.current_stream(self.device)            # the stream that will consume the batch
+        st = stream if stream is not None else home
         D, F = self.att16.shape[1], self.fc.shape[1]
         nb = lambda t: t.numel() * t.element_size()
+        # Outputs come from the CONSUMER stream's allocator pool (no record_stream bookkeeping, no
+        # delayed frees, hence no cudaMalloc in steady state: a 230 MB cudaMalloc next to a busy
+        # GPU cost tens of ms); the staging stream first waits until the consumer has reached this
+        # point, i.e. until whatever used these blocks before has finished.
+        i64 = dict(dtype=torch.int64, device=self.device)
+        ix_d = torch.empty(B, **i64)
+        off_d = torch.empty(B + 1, dtype=torch.int32, device=self.device)
+        order_d = torch.empty(B, dtype=torch.int32, device=self.device)
+        lab = torch.empty(labels.shape, dtype=labels.dtype, device=self.device)
+        msk = torch.empty(masks.shape, dtype=masks.dtype, device=self.device)
+        att16 = torch.empty(NL, D, dtype=torch.bfloat16, device=self.device)
+        fc = torch.empty(B, F, dtype=torch.float32, device=self.device)
+        am = torch.empty(B, L, dtype=torch.float32, device=self.device)
+        if st != home:
+            ev = torch.cuda.Event()
+            ev.record(home)
+            st.wait_event(ev)
         with torch.cuda.stream(st):
-            ix_d = ix.to(self.device, non_blocking=True)
-            off_d = off.to(self.device, non_blocking=True)
-            order_d = order.to(self.device, non_blocking=True)
-            lab = labels.to(self.device, non_blocking=True)
-            msk = masks.to(self.device, non_blocking=True)
-            att16 = torch.empty(NL, D, dtype=torch.bfloat16, device=self.device)
-            fc = torch.empty(B, F, dtype=torch.float32, device=self.device)
+            ix_d.copy_(ix, non_blocking=True)
+            off_d.copy_(off, non_blocking=True)
+            order_d.copy_(order, non_blocking=True)
+            lab.copy_(labels, non_blocking=True)
+            msk.copy_(masks, non_blocking=True)
             check(_lib.load().coopcap_store_gather(
                 C.c_void_p(self.att16.data_ptr()), C.c_void_p(self.off.data_ptr()),
                 C.c_void_p(self.fc.data_ptr()), self.n_img, C.c_void_p(ix_d.data_ptr()), B, D, F,
                 C.c_void_p(off_d.data_ptr()), C.c_void_p(att16.data_ptr()), C.c_void_p(fc.data_ptr()),
                 C.c_void_p(st.cuda_stream)))
             # att_masks as the reference's loader shapes it: 1 on the valid regions, width = longest row
-            lens_d = (off_d[1:] - off_d[:-1])
-            am = (torch.arange(L, device=self.device, dtype=torch.int32)[None, :] < lens_d[:, None]).float()
+            am.copy_(torch.arange(L, device=self.device, dtype=torch.int32)[None, :]
+                     < (off_d[1:] - off_d[:-1])[:, None])
             am._coopcap_off = (off_d, NL)
             am._coopcap_order = order_d
             am._coopcap_att16 = att16
             am._coopcap_src = (ix_d,)
+            am._coopcap_home = True          # buffers live in the consumer stream's pool: no record_stream
             att = torch.zeros(1, 1, 1, device=self.device).expand(B, L, D)      # shape carrier only
             sl["ev"] = torch.cuda.Event()
             sl["ev"].record(st)
@@ -279,6 +296,9 @@ class FeatureStore:
 def record_stream(batch, stream):
     """Tell the caching allocator that `stream` uses the tensors of an uploaded batch (they were
     allocated on the upload stream), including the packed side buffers."""
+    batch = list(batch)
+    if any(getattr(t, "_coopcap_home", False) for t in batch if t is not None):
+        return                      # FeatureStore batches already live in the consumer stream's pool
     for t in batch:
         if t is None:
             continue

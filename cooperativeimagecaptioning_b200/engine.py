@@ -339,11 +339,43 @@ def logp_logit_grads(sp: SpeakerPass, tok: torch.Tensor, coef: torch.Tensor) -> 
     return dz16
 
 
+def grad_targets(P: Dict[str, torch.Tensor], names):
+    """Where the fused backward nodes write each parameter's gradient.
+
+    A parameter that belongs to a FlatAdam bucket, requires grad and has received no gradient yet
+    in this backward pass gets the bucket's own gradient view: the kernels write there, the node
+    sets `p.grad` to that view and returns None to autograd, so the gradient is never copied
+    (no accumulation kernel, no gather into the bucket) and the optimizer can exchange that bucket
+    range between ranks while the rest of backward still runs.  Everything else gets a fresh
+    tensor that travels through autograd as usual.  Returns ({name: tensor}, {names written direct})."""
+    G, direct, seen = {}, set(), set()
+    for n in names:
+        p = P[n]
+        bucket = getattr(p, "_coopcap_bucket", None)
+        view = bucket.grad_view(p) if bucket is not None else None
+        if view is not None and p.requires_grad and p.grad is None and id(p) not in seen \
+                and view.device == p.device:
+            G[n] = view
+            direct.add(n)
+            seen.add(id(p))
+        else:
+            G[n] = torch.empty_like(p, dtype=torch.float32)
+    return G, direct
+
+
+def adopt_direct(P, G, direct):
+    """After the kernels ran: the parameters written direct now own their bucket view as .grad."""
+    for n in direct:
+        P[n].grad = G[n]
+
+
 def speaker_backward(sp: SpeakerPass, dz16: Optional[torch.Tensor], P: Dict[str, torch.Tensor],
                      ps_demb16: Optional[torch.Tensor] = None,
                      ps_w_emb16: Optional[torch.Tensor] = None,
-                     ps_g_dense: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-    """BPTT + prologue backward.  Returns {reference parameter name: fp32 gradient}.
+                     ps_g_dense: Optional[torch.Tensor] = None,
+                     out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """BPTT + prologue backward.  Returns {reference parameter name: fp32 gradient}; `out` gives the
+    tensors to write them into (see grad_targets), else fresh ones are allocated.
 
     Partial-sampling passes take the upstream gradient of the emitted vectors instead of dz16:
     factored (`ps_demb16` bf16 [n_steps, B, E] + `ps_w_emb16`) or dense (`ps_g_dense` fp32
@@ -364,11 +396,14 @@ def speaker_backward(sp: SpeakerPass, dz16: Optional[torch.Tensor], P: Dict[str,
         d_xh=torch.empty(cap * B, XH, **f32), dc=torch.empty(2, B, d.R, **f32),
         d_att_e=torch.empty(NL, d.R, **f32), d_p_att16=torch.empty(NL, d.A, **bf),
         d_pre16=torch.empty(NL, d.R, **bf))
-    G = {n: torch.empty_like(P[n], dtype=torch.float32) for n in SPEAKER_PARAM_NAMES
-         if n not in ("embed.0.weight", "core.attention.alpha_net.bias", "core.h2h.bias")}
-    G["embed.0.weight"] = torch.zeros_like(P["embed.0.weight"], dtype=torch.float32)
+    if out is None:
+        G = {n: torch.empty_like(P[n], dtype=torch.float32) for n in SPEAKER_PARAM_NAMES
+             if n not in ("core.h2h.bias",)}
+    else:
+        G = dict(out)
+    G["embed.0.weight"].zero_()                     # accumulated into by atomics
     # the alpha_net bias shifts every score of a row equally: its gradient is identically 0
-    G["core.attention.alpha_net.bias"] = torch.zeros_like(P["core.attention.alpha_net.bias"])
+    G["core.attention.alpha_net.bias"].zero_()
     g = _lib.SpeakerGrads()
     g.dz16 = _p(dz16)
     if is_ps:
@@ -399,7 +434,10 @@ def speaker_backward(sp: SpeakerPass, dz16: Optional[torch.Tensor], P: Dict[str,
     check(_lib.load().coopcap_speaker_decode_bwd(C.byref(sp.ctx), C.byref(g), _stream()))
     if getattr(sp, "pinned", False):     # tests inspect the logit gradient of pinned passes
         sp.t["dz16"] = dz16
-    G["core.h2h.bias"] = G["core.i2h.bias"]     # both biases enter the same sum
+    if out is None:
+        G["core.h2h.bias"] = G["core.i2h.bias"]     # both biases enter the same sum
+    else:
+        G["core.h2h.bias"].copy_(G["core.i2h.bias"])
     return G
 
 
@@ -525,8 +563,10 @@ def listener_forward(P, packed, fc_feats, tok_sb, lens, *, margin=0.2, only_one_
     return lp
 
 
-def listener_backward(lp: ListenerPass, P, *, g_loss=None, g_rows=None, need_param_grads=True):
-    """Returns (grads {name: tensor} or None, demb16 [S, B, E] bf16)."""
+def listener_backward(lp: ListenerPass, P, *, g_loss=None, g_rows=None, need_param_grads=True,
+                      out=None):
+    """Returns (grads {name: tensor} or None, demb16 [S, B, E] bf16); `out` gives the tensors the
+    parameter gradients are written into (see grad_targets)."""
     d = lp.dims
     B, S = lp.B, lp.S
     dev = lp.t["im"].device
@@ -552,9 +592,9 @@ def listener_backward(lp: ListenerPass, P, *, g_loss=None, g_rows=None, need_par
         setattr(g, n, _p(tsr))
     G = None
     if need_param_grads:
-        G = {n: torch.empty_like(P[n], dtype=torch.float32) for n in LISTENER_PARAM_NAMES
-             if n != "txt_enc.embed.weight"}
-        G["txt_enc.embed.weight"] = torch.zeros_like(P["txt_enc.embed.weight"], dtype=torch.float32)
+        G = dict(out) if out is not None else \
+            {n: torch.empty_like(P[n], dtype=torch.float32) for n in LISTENER_PARAM_NAMES}
+        G["txt_enc.embed.weight"].zero_()           # accumulated into by atomics
         g.g_w_img, g.g_b_img = _p(G["img_enc.fc.weight"]), _p(G["img_enc.fc.bias"])
         g.g_w_emb = _p(G["txt_enc.embed.weight"])
         g.g_w_ih, g.g_w_hh = _p(G["txt_enc.rnn.weight_ih_l0"]), _p(G["txt_enc.rnn.weight_hh_l0"])

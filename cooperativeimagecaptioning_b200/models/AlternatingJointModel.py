@@ -44,15 +44,29 @@ class _StJointFn(torch.autograd.Function):
         Ps, Pl = spk._params(), lis._params()
         need_l = any(p.requires_grad for p in Pl.values())
         need_s = any(p.requires_grad for p in Ps.values())
+        # gradients of bucketed parameters are written straight into the optimizer's flat bucket
+        Gl_t, dl = EN.grad_targets(Pl, EN.LISTENER_PARAM_NAMES) if need_l else (None, set())
         Gl, demb16 = EN.listener_backward(lp, Pl, g_loss=g.contiguous().float().reshape(1),
-                                          need_param_grads=need_l)
+                                          need_param_grads=need_l, out=Gl_t)
+        if need_l:
+            EN.adopt_direct(Pl, Gl, dl)
+            # the listener's gradients are final here (unless a parameter is shared with the
+            # speaker): exchange them between the ranks now, hidden behind the speaker's BPTT
+            mine = {id(p) for p in Ps.values()}
+            final = [Pl[n] for n in dl if id(Pl[n]) not in mine]
+            buckets = {id(getattr(p, "_coopcap_bucket", None)): p._coopcap_bucket for p in final}
+            if len(final) == len(dl) == len(EN.LISTENER_PARAM_NAMES) and len(buckets) == 1:
+                next(iter(buckets.values())).reduce_async(final)
         gs = (None,) * len(EN.SPEAKER_PARAM_NAMES)
         if need_s:
             T = sp.n_steps
             dz16 = EN.st_logit_grads(sp, demb16[1:T + 1], lis._packed.get(Pl)["w_emb16"])
-            Gs = EN.speaker_backward(sp, dz16, Ps)
-            gs = tuple(Gs[n].view_as(Ps[n]) for n in EN.SPEAKER_PARAM_NAMES)
-        gl = tuple((Gl[n].view_as(Pl[n]) if need_l else None) for n in EN.LISTENER_PARAM_NAMES)
+            Gs_t, ds = EN.grad_targets(Ps, EN.SPEAKER_PARAM_NAMES)
+            Gs = EN.speaker_backward(sp, dz16, Ps, out=Gs_t)
+            EN.adopt_direct(Ps, Gs, ds)
+            gs = tuple((None if n in ds else Gs[n].view_as(Ps[n])) for n in EN.SPEAKER_PARAM_NAMES)
+        gl = tuple((None if (not need_l or n in dl) else Gl[n].view_as(Pl[n]))
+                   for n in EN.LISTENER_PARAM_NAMES)
         EN.release(sp)
         EN.release(lp)
         ctx.sp = ctx.lp = None
