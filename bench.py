@@ -310,6 +310,123 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def side_configs(model, dev, lib):
+    """BASELINE.json configs[1..3] on one GPU, device-resident inputs, CUDA-event timed:
+    configs[2] decode (512 rows x 36 regions, 16 tokens; the ids are copied to the host inside the
+    timed region), configs[1] speaker MLE step (250 rows = 50 images x 5, teacher-forced
+    forward + backward + clamp + Adam) and one rank's shard of configs[3] (REINFORCE with the
+    listener reward and the ground-truth baseline, 160 rows = 1280 / 8: speaker turn + listener
+    turn, each with its own clamp + Adam, run_joint.sh example 2 weights)."""
+    import cooperativeimagecaptioning_b200.models as models
+    from cooperativeimagecaptioning_b200 import optimizer as OPT
+    spk = model.caption_generator
+    g = torch.Generator().manual_seed(77)
+    d_att = torch.randn(512, 36, 2048, generator=g).to(dev)
+    ids_host = torch.zeros(512, 16, dtype=torch.int64).pin_memory()
+    decode = {}
+    for name, train_mode, sopt in (("greedy_eval", False, {"sample_max": 1}),
+                                   ("multinomial_train", True, {"sample_max": 0, "temperature": 1.0}),
+                                   ("st_gumbel_train", True, {"sample_max": 0, "use_one_hot": 1})):
+        spk.train(train_mode)
+
+        def once():
+            sp = spk._sample_pass(d_att, None, sopt.get("sample_max", 1), sopt.get("temperature", 1.0),
+                                  sopt.get("use_one_hot", 0))[0]
+            ids_host.copy_(sp.t["tok_out"][:16].t(), non_blocking=True)      # captions back on the host
+            return sp
+        with torch.no_grad():
+            for _ in range(3):
+                once()
+            torch.cuda.synchronize()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            d0.record()
+            for _ in range(reps):
+                sp = once()
+            d1.record()
+            torch.cuda.synchronize()
+        ms_d = d0.elapsed_time(d1) / reps
+        decode[name] = dict(tokens_per_s=512 * 16 / (ms_d * 1e-3), ms=ms_d, rows=512, steps=16,
+                            tokens_before_all_eos=int(sp.t["n_out"].item()),
+                            ids_to_host_bytes=ids_host.numel() * 8)
+    decode["note"] = ("BASELINE.json configs[2]: AttModel.sample decode loop (prologue + 16 steps) on 512 rows x "
+                      "36 regions, device-resident features; the sampled ids are copied to pinned host memory "
+                      "inside the timed region; EOS bias -1e4 so all 16 steps produce tokens")
+    model.train()
+
+    def timed(step, reps=20, warm=5):
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.coopcap_launch_count()
+        e0.record()
+        for _ in range(reps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, (lib.coopcap_launch_count() - l0) / reps
+
+    def caption_batch(rows, regions, seed):
+        gg = torch.Generator().manual_seed(seed)
+        n_img = rows // 5
+        fc = torch.randn(n_img, 2048, generator=gg).repeat_interleave(5, 0).to(dev)
+        att = torch.randn(n_img, regions, 2048, generator=gg).repeat_interleave(5, 0).to(dev)
+        clen = torch.randint(6, 17, (rows,), generator=gg)
+        labels = torch.zeros(rows, 18, dtype=torch.long)
+        words = torch.randint(1, 9488, (rows, 16), generator=gg)
+        labels[:, 1:17] = torch.where(torch.arange(16)[None, :] < clen[:, None], words, torch.zeros_like(words))
+        masks = (torch.arange(18)[None, :] < (clen + 2)[:, None]).float()
+        return fc, att, labels.to(dev), masks.to(dev)
+
+    side = {}
+    # ---- configs[1]: speaker MLE pretraining step, 50 images x 5 captions
+    rows = 250
+    opt2 = make_opt(rows)
+    opt2.is_alternating, opt2.alternating_turn = 0, None
+    opt2.caption_loss_weight, opt2.retrieval_reward_weight, opt2.phase = 1.0, 0.0, 2
+    torch.manual_seed(1)
+    m2 = models.AlternatingJointModel(opt2).to(dev).train()
+    o2 = OPT.define_optimizer(m2.caption_generator, opt2)
+    fc, att, labels, masks = caption_batch(rows, 36, 501)
+
+    def mle_step():
+        o2.zero_grad()
+        m2(fc, labels, masks, None, att, None).backward()
+        o2.step()
+    ms, launches = timed(mle_step)
+    side["config2_speaker_mle_step"] = dict(images_per_s=rows / (ms * 1e-3), ms_per_step=ms, rows=rows,
+                                            regions=36, launches_per_step=launches,
+                                            step="AttModel.forward (teacher forcing, dropout 0.5) + backward + clamp + Adam")
+    del m2, o2
+    # ---- configs[3]: REINFORCE with listener reward + ground-truth baseline, one rank's 160-row shard
+    rows = 160
+    opt4 = make_opt(rows)
+    opt4.retrieval_reward, opt4.reinforce_baseline_type = "reinforce", "gt"
+    opt4.retrieval_reward_weight, opt4.vse_loss_weight = 0.8, 0.1
+    opt4.alternating_turn = ["speaker", "listener"]
+    torch.manual_seed(2)
+    m4 = models.AlternatingJointModel(opt4).to(dev).train()
+    with torch.no_grad():
+        m4.caption_generator.logit.bias[0] = -2.0        # captions of realistic length, as in training
+    od = OPT.define_joint_optimizers(m4, opt4)
+    fc, att, labels, masks = caption_batch(rows, 36, 502)
+
+    def reinforce_pair():
+        for turn in ("speaker", "listener"):
+            OPT.zeroing_optimizer(opt4, od, od[turn])
+            m4(fc, labels, masks, None, att, None, is_alternating=True, alternating_turn=turn).backward()
+            OPT.update_optimizer(od, od[turn], opt4)
+    ms, launches = timed(reinforce_pair)
+    side["config4_reinforce_gt_turn_pair"] = dict(
+        images_per_s=rows / (ms * 1e-3), ms_per_turn_pair=ms, rows_per_rank=rows, regions=36,
+        launches_per_pair=launches,
+        step="speaker turn (sample -> listener reward vs. ground-truth baseline -> REINFORCE backward -> "
+             "clamp + Adam on the speaker) + listener turn (sample -> contrastive loss -> backward -> clamp + "
+             "Adam on the listener); one rank's shard of the 8 x 160 job")
+    return decode, side
+
+
 def main():
     args = parse()
     # stdout carries exactly ONE JSON line: anything else a library prints (the NCCL version banner)
@@ -636,39 +753,10 @@ def main():
             breakdown["gemm"]["tensor_frac"] = breakdown["gemm"]["achieved_TFLOPs"] / pk["tf_sustained"]
         del resident
 
-    # ---------------- decode side metric (BASELINE.json configs[2]: 512 rows, 16 tokens) -------
-    decode = None
+    # ---------------- the other BASELINE.json configurations (side lines, rank 0) ----------------
+    decode, side = None, None
     if rank == 0 and not args.no_decode:
-        spk = model.caption_generator
-        g = torch.Generator().manual_seed(77)
-        d_att = torch.randn(512, 36, 2048, generator=g).to(dev)
-        d_fc = torch.randn(512, 2048, generator=g).to(dev)
-        decode = {}
-        for name, train_mode, sopt in (("greedy_eval", False, {"sample_max": 1}),
-                                       ("multinomial_train", True, {"sample_max": 0, "temperature": 1.0}),
-                                       ("st_gumbel_train", True, {"sample_max": 0, "use_one_hot": 1})):
-            spk.train(train_mode)
-            with torch.no_grad():
-                for _ in range(3):
-                    spk._sample_pass(d_att, None, sopt.get("sample_max", 1), sopt.get("temperature", 1.0),
-                                     sopt.get("use_one_hot", 0))
-                torch.cuda.synchronize()
-                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                reps = 10
-                d0.record()
-                for _ in range(reps):
-                    sp = spk._sample_pass(d_att, None, sopt.get("sample_max", 1),
-                                          sopt.get("temperature", 1.0), sopt.get("use_one_hot", 0))[0]
-                d1.record()
-                torch.cuda.synchronize()
-            ms_d = d0.elapsed_time(d1) / reps
-            n_tok = int(sp.t["n_out"].item())
-            decode[name] = dict(tokens_per_s=512 * 16 / (ms_d * 1e-3), ms=ms_d, rows=512, steps=16,
-                                tokens_before_all_eos=n_tok)
-        decode["note"] = ("AttModel.sample decode loop (prologue + 16 steps) on 512 rows x 36 regions, "
-                          "device-resident inputs, ids left on the device; EOS bias -1e4 so all 16 "
-                          "steps produce tokens")
-        model.train()
+        decode, side = side_configs(model, dev, lib)
 
     # ---------------- CPU baseline (rank 0, N = 1) ----------------
     cpu = None
@@ -696,7 +784,7 @@ def main():
             value_loop_debug=loop_debug,
             ms_per_step_by_rank=[m / args.steps for m in ms_ranks],
             loss=loss_value, clocks=clk, roofline=roof,
-            cpu_baseline=cpu, decode=decode, breakdown=breakdown)
+            cpu_baseline=cpu, decode=decode, side_configs=side, breakdown=breakdown)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -145,8 +145,25 @@ int wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, 
 //   y = softmax(score), score = (z+G)/tau (gumbel) or z/tau (multinomial), rebuilt from the saved
 //   (max, sum) and the regenerated / injected noise;  dz = y (g - <y,g>) / tau on unfinished rows.
 // ------------------------------------------------------------------------------------------
+// GT = float (dense upstream gradient handed in by a foreign caller, partial-sampling scratch) or
+// bf16 (the factored path's demb . W_emb^T, which never needs more: dz is stored in bf16 anyway)
+template <typename GT>
+__device__ __forceinline__ void ld_g4(const GT* p, float (&o)[4]);
+template <>
+__device__ __forceinline__ void ld_g4<float>(const float* p, float (&o)[4]) {
+  o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = p[3];
+}
+template <>
+__device__ __forceinline__ void ld_g4<bf16>(const bf16* p, float (&o)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+template <typename GT>
 __global__ void __launch_bounds__(256)
-st_bwd_kernel(const __half* __restrict__ z, const float* __restrict__ g, int64_t ldg, int V1, int mode,
+st_bwd_kernel(const __half* __restrict__ z, const GT* __restrict__ g, int64_t ldg, int V1, int mode,
               float inv_tau, const float* __restrict__ noise, uint64_t seed, uint64_t nstream0,
               int B, const float* __restrict__ ymax, const float* __restrict__ ysum,
               const uint8_t* __restrict__ unf, bf16* __restrict__ dz,
@@ -165,7 +182,7 @@ st_bwd_kernel(const __half* __restrict__ z, const float* __restrict__ g, int64_t
     return;
   }
   const __half* zr = z + row * V1;
-  const float* gr = g + row * ldg;
+  const GT* gr = g + row * ldg;
   const float* nr = noise ? noise + row * V1 : nullptr;
   const float m = ymax[row], inv_s = 1.f / ysum[row];
   const bool fast = (noise == nullptr);
@@ -173,7 +190,8 @@ st_bwd_kernel(const __half* __restrict__ z, const float* __restrict__ g, int64_t
   for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
     float x4[4];
     f16x4_to_float(zr + 4 * v4, x4);
-    const float g4[4] = {gr[4 * v4], gr[4 * v4 + 1], gr[4 * v4 + 2], gr[4 * v4 + 3]};
+    float g4[4];
+    ld_g4<GT>(gr + 4 * v4, g4);
     float u4[4] = {0.f, 0.f, 0.f, 0.f};
     if (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_PS_GUMBEL)
       noise4(nr, v4, seed, nstream, uint64_t(b) * (V1 / 4) + v4, u4);
@@ -195,17 +213,19 @@ st_bwd_kernel(const __half* __restrict__ z, const float* __restrict__ g, int64_t
       f16x4_to_float(zr + 4 * v4, zq);
       const float p0 = ex2_ftz((zq[0] - l) * 1.4426950408889634f), p1 = ex2_ftz((zq[1] - l) * 1.4426950408889634f);
       const float p2 = ex2_ftz((zq[2] - l) * 1.4426950408889634f), p3 = ex2_ftz((zq[3] - l) * 1.4426950408889634f);
-      store_bf16x4(dr + 4 * v4, inv_tau * (yv.x * gr[4 * v4] - p0 * dot),
-                   inv_tau * (yv.y * gr[4 * v4 + 1] - p1 * dot),
-                   inv_tau * (yv.z * gr[4 * v4 + 2] - p2 * dot),
-                   inv_tau * (yv.w * gr[4 * v4 + 3] - p3 * dot));
+      float g4[4];
+      ld_g4<GT>(gr + 4 * v4, g4);
+      store_bf16x4(dr + 4 * v4, inv_tau * (yv.x * g4[0] - p0 * dot), inv_tau * (yv.y * g4[1] - p1 * dot),
+                   inv_tau * (yv.z * g4[2] - p2 * dot), inv_tau * (yv.w * g4[3] - p3 * dot));
     }
     return;
   }
   for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) {
     const float4 yv = *reinterpret_cast<const float4*>(s_y + 4 * v4);
-    store_bf16x4(dr + 4 * v4, inv_tau * yv.x * (gr[4 * v4] - dot), inv_tau * yv.y * (gr[4 * v4 + 1] - dot),
-                 inv_tau * yv.z * (gr[4 * v4 + 2] - dot), inv_tau * yv.w * (gr[4 * v4 + 3] - dot));
+    float g4[4];
+    ld_g4<GT>(gr + 4 * v4, g4);
+    store_bf16x4(dr + 4 * v4, inv_tau * yv.x * (g4[0] - dot), inv_tau * yv.y * (g4[1] - dot),
+                 inv_tau * yv.z * (g4[2] - dot), inv_tau * yv.w * (g4[3] - dot));
   }
 }
 
@@ -531,7 +551,7 @@ static int check_dims(const coopcap_speaker* c) {
   return CC_OK;
 }
 
-int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb16, float* g_ws,
+int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb16, void* g_ws,
                 int g_chunk_steps, int64_t ldg, void* dz16, cudaStream_t s) {
   int rc = check_dims(c);
   if (rc) return rc;
@@ -541,33 +561,44 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
              c->mode);
   const int B = c->B, V1 = c->V1, E = c->E;
   const size_t smem = sizeof(float) * V1;
-  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel), int(smem)))) return rc;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel<float>), int(smem)))) return rc;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel<bf16>), int(smem)))) return rc;
   // several steps per launch: M = chunk * B rows give properly sized GEMM tiles instead of
   // n_steps launches at the latency floor (g_ws holds `g_chunk_steps` steps)
   const int chunk = demb16 ? (g_chunk_steps < 1 ? 1 : g_chunk_steps) : c->n_steps;
   for (int t0 = 0; t0 < c->n_steps; t0 += chunk) {
     const int nt = min(chunk, c->n_steps - t0);
     const int64_t rows = int64_t(nt) * B;
-    const float* g_t = g_ws;
+    const __half* z_t = reinterpret_cast<const __half*>(c->z16_all) + int64_t(t0) * B * V1;
+    const float* n_t = c->noise ? c->noise + int64_t(t0) * B * V1 : nullptr;
+    bf16* dz_t = reinterpret_cast<bf16*>(dz16) + int64_t(t0) * B * V1;
     if (demb16) {
-      // g = demb[t0..] . W_emb^T   ([rows,E] x [V1,E]^T)
+      // g = demb[t0..] . W_emb^T   ([rows,E] x [V1,E]^T), kept in bf16: half the bytes of this
+      // [4096, 9488] intermediate in both directions
       EpiStoreParams e = {};
-      e.alpha = 1.f; e.C = g_ws; e.ldc = V1;
+      e.alpha = 1.f; e.C16 = reinterpret_cast<bf16*>(g_ws); e.ldc16 = V1;
       rc = gemm_run(0, 0, 0, reinterpret_cast<const bf16*>(demb16) + int64_t(t0) * B * E, E, w_emb16,
                     E, int(rows), V1, E, 1, 0, e, s);
       if (rc) return rc;
+      CC_CHECK_CUDA(launch_pdl(
+          st_bwd_kernel<bf16>, dim3((unsigned)rows), dim3(256), smem, s, z_t,
+          static_cast<const bf16*>(reinterpret_cast<bf16*>(g_ws)), int64_t(V1), V1, c->mode, c->inv_tau, n_t,
+          c->seed, uint64_t(SITE_NOISE + t0), B, static_cast<const float*>(c->y_max + int64_t(t0) * B),
+          static_cast<const float*>(c->y_sum + int64_t(t0) * B),
+          static_cast<const uint8_t*>(c->unfinished + int64_t(t0) * B), dz_t,
+          static_cast<const float*>(c->lse + int64_t(t0) * B)));
     } else {
-      g_t = g_ws + int64_t(t0) * B * ldg;   // dense upstream gradient, all steps
+      const float* g_t = reinterpret_cast<const float*>(g_ws) + int64_t(t0) * B * ldg;   // dense, all steps
+      CC_CHECK_CUDA(launch_pdl(
+          st_bwd_kernel<float>, dim3((unsigned)rows), dim3(256), smem, s, z_t, g_t, ldg, V1, c->mode,
+          c->inv_tau, n_t, c->seed, uint64_t(SITE_NOISE + t0), B,
+          static_cast<const float*>(c->y_max + int64_t(t0) * B),
+          static_cast<const float*>(c->y_sum + int64_t(t0) * B),
+          static_cast<const uint8_t*>(c->unfinished + int64_t(t0) * B), dz_t,
+          static_cast<const float*>(c->lse + int64_t(t0) * B)));
     }
-    CC_CHECK_CUDA(launch_pdl(
-        st_bwd_kernel, dim3((unsigned)rows), dim3(256), smem, s,
-        reinterpret_cast<const __half*>(c->z16_all) + int64_t(t0) * B * V1, g_t,
-        ldg, V1, c->mode, c->inv_tau, c->noise ? c->noise + int64_t(t0) * B * V1 : nullptr, c->seed,
-        uint64_t(SITE_NOISE + t0), B, c->y_max + int64_t(t0) * B, c->y_sum + int64_t(t0) * B,
-        c->unfinished + int64_t(t0) * B, reinterpret_cast<bf16*>(dz16) + int64_t(t0) * B * V1,
-        c->lse + int64_t(t0) * B));
     // logits + upstream gradient (+ injected noise) read, bf16 dz written
-    CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(rows) * V1 * (2.0 + 4.0 + 2.0 + (c->noise ? 4.0 : 0.0)));
+    CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(rows) * V1 * (2.0 + (demb16 ? 2.0 : 4.0) + 2.0 + (c->noise ? 4.0 : 0.0)));
   }
   return CC_OK;
 }
@@ -600,18 +631,21 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
   const bf16* out16 = reinterpret_cast<const bf16*>(c->out16);
   const float scale = c->drop_p > 0.f ? 1.f / (1.f - c->drop_p) : 1.f;
 
+  CC_REQUIRE(g->phase >= 0 && g->phase <= 2 && (!ps || g->phase == 0),
+             "speaker_decode_bwd: phase %d (partial-sampling passes take 0 only)", g->phase);
   // logit layer: d_out = dz . W_logit ; g_w_logit = dz^T . out ; g_b_logit = colsum(dz)
-  if (!ps) {
+  if (!ps && g->phase != 2) {
     EpiStoreParams e = {};
     e.alpha = 1.f; e.C = g->d_out; e.ldc = R;
     if ((rc = gemm_run(0, 0, 1, dz16, V1, c->w_logit16, R, int(rows), R, V1, 1, 0, e, s))) return rc;
     if ((rc = wgrad(dz16, V1, out16, R, V1, R, int(rows), g->g_w_logit, R, s))) return rc;
     if ((rc = colsum_bf16(dz16, rows, V1, V1, g->g_b_logit, s))) return rc;
   }
+  if (g->phase == 1) return CC_OK;
   bf16* ps_dpre16 = reinterpret_cast<bf16*>(g->ps_dpre16);
   if (ps) {
     const size_t smem = sizeof(float) * V1;
-    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel), int(smem)))) return rc;
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel<float>), int(smem)))) return rc;
   }
 
   const size_t att_smem = attention_smem_bytes(A, R, c->L);
@@ -649,7 +683,7 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
       }
       bf16* dz_t = const_cast<bf16*>(dz16) + int64_t(t) * B * V1;
       CC_CHECK_CUDA(launch_pdl(
-          st_bwd_kernel, dim3((unsigned)B), dim3(256), sizeof(float) * V1, s,
+          st_bwd_kernel<float>, dim3((unsigned)B), dim3(256), sizeof(float) * V1, s,
           reinterpret_cast<const __half*>(c->z16_all) + int64_t(t) * B * V1, static_cast<const float*>(g_t),
           ldg, V1, c->mode, c->inv_tau,
           c->noise ? c->noise + int64_t(t) * B * V1 : static_cast<const float*>(nullptr), c->seed,
@@ -832,7 +866,7 @@ __global__ void clamp_adam_kernel(float* __restrict__ p, const float* __restrict
 extern "C" {
 
 int coopcap_st_backward(const coopcap_speaker* ctx, const void* demb16, const void* w_emb16,
-                        float* g_ws, int g_chunk_steps, void* dz16, coopcap_stream_t stream) {
+                        void* g_ws, int g_chunk_steps, void* dz16, coopcap_stream_t stream) {
   if (!demb16 || !w_emb16 || !g_ws) {
     coopcap::set_last_error("st_backward: null demb16 / w_emb16 / g_ws");
     return coopcap::CC_ERR_ARG;

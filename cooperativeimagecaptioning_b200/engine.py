@@ -282,7 +282,7 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     return sp
 
 
-ST_CHUNK_ROWS = 4096   # rows of the upstream-gradient scratch per launch (155 MB fp32 at V1 = 9488)
+ST_CHUNK_ROWS = 4096   # rows of the upstream-gradient scratch per launch (78 MB bf16 at V1 = 9488)
 
 
 def st_logit_grads(sp: SpeakerPass, demb16: torch.Tensor, w_emb16: torch.Tensor) -> torch.Tensor:
@@ -293,7 +293,7 @@ def st_logit_grads(sp: SpeakerPass, demb16: torch.Tensor, w_emb16: torch.Tensor)
     assert demb16.dtype == torch.bfloat16 and demb16.is_contiguous()
     assert demb16.shape == (sp.n_steps, sp.B, d.E)
     chunk = max(1, min(sp.n_steps, ST_CHUNK_ROWS // max(sp.B, 1)))
-    g_ws = torch.empty(chunk * sp.B, d.V1, dtype=torch.float32, device=dev)
+    g_ws = torch.empty(chunk * sp.B, d.V1, dtype=torch.bfloat16, device=dev)
     dz16 = torch.empty(sp.n_steps * sp.B, d.V1, dtype=torch.bfloat16, device=dev)
     check(_lib.load().coopcap_st_backward(C.byref(sp.ctx), _p(demb16), _p(w_emb16), _p(g_ws),
                                           chunk, _p(dz16), _stream()))
@@ -373,7 +373,8 @@ def speaker_backward(sp: SpeakerPass, dz16: Optional[torch.Tensor], P: Dict[str,
                      ps_demb16: Optional[torch.Tensor] = None,
                      ps_w_emb16: Optional[torch.Tensor] = None,
                      ps_g_dense: Optional[torch.Tensor] = None,
-                     out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                     out: Optional[Dict[str, torch.Tensor]] = None,
+                     after_logit_layer=None) -> Dict[str, torch.Tensor]:
     """BPTT + prologue backward.  Returns {reference parameter name: fp32 gradient}; `out` gives the
     tensors to write them into (see grad_targets), else fresh ones are allocated.
 
@@ -431,6 +432,13 @@ def speaker_backward(sp: SpeakerPass, dz16: Optional[torch.Tensor], P: Dict[str,
     g.g_w_a2c, g.g_b_a2c = _p(G["core.a2c.weight"]), _p(G["core.a2c.bias"])
     g.g_w_logit, g.g_b_logit = _p(G["logit.weight"]), _p(G["logit.bias"])
     g.g_w_alpha = _p(G["core.attention.alpha_net.weight"])
+    if after_logit_layer is not None and not is_ps:
+        # vocabulary layer first; the caller may start exchanging its gradients between the ranks
+        # while the BPTT loop runs (coopcap_speaker_grads.phase)
+        g.phase = 1
+        check(_lib.load().coopcap_speaker_decode_bwd(C.byref(sp.ctx), C.byref(g), _stream()))
+        after_logit_layer(G)
+        g.phase = 2
     check(_lib.load().coopcap_speaker_decode_bwd(C.byref(sp.ctx), C.byref(g), _stream()))
     if getattr(sp, "pinned", False):     # tests inspect the logit gradient of pinned passes
         sp.t["dz16"] = dz16

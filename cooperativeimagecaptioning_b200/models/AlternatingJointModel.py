@@ -62,7 +62,16 @@ class _StJointFn(torch.autograd.Function):
             T = sp.n_steps
             dz16 = EN.st_logit_grads(sp, demb16[1:T + 1], lis._packed.get(Pl)["w_emb16"])
             Gs_t, ds = EN.grad_targets(Ps, EN.SPEAKER_PARAM_NAMES)
-            Gs = EN.speaker_backward(sp, dz16, Ps, out=Gs_t)
+
+            def logit_grads_ready(G):
+                # 19.5 MB of the speaker's 57.8 MB are final after the vocabulary layer's backward
+                names = ("logit.weight", "logit.bias")
+                if all(n in ds for n in names):
+                    b = Ps[names[0]]._coopcap_bucket
+                    if all(getattr(Ps[n], "_coopcap_bucket", None) is b for n in names):
+                        b.reduce_async([Ps[n] for n in names])
+
+            Gs = EN.speaker_backward(sp, dz16, Ps, out=Gs_t, after_logit_layer=logit_grads_ready)
             EN.adopt_direct(Ps, Gs, ds)
             gs = tuple((None if n in ds else Gs[n].view_as(Ps[n])) for n in EN.SPEAKER_PARAM_NAMES)
         gl = tuple((None if (not need_l or n in dl) else Gl[n].view_as(Pl[n]))

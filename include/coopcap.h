@@ -256,11 +256,11 @@ int coopcap_speaker_decode_fwd(const coopcap_speaker* ctx, coopcap_stream_t stre
  *   g  = demb[t+1] . W_emb^T                  (listener-embedding dgrad, VSEFCModel.py:104)
  *   dz = inv_tau * y * (g - <y, g>) on unfinished rows, 0 elsewhere, y = softmax((z+G)*inv_tau)
  * demb16: bf16 [n_steps*B, E] gradient w.r.t. the listener's word embedding at caption positions
- * 1..n_steps; w_emb16: bf16 [>=V1, E]; g_ws: fp32 [g_chunk_steps*B, V1] workspace (g is formed for
+ * 1..n_steps; w_emb16: bf16 [>=V1, E]; g_ws: bf16 [g_chunk_steps*B, V1] workspace (g is formed for
  * g_chunk_steps steps per launch: larger GEMM tiles, scratch mostly L2-resident);
  * dz16: bf16 [n_steps*B, V1]. */
 int coopcap_st_backward(const coopcap_speaker* ctx, const void* demb16, const void* w_emb16,
-                        float* g_ws, int g_chunk_steps, void* dz16, coopcap_stream_t stream);
+                        void* g_ws, int g_chunk_steps, void* dz16, coopcap_stream_t stream);
 /* Same with a dense upstream gradient g = d(loss)/d(one_hots[:, :, :V1]) given explicitly
  * (fp32 [n_steps*B, ldg]); used when foreign code consumed the dense one-hot tensor. */
 int coopcap_st_backward_dense(const coopcap_speaker* ctx, const float* g, int64_t ldg, void* dz16,
@@ -313,6 +313,11 @@ typedef struct coopcap_speaker_grads {
   float* ps_g;
   int64_t ps_ldg;
   void* ps_dpre16;      /* bf16 [n_steps*B, E] workspace: d(loss)/d(v_{t-1} . embed) */
+  /* 0 = the whole backward pass; 1 = only the vocabulary layer (d_out, g_w_logit, g_b_logit);
+   * 2 = everything after it.  A data-parallel caller runs 1, starts the exchange of the 19.5 MB
+   * logit gradients between the ranks, then runs 2 (the BPTT loop hides the exchange).  The
+   * partial-sampling modes form the logit gradients inside the loop: they take 0 only. */
+  int phase;
 } coopcap_speaker_grads;
 
 /* BPTT through the decode loop and the prologue given d(loss)/d(logits). */
