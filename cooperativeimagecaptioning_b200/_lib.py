@@ -72,7 +72,7 @@ def _parse_header(path):
         order.append(name)
     funcs = {}
     body = re.sub(r"typedef\s+struct\s+\w+\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
-    for m in re.finditer(r"\b(int|long long|const char\s*\*)\s+(coopcap_\w+)\s*\(([^)]*)\)\s*;", body):
+    for m in re.finditer(r"\b(int|long long|uint64_t|const char\s*\*)\s+(coopcap_\w+)\s*\(([^)]*)\)\s*;", body):
         ret, fname, args = m.group(1), m.group(2), m.group(3).strip()
         argtypes = []
         if args and args != "void":
@@ -80,7 +80,8 @@ def _parse_header(path):
                 a = " ".join(a.split())
                 am = re.match(r"^(.*?[\s\*])(\w+)$", a)
                 argtypes.append(_ctype_of(am.group(1).strip(), structs))
-        restype = C.c_char_p if "char" in ret else (C.c_longlong if "long" in ret else C.c_int)
+        restype = C.c_char_p if "char" in ret else (C.c_longlong if "long" in ret else
+                                                    (C.c_uint64 if "uint64" in ret else C.c_int))
         funcs[fname] = (restype, argtypes)
     return structs, order, funcs
 
@@ -94,10 +95,11 @@ SpeakerGrads = STRUCTS["coopcap_speaker_grads"]
 ListenerPack = STRUCTS["coopcap_listener_pack"]
 Listener = STRUCTS["coopcap_listener"]
 ListenerGrads = STRUCTS["coopcap_listener_grads"]
+Cider = STRUCTS["coopcap_cider"]
 
 _SIZEOF_IDS = {"coopcap_gemm_args": 0, "coopcap_speaker_pack": 1, "coopcap_speaker": 2,
                "coopcap_speaker_grads": 3, "coopcap_listener_pack": 4, "coopcap_listener": 5,
-               "coopcap_listener_grads": 6}
+               "coopcap_listener_grads": 6, "coopcap_cider": 7}
 
 # kept for tests: name -> argtypes
 SIGNATURES = {k: v[1] for k, v in FUNCTIONS.items()}

@@ -244,6 +244,7 @@ int coopcap_sizeof(int which) {
     case 4: return (int)sizeof(coopcap_listener_pack);
     case 5: return (int)sizeof(coopcap_listener);
     case 6: return (int)sizeof(coopcap_listener_grads);
+    case 7: return (int)sizeof(coopcap_cider);
     default: return -1;
   }
 }

@@ -239,7 +239,10 @@ __global__ void ps_dpre_kernel(const float* __restrict__ d_xh, const bf16* __res
         __bfloat162float(xh16[row * XH + i]) > 0.f ? d_xh[row * XH + i] * scale : 0.f);
 }
 
-// dz = coef * (onehot(tok) - softmax(z))   (REINFORCE / XE), one CTA per (step, row)
+// dz = coef * (onehot(tok) - softmax(z))   (REINFORCE / XE), one CTA per (step, row); ACC: added to
+// the gradient already in dz (a second loss term on the same pass, e.g. the CIDEr term next to the
+// straight-through listener gradient, AlternatingJointModel.py:490-503)
+template <bool ACC>
 __global__ void __launch_bounds__(256)
 logp_bwd_kernel(const __half* __restrict__ z, int V1, const float* __restrict__ lse,
                 const int64_t* __restrict__ tok, const float* __restrict__ coef,
@@ -248,7 +251,8 @@ logp_bwd_kernel(const __half* __restrict__ z, int V1, const float* __restrict__ 
   bf16* dr = dz + row * V1;
   const float c = coef[row];
   if (c == 0.f) {
-    for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) store_bf16x4(dr + 4 * v4, 0.f, 0.f, 0.f, 0.f);
+    if (!ACC)
+      for (int v4 = threadIdx.x; v4 < V1 / 4; v4 += 256) store_bf16x4(dr + 4 * v4, 0.f, 0.f, 0.f, 0.f);
     return;
   }
   const __half* zr = z + row * V1;
@@ -261,6 +265,11 @@ logp_bwd_kernel(const __half* __restrict__ z, int V1, const float* __restrict__ 
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       o[q] = c * ((4 * v4 + q == t ? 1.f : 0.f) - ex2_ftz((x4[q] - l) * 1.4426950408889634f));
+    if (ACC) {
+      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(dr + 4 * v4);
+      const float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
+      o[0] += a.x; o[1] += a.y; o[2] += b.x; o[3] += b.y;
+    }
     store_bf16x4(dr + 4 * v4, o[0], o[1], o[2], o[3]);
   }
 }
@@ -604,11 +613,15 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
 }
 
 int logp_backward(const coopcap_speaker* c, const int64_t* tok, const float* coef, void* dz16,
-                  cudaStream_t s) {
+                  bool accumulate, cudaStream_t s) {
   int rc = check_dims(c);
   if (rc) return rc;
-  logp_bwd_kernel<<<c->n_steps * c->B, 256, 0, s>>>(reinterpret_cast<const __half*>(c->z16_all), c->V1, c->lse, tok, coef,
-                                                    reinterpret_cast<bf16*>(dz16));
+  if (accumulate)
+    logp_bwd_kernel<true><<<c->n_steps * c->B, 256, 0, s>>>(reinterpret_cast<const __half*>(c->z16_all), c->V1,
+                                                            c->lse, tok, coef, reinterpret_cast<bf16*>(dz16));
+  else
+    logp_bwd_kernel<false><<<c->n_steps * c->B, 256, 0, s>>>(reinterpret_cast<const __half*>(c->z16_all), c->V1,
+                                                             c->lse, tok, coef, reinterpret_cast<bf16*>(dz16));
   CC_LAUNCH_CHECK_K(PROF_LOGP_BWD, s, 0.0, 0.0);
   return CC_OK;
 }
@@ -887,7 +900,12 @@ int coopcap_st_backward_dense(const coopcap_speaker* ctx, const float* g, int64_
 
 int coopcap_logp_backward(const coopcap_speaker* ctx, const int64_t* tok, const float* coef,
                           void* dz16, coopcap_stream_t stream) {
-  return coopcap::logp_backward(ctx, tok, coef, dz16, reinterpret_cast<cudaStream_t>(stream));
+  return coopcap::logp_backward(ctx, tok, coef, dz16, false, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int coopcap_logp_backward_acc(const coopcap_speaker* ctx, const int64_t* tok, const float* coef,
+                              void* dz16, coopcap_stream_t stream) {
+  return coopcap::logp_backward(ctx, tok, coef, dz16, true, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int coopcap_speaker_decode_bwd(const coopcap_speaker* ctx, const coopcap_speaker_grads* gr,

@@ -328,12 +328,19 @@ def st_logit_grads_dense(sp: SpeakerPass, g: torch.Tensor) -> torch.Tensor:
     return dz16
 
 
-def logp_logit_grads(sp: SpeakerPass, tok: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
-    """dz16 for sum coef[t,b] * log_softmax(z[t,b])[tok[t,b]]; tok int64 / coef fp32 [n_steps, B]."""
+def logp_logit_grads(sp: SpeakerPass, tok: torch.Tensor, coef: torch.Tensor,
+                     into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dz16 for sum coef[t,b] * log_softmax(z[t,b])[tok[t,b]]; tok int64 / coef fp32 [n_steps, B].
+    `into`: an existing dz16 of the same pass that the term is ADDED to."""
     d = sp.dims
     assert tok.dtype == torch.int64 and tok.is_contiguous() and tok.shape == (sp.n_steps, sp.B)
     coef = _f32c(coef)
     assert coef.shape == (sp.n_steps, sp.B)
+    if into is not None:
+        assert into.dtype == torch.bfloat16 and into.shape == (sp.n_steps * sp.B, d.V1)
+        check(_lib.load().coopcap_logp_backward_acc(C.byref(sp.ctx), _p(tok), _p(coef), _p(into),
+                                                    _stream()))
+        return into
     dz16 = torch.empty(sp.n_steps * sp.B, d.V1, dtype=torch.bfloat16, device=tok.device)
     check(_lib.load().coopcap_logp_backward(C.byref(sp.ctx), _p(tok), _p(coef), _p(dz16), _stream()))
     return dz16

@@ -3,8 +3,9 @@
 Keeps the reference's constructor, `forward(fc_feats, seq, masks, data, att_feats, att_masks,
 is_alternating, alternating_turn)` turn logic (:433-555), the loss recipes of the hot path
 (`ce_loss`, `vse_loss`, `reinforce_disc`, `gt/greedy/no_baseline`, `loss_configuration`,
-`st_and_ps_methods`), `sample`, `loss()`, `get/setLossFlages`.  Out of scope:
-the CIDEr self-critical terms (`cider_optimization` must be 0).
+`st_and_ps_methods`, `gen_result_for_cider`, `greedy_res_for_cider`, `traditional_cider`), `sample`,
+`loss()`, `get/setLossFlages`.  The CIDEr-D self-critical reward (misc/rewards.py) is scored on the
+device (rewards.py / csrc/cider.cu): captions never travel to the host.
 
 The straight-through joint step (`retrieval_reward` in {'gumbel','multinomial'}) runs as ONE fused
 autograd node: speaker decode -> listener loss forward; listener backward -> factored
@@ -21,6 +22,8 @@ import torch
 import torch.nn as nn
 
 from .. import engine as EN
+from .. import rewards
+from .AttModel import _SpeakerLossFn
 from .AttModel import _ordered as _ordered_s
 
 
@@ -30,16 +33,22 @@ def _setup(*a, **k):
 
 
 class _StJointFn(torch.autograd.Function):
-    """loss_vse of st_and_ps_methods (:343-376) as a function of speaker + listener parameters."""
+    """loss_vse of st_and_ps_methods (:343-376) as a function of speaker + listener parameters.
+    Second output: the sampled ids' log-probabilities [n_steps, B] (sampleLogprobs, AttModel.py:
+    346,357), which the CIDEr term differentiates through the same pass (:490-503); when nothing
+    consumes them their gradient arrives as None and costs nothing."""
 
     @staticmethod
     def forward(ctx, owner, sp, lp, *params):
         ctx.owner, ctx.sp, ctx.lp = owner, EN.retain(sp), EN.retain(lp)
-        return lp.t["loss"][0].clone()
+        ctx.set_materialize_grads(False)
+        return lp.t["loss"][0].clone(), sp.t["logp"][: sp.n_steps].clone()
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, g_logp=None):
         owner, sp, lp = ctx.owner, ctx.sp, ctx.lp
+        if g is None:
+            g = torch.zeros(1, device=lp.t["loss"].device)
         spk, lis = owner.caption_generator, owner.vse
         Ps, Pl = spk._params(), lis._params()
         need_l = any(p.requires_grad for p in Pl.values())
@@ -61,6 +70,9 @@ class _StJointFn(torch.autograd.Function):
         if need_s:
             T = sp.n_steps
             dz16 = EN.st_logit_grads(sp, demb16[1:T + 1], lis._packed.get(Pl)["w_emb16"])
+            if g_logp is not None:
+                EN.logp_logit_grads(sp, sp.t["tok_fed"][1:T + 1].contiguous(),
+                                    g_logp.contiguous().float(), into=dz16)
             Gs_t, ds = EN.grad_targets(Ps, EN.SPEAKER_PARAM_NAMES)
 
             def logit_grads_ready(G):
@@ -296,24 +308,85 @@ class AlternatingJointModel(nn.Module):
             lp.pinned = True
             lis._passes.append(lp)
         Ps = spk._params()
+        logp = sp.t["logp"][: sp.n_steps]
         if torch.is_grad_enabled():
-            fn = _PsJointFn if is_ps else _StJointFn
-            loss_vse = fn.apply(self, sp, lp, *_ordered_s(Ps),
-                                *[Pl[n] for n in EN.LISTENER_PARAM_NAMES])
+            if is_ps:
+                loss_vse = _PsJointFn.apply(self, sp, lp, *_ordered_s(Ps),
+                                            *[Pl[n] for n in EN.LISTENER_PARAM_NAMES])
+            else:
+                loss_vse, logp = _StJointFn.apply(self, sp, lp, *_ordered_s(Ps),
+                                                  *[Pl[n] for n in EN.LISTENER_PARAM_NAMES])
         else:
             loss_vse = lp.t["loss"][0].clone()
         lis._loss["contrastive"] = loss_vse.detach()
         term = loss_vse * self.retrieval_reward_weight                                  # :374
         loss = term if (isinstance(loss, float) and loss == 0.0) else loss + term
-        return loss, sp.t["tok_out"], sp.t["logp"], sp.t["cap_len"], tok_sb
+        return loss, sp.t["tok_out"][: sp.n_steps], logp, sp.t["cap_len"], tok_sb
+
+    # ------------------------------------------------------------------ CIDEr terms (:378-431)
+    def gen_result_for_cider(self, fc_feats, att_feats, att_masks):
+        """Sampled index captions with differentiable log-probabilities (:378-389), kept time-major
+        [T, B] on the device (no host sync for the caption width)."""
+        spk = self.caption_generator
+        sp, _ = spk._sample_pass(att_feats, att_masks, 0, 1.0, 0)
+        T = sp.n_steps
+        if spk._needs_grad():
+            logp = _SpeakerLossFn.apply(sp, sp.t["tok_fed"][1:T + 1].contiguous(), spk,
+                                        *_ordered_s(spk._params()))
+        else:
+            logp = sp.t["logp"][:T]
+        return sp.t["tok_out"][:T], logp
+
+    def greedy_res_for_cider(self, fc_feats, att_feats, att_masks):
+        """Greedy captions of the CURRENT mode of the module (the reference does not switch to eval
+        here, :391-405, so dropout stays on in training), time-major [T, B]."""
+        with torch.no_grad():
+            sp, _ = self.caption_generator._sample_pass(att_feats, att_masks, 1, 1.0, 0)
+        return sp.t["tok_out"][: sp.n_steps]
+
+    def _time_major_ids(self, x):
+        """[B, n] ids as returned by `sample` -> [T, B] (0-padded to the full length)."""
+        T = self.caption_generator.seq_length
+        x = x.detach().long()
+        if x.size(1) < T:
+            x = torch.nn.functional.pad(x, (0, T - x.size(1)))
+        return x.t().contiguous()
+
+    def traditional_cider(self, fc_feats, att_feats, att_masks, data, loss, gen_result, greedy_res,
+                          sample_logprobs, gen_masks):
+        """The reference's signature (:407-431): gen_result / greedy_res [B, n] ids and
+        sample_logprobs [B, n] as returned by `sample`."""
+        return self._cider_term(loss, data, fc_feats, self._time_major_ids(gen_result),
+                                self._time_major_ids(greedy_res), sample_logprobs, False)
+
+    def _cider_term(self, loss, data, fc_feats, hyp0, hyp1, logp, logp_time_major):
+        """loss += cider_optimization * sum(logp * -reward * mask) / sum(mask)          (:407-431)
+        with reward = CIDEr-D(sampled) - CIDEr-D(greedy) (or the sampled score alone when
+        use_gen_cider_scores != 0) scored on the device; hyp0 / hyp1 int64 [T, B]."""
+        if rewards.CiderD_scorer is None:
+            rewards.init_scorer(getattr(self.opt, "cached_tokens", "corpus"))           # train.py:483
+        B = fc_feats.size(0)
+        gts = data.get("_coopcap_gts") if isinstance(data, dict) else None
+        if gts is None:
+            if not isinstance(data, dict) or "gts" not in data:
+                raise ValueError("cider_optimization needs data['gts'] (dataloader.py:239)")
+            gts = rewards.stage_gts(data["gts"], B, fc_feats.device)
+        res = rewards.reward_on_device(rewards.CiderD_scorer, gts, hyp0.contiguous(), hyp1.contiguous(),
+                                       differenced=(self.use_gen_cider_scores == 0))
+        coef = res.coef if logp_time_major else res.coef[: logp.size(1)].t()
+        loss_cider = (logp * coef).sum()
+        self._loss["avg_reward"] = res.stats[0].float()
+        self._loss["cider_greedy"] = res.stats[1].float()
+        self._loss["loss_cider"] = loss_cider.detach()
+        self._cider_last = res
+        term = self.cider_optimization * loss_cider
+        return term if (isinstance(loss, float) and loss == 0.0) else loss + term
 
     # ------------------------------------------------------------------ forward (:433-555)
     def forward(self, fc_feats, seq, masks, data, att_feats, att_masks, is_alternating=False,
                 alternating_turn=None):
         if not is_alternating:
-            if self.cider_optimization:
-                raise NotImplementedError("CIDEr self-critical terms are outside the hot path "
-                                          "(SURVEY.md §2 row 8): run with cider_optimization=0")
+            gen = greedy_tb = None    # (ids [T,B], sampleLogprobs, time-major?) of the sampled captions
             # (:449-454) caption_loss_weight * loss_cap + vse_loss_weight * loss_vse; a term whose
             # weight is 0 is skipped instead of being materialised as a zero tensor, so the speaker
             # turn does not queue half a dozen one-element kernels between decode and listener
@@ -329,9 +402,10 @@ class AlternatingJointModel(nn.Module):
                         retrieval_loss = self.reinforce(fc_feats, att_feats, att_masks, seq, masks,
                                                         data, loss)
                     if self.reinforce_baseline_type == "greedy":
-                        baseline, sc_loss, _ = self.greedy_baseline(
+                        baseline, sc_loss, greedy_res = self.greedy_baseline(
                             fc_feats, att_feats, att_masks, retrieval_loss, _seqs, sample_logprobs,
                             _masks)
+                        greedy_tb = self._time_major_ids(greedy_res)
                     elif self.reinforce_baseline_type == "gt":
                         baseline, sc_loss = self.gt_baseline(
                             fc_feats, att_feats, att_masks, retrieval_loss, _seqs, sample_logprobs,
@@ -339,9 +413,18 @@ class AlternatingJointModel(nn.Module):
                     else:
                         baseline, sc_loss = self.no_baseline(retrieval_loss, sample_logprobs, _masks)
                     loss = self.loss_configuration(loss, sc_loss, baseline, retrieval_loss, _masks)
+                    gen = (self._time_major_ids(gen_result), sample_logprobs, False)
                 else:
-                    loss, *_ = self.st_and_ps_methods(fc_feats, att_feats, att_masks, seq, masks,
-                                                      data, loss)
+                    loss, tok_tb, logp_tb, *_ = self.st_and_ps_methods(
+                        fc_feats, att_feats, att_masks, seq, masks, data, loss)
+                    if self.retrieval_reward in ("gumbel", "multinomial"):
+                        gen = (tok_tb, logp_tb, True)
+            if self.cider_optimization:                                                 # :490-503
+                if gen is None:    # no sampled captions yet, or a partial-sampling mode (:492-496)
+                    gen = self.gen_result_for_cider(fc_feats, att_feats, att_masks) + (True,)
+                if greedy_tb is None:
+                    greedy_tb = self.greedy_res_for_cider(fc_feats, att_feats, att_masks)
+                loss = self._cider_term(loss, data, fc_feats, gen[0], greedy_tb, gen[1], gen[2])
             return loss if torch.is_tensor(loss) else self._zero(fc_feats)
         if alternating_turn == "speaker":                                               # :508-526
             if self.retrieval_reward == "reinforce":

@@ -270,6 +270,11 @@ int coopcap_st_backward_dense(const coopcap_speaker* ctx, const float* g, int64_
  * tok: int64 [n_steps, B]; coef: fp32 [n_steps, B]. */
 int coopcap_logp_backward(const coopcap_speaker* ctx, const int64_t* tok, const float* coef,
                           void* dz16, coopcap_stream_t stream);
+/* Same, ADDED to the gradient already in dz16: a second loss term on the log-probabilities of a
+ * pass whose logits already carry another gradient (the CIDEr term of traditional_cider next to
+ * the straight-through listener gradient, AlternatingJointModel.py:409-431,490-503). */
+int coopcap_logp_backward_acc(const coopcap_speaker* ctx, const int64_t* tok, const float* coef,
+                              void* dz16, coopcap_stream_t stream);
 
 typedef struct coopcap_speaker_grads {
   /* input */
@@ -510,6 +515,63 @@ int coopcap_store_gather(const void* store_att16, const int64_t* store_off, cons
                          int64_t n_img, const int64_t* ix, int B, int D, int F, const int* att_off,
                          void* att16_out, float* fc_out, coopcap_stream_t stream);
 
+/* ---- CIDEr-D self-critical reward (misc/rewards.py:34-71, ciderD_scorer.py:13-28,105-215) --------
+ * The reference scores the sampled and the greedy captions of a batch against each image's
+ * ground-truth captions on the host (Python dictionaries of word n-grams, float64) every step.
+ * Here the ids stay on the device.  An n-gram (n = 1..4) of ids < 65535 is one exact 64-bit key
+ * (16 bits per id + 1, 0 = absent), so nothing is hashed lossily:
+ *   cook    one warp per caption: words up to AND INCLUDING the first 0 (rewards.py:26-32), unique
+ *           n-grams with counts in first-occurrence order (precook's dictionary order)
+ *   df      "corpus" mode (opts.py:27 default): number of ENTRIES (hypotheses) whose image's
+ *           references contain the n-gram (ciderD_scorer.py:105-118), built in an open-addressing
+ *           table of exact keys; cached mode (--cached_tokens file): the caller uploads the table
+ *   vec     tf-idf weight cnt * (log_ref_len - log(max(1, df))) and per-order norms, float64
+ *   score   clipped dot products, cosine normalisation, Gaussian length penalty on the bigram
+ *           counts (sic), mean over orders / references, x 10  (ciderD_scorer.py:147-203)
+ *   finish  reward = score(sampled) - score(greedy) (or the sampled score alone) as fp32, and the
+ *           per-token REINFORCE coefficients of traditional_cider
+ *           (AlternatingJointModel.py:409-431): coef[t,b] = -reward[b] * mask[b,t] / sum(mask),
+ *           mask[b,t] = 1 for t <= (leading non-zero ids of row b) and t < n, n = caption width.
+ * Sums run in the reference's order, so scores agree with it to float64 rounding of log/pow.
+ * Captions c = 0 .. n_sets*B-1 are the hypotheses (set-major), then the n_ref references. */
+typedef struct coopcap_cider {
+  int B;                 /* rows per hypothesis set */
+  int n_sets;            /* 1 (sampled only) or 2 (sampled, greedy) */
+  int T;                 /* steps in the hypothesis arrays, <= 16 */
+  int W;                 /* width of a reference caption, <= 16 */
+  int n_img;             /* images in the batch */
+  int n_ref;             /* reference captions of all images */
+  int corpus;            /* 1: document frequencies from this batch; 0: df table given */
+  int differenced;       /* 1: reward = sampled - greedy (use_gen_cider_scores == 0); 0: sampled */
+  double log_ref_len;    /* cached mode: log(ref_len of the table); corpus mode: ignored */
+  const int64_t* hyp0;   /* int64 [T, B] time-major ids of the sampled captions */
+  const int64_t* hyp1;   /* int64 [T, B] greedy captions (n_sets == 2) or NULL */
+  const int64_t* refs;   /* int64 [n_ref, W] ground-truth captions, 0-padded */
+  const int* ref_off;    /* [n_img + 1]: image i owns refs ref_off[i] .. ref_off[i+1]-1 */
+  const int* row_img;    /* [B]: image of row b (b / seq_per_img in the reference) */
+  uint64_t* df_keys;     /* [df_cap] open-addressing table, 0 = empty (corpus mode: workspace) */
+  float* df_val;         /* [df_cap] document frequencies (integers, exact in fp32) */
+  int df_cap;            /* power of two; corpus mode needs >= 2 * 58 * n_ref */
+  int reserved;
+  /* workspaces, C = n_sets*B + n_ref captions */
+  uint64_t* ng_key;      /* [C, 64] unique n-gram keys, order n at slots 16n .. 16n+15 */
+  int* ng_cnt;           /* [C, 64] term frequencies */
+  int* ng_n;             /* [C, 4] unique n-grams per order */
+  int* ng_len;           /* [C] "length" = number of bigrams (ciderD_scorer.py:143-144) */
+  double* ng_w;          /* [C, 64] tf-idf weights */
+  double* ng_norm;       /* [C, 4] */
+  int* img_rows;         /* [n_img] rows per image */
+  /* outputs */
+  double* scores;        /* [n_sets * B] CIDEr-D of every hypothesis */
+  float* reward;         /* [B] */
+  float* coef;           /* [T, B] or NULL */
+  double* stats;         /* [4]: mean reward, mean greedy score, sum(mask), mean sampled score */
+} coopcap_cider;
+int coopcap_cider_reward(const coopcap_cider* ctx, coopcap_stream_t stream);
+/* Slot of `key` in a table of `cap` (power of two) entries before probing; the caller that
+ * builds a cached table on the host probes linearly from here (same function as the device). */
+uint64_t coopcap_cider_hash(uint64_t key);
+
 /* ---- instrumentation ---------------------------------------------------------------------------
  * coopcap_launch_count: kernels launched by this library since load (all streams).
  * coopcap_prof_enable(1, stream): start an event timeline on `stream` (one event after every
@@ -529,7 +591,7 @@ int coopcap_prof_report(double* ms, double* flops, double* bytes, long long* lau
 int coopcap_measure_sm_clock(float* mhz_out, int spin_ns, coopcap_stream_t stream);
 
 /* sizeof() of the structs above, for binding self-checks: which = 0 gemm_args, 1 speaker_pack,
- * 2 speaker, 3 speaker_grads, 4 listener_pack, 5 listener, 6 listener_grads. */
+ * 2 speaker, 3 speaker_grads, 4 listener_pack, 5 listener, 6 listener_grads, 7 cider. */
 int coopcap_sizeof(int which);
 
 #ifdef __cplusplus

@@ -26,7 +26,27 @@ def load_golden(name: str):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    """Joint / decode / listener cases (make_golden.py); the scorer-only CIDEr-D cases
+    (make_golden_cider.py, `cider_*.npz`) are listed by cider_golden_names()."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
+                  if f.endswith(".npz") and not f.startswith("cider_"))
+
+
+def cider_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("cider_"))
+
+
+def load_cider_golden(name: str):
+    """(meta, gts list, gen [B,16], greedy [B,16], doc_freq dict or None, ref_len or None, npz)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    off = z["gts_off"]
+    gts = [z["gts"][off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    df = ref_len = None
+    if "df_keys" in z.files:
+        df = {tuple(int(x) for x in k if x >= 0): float(v) for k, v in zip(z["df_keys"], z["df_val"])}
+        ref_len = float(z["ref_len"])
+    return meta, gts, z["gen"], z["greedy"], df, ref_len, z
 
 
 def build_case(meta: Dict):
@@ -56,7 +76,7 @@ def build_case(meta: Dict):
     return dims, Ps, Pl, batch, noise, noise2, cfg
 
 
-def run_oracle(meta: Dict, forced_tokens=None, keep_all_steps=False):
+def run_oracle(meta: Dict, forced_tokens=None, keep_all_steps=False, forced_tokens_greedy=None):
     """Returns dict(loss, seq, logprobs, ..., grads={name: tensor})."""
     dims, Ps, Pl, batch, noise, noise2, cfg = build_case(meta)
     Pso = {k: v.clone().requires_grad_(True) for k, v in Ps.items()}
@@ -91,6 +111,15 @@ def run_oracle(meta: Dict, forced_tokens=None, keep_all_steps=False):
                                              batch.att_masks, noise, cfg, forced_tokens,
                                              keep_all_steps)
         out.update(seq=res.seq, logprobs=res.logprobs.detach())
+    elif mode == "reinforce" and meta["weight"] == 0 and meta.get("cider", 0) > 0:
+        # CIDEr term alone: gen_result_for_cider samples index captions (:378-389,492-496)
+        from . import speaker as OS
+        res = OS.sample(Pso, batch.att_feats, batch.att_masks, mode="reinforce",
+                        seq_length=dims.seq_length, vocab_size=dims.vocab_size, noise=noise,
+                        drop_p=cfg.drop_p, sample_max=0, temperature=1.0, forced_tokens=forced_tokens,
+                        keep_all_steps=keep_all_steps)
+        loss = 0.0
+        out.update(seq=res.seq, logprobs=res.logprobs.detach())
     elif mode == "reinforce":
         loss, res, r, b = OJ.reinforce_speaker_loss(
             Pso, Plo, batch.fc_feats, batch.att_feats, batch.att_masks, batch.labels, batch.masks,
@@ -103,6 +132,20 @@ def run_oracle(meta: Dict, forced_tokens=None, keep_all_steps=False):
                                                       keep_all_steps)
         out.update(seq=res.seq, logprobs=res.logprobs.detach(), loss_vse=loss_vse.detach(),
                    sample=res)
+    if meta.get("cider", 0) > 0:
+        gts = OJ.gts_from_labels(batch.labels, meta["spi"], meta["seed"])
+        g = OJ.greedy_for_cider(Ps, batch.att_feats, batch.att_masks, noise2, cfg,
+                                forced_tokens_greedy, keep_all_steps)
+        # with keep_all_steps the oracle records all T steps; the reference's caption width is the
+        # largest number of leading non-zero ids (AttModel.py:404-408)
+        n = max(1, int((res.seq > 0).sum(1).max())) if keep_all_steps else res.seq.size(1)
+        loss_cider, reward, cider_greedy = OJ.cider_term(
+            res.logprobs[:, :n], res.seq[:, :n], g.seq, gts,
+            use_gen_cider_scores=meta.get("use_gen", 0))
+        loss = loss + meta["cider"] * loss_cider
+        out.update(loss_cider=loss_cider.detach(), avg_reward=torch.tensor(reward.mean()),
+                   cider_greedy=torch.tensor(cider_greedy), seq_greedy=g.seq,
+                   cider_reward=torch.from_numpy(reward), gts=gts)
     out["loss"] = loss.detach()
     names = ["caption_generator." + k for k in Pso] + ["vse." + k for k in Plo]
     tensors = list(Pso.values()) + list(Plo.values())

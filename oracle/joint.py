@@ -3,7 +3,7 @@
 CPU fp32 restatement of the loss recipes of AlternatingJointModel for the hot path: the
 straight-through / partial-sampling joint loss (`st_and_ps_methods`), REINFORCE with the listener
 reward and its baselines, the listener turn on generated captions and the MLE/VSE terms.
-CIDEr self-critical terms are out of scope (cider_optimization = 0).
+The CIDEr self-critical term (`traditional_cider`) uses the scorer restatement in oracle/cider.py.
 """
 from __future__ import annotations
 
@@ -12,6 +12,9 @@ from typing import Optional
 
 import torch
 
+import numpy as np
+
+from . import cider as CD
 from . import listener as L
 from . import speaker as S
 
@@ -131,3 +134,49 @@ def listener_turn_loss(Ps, Pl, fc_feats, att_feats, att_masks, noise, cfg: Joint
     _seqs = torch.cat([torch.full((B, 1), V + 1, dtype=torch.long), res.seq], 1)     # :545-547
     loss_vse = vse_gt_loss(Pl, fc_feats, _seqs, _masks, cfg)
     return cfg.vse_loss_weight * loss_vse, res, loss_vse
+
+
+def cider_term(sample_logprobs, gen_seq, greedy_seq, gts, *, use_gen_cider_scores: int = 0,
+               doc_freq=None, ref_len=None):
+    """traditional_cider (AlternatingJointModel.py:407-431): returns (loss_cider, reward [B] float64,
+    cider_greedy).  gen_seq / greedy_seq int [B, n]; sample_logprobs [B, n] with autograd;
+    gts: list over images of int arrays [n_captions, 16]."""
+    gen = gen_seq.detach().cpu().numpy()
+    gr = greedy_seq.detach().cpu().numpy()
+    cider_gen, diff, cider_greedy = CD.self_critical_reward(gts, gen, gr, doc_freq, ref_len)
+    reward = diff if use_gen_cider_scores == 0 else cider_gen                     # :412-419
+    gen_masks = caption_masks(gen_seq)                                               # :385-387
+    r = torch.from_numpy(-reward.astype("float32"))
+    loss_cider = (sample_logprobs * r.unsqueeze(1) * gen_masks[:, 1:]).sum() / gen_masks[:, 1:].sum()
+    return loss_cider, reward, cider_greedy
+
+
+def greedy_for_cider(Ps, att_feats, att_masks, noise, cfg: JointCfg, forced_tokens=None,
+                     keep_all_steps=False):
+    """greedy_res_for_cider (:391-405): greedy decode in the module's current (training) mode."""
+    with torch.no_grad():
+        g = S.sample(Ps, att_feats, att_masks, mode="reinforce", seq_length=cfg.seq_length,
+                     vocab_size=cfg.vocab_size, noise=noise, drop_p=cfg.drop_p, sample_max=1,
+                     temperature=1.0, forced_tokens=forced_tokens, keep_all_steps=keep_all_steps)
+    return g
+
+
+def gts_from_labels(labels, spi: int, extra_seed: int = 0):
+    """data['gts'] of a synthetic batch: image i owns the captions of rows i*spi .. (i+1)*spi-1
+    (columns 1..T of the label rows, dataloader.py:199-203) plus, for every other image, one more
+    seeded random caption (real images have more captions than seq_per_img)."""
+    lab = labels.cpu().numpy()
+    rows, T = lab.shape[0], lab.shape[1] - 2
+    assert rows % spi == 0
+    rng = np.random.default_rng(1000 + extra_seed)
+    vmax = int(lab.max())
+    gts = []
+    for i in range(rows // spi):
+        caps = [lab[r, 1:T + 1] for r in range(i * spi, (i + 1) * spi)]
+        if i % 2 == 0:
+            extra = np.zeros(T, lab.dtype)
+            k = int(rng.integers(2, T))
+            extra[:k] = rng.integers(1, max(vmax, 2) + 1, size=k)
+            caps.append(extra)
+        gts.append(np.stack(caps, 0))
+    return gts

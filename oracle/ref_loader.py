@@ -8,8 +8,9 @@ copied into this repository and nothing is written to /root/reference:
   R1  `.data[0]`  ->  `.item()`                       (0-dim indexing removed after torch 0.4)
   R2  drop the unused skimage / scipy.misc imports    (misc/utils.py:8-11)
   R3  drop the cider_diff import                      (models/AlternatingJointModel.py:53; the
-      class body needs a large blob that is not in the tree) and stub `misc.rewards`
-      (CIDEr reward; out of scope, never called with cider_optimization = 0)
+      class body needs a large blob that is not in the tree; the name is never used).
+      `misc.rewards` and the pure-Python CIDEr-D scorer it imports load unmodified
+      (`<reference>/cider` is put on sys.path, as misc/rewards.py:13-16 does itself)
 
 It exists so that (a) the oracle restatement in oracle/*.py can be validated against the code it
 restates and (b) tests/golden/make_golden.py can produce golden vectors.  The reference tree is
@@ -52,10 +53,9 @@ class _RefLoader(importlib.abc.Loader):
         return None
 
     def exec_module(self, module):
-        if self.fullname == "misc.rewards":        # R3: CIDEr reward is out of scope
-            return
         with open(self.path, "r") as f:
             src = _patch(self.fullname, f.read())
+        module.__dict__.setdefault("__file__", self.path)    # misc/rewards.py:15-16 reads it
         exec(compile(src, self.path, "exec"), module.__dict__)
 
 
@@ -90,6 +90,7 @@ def load_reference() -> types.ModuleType:
             if k.split(".")[0] in _PKGS:
                 raise RuntimeError(f"module {k!r} already imported; cannot hook the reference")
         sys.meta_path.insert(0, _RefFinder())
+        sys.path.append(os.path.join(REFERENCE_ROOT, "cider"))
         _installed = True
     import models  # noqa: F401  (served by _RefFinder)
     return sys.modules["models"]

@@ -167,7 +167,7 @@ def compare(tag, a, b, rtol=2e-4, atol=2e-6):
 
 def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dropout=True,
              baseline="gt", weight=0.01, seed=0, eos_bias=0.0, prob=0.25, ss_prob=0.0,
-             sample_max=0, decoding_constraint=0, vse=None):
+             sample_max=0, decoding_constraint=0, vse=None, cider=0.0, spi=1, use_gen=0):
     Ps = synth.speaker_params(dims, seed=seed, eos_bias=eos_bias)
     Pl = synth.listener_params(dims, seed=seed + 1)
     batch = synth.make_batch(dims, rows, regions, seed=seed + 2, varlen=varlen, min_regions=2)
@@ -190,7 +190,14 @@ def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dro
         reinforce_baseline_type=baseline, prob_gumbel_softmax=prob, prob_multinomial_soft=prob,
         vse_loss_weight=cfg.vse_loss_weight, caption_loss_weight=cfg.caption_loss_weight,
         is_alternating=0 if kind == "mle" else 1, continue_from_existing_models=False,
-        alternating_turn=None if kind == "mle" else ["speaker", "listener"])
+        alternating_turn=None if kind == "mle" else ["speaker", "listener"],
+        cider_optimization=cider, use_gen_cider_scores=use_gen)
+    data = {}
+    if cider > 0:
+        import misc.rewards as R                      # the reference's own scorer, "corpus" mode
+        R.CiderD_scorer = None
+        R.init_scorer("corpus")
+        data = {"gts": OJ.gts_from_labels(batch.labels, spi, seed)}
     captured = {}
     orig_sample = model.caption_generator.sample
 
@@ -206,6 +213,8 @@ def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dro
                 kind=kind, tau=tau, dropout=dropout, baseline=baseline, weight=weight, seed=seed,
                 eos_bias=eos_bias, prob=prob, ss_prob=ss_prob, sample_max=sample_max,
                 decoding_constraint=decoding_constraint, vse=vse)
+    if cider > 0:
+        meta.update(cider=cider, spi=spi, use_gen=use_gen)
     if kind == "vse":
         # VSEFCModel.forward alone, non-default listener options (vse_pool_type / vse_use_abs /
         # vse_max_violation), loss and parameter gradients
@@ -254,7 +263,7 @@ def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dro
             loss = model(batch.fc_feats, batch.labels, batch.masks, {}, batch.att_feats,
                          batch.att_masks, is_alternating=True, alternating_turn="listener")
         else:
-            loss = model(batch.fc_feats, batch.labels, batch.masks, {}, batch.att_feats,
+            loss = model(batch.fc_feats, batch.labels, batch.masks, data, batch.att_feats,
                          batch.att_masks, is_alternating=True, alternating_turn="speaker")
         loss = loss.sum()
         loss.backward()
@@ -266,8 +275,27 @@ def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dro
         out["logprobs"] = s0[-1].detach()
         if len(captured["samples"]) > 1:
             out["seq_greedy"] = captured["samples"][1][0].detach()
+    if cider > 0:
+        for k in ("loss_cider", "avg_reward", "cider_greedy"):
+            out[k] = torch.as_tensor(float(model._loss[k]), dtype=torch.float64)
 
     # ---- oracle on the same tensors ---------------------------------------------------------
+    if cider > 0:
+        from oracle import cases as OC
+        o = OC.run_oracle(meta)
+        for k in ("seq", "logprobs", "seq_greedy", "loss_cider", "avg_reward", "cider_greedy", "loss"):
+            compare(f"{name}.{k}", o[k], out[k], rtol=2e-4, atol=2e-6)
+        for k in ref_grads:
+            compare(f"{name}.grad[{k}]", o["grads"][k], ref_grads[k], rtol=5e-4, atol=1e-7)
+        blob = {"meta": np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)}
+        for k, v in out.items():
+            blob["out." + k] = v.numpy()
+        for k, v in ref_grads.items():
+            blob["grad." + k] = v.numpy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+        print(f"[golden] {name:34s} loss={out['loss'].item():+.6f} loss_cider={float(out['loss_cider']):+.6f} "
+              f"avg_reward={float(out['avg_reward']):+.4f} OK")
+        return
     Pso, Plo = leaf(Ps), leaf(Pl)
     if kind == "mle":
         fed = []
@@ -354,6 +382,16 @@ CASES = [
                                                           kind="vse", seed=160,
                                                           vse=dict(pool_type="last", use_abs=0, max_violation=0,
                                                                    whole_batch=False, only="image"))),
+    ("tiny_gumbel_cider", synth.TINY, dict(rows=6, regions=5, varlen=True, mode="gumbel", kind="speaker_turn",
+                                           seed=300, cider=0.5, spi=2)),
+    ("tiny_reinforce_gt_cider", synth.TINY, dict(rows=6, regions=5, varlen=False, mode="reinforce",
+                                                 kind="speaker_turn", baseline="gt", weight=0.8, seed=310,
+                                                 cider=0.2, spi=3)),
+    ("tiny_reinforce_greedy_cider_gen", synth.TINY, dict(rows=6, regions=5, varlen=False, mode="reinforce",
+                                                         kind="speaker_turn", baseline="greedy", weight=0.8,
+                                                         seed=320, cider=1.0, spi=2, use_gen=1)),
+    ("tiny_cider_only", synth.TINY, dict(rows=8, regions=4, varlen=True, mode="reinforce", kind="speaker_turn",
+                                         weight=0.0, seed=330, cider=1.0, spi=2)),
     ("real_gumbel_b4", synth.Dims(), dict(rows=4, regions=6, varlen=True, mode="gumbel",
                                           kind="speaker_turn", seed=200, eos_bias=6.0)),
     ("real_mle_b4", synth.Dims(), dict(rows=4, regions=6, varlen=False, mode="gumbel", kind="mle",

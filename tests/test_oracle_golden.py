@@ -39,3 +39,26 @@ def test_oracle_matches_reference_golden(name):
             g = out["grads"][key[11:]]
             s = g.flatten()[:: max(1, g.numel() // 257)][:257]
             _close(f"{name}.{key}", s, z[key], rtol=1e-3, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", cases.cider_golden_names())
+def test_cider_oracle_matches_reference_scorer(name):
+    """oracle/cider.py against scores produced by the reference's own CiderD scorer
+    (tests/golden/make_golden_cider.py): float64, sums in the reference's order -> 1e-12."""
+    from oracle import cider as OC
+    meta, gts, gen, greedy, df, ref_len, z = cases.load_cider_golden(name)
+    cg, diff, gm = OC.self_critical_reward(gts, gen, greedy, df, ref_len)
+    assert np.max(np.abs(cg - z["out.cider_gen"])) <= 1e-12
+    assert np.max(np.abs(diff - z["out.reward"])) <= 1e-12
+    assert abs(gm - float(z["out.cider_greedy"])) <= 1e-12
+
+
+def test_cider_caption_conventions():
+    """The first 0 is a word, later ids are ignored; `length` counts bigrams (ciderD_scorer.py:143)."""
+    from oracle import cider as OC
+    assert OC.caption_words([4, 7, 0, 9, 0]) == (4, 7, 0)
+    assert OC.caption_words([4, 7, 9]) == (4, 7, 9)
+    c = OC.precook((4, 7, 4, 7, 0))
+    assert c[(4,)] == 2 and c[(4, 7)] == 2 and c[(4, 7, 4, 7)] == 1 and list(c)[:3] == [(4,), (7,), (0,)]
+    same = OC.ciderd_scores([(4, 7, 0), (5, 0)], [[(4, 7, 0)], [(9, 9, 0)]])
+    assert same[0] > 0 and same[1] == 0.0
