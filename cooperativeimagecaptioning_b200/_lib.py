@@ -96,10 +96,11 @@ ListenerPack = STRUCTS["coopcap_listener_pack"]
 Listener = STRUCTS["coopcap_listener"]
 ListenerGrads = STRUCTS["coopcap_listener_grads"]
 Cider = STRUCTS["coopcap_cider"]
+Beam = STRUCTS["coopcap_beam"]
 
 _SIZEOF_IDS = {"coopcap_gemm_args": 0, "coopcap_speaker_pack": 1, "coopcap_speaker": 2,
                "coopcap_speaker_grads": 3, "coopcap_listener_pack": 4, "coopcap_listener": 5,
-               "coopcap_listener_grads": 6, "coopcap_cider": 7}
+               "coopcap_listener_grads": 6, "coopcap_cider": 7, "coopcap_beam": 8}
 
 # kept for tests: name -> argtypes
 SIGNATURES = {k: v[1] for k, v in FUNCTIONS.items()}

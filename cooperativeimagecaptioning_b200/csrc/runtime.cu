@@ -245,6 +245,7 @@ int coopcap_sizeof(int which) {
     case 5: return (int)sizeof(coopcap_listener);
     case 6: return (int)sizeof(coopcap_listener_grads);
     case 7: return (int)sizeof(coopcap_cider);
+    case 8: return (int)sizeof(coopcap_beam);
     default: return -1;
   }
 }

@@ -544,6 +544,43 @@ static int logit_sample_step(const coopcap_speaker* c, int t, const bf16* out16_
   return CC_OK;
 }
 
+// One attention step over the rows of `c` (c->B rows, regions c->att_off): s_t holds att_h at column
+// 5R of every row.  Shared by the decode loop and the beam search (csrc/beam.cu), which calls it once
+// per beam slot with that slot's rows.
+int attention_fwd_launch(const coopcap_speaker* c, const float* s_t, bf16* att_res16_t, float* att_w_t,
+                         cudaStream_t s) {
+  const int B = c->B, R = c->R, A = c->A, NS = 5 * R + A;
+  int rc;
+  if (A == 512 && R == 512) {
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_fwd4_kernel<512>), ATT4_SMEM))) return rc;
+    CC_CHECK_CUDA(launch_pdl(attention_fwd4_kernel<512>, dim3(std::min(num_sms(), B)), dim3(ATT4_THREADS),
+                             size_t(ATT4_SMEM), s, reinterpret_cast<const bf16*>(c->p_att16),
+                             reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L, c->att_order, s_t,
+                             int64_t(NS), 5 * R, c->w_alpha, att_res16_t, att_w_t, B));
+  } else {
+    const size_t att_smem = attention_smem_bytes(A, R, c->L);
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_fwd_kernel), int(att_smem)))) return rc;
+    attention_fwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
+        reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L,
+        s_t, NS, 5 * R, c->w_alpha, att_res16_t, att_w_t, A, R);
+  }
+  // algorithmic bytes: p_att + att_e read once (bf16), att_h in, att_res + weights out
+  CC_LAUNCH_CHECK_K(PROF_ATT_FWD, s, 0.0, 2.0 * c->NL * (A + R) + 4.0 * B * A + 2.0 * B * R + 4.0 * c->NL);
+  return CC_OK;
+}
+
+// maxout-LSTM pointwise step over `rows` rows (AttModel.py:515-531)
+int lstm_fwd_launch(const coopcap_speaker* c, const float* s_t, const float* u_t, const float* c_prev,
+                    float* c_next, bf16* h_out16, int64_t ld_h, bf16* out16_t, const uint8_t* keep,
+                    uint64_t site, float drop_p, int rows, cudaStream_t s) {
+  const int R = c->R, NS = 5 * R + c->A;
+  const int n = rows * (R / 4);
+  CC_CHECK_CUDA(launch_pdl(lstm_fwd_kernel, dim3((n + 255) / 256), dim3(256), 0, s, s_t, int64_t(NS), u_t, c_prev,
+                           c_next, h_out16, ld_h, out16_t, keep, c->seed, site, drop_p, rows, R));
+  CC_LAUNCH_CHECK_K(PROF_LSTM, s, 0.0, 0.0);
+  return CC_OK;
+}
+
 int speaker_prologue_fwd(const coopcap_speaker* c, cudaStream_t s) {
   int rc = check_dims(c);
   if (rc) return rc;
@@ -582,8 +619,6 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
   bf16* xh16 = reinterpret_cast<bf16*>(c->xh16);
   bf16* att_res16 = reinterpret_cast<bf16*>(c->att_res16);
   bf16* out16 = reinterpret_cast<bf16*>(c->out16);
-  const size_t att_smem = attention_smem_bytes(A, R, c->L);
-  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_fwd_kernel), int(att_smem)))) return rc;
   start_step_kernel<<<B, 128, 0, s>>>(c->embed, c->start_token, c->start_tokens, B, E, R, c->keep_embed, c->seed,
                                       c->drop_p, xh16, c->c_all, c->tok_fed);
   CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 0.0);
@@ -595,38 +630,17 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     e1.alpha = 1.f; e1.bias = c->b_cat; e1.C = s_t; e1.ldc = NS;
     rc = gemm_run(0, 0, 0, xh16 + int64_t(t) * B * XH, XH, c->w_cat16, XH, B, NS, XH, 1, 0, e1, s);
     if (rc) return rc;
-    if (A == 512 && R == 512) {
-      if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_fwd4_kernel<512>), ATT4_SMEM))) return rc;
-      CC_CHECK_CUDA(launch_pdl(attention_fwd4_kernel<512>, dim3(std::min(num_sms(), B)),
-                               dim3(ATT4_THREADS), size_t(ATT4_SMEM), s,
-                               reinterpret_cast<const bf16*>(c->p_att16),
-                               reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L,
-                               c->att_order, s_t,
-                               int64_t(NS), 5 * R, c->w_alpha, att_res16 + int64_t(t) * B * R,
-                               c->att_w + int64_t(t) * c->NL, B));
-    } else {
-      attention_fwd_kernel<<<B, ATT_THREADS, att_smem, s>>>(
-          reinterpret_cast<const bf16*>(c->p_att16), reinterpret_cast<const bf16*>(c->att_e16),
-          c->att_off, c->L, s_t, NS, 5 * R, c->w_alpha, att_res16 + int64_t(t) * B * R,
-          c->att_w + int64_t(t) * c->NL, A, R);
-    }
-    // algorithmic bytes: p_att + att_e read once (bf16), att_h in, att_res + weights out
-    CC_LAUNCH_CHECK_K(PROF_ATT_FWD, s, 0.0,
-                      2.0 * c->NL * (A + R) + 4.0 * B * A + 2.0 * B * R + 4.0 * c->NL);
+    if ((rc = attention_fwd_launch(c, s_t, att_res16 + int64_t(t) * B * R, c->att_w + int64_t(t) * c->NL, s)))
+      return rc;
     EpiStoreParams e2 = {};
     e2.alpha = 1.f; e2.bias = c->b_a2c; e2.C = u_t; e2.ldc = 2 * R;
     rc = gemm_run(0, 0, 0, att_res16 + int64_t(t) * B * R, R, c->w_a2c16, R, B, 2 * R, R, 1, 0, e2, s);
     if (rc) return rc;
-    {
-      const int n = B * (R / 4);
-      CC_CHECK_CUDA(launch_pdl(
-          lstm_fwd_kernel, dim3((n + 255) / 256), dim3(256), 0, s, s_t, int64_t(NS), u_t,
-          c->c_all + int64_t(t) * B * R, c->c_all + int64_t(t + 1) * B * R,
-          xh16 + int64_t(t + 1) * B * XH + E, int64_t(XH), out16 + int64_t(t) * B * R,
-          c->keep_core ? c->keep_core + int64_t(t) * B * R : nullptr, c->seed,
-          uint64_t(SITE_DROP_CORE + t), c->drop_p, B, R));
-      CC_LAUNCH_CHECK_K(PROF_LSTM, s, 0.0, 0.0);
-    }
+    if ((rc = lstm_fwd_launch(c, s_t, u_t, c->c_all + int64_t(t) * B * R, c->c_all + int64_t(t + 1) * B * R,
+                              xh16 + int64_t(t + 1) * B * XH + E, int64_t(XH), out16 + int64_t(t) * B * R,
+                              c->keep_core ? c->keep_core + int64_t(t) * B * R : nullptr,
+                              uint64_t(SITE_DROP_CORE + t), c->drop_p, B, s)))
+      return rc;
     __half* z_t = reinterpret_cast<__half*>(c->z16_all) + int64_t(t) * B * V1;
     const bool ps = (c->mode == COOPCAP_SAMPLE_PS_GUMBEL || c->mode == COOPCAP_SAMPLE_PS_MULTINOMIAL);
     bf16* x_next = (t + 1 < c->n_steps) ? xh16 + int64_t(t + 1) * B * XH : nullptr;

@@ -282,6 +282,98 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     return sp
 
 
+@dataclass
+class BeamOutput:
+    seq: torch.Tensor          # int64 [n_img, T]
+    logprobs: torch.Tensor     # fp32 [n_img, T]
+    t: Dict[str, torch.Tensor] = field(default_factory=dict)
+
+
+def beam_search(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.Tensor,
+                att_off: Optional[torch.Tensor], NL: int, *, beam_size: int, seq_length: int,
+                start_token: int, no_repeat: bool = False, att16: Optional[torch.Tensor] = None,
+                att_order: Optional[torch.Tensor] = None, forced_parent: Optional[torch.Tensor] = None,
+                forced_tok: Optional[torch.Tensor] = None) -> BeamOutput:
+    """AttModel.sample_beam (AttModel.py:150-289) for all images at once (evaluation mode).
+    forced_parent int32 / forced_tok int64 [T, n_img, beam]: decisions to replay (parity tests)."""
+    _need_cuda(att_feats, att_off, forced_parent, forced_tok)
+    d: SpeakerDims = packed["dims"]
+    B, L, D = att_feats.shape
+    if att16 is None:
+        att_feats = _f32c(att_feats)
+    dev = att16.device if att16 is not None else att_feats.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    i64 = dict(dtype=torch.int64, device=dev)
+    T, bs = int(seq_length), int(beam_size)
+    rows, NS, XH = B * bs, 5 * d.R + d.A, d.E + d.R
+    c = _lib.Speaker()
+    c.B, c.L, c.D, c.R, c.E, c.A, c.V1 = B, L, d.D, d.R, d.E, d.A, d.V1
+    c.NL, c.cap, c.n_steps = NL, 1, 0
+    ctx_t = dict(att16=att16 if att16 is not None else torch.empty(NL, d.D, **bf),
+                 att_e16=torch.empty(NL, d.R, **bf), p_att16=torch.empty(NL, d.A, **bf))
+    c.att_feats, c.att_off = (None if att16 is not None else _p(att_feats)), _p(att_off)
+    if att_order is None and att_off is not None and B > 1:
+        att_order = torch.argsort(att_off[1:] - att_off[:-1], descending=True).to(torch.int32)
+    c.att_order = _p(att_order)
+    c.att_prepacked = int(att16 is not None)
+    c.embed = _p(_f32c(P["embed.0.weight"].detach()))
+    c.b_att_embed = _p(_f32c(P["att_embed.0.bias"].detach()))
+    c.b_ctx2att = _p(_f32c(P["ctx2att.bias"].detach()))
+    c.b_cat = _p(packed["b_cat"])
+    c.b_a2c = _p(_f32c(P["core.a2c.bias"].detach()))
+    c.b_logit = _p(_f32c(P["logit.bias"].detach()))
+    c.w_alpha = _p(_f32c(P["core.attention.alpha_net.weight"].detach()))
+    for n in ("w_att_embed16", "w_ctx2att16", "w_cat16", "w_a2c16", "w_logit16"):
+        setattr(c, n, _p(packed[n]))
+    c.seed, c.drop_p, c.mode, c.inv_tau, c.start_token = 0, 0.0, MODE_GREEDY, 1.0, int(start_token)
+    for n, tsr in ctx_t.items():
+        setattr(c, n, _p(tsr))
+    W = dict(xh16=torch.empty(2, rows, XH, **bf), c2=torch.empty(2, rows, d.R, **f32),
+             s_t=torch.empty(rows, NS, **f32), u_t=torch.empty(rows, 2 * d.R, **f32),
+             att_res16=torch.empty(rows, d.R, **bf), att_w=torch.empty(bs, NL, **f32),
+             h_stage16=torch.empty(rows, d.R, **bf), c_stage=torch.empty(rows, d.R, **f32),
+             logits=torch.empty(rows, d.V1, **f32), parent=torch.empty(rows, **i32),
+             tok=torch.empty(rows, **i64), hist_seq=torch.empty(2, B, T, bs, **i64),
+             hist_lp=torch.empty(2, B, T, bs, **f32), beam_sum=torch.empty(B, bs, **f32),
+             raw_parent=torch.empty(T, B, bs, **i32), raw_tok=torch.empty(T, B, bs, **i64),
+             done_seq=torch.empty(B, bs * T, T, **i64), done_lp=torch.empty(B, bs * T, T, **f32),
+             done_slot=torch.empty(B, bs * T, **i32), done_p_rec=torch.empty(B, bs * T, **f32),
+             done_p=torch.empty(B, bs * T, **f32), done_n=torch.empty(B, **i32),
+             seq=torch.empty(B, T, **i64), seq_logp=torch.empty(B, T, **f32))
+    b = _lib.Beam()
+    b.beam_size, b.no_repeat, b.T = bs, int(bool(no_repeat)), T
+    for n, tsr in W.items():
+        setattr(b, n, _p(tsr))
+    if forced_parent is not None:
+        assert forced_parent.dtype == torch.int32 and forced_parent.is_contiguous()
+        assert forced_tok.dtype == torch.int64 and forced_tok.is_contiguous()
+        assert forced_parent.shape == (T, B, bs) and forced_tok.shape == (T, B, bs)
+    b.forced_parent, b.forced_tok = _p(forced_parent), _p(forced_tok)
+    lib = _lib.load()
+    check(lib.coopcap_speaker_prologue_fwd(C.byref(c), _stream()))
+    check(lib.coopcap_speaker_beam_fwd(C.byref(c), C.byref(b), _stream()))
+    W.update(ctx_t)
+    out = BeamOutput(seq=W["seq"], logprobs=W["seq_logp"], t=W)
+    out.keep = [att_feats, att_off, att_order, packed, P, forced_parent, forced_tok]
+    return out
+
+
+def retrieval_ranks(scores: torch.Tensor, first: torch.Tensor, count: int):
+    """(ranks int32 [n_query], top1 int32 [n_query]) of a fp32 score matrix [n_query, n_cand];
+    query q's correct candidates are first[q] .. first[q]+count-1 (eval_utils.py:545-720)."""
+    _need_cuda(scores, first)
+    scores = _f32c(scores)
+    assert first.dtype == torch.int32 and first.is_contiguous() and first.numel() == scores.shape[0]
+    nq, nc = scores.shape
+    ranks = torch.empty(nq, dtype=torch.int32, device=scores.device)
+    top1 = torch.empty(nq, dtype=torch.int32, device=scores.device)
+    check(_lib.load().coopcap_retrieval_ranks(_p(scores), nc, nq, nc, _p(first), int(count), _p(ranks),
+                                              _p(top1), _stream()))
+    return ranks, top1
+
+
 ST_CHUNK_ROWS = 4096   # rows of the upstream-gradient scratch per launch (78 MB bf16 at V1 = 9488)
 
 

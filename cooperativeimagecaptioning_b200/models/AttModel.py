@@ -283,7 +283,7 @@ class AttModel(nn.Module):
         temperature = opt.get("temperature", 1.0)
         use_one_hot = opt.get("use_one_hot", 0)
         if beam_size > 1:
-            raise NotImplementedError("beam search is evaluation-only and outside the hot path")
+            return self.sample_beam(fc_feats, att_feats, att_masks, opt)                 # :307-308
         no_repeat = bool(opt.get("decoding_constraint", self.decoding_constraint))      # :305-306
         sp, st_mode = self._sample_pass(att_feats, att_masks, sample_max, temperature, use_one_hot,
                                         **({"no_repeat": True} if no_repeat else {}))
@@ -312,6 +312,44 @@ class AttModel(nn.Module):
         return seq, logprobs
 
     _sample = sample
+
+    # ------------------------------------------------------------------ AttModel.sample_beam
+    def sample_beam(self, fc_feats, att_feats, att_masks, opt={}):
+        """Beam search (AttModel.py:150-289) for all images at once: returns (seq [B, T] int64,
+        seqLogprobs [B, T]) and fills `self.done_beams` (per image: the recorded beams as dicts
+        'seq' / 'logps' / 'p', ranked as the reference ranks them).  Evaluation mode only: the
+        reference's own callers run it under model.eval() (eval_utils.py:187)."""
+        beam_size = opt.get("beam_size", 10)
+        no_repeat = bool(opt.get("decoding_constraint", self.decoding_constraint))
+        if self.training and float(self.drop_prob_lm) > 0.0:
+            raise RuntimeError("sample_beam runs in evaluation mode (call model.eval() first)")
+        if not att_feats.is_cuda:
+            raise EN._lib.CoopcapError("Att2in2Model runs on CUDA only (no CPU path)")
+        if beam_size > self.vocab_size + 1:
+            raise AssertionError("beam_size must not exceed the vocabulary (AttModel.py:164)")
+        P = self._params()
+        packed = self._packed.get(P)
+        att16 = getattr(att_masks, "_coopcap_att16", None) if att_masks is not None else None
+        if att16 is None:
+            att_feats = att_feats.detach().float().contiguous()
+        B, L = att_feats.shape[:2]
+        pre = getattr(att_masks, "_coopcap_off", None) if att_masks is not None else None
+        if pre is not None:
+            off, NL = pre
+        else:
+            if att_masks is not None:
+                att_masks = att_masks[:, :L]
+            off, NL = EN.region_offsets(att_masks, B, L)
+        forced = getattr(self, "forced_beam", None)          # parity hook: (parent, tok) [T, B, beam]
+        out = EN.beam_search(P, packed, att_feats, off, NL, beam_size=beam_size,
+                             seq_length=self.seq_length, start_token=self.vocab_size + 1,
+                             no_repeat=no_repeat, att16=att16,
+                             att_order=getattr(att_masks, "_coopcap_order", None) if att_masks is not None else None,
+                             forced_parent=None if forced is None else forced[0],
+                             forced_tok=None if forced is None else forced[1])
+        self._beam_last = out
+        self.done_beams = _LazyDoneBeams(out, beam_size, self.seq_length)
+        return out.seq, out.logprobs
 
     def _sample_pass(self, att_feats, att_masks, sample_max, temperature, use_one_hot,
                      no_repeat=False):
@@ -350,6 +388,37 @@ class AttModel(nn.Module):
 
 class _Dummy:
     pass
+
+
+class _LazyDoneBeams:
+    """`self.done_beams[k]` of the reference (AttModel.py:168,283-284): the recorded beams of image
+    k sorted by -p.  Materialised on first access (one device->host copy), so a caller that only
+    wants (seq, seqLogprobs) never synchronises."""
+
+    def __init__(self, out, beam_size, T):
+        self._out, self._bs, self._T, self._lists = out, beam_size, T, None
+
+    def _build(self):
+        if self._lists is None:
+            t = self._out.t
+            n = t["done_n"].cpu().tolist()
+            seq, lp, p = t["done_seq"].cpu(), t["done_lp"].cpu(), t["done_p"].cpu()
+            rec = t["done_p_rec"].cpu()
+            self._lists = []
+            for k, nk in enumerate(n):
+                ent = [dict(seq=seq[k, e].clone(), logps=lp[k, e].clone(), p=float(p[k, e]),
+                            p_recorded=float(rec[k, e])) for e in range(nk)]
+                self._lists.append(sorted(ent, key=lambda x: -x["p"]))        # stable, as :283-284
+        return self._lists
+
+    def __getitem__(self, k):
+        return self._build()[k]
+
+    def __len__(self):
+        return len(self._build())
+
+    def __iter__(self):
+        return iter(self._build())
 
 
 class Att2in2Model(AttModel):

@@ -515,6 +515,72 @@ int coopcap_store_gather(const void* store_att16, const int64_t* store_off, cons
                          int64_t n_img, const int64_t* ix, int B, int D, int F, const int* att_off,
                          void* att16_out, float* fc_out, coopcap_stream_t stream);
 
+/* ---- beam search (AttModel.py:150-289 `sample_beam`, evaluation) ----------------------------------
+ * The reference decodes one image at a time in Python: beam_size rows through the core, a CPU sort
+ * of the [beam, V+1] log-probabilities, a Python list of candidates, per-beam state copies.  Here
+ * all images advance together: rows are BEAM-MAJOR (row = slot * n_img + image), so every per-step
+ * kernel of the decode loop is reused as is (the attention kernel runs once per slot over the
+ * n_img images with the context's own region offsets), and one CTA per image does the merge.
+ * Semantics kept exactly, quirks included (oracle/speaker.py `sample_beam` lists them): the first
+ * merge looks at slot 0 only; candidates are the top beam_size words of every slot, listed
+ * word-rank-major, stable-sorted by total log-probability; a slot that emitted the end token is
+ * recorded but NOT retired; at step T every slot is recorded; the recorded score is a VIEW of the
+ * running sum, so the done list is ranked by each slot's FINAL sum (ties: recording order).
+ * `ctx` is an ordinary speaker context for the n_img images (ctx->B = n_img) whose prologue has run
+ * (coopcap_speaker_prologue_fwd); only its parameters, att_e16 / p_att16 / att_off / att_order are
+ * read.  Evaluation mode: no dropout. */
+typedef struct coopcap_beam {
+  int beam_size;          /* 1 .. 8 */
+  int no_repeat;          /* decoding_constraint (:204-207): -inf on the slot's previous word, t > 1 */
+  int T;                  /* seq_length */
+  int reserved;
+  /* step buffers, rows = beam_size * n_img */
+  void* xh16;             /* bf16 [2, rows, E+R] */
+  float* c2;              /* [2, rows, R] */
+  float* s_t;             /* [rows, 5R+A] */
+  float* u_t;             /* [rows, 2R] */
+  void* att_res16;        /* bf16 [rows, R] */
+  float* att_w;           /* [beam_size, NL] */
+  void* h_stage16;        /* bf16 [rows, R] */
+  float* c_stage;         /* [rows, R] */
+  float* logits;          /* [rows, V1] */
+  int* parent;            /* [rows] */
+  int64_t* tok;           /* [rows] */
+  int64_t* hist_seq;      /* [2, n_img, T, beam_size], zero-initialised by the call */
+  float* hist_lp;         /* [2, n_img, T, beam_size] */
+  float* beam_sum;        /* [n_img, beam_size] */
+  /* replay aid for parity tests: decisions to APPLY at merge step t = 1..T (NULL: the kernel's own)
+   * and the decisions the kernel WOULD have taken, both [T, n_img, beam_size] */
+  const int* forced_parent;
+  const int64_t* forced_tok;
+  int* raw_parent;
+  int64_t* raw_tok;
+  /* outputs */
+  int64_t* done_seq;      /* [n_img, beam_size*T, T] every recorded beam, in recording order */
+  float* done_lp;         /* [n_img, beam_size*T, T] */
+  int* done_slot;         /* [n_img, beam_size*T] */
+  float* done_p_rec;      /* [n_img, beam_size*T] sum at recording time */
+  float* done_p;          /* [n_img, beam_size*T] the score the reference ranks by (slot's final sum) */
+  int* done_n;            /* [n_img] */
+  int64_t* seq;           /* [n_img, T] first of the ranked list (:286) */
+  float* seq_logp;        /* [n_img, T] (:287) */
+} coopcap_beam;
+int coopcap_speaker_beam_fwd(const coopcap_speaker* ctx, const coopcap_beam* beam, coopcap_stream_t stream);
+
+/* ---- retrieval evaluation (eval_utils.py:545-595 `i2t`, :598-720 `t2i`) ------------------------------
+ * Rank of the correct item for every query of a [n_query, n_cand] fp32 score matrix: the number
+ * of candidates scoring strictly higher than the best-scoring correct one (numpy argsort
+ * descending + np.where, ties aside).  Query q's correct candidates are
+ * first[q] .. first[q] + count - 1 (i2t: the image's 5 captions; t2i: the caption's image).
+ * ranks / top1: int32 [n_query]. */
+int coopcap_retrieval_ranks(const float* scores, int64_t ld, int n_query, int n_cand, const int* first,
+                            int count, int* ranks, int* top1, coopcap_stream_t stream);
+/* scores[q, n] = <queries[q, :], cands[n, :]> in fp32 FMAs (np.dot of float32 arrays,
+ * eval_utils.py:573,631): the ranks above must not depend on bf16 / tf32 rounding.
+ * queries [n_query, K], cands [n_cand, K], scores [n_query, ld]. */
+int coopcap_retrieval_scores(const float* queries, const float* cands, int n_query, int n_cand, int K,
+                             float* scores, int64_t ld, coopcap_stream_t stream);
+
 /* ---- CIDEr-D self-critical reward (misc/rewards.py:34-71, ciderD_scorer.py:13-28,105-215) --------
  * The reference scores the sampled and the greedy captions of a batch against each image's
  * ground-truth captions on the host (Python dictionaries of word n-grams, float64) every step.
@@ -591,7 +657,7 @@ int coopcap_prof_report(double* ms, double* flops, double* bytes, long long* lau
 int coopcap_measure_sm_clock(float* mhz_out, int spin_ns, coopcap_stream_t stream);
 
 /* sizeof() of the structs above, for binding self-checks: which = 0 gemm_args, 1 speaker_pack,
- * 2 speaker, 3 speaker_grads, 4 listener_pack, 5 listener, 6 listener_grads, 7 cider. */
+ * 2 speaker, 3 speaker_grads, 4 listener_pack, 5 listener, 6 listener_grads, 7 cider, 8 beam. */
 int coopcap_sizeof(int which);
 
 #ifdef __cplusplus

@@ -29,7 +29,11 @@ def golden_names():
     """Joint / decode / listener cases (make_golden.py); the scorer-only CIDEr-D cases
     (make_golden_cider.py, `cider_*.npz`) are listed by cider_golden_names()."""
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
-                  if f.endswith(".npz") and not f.startswith("cider_"))
+                  if f.endswith(".npz") and not f.startswith(("cider_", "retrieval_")))
+
+
+def retrieval_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("retrieval_"))
 
 
 def cider_golden_names():
@@ -92,6 +96,22 @@ def run_oracle(meta: Dict, forced_tokens=None, keep_all_steps=False, forced_toke
                             temperature=meta["tau"],
                             decoding_constraint=meta.get("decoding_constraint", 0))
         return dict(seq=res.seq, logprobs=res.logprobs, grads={})
+    if kind == "beam":
+        from . import speaker as OS
+        with torch.no_grad():
+            res = OS.sample_beam(Ps, batch.att_feats, batch.att_masks, seq_length=dims.seq_length,
+                                 vocab_size=dims.vocab_size, beam_size=meta["beam_size"],
+                                 decoding_constraint=meta.get("decoding_constraint", 0))
+        done_n = torch.tensor([len(d) for d in res.done_beams])
+        w = int(done_n.max())
+        done_p = torch.full((len(res.done_beams), w), float("nan"))
+        done_seq = torch.zeros(len(res.done_beams), w, dims.seq_length, dtype=torch.long)
+        for k, dl in enumerate(res.done_beams):
+            for e, ent in enumerate(dl):
+                done_p[k, e], done_seq[k, e] = ent["p"], ent["seq"]
+        return dict(seq=res.seq, logprobs=res.logprobs, done_beams=res.done_beams, done_n=done_n,
+                    done_p=done_p, done_seq=done_seq, parents=res.parents, toks=res.toks,
+                    gaps=res.gaps, grads={})
     if kind == "vse":
         from . import listener as OL
         v = meta["vse"]

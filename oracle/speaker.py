@@ -370,3 +370,101 @@ def forward_xe(P: Params, att_feats, att_masks, seq, masks, *, noise: SpeakerNoi
     logp = torch.stack(outputs, 1)                                            # :143
     loss = language_model_criterion(logp, seq[:, 1:], masks[:, 1:])           # :144
     return (loss, logp) if return_logprobs else loss
+
+
+# --------------------------------------------------------------------------------------------
+# AttModel.sample_beam                                                   (AttModel.py:150-289)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class BeamResult:
+    seq: torch.Tensor                      # [B, T] int64: best finished beam per image
+    logprobs: torch.Tensor                 # [B, T] its per-token log-probabilities
+    done_beams: List[list]                 # per image: [{'seq','logps','p'}] sorted by -p (stable)
+    parents: Optional[torch.Tensor] = None   # int32 [T, B, beam]: slot each new slot was forked from
+    toks: Optional[torch.Tensor] = None      # int64 [T, B, beam]: word appended to it
+    gaps: Optional[torch.Tensor] = None      # fp32 [T, B]: smallest score gap that decided a merge step
+
+
+def sample_beam(P: Params, att_feats, att_masks, *, seq_length: int, vocab_size: int, beam_size: int,
+                decoding_constraint: int = 0) -> BeamResult:
+    """Beam search exactly as the reference runs it, one image at a time (eval mode: no dropout).
+
+    Quirks kept (they change the result): the first merge only looks at beam 0 (:208-210);
+    candidates are the top `beam_size` words of every beam, listed word-rank-major and then sorted
+    by total log-probability with a STABLE sort (:211-221); a beam that emitted the end token is
+    recorded in done_beams but is NOT retired -- it keeps its place, is fed embed(0) and goes on
+    accumulating log-probability (:247-255 has no suppression); at t = seq_length every beam is
+    recorded (:247); the answer is the first of done_beams sorted by -p (:283-287) -- where the
+    recorded 'p' is `beam_logprobs_sum[vix]`, a 0-dim VIEW of the running-sum tensor (:250-253, not
+    a copy), so every entry recorded in beam slot vix ends up carrying that slot's FINAL sum: the
+    ranking is by the slot's final score, ties (same slot) by recording order.  `p_recorded` keeps
+    the score at recording time (what the code evidently meant) for callers that want it."""
+    B = att_feats.size(0)
+    T = seq_length
+    noise = SpeakerNoise()
+    att_e_all, p_att_all = prologue(P, att_feats, att_masks, noise, 0.0)      # :157-162
+    seq_out = torch.zeros(B, T, dtype=torch.long)
+    lp_out = torch.zeros(B, T)
+    all_done = []
+    parents = torch.zeros(T, B, beam_size, dtype=torch.int32)
+    toks = torch.zeros(T, B, beam_size, dtype=torch.long)
+    gaps = torch.full((T, B), float("inf"))
+    for k in range(B):
+        bs = beam_size
+        att_e = att_e_all[k:k + 1].expand(bs, *att_e_all.shape[1:]).contiguous()
+        p_att = p_att_all[k:k + 1].expand(bs, *p_att_all.shape[1:]).contiguous()
+        am = None if att_masks is None else att_masks[k:k + 1].expand(bs, att_masks.size(1)).contiguous()
+        h = att_feats.new_zeros(bs, P["core.h2h.weight"].size(1))
+        c = torch.zeros_like(h)
+        beam_seq = torch.zeros(T, bs, dtype=torch.long)
+        beam_lp = torch.zeros(T, bs)
+        beam_sum = torch.zeros(bs)
+        done = []
+        logprobs = None
+        for t in range(T + 1):
+            if t == 0:
+                it = torch.full((bs,), vocab_size + 1, dtype=torch.long)      # :192-195
+            else:
+                lpf = logprobs.float()
+                if decoding_constraint and t > 1:                             # :204-207
+                    lpf = lpf + torch.zeros_like(lpf).scatter_(1, beam_seq[t - 2:t - 1].t(), float("-inf"))
+                ys, ix = torch.sort(lpf, 1, True)                             # :210
+                cols, rows = min(bs, ys.size(1)), (1 if t == 1 else bs)
+                cands = []
+                for cc in range(cols):
+                    for q in range(rows):
+                        r = ys[q, cc]
+                        cands.append(dict(c=int(ix[q, cc]), q=q, p=float(beam_sum[q] + r), r=float(r)))
+                cands = sorted(cands, key=lambda x: -x["p"])                  # :221 (stable)
+                # what a different rounding could flip: the order of the kept candidates and the
+                # cut after them, and -- for a kept candidate at the last word rank -- the next word
+                g = [cands[i]["p"] - cands[i + 1]["p"] for i in range(min(bs, len(cands) - 1))]
+                g += [float(ys[v["q"], cols - 1] - ys[v["q"], cols]) for v in cands[:bs]
+                      if cols < ys.size(1) and v["r"] == float(ys[v["q"], cols - 1])]
+                gaps[t - 1, k] = min([x for x in g if x == x] + [float("inf")])
+                nh, nc = h.clone(), c.clone()
+                prev_seq, prev_lp = beam_seq[:t - 1].clone(), beam_lp[:t - 1].clone()
+                for vix in range(bs):
+                    v = cands[vix]
+                    if t > 1:
+                        beam_seq[:t - 1, vix] = prev_seq[:, v["q"]]
+                        beam_lp[:t - 1, vix] = prev_lp[:, v["q"]]
+                    nh[vix], nc[vix] = h[v["q"]], c[v["q"]]
+                    beam_seq[t - 1, vix] = v["c"]
+                    beam_lp[t - 1, vix] = v["r"]
+                    beam_sum[vix] = v["p"]
+                    parents[t - 1, k, vix], toks[t - 1, k, vix] = v["q"], v["c"]
+                    if v["c"] == 0 or t == T:                                 # :247
+                        done.append(dict(seq=beam_seq[:, vix].clone(), logps=beam_lp[:, vix].clone(),
+                                         slot=vix, p_recorded=float(beam_sum[vix])))
+                it = beam_seq[t - 1].clone()
+                h, c = nh, nc
+            xt = embed_tokens(P, it, None, 0.0)
+            out, h, c, _ = core_step(P, xt, h, c, att_e, p_att, am, None, 0.0)     # :275-276
+            logprobs = F.log_softmax(logits_of(P, out), dim=1)                # :277
+        for e in done:
+            e["p"] = float(beam_sum[e["slot"]])                               # the aliased view
+        done = sorted(done, key=lambda x: -x["p"])                            # :283-284
+        seq_out[k], lp_out[k] = done[0]["seq"], done[0]["logps"]
+        all_done.append(done)
+    return BeamResult(seq_out, lp_out, all_done, parents, toks, gaps)

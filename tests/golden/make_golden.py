@@ -167,7 +167,7 @@ def compare(tag, a, b, rtol=2e-4, atol=2e-6):
 
 def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dropout=True,
              baseline="gt", weight=0.01, seed=0, eos_bias=0.0, prob=0.25, ss_prob=0.0,
-             sample_max=0, decoding_constraint=0, vse=None, cider=0.0, spi=1, use_gen=0):
+             sample_max=0, decoding_constraint=0, vse=None, cider=0.0, spi=1, use_gen=0, beam_size=1):
     Ps = synth.speaker_params(dims, seed=seed, eos_bias=eos_bias)
     Pl = synth.listener_params(dims, seed=seed + 1)
     batch = synth.make_batch(dims, rows, regions, seed=seed + 2, varlen=varlen, min_regions=2)
@@ -215,6 +215,32 @@ def run_case(ref, name, dims, *, rows, regions, varlen, mode, kind, tau=1.0, dro
                 decoding_constraint=decoding_constraint, vse=vse)
     if cider > 0:
         meta.update(cider=cider, spi=spi, use_gen=use_gen)
+    if kind == "beam":
+        # AttModel.sample_beam under model.eval() (eval_utils.py:187 style call)
+        from oracle import cases as OC
+        meta.update(beam_size=beam_size)
+        spk = model.caption_generator
+        spk.eval()
+        with torch.no_grad():
+            seq, lp = orig_sample(batch.fc_feats, batch.att_feats, batch.att_masks,
+                                  {"beam_size": beam_size, "decoding_constraint": decoding_constraint})
+        o = OC.run_oracle(meta)
+        compare(name + ".seq", o["seq"], seq)
+        compare(name + ".logprobs", o["logprobs"], lp)
+        done_n = np.array([len(d) for d in spk.done_beams], np.int64)
+        assert done_n.tolist() == [len(d) for d in o["done_beams"]]
+        done_p = np.full((rows, int(done_n.max())), np.nan, np.float32)
+        done_seq = np.zeros((rows, int(done_n.max()), dims.seq_length), np.int64)
+        for k in range(rows):
+            for e, (a, b) in enumerate(zip(spk.done_beams[k], o["done_beams"][k])):
+                assert torch.equal(a["seq"], b["seq"]) and abs(float(a["p"]) - b["p"]) <= 1e-4
+                done_p[k, e], done_seq[k, e] = float(a["p"]), a["seq"].numpy()
+        blob = {"meta": np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8),
+                "out.seq": seq.numpy(), "out.logprobs": lp.numpy(), "out.done_n": done_n,
+                "out.done_p": done_p, "out.done_seq": done_seq}
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+        print(f"[golden] {name:34s} beam {beam_size} done {done_n.tolist()} min gap {float(o['gaps'].min()):.2e} OK")
+        return
     if kind == "vse":
         # VSEFCModel.forward alone, non-default listener options (vse_pool_type / vse_use_abs /
         # vse_max_violation), loss and parameter gradients
@@ -392,6 +418,15 @@ CASES = [
                                                          seed=320, cider=1.0, spi=2, use_gen=1)),
     ("tiny_cider_only", synth.TINY, dict(rows=8, regions=4, varlen=True, mode="reinforce", kind="speaker_turn",
                                          weight=0.0, seed=330, cider=1.0, spi=2)),
+    ("tiny_beam3", synth.TINY, dict(rows=5, regions=4, varlen=True, mode="reinforce", kind="beam", seed=400,
+                                    beam_size=3, dropout=False)),
+    ("tiny_beam2_constraint", synth.TINY, dict(rows=4, regions=5, varlen=False, mode="reinforce", kind="beam",
+                                               seed=410, beam_size=2, decoding_constraint=1, eos_bias=1.0,
+                                               dropout=False)),
+    ("real_beam2_eos", synth.Dims(), dict(rows=3, regions=6, varlen=True, mode="reinforce", kind="beam",
+                                          seed=420, beam_size=2, eos_bias=4.0, dropout=False)),
+    ("real_beam3_constraint", synth.Dims(), dict(rows=3, regions=6, varlen=False, mode="reinforce", kind="beam",
+                                                 seed=430, beam_size=3, decoding_constraint=1, dropout=False)),
     ("real_gumbel_b4", synth.Dims(), dict(rows=4, regions=6, varlen=True, mode="gumbel",
                                           kind="speaker_turn", seed=200, eos_bias=6.0)),
     ("real_mle_b4", synth.Dims(), dict(rows=4, regions=6, varlen=False, mode="gumbel", kind="mle",
