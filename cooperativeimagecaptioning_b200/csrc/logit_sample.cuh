@@ -57,6 +57,7 @@ struct LogitSampleParams {
   float* z_tgt;             // [M] logit of forced[b] (written only when forced != null)
   uint64_t seed, nstream;
   float inv_tau;
+  int store_pert;           // ST-Gumbel only: z16 receives the PERTURBED logits z + G (see coopcap_speaker)
 };
 
 __device__ __forceinline__ void epi_barrier() {       // the epilogue warps only
@@ -241,7 +242,8 @@ logit_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           o.y = *reinterpret_cast<const uint32_t*>(&h[1]);
           o.z = *reinterpret_cast<const uint32_t*>(&h[2]);
           o.w = *reinterpret_cast<const uint32_t*>(&h[3]);
-          if (live && 8 * jj < ncols) *reinterpret_cast<uint4*>(zrow + col0 + 8 * jj) = o;   // N % 8 == 0
+          if (live && 8 * jj < ncols && !(gum && p.store_pert))
+            *reinterpret_cast<uint4*>(zrow + col0 + 8 * jj) = o;   // N % 8 == 0
         }
         if (__any_sync(0xffffffffu, unsigned(tgt - col0) < unsigned(LS_SUB))) {
           const int d = tgt - col0;
@@ -282,10 +284,6 @@ logit_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        // ---- log-sum-exp of the logits, and of the relaxed sample's scores
-        l1.fold(x, LOG2E);
-        if constexpr (gum) l2.fold(a2, 1.f);
-        else if constexpr (st) l2.fold(x, k_tau2);
         if constexpr (MODE == COOPCAP_SAMPLE_GREEDY) {
 #pragma unroll
           for (int j = 0; j < LS_SUB; ++j) a2[j] = x[j];
@@ -296,6 +294,35 @@ logit_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < LS_SUB; ++j)
             if (a2[j] > bv) { bv = a2[j]; bi = col0 + j; bz = x[j]; }
         }
+        if constexpr (gum) {
+          if (p.store_pert) {
+            // what leaves the SM is z + G, rounded to fp16, and the relaxed sample y is computed from
+            // exactly those rounded values: backward rebuilds y from them without regenerating a
+            // single noise value (the id above was drawn from the unrounded scores)
+            const float inv_k = 1.f / k_tau2;
+#pragma unroll
+            for (int jj = 0; jj < LS_SUB / 8; ++jj) {
+              __half2 h[4];
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                h[k2] = __floats2half2_rn(a2[8 * jj + 2 * k2] * inv_k, a2[8 * jj + 2 * k2 + 1] * inv_k);
+                const float2 f = __half22float2(h[k2]);
+                a2[8 * jj + 2 * k2] = f.x * k_tau2;
+                a2[8 * jj + 2 * k2 + 1] = f.y * k_tau2;
+              }
+              uint4 o;
+              o.x = *reinterpret_cast<const uint32_t*>(&h[0]);
+              o.y = *reinterpret_cast<const uint32_t*>(&h[1]);
+              o.z = *reinterpret_cast<const uint32_t*>(&h[2]);
+              o.w = *reinterpret_cast<const uint32_t*>(&h[3]);
+              if (live && 8 * jj < ncols) *reinterpret_cast<uint4*>(zrow + col0 + 8 * jj) = o;
+            }
+          }
+        }
+        // ---- log-sum-exp of the logits, and of the relaxed sample's scores
+        l1.fold(x, LOG2E);
+        if constexpr (gum) l2.fold(a2, 1.f);
+        else if constexpr (st) l2.fold(x, k_tau2);
       }
       if (live) {
         float4* rec = reinterpret_cast<float4*>(

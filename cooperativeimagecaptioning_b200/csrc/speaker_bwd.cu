@@ -161,7 +161,8 @@ __device__ __forceinline__ void ld_g4<bf16>(const bf16* p, float (&o)[4]) {
   o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
 }
 
-template <typename GT>
+// PERT: z holds the perturbed logits z + G (coopcap_speaker.store_perturbed): no noise is regenerated
+template <typename GT, bool PERT = false>
 __global__ void __launch_bounds__(256)
 st_bwd_kernel(const __half* __restrict__ z, const GT* __restrict__ g, int64_t ldg, int V1, int mode,
               float inv_tau, const float* __restrict__ noise, uint64_t seed, uint64_t nstream0,
@@ -193,11 +194,11 @@ st_bwd_kernel(const __half* __restrict__ z, const GT* __restrict__ g, int64_t ld
     float g4[4];
     ld_g4<GT>(gr + 4 * v4, g4);
     float u4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_PS_GUMBEL)
+    if (!PERT && (mode == COOPCAP_SAMPLE_ST_GUMBEL || mode == COOPCAP_SAMPLE_PS_GUMBEL))
       noise4(nr, v4, seed, nstream, uint64_t(b) * (V1 / 4) + v4, u4);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float score = st_score(mode, x4[q], u4[q], inv_tau, fast);
+      const float score = PERT ? x4[q] * inv_tau : st_score(mode, x4[q], u4[q], inv_tau, fast);
       const float y = ex2_ftz((score - m) * 1.4426950408889634f) * inv_s;
       s_y[4 * v4 + q] = y;
       dot += y * g4[q];
@@ -570,8 +571,11 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
              c->mode);
   const int B = c->B, V1 = c->V1, E = c->E;
   const size_t smem = sizeof(float) * V1;
-  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel<float>), int(smem)))) return rc;
-  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel<bf16>), int(smem)))) return rc;
+  const bool pert = c->store_perturbed && c->mode == COOPCAP_SAMPLE_ST_GUMBEL;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel<float, false>), int(smem)))) return rc;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel<bf16, false>), int(smem)))) return rc;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel<float, true>), int(smem)))) return rc;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(st_bwd_kernel<bf16, true>), int(smem)))) return rc;
   // several steps per launch: M = chunk * B rows give properly sized GEMM tiles instead of
   // n_steps launches at the latency floor (g_ws holds `g_chunk_steps` steps)
   const int chunk = demb16 ? (g_chunk_steps < 1 ? 1 : g_chunk_steps) : c->n_steps;
@@ -590,7 +594,7 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
                     E, int(rows), V1, E, 1, 0, e, s);
       if (rc) return rc;
       CC_CHECK_CUDA(launch_pdl(
-          st_bwd_kernel<bf16>, dim3((unsigned)rows), dim3(256), smem, s, z_t,
+          pert ? st_bwd_kernel<bf16, true> : st_bwd_kernel<bf16, false>, dim3((unsigned)rows), dim3(256), smem, s, z_t,
           static_cast<const bf16*>(reinterpret_cast<bf16*>(g_ws)), int64_t(V1), V1, c->mode, c->inv_tau, n_t,
           c->seed, uint64_t(SITE_NOISE + t0), B, static_cast<const float*>(c->y_max + int64_t(t0) * B),
           static_cast<const float*>(c->y_sum + int64_t(t0) * B),
@@ -599,7 +603,7 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
     } else {
       const float* g_t = reinterpret_cast<const float*>(g_ws) + int64_t(t0) * B * ldg;   // dense, all steps
       CC_CHECK_CUDA(launch_pdl(
-          st_bwd_kernel<float>, dim3((unsigned)rows), dim3(256), smem, s, z_t, g_t, ldg, V1, c->mode,
+          pert ? st_bwd_kernel<float, true> : st_bwd_kernel<float, false>, dim3((unsigned)rows), dim3(256), smem, s, z_t, g_t, ldg, V1, c->mode,
           c->inv_tau, n_t, c->seed, uint64_t(SITE_NOISE + t0), B,
           static_cast<const float*>(c->y_max + int64_t(t0) * B),
           static_cast<const float*>(c->y_sum + int64_t(t0) * B),
@@ -607,7 +611,8 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
           static_cast<const float*>(c->lse + int64_t(t0) * B)));
     }
     // logits + upstream gradient (+ injected noise) read, bf16 dz written
-    CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0, double(rows) * V1 * (2.0 + (demb16 ? 2.0 : 4.0) + 2.0 + (c->noise ? 4.0 : 0.0)));
+    CC_LAUNCH_CHECK_K(PROF_ST_BWD, s, 0.0,
+                      double(rows) * V1 * (2.0 + (demb16 ? 2.0 : 4.0) + 2.0 + ((c->noise && !pert) ? 4.0 : 0.0)));
   }
   return CC_OK;
 }
@@ -616,6 +621,8 @@ int logp_backward(const coopcap_speaker* c, const int64_t* tok, const float* coe
                   bool accumulate, cudaStream_t s) {
   int rc = check_dims(c);
   if (rc) return rc;
+  CC_REQUIRE(!(c->store_perturbed && c->mode == COOPCAP_SAMPLE_ST_GUMBEL),
+             "logp_backward: this pass stored perturbed logits (store_perturbed = 1); softmax(z) cannot be rebuilt");
   if (accumulate)
     logp_bwd_kernel<true><<<c->n_steps * c->B, 256, 0, s>>>(reinterpret_cast<const __half*>(c->z16_all), c->V1,
                                                             c->lse, tok, coef, reinterpret_cast<bf16*>(dz16));

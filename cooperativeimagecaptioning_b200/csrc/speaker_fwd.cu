@@ -502,6 +502,7 @@ static int logit_sample_step(const coopcap_speaker* c, int t, const bf16* out16_
   p.seed = c->seed;
   p.nstream = uint64_t(SITE_NOISE + t);
   p.inv_tau = c->inv_tau;
+  p.store_pert = (c->store_perturbed && c->mode == COOPCAP_SAMPLE_ST_GUMBEL) ? 1 : 0;
   const bool inj = c->noise != nullptr;
   switch (c->mode) {
     case COOPCAP_SAMPLE_GREEDY:

@@ -180,9 +180,11 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
                     start_tokens: Optional[torch.Tensor] = None,
                     att16: Optional[torch.Tensor] = None, ps_prob: float = 0.0,
                     w_embed16: Optional[torch.Tensor] = None, ss_prob: float = 0.0,
-                    no_repeat: bool = False, att_order: Optional[torch.Tensor] = None) -> SpeakerPass:
+                    no_repeat: bool = False, att_order: Optional[torch.Tensor] = None,
+                    store_perturbed: bool = False) -> SpeakerPass:
     """Prologue + n_steps decode steps.  `forced` int64 [n_steps, B] (time-major);
-    `start_tokens` int64 [B] overrides the scalar start id per row."""
+    `start_tokens` int64 [B] overrides the scalar start id per row.  `store_perturbed` (ST-Gumbel):
+    keep z + G instead of z for backward (coopcap_speaker.store_perturbed)."""
     _need_cuda(att_feats, att_off, forced, start_tokens)
     d: SpeakerDims = packed["dims"]
     B, L, D = att_feats.shape
@@ -257,6 +259,7 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     c.noise = _p(rnd.noise) if uses_noise else None
     c.mode, c.inv_tau, c.start_token = mode, float(inv_tau), int(start_token)
     c.ps_prob, c.ss_prob, c.no_repeat = float(ps_prob), float(ss_prob), int(bool(no_repeat))
+    c.store_perturbed = int(bool(store_perturbed) and mode == MODE_ST_GUMBEL)
     c.w_embed16 = _p(w_embed16)
     for n, on in (("part_u", mode in PS_MODES), ("ss_u", ss_prob > 0.0)):
         u = getattr(rnd, n)

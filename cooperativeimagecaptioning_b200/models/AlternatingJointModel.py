@@ -288,7 +288,10 @@ class AlternatingJointModel(nn.Module):
         (loss, word_index, logprobs, masks, _seqs) with the caption tensors left time-major and
         unsliced on the device (they only feed the out-of-scope CIDEr branch in the reference)."""
         spk, lis = self.caption_generator, self.vse
-        sp, st_mode = spk._sample_pass(att_feats, att_masks, 0, 1, 1)                   # :346-348
+        # nothing differentiates the sampled ids' log-probabilities unless the CIDEr term is on:
+        # the Gumbel pass may then keep z + G instead of z (no noise regenerated in backward)
+        sp, st_mode = spk._sample_pass(att_feats, att_masks, 0, 1, 1,
+                                       **({} if self.cider_optimization else {"store_perturbed": True}))  # :346-348
         assert st_mode
         B, V = sp.B, spk.vocab_size
         tok_sb = torch.cat([torch.full((1, B), V + 1, dtype=torch.int64, device=fc_feats.device),

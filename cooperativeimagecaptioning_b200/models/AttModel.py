@@ -214,7 +214,8 @@ class AttModel(nn.Module):
         return EN.SpeakerRandom(seed=_next_seed(), drop_p=p)
 
     def _run(self, att_feats, att_masks, *, n_steps, mode, inv_tau, start_token, forced=None,
-             start_tokens=None, ps_prob=0.0, ss_prob=0.0, no_repeat=False) -> EN.SpeakerPass:
+             start_tokens=None, ps_prob=0.0, ss_prob=0.0, no_repeat=False,
+             store_perturbed=False) -> EN.SpeakerPass:
         if not att_feats.is_cuda:
             raise EN._lib.CoopcapError("Att2in2Model runs on CUDA only (no CPU path)")
         P = self._params()
@@ -237,6 +238,7 @@ class AttModel(nn.Module):
                                 inv_tau=inv_tau, start_token=start_token, rnd=self._random(),
                                 forced=forced, start_tokens=start_tokens, att16=att16, att_order=order,
                                 ps_prob=ps_prob, ss_prob=ss_prob, no_repeat=no_repeat,
+                                store_perturbed=store_perturbed,
                                 w_embed16=self._packed.get_embed16(P) if mode in EN.PS_MODES else None)
         if self.keep_passes:
             sp.pinned = True
@@ -352,7 +354,7 @@ class AttModel(nn.Module):
         return out.seq, out.logprobs
 
     def _sample_pass(self, att_feats, att_masks, sample_max, temperature, use_one_hot,
-                     no_repeat=False):
+                     no_repeat=False, store_perturbed=False):
         """Run the decode loop in the mode AttModel.sample would pick; returns (pass, is_ST) with
         is_ST true for the modes that return dense vectors (straight-through / partial sampling)."""
         T = self.seq_length
@@ -382,7 +384,7 @@ class AttModel(nn.Module):
             forced = self.forced_tokens.t().contiguous()
         sp = self._run(att_feats, att_masks, n_steps=T, mode=mode, inv_tau=inv_tau,
                        start_token=self.vocab_size + 1, forced=forced, ps_prob=ps_prob,
-                       no_repeat=no_repeat)
+                       no_repeat=no_repeat, store_perturbed=store_perturbed)
         return sp, st_mode
 
 

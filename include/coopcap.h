@@ -243,6 +243,13 @@ typedef struct coopcap_speaker {
   const float* ss_u;         /* [cap, B] injected uniforms or NULL -> Philox */
   /* decoding_constraint (AttModel.py:437-442): the logit of the previously emitted id is -inf */
   int no_repeat;
+  /* COOPCAP_SAMPLE_ST_GUMBEL only: z16_all receives the PERTURBED logits z + G instead of z.  The
+   * relaxed sample y = softmax((z+G)/tau) -- all the straight-through backward needs (gumbel.py:13-30,
+   * SURVEY.md A.3) -- is then rebuilt from one fp16 read, with no noise regenerated (st_bwd: 95 -> ~50 us
+   * per 4096 rows).  logp / lse are still exact outputs of the forward pass, but softmax(z) can no
+   * longer be rebuilt, so coopcap_logp_backward refuses such a context: callers that differentiate
+   * the sampled ids' log-probabilities (the CIDEr term) leave this 0. */
+  int store_perturbed;
 } coopcap_speaker;
 
 /* att16, att_e16, p_att16 from att_feats (AttModel.py:110-114 / :315-319). */
