@@ -754,8 +754,9 @@ def main():
         del resident
 
     # ---------------- the other BASELINE.json configurations (side lines, rank 0) ----------------
+    # single-GPU measurements: their optimizers would enter all-reduces the other ranks never join
     decode, side = None, None
-    if rank == 0 and not args.no_decode:
+    if rank == 0 and world == 1 and not args.no_decode:
         decode, side = side_configs(model, dev, lib)
 
     # ---------------- CPU baseline (rank 0, N = 1) ----------------
