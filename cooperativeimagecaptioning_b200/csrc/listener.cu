@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "speaker_kernels.cuh"
+#include "cell_step.cuh"
 
 namespace coopcap {
 
@@ -453,6 +454,15 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
   CC_CHECK_CUDA(cudaMemsetAsync(c->h32, 0, sizeof(float) * B * M, s));
   CC_CHECK_CUDA(cudaMemsetAsync(h16, 0, sizeof(bf16) * B * M, s));
   for (int t = 0; t < S; ++t) {
+    if (cell_step_ok<GruCell>(M, M)) {
+      // gh GEMM with the GRU update as its epilogue (csrc/cell_step.cuh); c->gh is not written
+      GruStepParams gp = {};
+      gp.b_hh = c->b_hh; gp.gi = c->gi_all + int64_t(t) * B * 3 * M; gp.h_prev = c->h32 + int64_t(t) * B * M;
+      gp.len = c->len; gp.gates = c->gates + int64_t(t) * B * 4 * M;
+      gp.h_next = c->h32 + int64_t(t + 1) * B * M; gp.h_next16 = h16 + int64_t(t + 1) * B * M; gp.t = t;
+      if ((rc = launch_cell_step<GruCell>(h16 + int64_t(t) * B * M, M, c->w_hh16, B, M, M, gp, s))) return rc;
+      continue;
+    }
     EpiStoreParams e = {};
     e.alpha = 1.f; e.bias = c->b_hh; e.C = c->gh; e.ldc = 3 * M;
     if ((rc = gemm_run(0, 0, 0, h16 + int64_t(t) * B * M, M, c->w_hh16, M, B, 3 * M, M, 1, 0, e, s)))

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "speaker_kernels.cuh"
+#include "cell_step.cuh"
 #include "attention.cuh"
 #include "logit_sample.cuh"
 
@@ -633,15 +634,26 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     if (rc) return rc;
     if ((rc = attention_fwd_launch(c, s_t, att_res16 + int64_t(t) * B * R, c->att_w + int64_t(t) * c->NL, s)))
       return rc;
-    EpiStoreParams e2 = {};
-    e2.alpha = 1.f; e2.bias = c->b_a2c; e2.C = u_t; e2.ldc = 2 * R;
-    rc = gemm_run(0, 0, 0, att_res16 + int64_t(t) * B * R, R, c->w_a2c16, R, B, 2 * R, R, 1, 0, e2, s);
-    if (rc) return rc;
-    if ((rc = lstm_fwd_launch(c, s_t, u_t, c->c_all + int64_t(t) * B * R, c->c_all + int64_t(t + 1) * B * R,
-                              xh16 + int64_t(t + 1) * B * XH + E, int64_t(XH), out16 + int64_t(t) * B * R,
-                              c->keep_core ? c->keep_core + int64_t(t) * B * R : nullptr,
-                              uint64_t(SITE_DROP_CORE + t), c->drop_p, B, s)))
-      return rc;
+    if (cell_step_ok<LstmCell>(R, R)) {
+      // a2c GEMM with the maxout-LSTM update as its epilogue (csrc/cell_step.cuh)
+      LstmStepParams lp = {};
+      lp.b_a2c = c->b_a2c; lp.s = s_t; lp.lds = NS; lp.c_prev = c->c_all + int64_t(t) * B * R; lp.u = u_t;
+      lp.c_next = c->c_all + int64_t(t + 1) * B * R; lp.h_dst = xh16 + int64_t(t + 1) * B * XH + E; lp.ld_h = XH;
+      lp.out16 = out16 + int64_t(t) * B * R;
+      lp.keep = c->keep_core ? c->keep_core + int64_t(t) * B * R : nullptr;
+      lp.seed = c->seed; lp.stream = uint64_t(SITE_DROP_CORE + t); lp.drop_p = c->drop_p;
+      if ((rc = launch_cell_step<LstmCell>(att_res16 + int64_t(t) * B * R, R, c->w_a2c16, B, R, R, lp, s))) return rc;
+    } else {
+      EpiStoreParams e2 = {};
+      e2.alpha = 1.f; e2.bias = c->b_a2c; e2.C = u_t; e2.ldc = 2 * R;
+      rc = gemm_run(0, 0, 0, att_res16 + int64_t(t) * B * R, R, c->w_a2c16, R, B, 2 * R, R, 1, 0, e2, s);
+      if (rc) return rc;
+      if ((rc = lstm_fwd_launch(c, s_t, u_t, c->c_all + int64_t(t) * B * R, c->c_all + int64_t(t + 1) * B * R,
+                                xh16 + int64_t(t + 1) * B * XH + E, int64_t(XH), out16 + int64_t(t) * B * R,
+                                c->keep_core ? c->keep_core + int64_t(t) * B * R : nullptr,
+                                uint64_t(SITE_DROP_CORE + t), c->drop_p, B, s)))
+        return rc;
+    }
     __half* z_t = reinterpret_cast<__half*>(c->z16_all) + int64_t(t) * B * V1;
     const bool ps = (c->mode == COOPCAP_SAMPLE_PS_GUMBEL || c->mode == COOPCAP_SAMPLE_PS_MULTINOMIAL);
     bf16* x_next = (t + 1 < c->n_steps) ? xh16 + int64_t(t + 1) * B * XH : nullptr;
