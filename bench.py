@@ -561,6 +561,42 @@ def main():
     ms_max = float(t)
     value = args.rows * world * args.steps / (ms_max * 1e-3)
 
+    # ---------------- host cost of one step, and the plain-tensor call path ----------------
+    # (a) `host_enqueue_ms_per_step` above is measured INSIDE the timed loop, where the CPU runs ahead
+    # until the driver's launch queue is full and is then throttled to the device's pace (see
+    # value_loop_debug.host_ms_per_step: the first steps return in ~2 ms, the later ones in one
+    # device step).  The CPU time one step really needs is measured here on an empty queue.
+    # (b) the same step called with plain tensors, i.e. without the loader-side `_coopcap_off` /
+    # `_coopcap_order` hints on att_masks (what a caller of the reference's train.py:162-178
+    # passes): region offsets and row order are then derived on the device and the region count
+    # is read back (one .item() sync per forward).
+    host_free_ms, plain = None, None
+    if world == 1:
+        torch.cuda.synchronize()
+        hs = []
+        for i in range(3):
+            g0 = time.perf_counter()
+            train_step(resident[i % 2])
+            hs.append((time.perf_counter() - g0) * 1e3)
+            torch.cuda.synchronize()
+        host_free_ms = min(hs)
+        bare = [{k: v.clone() for k, v in r.items()} for r in resident]      # clones carry no hints
+        for i in range(max(3, args.warmup)):
+            train_step(bare[i % 2])
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(args.steps):
+            train_step(bare[i % 2])
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1) / args.steps
+        plain = dict(ms_per_step=pms, images_per_s=args.rows / (pms * 1e-3),
+                     ratio_to_value=(args.rows / (pms * 1e-3)) / value,
+                     note="AlternatingJointModel.forward called with plain CUDA tensors (no loader hints on "
+                          "att_masks): offsets / row order computed on the device, one .item() sync per forward")
+        bare = None
+
     # ---------------- end to end from pinned host buffers (`e2e`) ----------------
     from cooperativeimagecaptioning_b200.data import FeatureStore, HostPacker, record_stream, upload_batch
     resident = None
@@ -730,17 +766,25 @@ def main():
             roof = dict(kernel=KIND_NAMES[top], bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s",
                         frac=ach / pk["hbm"], traffic=None, peak_source=pk["source"],
                         launches_per_step=pln[top] / psteps, ms_per_step=pms[top] / psteps)
-        # DRAM traffic of the same kernel class from the committed ncu capture (per launch)
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_final_ncu_launch_summary.json")) as f:
-                summ = json.load(f)
-            cls = summ["by_class"].get(KIND_NAMES[top])
-            if roof is not None and cls:
-                roof["traffic"] = cls["dram_MB"] * 1e6 / cls["launches"]
-                roof["traffic_unit"] = "bytes per launch (dram read+write, ncu, profiles/r01_final_ncu_launch_summary.json)"
-                roof["algorithmic_per_launch"] = (pfl[top] if pfl[top] > 0 else pby[top]) / max(pln[top], 1)
-        except (OSError, KeyError, ValueError):
-            pass
+        # DRAM traffic of the same kernel class from the committed ncu capture of this build (per
+        # launch, like `achieved`); `algorithmic_bytes_per_launch` is the operand + result bytes
+        # declared at the launch sites, the figure `traffic` is to be compared with
+        for summ_name in ("r02_final_ncu_launch_summary.json", "r02_s2_ncu_launch_summary.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", summ_name)) as f:
+                    summ = json.load(f)
+                cls = dict(summ["by_class"].get(KIND_NAMES[top]) or {})
+                if roof is not None and cls:
+                    roof["traffic"] = cls["dram_MB"] * 1e6 / cls["launches"]
+                    roof["traffic_unit"] = f"bytes per launch (dram read+write, ncu, profiles/{summ_name})"
+                    roof["algorithmic_per_launch"] = (pfl[top] if pfl[top] > 0 else pby[top]) / max(pln[top], 1)
+                    roof["algorithmic_unit"] = "FLOP per launch" if pfl[top] > 0 else "bytes per launch"
+                    roof["algorithmic_bytes_per_launch"] = pby[top] / max(pln[top], 1)
+                    roof["traffic_over_algorithmic_bytes"] = (roof["traffic"] / roof["algorithmic_bytes_per_launch"]
+                                                              if pby[top] > 0 else None)
+                    break
+            except (OSError, KeyError, ValueError):
+                continue
         # the HBM-bound kernels of the path, for DESIGN.md / the judge
         for k in ("att_fwd", "att_bwd", "att_deferred", "sample", "st_bwd", "adam"):
             i = KIND_NAMES.index(k)
@@ -781,7 +825,12 @@ def main():
                         l2="inputs (839 MB att feats + 622 MB logits per step) exceed the 126 MB L2",
                         accumulate="fp32 accumulation, bf16 tensor-core operands, fp32 master weights"),
             e2e=e2e, e2e_host_features=e2e_host_features,
-            gpu_launches=int(launches), host_enqueue_ms_per_step=host_enqueue_ms,
+            gpu_launches=int(launches),
+            # CPU time to enqueue one step on an EMPTY launch queue; the in-loop figure is throttled by
+            # the full queue (the CPU waits for the device there, it is not the bottleneck)
+            host_enqueue_ms_per_step=host_free_ms if host_free_ms is not None else host_enqueue_ms,
+            host_enqueue_ms_per_step_in_timed_loop=host_enqueue_ms,
+            plain_tensor_call=plain,
             value_loop_debug=loop_debug,
             ms_per_step_by_rank=[m / args.steps for m in ms_ranks],
             loss=loss_value, clocks=clk, roofline=roof,
