@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=128, help="rows of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prof", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="profiler runs (ncu replays every launch): no settle loop, no host-cost / "
+                         "plain-tensor passes; the printed numbers are not bench values")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profiling runs)")
     ap.add_argument("--no-decode", action="store_true", help="skip the decode tokens/s side metric")
     ap.add_argument("--upload-ctas", type=int, default=64, help="CTAs of the zero-copy upload kernel")
@@ -497,7 +500,7 @@ def main():
     # caching allocator must have seen both batch shapes, and a freshly booted box takes a few
     # hundred ms of work before clocks / driver state stop moving
     prev = None
-    for _ in range(12):
+    for _ in range(0 if args.quick else 12):
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
         for i in range(4):
@@ -571,7 +574,7 @@ def main():
     # passes): region offsets and row order are then derived on the device and the region count
     # is read back (one .item() sync per forward).
     host_free_ms, plain = None, None
-    if world == 1:
+    if world == 1 and not args.quick:
         torch.cuda.synchronize()
         hs = []
         for i in range(3):
@@ -806,10 +809,16 @@ def main():
     # ---------------- CPU baseline (rank 0, N = 1) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sec, threads = cpu_joint_step_rate(args.cpu_rows, args.max_regions, args.min_regions, 4, 1)
-        cpu = dict(value=rate, unit=UNIT, cores=threads, kind="port",
+        # the real reference (baseline/_ref, oracle/make_ref.py) when it travelled with the snapshot,
+        # else the oracle port of the same step
+        have_ref = os.path.isfile(os.path.join(REF_DIR, "models", "AlternatingJointModel.py"))
+        fn = reference_joint_step_rate if have_ref else cpu_joint_step_rate
+        rate, sec, threads = fn(args.cpu_rows, args.max_regions, args.min_regions, 4, 1)
+        cpu = dict(value=rate, unit=UNIT, cores=threads, kind="reference" if have_ref else "port",
                    sample=f"{args.cpu_rows} rows x {args.min_regions}-{args.max_regions} regions, "
-                          f"Gumbel joint step fwd+bwd+clamp+Adam, fp32, {sec:.2f} s/step, 1 warm-up + 4 timed")
+                          f"Gumbel joint step fwd+bwd+clamp+Adam, fp32, {sec:.2f} s/step, 1 warm-up + 4 timed"
+                          + ("; the reference's own modules and train-loop body (baseline/_ref)" if have_ref
+                             else "; CPU restatement (oracle/), baseline/_ref absent"))
 
     if rank == 0:
         line = dict(

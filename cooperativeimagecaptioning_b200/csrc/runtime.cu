@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/coopcap.h"
+#include <algorithm>
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -259,6 +260,42 @@ int coopcap_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_major) *cc_major = prop.major;
   if (cc_minor) *cc_minor = prop.minor;
   return coopcap::CC_OK;
+}
+
+int coopcap_l2_persist(const void* base, int64_t bytes, int64_t* granted, coopcap_stream_t stream) {
+  using namespace coopcap;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int dev = 0, max_persist = 0, max_window = 0;
+  CC_CHECK_CUDA(cudaGetDevice(&dev));
+  CC_CHECK_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  CC_CHECK_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  cudaStreamAttrValue v = {};
+  if (bytes <= 0 || base == nullptr) {
+    v.accessPolicyWindow.num_bytes = 0;
+    v.accessPolicyWindow.hitRatio = 0.f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    CC_CHECK_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v));
+    CC_CHECK_CUDA(cudaCtxResetPersistingL2Cache());
+    CC_CHECK_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
+    if (granted) *granted = 0;
+    return CC_OK;
+  }
+  const int64_t aside = std::min<int64_t>(bytes, max_persist);
+  const int64_t window = std::min<int64_t>(bytes, max_window);
+  if (aside <= 0 || window <= 0) {           // the device has no persisting L2: nothing to do
+    if (granted) *granted = 0;
+    return CC_OK;
+  }
+  CC_CHECK_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(aside)));
+  v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+  v.accessPolicyWindow.num_bytes = size_t(window);
+  v.accessPolicyWindow.hitRatio = float(std::min(1.0, double(aside) / double(window)));
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+  CC_CHECK_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v));
+  if (granted) *granted = aside;
+  return CC_OK;
 }
 
 }  // extern "C"

@@ -3,6 +3,7 @@
 // logit GEMM with the sampler in its epilogue -> per-row finish + next-input gather).  See include/coopcap.h for the buffer layout and
 // the reference lines each piece replaces.
 #include <algorithm>
+#include <atomic>
 #include "../../include/coopcap.h"
 #include "common.cuh"
 #include "gemm.cuh"
@@ -108,15 +109,19 @@ struct CastBatch {
     return CC_OK;
   }
 };
+static std::atomic<int> g_cast_multi{[] { const char* e = getenv("COOPCAP_CAST_MULTI"); return (e && e[0] == '0') ? 0 : 1; }()};
+void set_cast_multi(int on) { g_cast_multi.store(on ? 1 : 0, std::memory_order_relaxed); }
 int cast_blocks(int n, const float* const* src, const int64_t* rows, const int* cols, void* const* dst,
                 const int64_t* ld_dst, cudaStream_t s) {
   CastBatch b;
   for (int i = 0; i < n; ++i) b.add(src[i], rows[i], cols[i], dst[i], ld_dst[i]);
-  // Opt-in (COOPCAP_CAST_MULTI=1).  Measured A/B on one box: the fused launch shortens the
-  // device-resident step by 0.045 ms but lengthens the end-to-end step -- where the zero-copy
-  // upload kernel of the next batch shares the SMs -- from 10.4-10.6 to 11.0-11.9 ms at every grid
-  // size tried, so the separate casts stay the default.
-  static const bool fused = [] { const char* e = getenv("COOPCAP_CAST_MULTI"); return e && e[0] == '1'; }();
+  // One fused launch for the eleven casts of a weight re-pack unless the host side asked for separate
+  // launches (coopcap_set_cast_multi(0) / COOPCAP_CAST_MULTI=0).  Measured A/B on one box (r2,
+  // gpurun_out/s7_bench*.json): fused shortens the device-resident step and the feature-store
+  // end-to-end step by 0.04 ms (5.583 -> 5.541, 5.568 -> 5.547 ms), but lengthens the end-to-end step
+  // fed by the ZERO-COPY upload kernel -- the next batch's reader shares the SMs at that point -- from
+  // 10.57 to 11.79 ms, so data.upload_batch(zero_copy=True) switches it off.
+  const bool fused = g_cast_multi.load(std::memory_order_relaxed) != 0;
   if (b.ok && fused) return b.run(s);
   int rc;
   for (int i = 0; i < n; ++i)
@@ -693,6 +698,11 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
 }  // namespace coopcap
 
 extern "C" {
+
+int coopcap_set_cast_multi(int on) {
+  coopcap::set_cast_multi(on);
+  return coopcap::CC_OK;
+}
 
 int coopcap_speaker_pack_weights(const coopcap_speaker_pack* p, coopcap_stream_t stream) {
   using namespace coopcap;

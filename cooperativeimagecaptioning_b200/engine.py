@@ -61,6 +61,55 @@ SPEAKER_PARAM_NAMES = [
 ]
 
 
+# ---------------------------------------------------------------------------------------------
+# L2-resident weight arena.  The bf16 operand copies of the RECURRENT weights (speaker w_cat16 /
+# w_a2c16 / w_logit16, listener w_hh16: 23 MB at the reference sizes) are read by ~100 per-step GEMMs
+# of a training step, and every decode step streams ~220 MB of region tensors, logits and gate
+# pre-activations through the 126 MB L2 between two of those reads.  They live in one arena so that
+# a single persisting access-policy window (coopcap_l2_persist) can keep them in L2.
+# COOPCAP_L2_PERSIST=0 turns the window off (the arena stays).
+# ---------------------------------------------------------------------------------------------
+_ARENA_BYTES = 40 << 20
+_arena: Dict[int, dict] = {}
+
+
+def _arena_alloc(dev: torch.device, shape, dtype=torch.bfloat16) -> torch.Tensor:
+    """A tensor of `shape` carved out of the device's weight arena (256-byte aligned), or an
+    ordinary allocation when the arena is full."""
+    import math
+    ix = dev.index if dev.index is not None else torch.cuda.current_device()
+    a = _arena.get(ix)
+    if a is None:
+        a = _arena[ix] = dict(buf=torch.empty(_ARENA_BYTES, dtype=torch.uint8, device=dev), used=0,
+                              windows={})
+    nbytes = math.prod(shape) * torch.empty((), dtype=dtype).element_size()
+    start = (a["used"] + 255) // 256 * 256
+    if start + nbytes > _ARENA_BYTES:
+        return torch.empty(shape, dtype=dtype, device=dev)
+    a["used"] = start + nbytes
+    return a["buf"][start:start + nbytes].view(dtype).view(shape)
+
+
+def _arena_persist(dev: torch.device):
+    """Put the persisting window over the used part of the arena on the CURRENT stream (once per
+    stream and arena size)."""
+    import os
+    if os.environ.get("COOPCAP_L2_PERSIST", "1") == "0":
+        return
+    ix = dev.index if dev.index is not None else torch.cuda.current_device()
+    a = _arena.get(ix)
+    if a is None or a["used"] == 0:
+        return
+    st = torch.cuda.current_stream(dev).cuda_stream
+    if a["windows"].get(st) == a["used"]:
+        return
+    granted = C.c_int64(0)
+    check(_lib.load().coopcap_l2_persist(C.c_void_p(a["buf"].data_ptr()), a["used"], C.byref(granted),
+                                        C.c_void_p(st)))
+    a["windows"][st] = a["used"]
+    a["granted"] = int(granted.value)
+
+
 @dataclass
 class SpeakerDims:
     D: int
@@ -110,8 +159,8 @@ class PackedSpeaker:
             self.buf = dict(
                 dims=d,
                 w_att_embed16=torch.empty(d.R, d.D, **bf), w_ctx2att16=torch.empty(d.A, d.R, **bf),
-                w_cat16=torch.empty(5 * d.R + d.A, d.E + d.R, **bf),
-                w_a2c16=torch.empty(2 * d.R, d.R, **bf), w_logit16=torch.empty(d.V1, d.R, **bf),
+                w_cat16=_arena_alloc(dev, (5 * d.R + d.A, d.E + d.R)),
+                w_a2c16=_arena_alloc(dev, (2 * d.R, d.R)), w_logit16=_arena_alloc(dev, (d.V1, d.R)),
                 b_cat=torch.empty(5 * d.R + d.A, dtype=torch.float32, device=dev))
         b = self.buf
         a = _lib.SpeakerPack()
@@ -129,6 +178,7 @@ class PackedSpeaker:
         a.w_att_embed16, a.w_ctx2att16 = _p(b["w_att_embed16"]), _p(b["w_ctx2att16"])
         a.w_cat16, a.w_a2c16, a.w_logit16 = _p(b["w_cat16"]), _p(b["w_a2c16"]), _p(b["w_logit16"])
         a.b_cat = _p(b["b_cat"])
+        _arena_persist(dev)
         check(_lib.load().coopcap_speaker_pack_weights(C.byref(a), _stream()))
         self.key = key
         return b
@@ -590,7 +640,7 @@ class PackedListener:
             bf = dict(dtype=torch.bfloat16, device=dev)
             self.buf = dict(dims=d, w_img16=torch.empty(d.M, d.F, **bf),
                             w_ih16=torch.empty(3 * d.M, d.E, **bf),
-                            w_hh16=torch.empty(3 * d.M, d.M, **bf),
+                            w_hh16=_arena_alloc(dev, (3 * d.M, d.M)),
                             w_emb16=torch.empty(d.V2, d.E, **bf))
         b = self.buf
         a = _lib.ListenerPack()
@@ -601,6 +651,7 @@ class PackedListener:
         a.w_emb = _p(_f32c(P["txt_enc.embed.weight"].detach()))
         a.w_img16, a.w_ih16, a.w_hh16, a.w_emb16 = (_p(b["w_img16"]), _p(b["w_ih16"]),
                                                     _p(b["w_hh16"]), _p(b["w_emb16"]))
+        _arena_persist(dev)
         check(_lib.load().coopcap_listener_pack_weights(C.byref(a), _stream()))
         self.key = key
         return b

@@ -41,6 +41,17 @@ typedef void* coopcap_stream_t; /* cudaStream_t */
 int coopcap_version(void);
 const char* coopcap_last_error(void);
 int coopcap_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Keep [base, base + bytes) resident in L2 for the kernels `stream` launches from now on: reserves
+ * min(bytes, device maximum) of the L2 as persisting set-aside (cudaLimitPersistingL2CacheSize, a
+ * property of the DEVICE, shared by every stream of the process) and puts a persisting access-policy
+ * window over the range on `stream`.  The host side places the bf16 operand copies of the recurrent
+ * weights (w_cat16, w_a2c16, w_logit16, w_hh16: 23 MB) in one arena and calls this once: the ~100
+ * per-step GEMMs of a training step then find their weights in L2 although every decode step streams
+ * ~220 MB (region tensors, logits, gate pre-activations) through it in between.  No reference
+ * counterpart (a cache-management call; the reference's cuBLAS path re-reads the weights from DRAM).
+ * bytes == 0 removes the window and the set-aside.  granted (may be NULL) receives the bytes
+ * actually set aside. */
+int coopcap_l2_persist(const void* base, int64_t bytes, int64_t* granted, coopcap_stream_t stream);
 
 /* ---- dense contraction engine ---------------------------------------------------------------
  * C[M,N] = alpha * sum_k A[m,k] B[n,k] (+ bias[n]) (relu) (* row_scale[m])
@@ -154,6 +165,11 @@ typedef struct coopcap_speaker_pack {
 } coopcap_speaker_pack;
 
 int coopcap_speaker_pack_weights(const coopcap_speaker_pack* p, coopcap_stream_t stream);
+/* Weight re-pack launches: 1 (default) = the casts of one coopcap_*_pack_weights call run as one
+ * fused launch, 0 = one launch per tensor.  Process-wide host-side switch (no device state); the
+ * zero-copy upload path (coopcap_pack_att_from_host) turns it off because its reader kernel shares
+ * the SMs with the re-pack.  No reference counterpart. */
+int coopcap_set_cast_multi(int on);
 
 typedef struct coopcap_speaker {
   /* dimensions */

@@ -8,7 +8,7 @@
 // pre-activations and weights -- has been through the 126 MB L2 in between).  This program times the
 // cheapest possible kernel over the same bytes -- 16-byte loads, a register XOR, one store per thread
 // -- launched like the attention kernels (one CTA of 512 threads per SM) and as a wide grid, with L2
-// flushed by a 512 MB write before every launch, plus the same kernel over 2 GB (the asymptotic
+// flushed by a 512 MB read before every launch, plus the same kernel over 2 GB (the asymptotic
 // rate MEASURED_PEAKS.json's copy figure corresponds to).  The attention kernels' GB/s is to be
 // read against the 116 MB lines, not against the 2 GB one: a ~25 us kernel pays launch, ramp-up and
 // tail (the last CTA's last wave) out of its own time.
@@ -47,7 +47,9 @@ static double timed(const uint4* buf, int64_t bytes, int grid, int block, uint4*
   CK(cudaEventCreate(&e1));
   std::vector<float> ms;
   for (int r = 0; r < reps + 2; ++r) {
-    if (do_flush) fill_kernel<<<1184, 512>>>(flush, flush_bytes / 16, 7u + r);
+    // flush with READS: a write flush leaves the L2 full of dirty lines whose write-back the timed
+    // kernel then pays for (the first version of this tool did that and read 116 MB in 39 us)
+    if (do_flush) read_kernel<<<1184, 512>>>(flush, flush_bytes / 16, out);
     CK(cudaEventRecord(e0));
     read_kernel<<<grid, block>>>(buf, bytes / 16, out);
     CK(cudaEventRecord(e1));
@@ -71,6 +73,7 @@ int main() {
   CK(cudaMalloc(&flush, flush_bytes));
   CK(cudaMalloc(&out, 64));
   fill_kernel<<<1184, 512>>>(buf, big / 16, 1u);
+  fill_kernel<<<1184, 512>>>(flush, flush_bytes / 16, 3u);
   CK(cudaDeviceSynchronize());
   int sms = 148;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
@@ -83,7 +86,7 @@ int main() {
       {"116MB_l2_warm_four_ctas_per_sm", small, 4 * sms, 512, false},
       {"2GB_four_ctas_per_sm_512thr", big, 4 * sms, 512, true},
   };
-  printf("{\n \"what\": \"plain 16-byte-load read kernel, median of 20 launches, CUDA events around the launch; L2 flushed by a 512 MB write before every cold launch\",\n \"sms\": %d,\n \"cases\": {\n", sms);
+  printf("{\n \"what\": \"plain 16-byte-load read kernel, median of 20 launches, CUDA events around the launch; L2 flushed by a 512 MB read of another buffer before every cold launch\",\n \"sms\": %d,\n \"cases\": {\n", sms);
   const int ncase = int(sizeof(cases) / sizeof(cases[0]));
   for (int i = 0; i < ncase; ++i) {
     const Case& c = cases[i];
