@@ -809,16 +809,28 @@ def main():
     # ---------------- CPU baseline (rank 0, N = 1) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # the real reference (baseline/_ref, oracle/make_ref.py) when it travelled with the snapshot,
+        # the real reference (baseline/_ref, oracle/make_ref.py) when it travelled with the snapshot --
+        # in a child process, because the reference moves its tensors to the GPU whenever
+        # torch.cuda.is_available() and the reference arm hides the device before importing torch --
         # else the oracle port of the same step
-        have_ref = os.path.isfile(os.path.join(REF_DIR, "models", "AlternatingJointModel.py"))
-        fn = reference_joint_step_rate if have_ref else cpu_joint_step_rate
-        rate, sec, threads = fn(args.cpu_rows, args.max_regions, args.min_regions, 4, 1)
-        cpu = dict(value=rate, unit=UNIT, cores=threads, kind="reference" if have_ref else "port",
-                   sample=f"{args.cpu_rows} rows x {args.min_regions}-{args.max_regions} regions, "
-                          f"Gumbel joint step fwd+bwd+clamp+Adam, fp32, {sec:.2f} s/step, 1 warm-up + 4 timed"
-                          + ("; the reference's own modules and train-loop body (baseline/_ref)" if have_ref
-                             else "; CPU restatement (oracle/), baseline/_ref absent"))
+        cpu = None
+        if os.path.isfile(os.path.join(REF_DIR, "models", "AlternatingJointModel.py")):
+            import subprocess
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4",
+                                    "--warmup", "1", "--cpu-rows", str(args.cpu_rows), "--rows", str(args.rows),
+                                    "--max-regions", str(args.max_regions), "--min-regions", str(args.min_regions)],
+                                   capture_output=True, text=True, timeout=600)
+                ref_line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+                cpu = ref_line["cpu_baseline"]
+            except Exception as e:          # noqa: BLE001  (any failure falls back to the port, and says so)
+                print(f"cpu_baseline: reference arm failed ({e}); timing the oracle port", file=sys.stderr)
+        if cpu is None:
+            rate, sec, threads = cpu_joint_step_rate(args.cpu_rows, args.max_regions, args.min_regions, 4, 1)
+            cpu = dict(value=rate, unit=UNIT, cores=threads, kind="port",
+                       sample=f"{args.cpu_rows} rows x {args.min_regions}-{args.max_regions} regions, "
+                              f"Gumbel joint step fwd+bwd+clamp+Adam, fp32, {sec:.2f} s/step, 1 warm-up + 4 timed; "
+                              "CPU restatement (oracle/), baseline/_ref absent or failed")
 
     if rank == 0:
         line = dict(
@@ -840,6 +852,8 @@ def main():
             host_enqueue_ms_per_step=host_free_ms if host_free_ms is not None else host_enqueue_ms,
             host_enqueue_ms_per_step_in_timed_loop=host_enqueue_ms,
             plain_tensor_call=plain,
+            l2_persist={k: dict(arena_bytes=a["used"], set_aside_bytes=a.get("granted"))
+                        for k, a in EN._arena.items()} or None,
             value_loop_debug=loop_debug,
             ms_per_step_by_rank=[m / args.steps for m in ms_ranks],
             loss=loss_value, clocks=clk, roofline=roof,

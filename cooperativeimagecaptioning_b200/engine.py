@@ -211,16 +211,29 @@ class SpeakerPass:
     keep: list = field(default_factory=list)   # tensors referenced by raw pointer in ctx
 
 
-def region_offsets(att_masks: Optional[torch.Tensor], B: int, L: int):
+def region_offsets(att_masks: Optional[torch.Tensor], B: int, L: int, lazy: bool = False):
     """att_masks [B, L] -> (att_off int32 [B+1] on device or None, NL).  One host sync (the
     valid-region count sizes the packed buffers), as pack_wrapper's own lengths do
-    (AttModel.py:47)."""
+    (AttModel.py:47).  lazy=True returns a zero-argument callable instead of NL: the count is
+    already on its way to pinned host memory, the caller resolves it (the sync) as late as it can --
+    speaker_forward does all its NL-independent host work first, so the device is idle only for
+    the few microseconds between the sync and the first launch."""
     if att_masks is None:
         return None, B * L
     lens = (att_masks > 0).sum(1).to(torch.int32)
     off = torch.zeros(B + 1, dtype=torch.int32, device=att_masks.device)
     off[1:] = torch.cumsum(lens, 0)
-    return off, int(off[-1].item())
+    if not lazy:
+        return off, int(off[-1].item())
+    host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+    host.copy_(off[-1:], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+
+    def resolve() -> int:
+        ev.synchronize()
+        return int(host[0])
+    return off, resolve
 
 
 def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.Tensor,
@@ -239,9 +252,11 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     d: SpeakerDims = packed["dims"]
     B, L, D = att_feats.shape
     assert D == d.D
+    nl_lazy = callable(NL)                 # region_offsets(..., lazy=True): resolved right before the launch
     if att16 is None:
         att_feats = _f32c(att_feats)       # `att16` given: att_feats is only a shape carrier
     else:
+        assert not nl_lazy
         assert att16.dtype == torch.bfloat16 and att16.is_contiguous() and att16.shape == (NL, d.D)
     dev = att16.device if att16 is not None else att_feats.device
     cap = max(n_steps, 1)
@@ -250,12 +265,10 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     i64 = dict(dtype=torch.int64, device=dev)
     NS, XH = 5 * d.R + d.A, d.E + d.R
     T = dict(
-        att16=att16 if att16 is not None else torch.empty(NL, d.D, **bf),
-        att_e16=torch.empty(NL, d.R, **bf),
-        p_att16=torch.empty(NL, d.A, **bf), xh16=torch.empty(cap + 1, B, XH, **bf),
+        xh16=torch.empty(cap + 1, B, XH, **bf),
         s_all=torch.empty(cap, B, NS, **f32), u_all=torch.empty(cap, B, 2 * d.R, **f32),
         c_all=torch.empty(cap + 1, B, d.R, **f32), att_res16=torch.empty(cap, B, d.R, **bf),
-        att_w=torch.empty(cap, NL, **f32), out16=torch.empty(cap, B, d.R, **bf),
+        out16=torch.empty(cap, B, d.R, **bf),
         # logits are kept in fp16 for the backward pass only; the sampler runs on the fp32
         # accumulators inside the logit GEMM (csrc/logit_sample.cuh)
         z16_all=torch.empty(cap, B, d.V1, dtype=torch.float16, device=dev),
@@ -274,7 +287,7 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
         T["ps_sel"] = torch.empty(cap, B, dtype=torch.uint8, device=dev)
     c = _lib.Speaker()
     c.B, c.L, c.D, c.R, c.E, c.A, c.V1 = B, L, d.D, d.R, d.E, d.A, d.V1
-    c.NL, c.cap, c.n_steps = NL, cap, n_steps
+    c.cap, c.n_steps = cap, n_steps
     c.att_feats, c.att_off = (None if att16 is not None else _p(att_feats)), _p(att_off)
     # longest rows first: the attention kernels deal rows to SMs by rank (load balance only)
     if att_order is None and att_off is not None and B > 1:
@@ -291,13 +304,13 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
     for n in ("w_att_embed16", "w_ctx2att16", "w_cat16", "w_a2c16", "w_logit16"):
         setattr(c, n, _p(packed[n]))
     c.seed, c.drop_p = int(rnd.seed) & (2 ** 64 - 1), float(rnd.drop_p)
-    want = {"keep_att": (NL, d.R), "keep_embed": (n_steps, B, d.E), "keep_core": (n_steps, B, d.R)}
+    want = {"keep_att": (None, d.R), "keep_embed": (n_steps, B, d.E), "keep_core": (n_steps, B, d.R)}
     for n in ("keep_att", "keep_embed", "keep_core"):
         k = getattr(rnd, n)
         if k is not None:
             assert k.dtype == torch.uint8 and k.is_contiguous() and k.is_cuda
             w = want[n]
-            if k.shape[0] < w[0] or tuple(k.shape[1:]) != tuple(w[1:]):
+            if (w[0] is not None and k.shape[0] < w[0]) or tuple(k.shape[1:]) != tuple(w[1:]):
                 raise _lib.CoopcapError(f"injected {n} has shape {tuple(k.shape)}, need >= {w}")
         setattr(c, n, _p(k))
     uses_noise = mode in (MODE_MULTINOMIAL, MODE_ST_GUMBEL, MODE_ST_MULTINOMIAL) + PS_MODES
@@ -325,6 +338,16 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
         assert start_tokens.dtype == torch.int64 and start_tokens.is_contiguous()
         assert start_tokens.shape == (B,)
     c.start_tokens = _p(start_tokens)
+    # ---- everything above is independent of the region count; the (only) host sync of the
+    # plain-tensor call path happens here, with the launches a few microseconds away
+    if nl_lazy:
+        NL = int(NL())
+    if rnd.keep_att is not None and rnd.keep_att.shape[0] < NL:
+        raise _lib.CoopcapError(f"injected keep_att has shape {tuple(rnd.keep_att.shape)}, need >= {(NL, d.R)}")
+    c.NL = NL
+    T.update(att16=att16 if att16 is not None else torch.empty(NL, d.D, **bf),
+             att_e16=torch.empty(NL, d.R, **bf), p_att16=torch.empty(NL, d.A, **bf),
+             att_w=torch.empty(cap, NL, **f32))
     for n, tsr in T.items():
         setattr(c, n, _p(tsr))
     sp = SpeakerPass(ctx=c, dims=d, B=B, L=L, NL=NL, cap=cap, n_steps=n_steps, t=T,

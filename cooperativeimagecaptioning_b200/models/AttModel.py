@@ -231,7 +231,9 @@ class AttModel(nn.Module):
             if att_masks is not None:
                 # precondition of the reference (Appendix D): padded width == longest row
                 att_masks = att_masks[:, :L]
-            off, NL = EN.region_offsets(att_masks, B, L)
+            # plain tensors: the region count is read back lazily (speaker_forward resolves it after
+            # its NL-independent host work; the pre-packed path needs it for the operand's shape)
+            off, NL = EN.region_offsets(att_masks, B, L, lazy=att16 is None)
         # rows by decreasing region count (schedule hint), if the loader side already knows it
         order = getattr(att_masks, "_coopcap_order", None) if att_masks is not None else None
         sp = EN.speaker_forward(P, packed, att_feats, off, NL, n_steps=n_steps, mode=mode,
