@@ -26,7 +26,7 @@ def _models(B, seed, eos_bias=0.0, **optkw):
     return m.cuda(), Ps, Pl
 
 
-@pytest.mark.parametrize("B,L,varlen", [(16, 36, False), (5, 3, True), (1, 1, False)])
+@pytest.mark.parametrize("B,L,varlen", [(16, 36, False), (5, 3, True), (1, 1, False), (512, 36, False)])
 def test_greedy_decode_is_bit_exact_off_near_ties(B, L, varlen):
     """Config 3: eval-mode greedy captions (AttModel.py:327-329).  A row may diverge from the
     oracle only at a step where the oracle's top-2 log-prob gap is below the near-tie tolerance;
@@ -45,7 +45,7 @@ def test_greedy_decode_is_bit_exact_off_near_ties(B, L, varlen):
     seq, logp = seq.cpu(), logp.cpu()
     ref_raw = torch.stack(ref.tokens_raw, 1)                           # [B, 16] before masking
     n = seq.shape[1]
-    exact, near = 0, 0
+    exact, near, worst_gap = 0, 0, 0.0
     for b in range(B):
         alive = True
         for t in range(n):
@@ -55,6 +55,7 @@ def test_greedy_decode_is_bit_exact_off_near_ties(B, L, varlen):
             if int(seq[b, t]) != want:
                 top2 = ref.step_logprobs[t][b].topk(2)[0]
                 assert float(top2[0] - top2[1]) < 5e-3, (b, t, float(top2[0] - top2[1]))
+                worst_gap = max(worst_gap, float(top2[0] - top2[1]))
                 near += 1
                 break
             exact += 1
@@ -63,6 +64,15 @@ def test_greedy_decode_is_bit_exact_off_near_ties(B, L, varlen):
             alive = want > 0
     print(f"greedy decode B={B} L={L}: {exact} tokens bit-exact, {near} rows stopped at a near-tie")
     assert exact >= B          # at least the first token of every row
+    if B == 512:               # BASELINE.json configs[2] at its size: keep the record
+        from gpu_util import write_report
+        write_report("config3_greedy_decode_512x36", dict(
+            case="config3_greedy_decode_512x36", rows=B, regions=L, tokens_bit_exact=exact,
+            rows_stopped_at_a_near_tie=near, largest_gap_at_a_stop=worst_gap, near_tie_gap_tolerance=5e-3,
+            logprob_rel_tolerance=2e-2,
+            note="free-running greedy decode with random-initialised weights: the 9488 logits of a row are "
+                 "nearly flat, so top-2 gaps below the bf16 resolution are frequent; every divergence is "
+                 "checked to sit at such a gap, rows are compared up to their first one"))
 
 
 @pytest.mark.parametrize("pool,use_abs,max_violation,whole_batch,only", [

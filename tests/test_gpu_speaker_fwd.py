@@ -45,14 +45,17 @@ def _run(mode, varlen, dropout, tau, B=6, L=9, seed=11):
     return ref, sp, forced_bt
 
 
-@pytest.mark.parametrize("mode,varlen,dropout,tau", [
-    ("gumbel", False, False, 1.0),
-    ("gumbel", True, True, 0.75),
-    ("multinomial", True, True, 1.0),
-    ("reinforce", False, True, 1.0),
+@pytest.mark.parametrize("mode,varlen,dropout,tau,B,L", [
+    ("gumbel", False, False, 1.0, 6, 9),
+    ("gumbel", True, True, 0.75, 6, 9),
+    ("multinomial", True, True, 1.0, 6, 9),
+    ("reinforce", False, True, 1.0, 6, 9),
+    # BASELINE.json configs[2] at its size: 512 rows x 36 regions, sampled decode
+    ("reinforce", False, True, 1.0, 512, 36),
+    ("gumbel", False, True, 1.0, 512, 36),
 ])
-def test_decode_matches_oracle(mode, varlen, dropout, tau):
-    ref, sp, forced_bt = _run(mode, varlen, dropout, tau)
+def test_decode_matches_oracle(mode, varlen, dropout, tau, B, L):
+    ref, sp, forced_bt = _run(mode, varlen, dropout, tau, B=B, L=L)
     T = forced_bt.shape[1]
     z = sp.t["z16_all"].float().cpu()        # the fp16 copy backward reads (sampling ran on fp32)
     lse = sp.t["lse"].cpu()
@@ -85,6 +88,11 @@ def test_decode_matches_oracle(mode, varlen, dropout, tau):
     print(f"[{mode}] worst rel logprob err {worst:.3e}, near-tie flips {flips}/{T * forced_bt.shape[0]}, "
           f"largest flipped gap {worst_gap:.3e}")
     assert worst <= BF16_TOL
+    if B == 512:
+        from gpu_util import write_report
+        write_report(f"config3_{mode}_decode_512x36", dict(
+            case=f"config3_{mode}_decode_512x36", rows=B, regions=L, worst_rel_logprob_err=worst,
+            near_tie_flips=flips, tokens=T * B, largest_flipped_gap=worst_gap))
     lp_tok = sp.t["logp"].cpu().t()                    # [B, T]
     ref_lp = torch.stack([ref.step_logprobs[t].gather(1, forced_bt[:, t:t + 1]).squeeze(1)
                           for t in range(T)], 1)
