@@ -25,6 +25,14 @@ import torch
 from . import engine as EN
 
 
+# Early exchange of gradient slices (FlatAdam.reduce_async) is OPT-IN (COOPCAP_EARLY_REDUCE=1).
+# Measured with tools/dp_probe.py (r2): on 2 GPUs the listener + logit slices exchanged under the
+# speaker's BPTT give 5.830 ms/step against 5.843 for one all-reduce after backward (5.565 without any
+# exchange) -- the NCCL kernels take from the BPTT kernels what they hide; on 8 GPUs (NVLS, 24
+# channels) four slices cost 5.989 ms/step against 5.891 for the single 104.5 MB all-reduce.
+_EARLY_REDUCE = os.environ.get("COOPCAP_EARLY_REDUCE", "0") == "1"
+
+
 class FlatAdam:
     """Adam over flat fp32 buckets (see the module docstring).
 
@@ -139,7 +147,7 @@ class FlatAdam:
         before the speaker's ~2.5 ms BPTT starts, so their exchange is hidden behind it.  The
         gradients must already sit in the bucket (grad_view) and be final.  Returns False (and does
         nothing) when the parameters do not form one contiguous bucket range of their own."""
-        if self._world() <= 1 or self.flat_grad.device.type != "cuda":
+        if self._world() <= 1 or self.flat_grad.device.type != "cuda" or not _EARLY_REDUCE:
             return False
         import torch.distributed as dist
         idx = sorted(self._index[id(p)] for p in params if id(p) in self._index)
