@@ -769,6 +769,12 @@ def main():
             roof = dict(kernel=KIND_NAMES[top], bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s",
                         frac=ach / pk["hbm"], traffic=None, peak_source=pk["source"],
                         launches_per_step=pln[top] / psteps, ms_per_step=pms[top] / psteps)
+        if roof is not None:
+            roof["how"] = ("per-class CUDA-event timeline of %d steps run right after the timed region: one event "
+                           "after every launch on the launching stream, i.e. plain stream order without the "
+                           "programmatic-dependent-launch overlap of the timed loop, so the class times sum to "
+                           "%.2f ms/step against %.2f ms/step timed; achieved = FLOPs declared at the launch "
+                           "sites / class time" % (psteps, total / psteps, ms_max / args.steps))
         # DRAM traffic of the same kernel class from the committed ncu capture of this build (per
         # launch, like `achieved`); `algorithmic_bytes_per_launch` is the operand + result bytes
         # declared at the launch sites, the figure `traffic` is to be compared with

@@ -410,6 +410,16 @@ __global__ void embed_scatter_kernel(const int64_t* __restrict__ tok, const int*
   const int s = int(row / B), b = int(row % B);
   if (s >= len[b]) return;
   float* dst = g_w_emb + tok[row] * E;
+  if ((E & 3) == 0) {
+    // four columns per 16-byte vector atomic (red.global.add.v4.f32)
+    for (int i = threadIdx.x * 4; i < E; i += blockDim.x * 4) {
+      const uint2 r = *reinterpret_cast<const uint2*>(demb16 + row * E + i);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+      const float2 a = __bfloat1622float2(h[0]), b2 = __bfloat1622float2(h[1]);
+      atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(a.x, a.y, b2.x, b2.y));
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < E; i += blockDim.x)
     atomicAdd(dst + i, __bfloat162float(demb16[row * E + i]));
 }

@@ -545,6 +545,20 @@ __global__ void embed_grad_kernel(const int64_t* __restrict__ tok_fed, const flo
   float* dst = g_embed + tok_fed[row] * E;
   const float* dx = d_xh + row * XH;
   const bf16* x = xh16 + row * XH;
+  if ((E & 3) == 0 && (XH & 3) == 0) {
+    // four columns per 16-byte vector atomic (red.global.add.v4.f32): a quarter of the L2 atomics
+    for (int i = threadIdx.x * 4; i < E; i += blockDim.x * 4) {
+      const float4 d = *reinterpret_cast<const float4*>(dx + i);
+      const uint2 xr = *reinterpret_cast<const uint2*>(x + i);
+      const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr);
+      const float2 x0 = __bfloat1622float2(xh[0]), x1 = __bfloat1622float2(xh[1]);
+      const float4 v = make_float4(x0.x > 0.f ? d.x * scale : 0.f, x0.y > 0.f ? d.y * scale : 0.f,
+                                   x1.x > 0.f ? d.z * scale : 0.f, x1.y > 0.f ? d.w * scale : 0.f);
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+        atomicAdd(reinterpret_cast<float4*>(dst + i), v);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
     if (__bfloat162float(x[i]) > 0.f) atomicAdd(dst + i, dx[i] * scale);
   }
@@ -775,7 +789,10 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
   if ((rc = wgrad(dscat16 + 3 * R, NS, c->att_res16, R, 2 * R, R, int(rows), g->g_w_a2c, R, s))) return rc;
   if ((rc = colsum_bf16(dscat16, rows, 5 * R, NS, g->g_b_gates, s))) return rc;
   if ((rc = colsum_bf16(dscat16 + 5 * R, rows, A, NS, g->g_b_h2att, s))) return rc;
-  if ((rc = colsum_bf16(dscat16 + 3 * R, rows, 2 * R, NS, g->g_b_a2c, s))) return rc;
+  // the a2c bias enters the two maxout pre-activations (columns 3R..5R) like the gate bias does: its
+  // gradient is that slice of g_b_gates (was a third pass over 34 MB of dscat16)
+  CC_CHECK_CUDA(cudaMemcpyAsync(g->g_b_a2c, g->g_b_gates + 3 * R, sizeof(float) * 2 * R,
+                                cudaMemcpyDeviceToDevice, s));
   // input embedding
   if (ps) {
     // steps >= 1 were fed v_{t-1} . embed:  g_embed[:V1] = sum_t v_{t-1}^T . dpre_t ; step 0 is a lookup
