@@ -38,7 +38,7 @@ import torch  # noqa: E402
 METRIC = "joint_gumbel_train_images_per_sec"
 UNIT = "images/s"
 KIND_NAMES = ["misc", "gemm", "att_fwd", "att_bwd", "att_deferred", "lstm", "sample", "st_bwd",
-              "logp_bwd", "gru", "hinge", "reduce", "pack", "adam"]
+              "logp_bwd", "gru", "hinge", "reduce", "pack", "adam", "logit_sample"]
 
 
 def parse():
@@ -800,10 +800,19 @@ def main():
             if pln[i] and pby[i] > 0:
                 breakdown[k]["achieved_GBps"] = pby[i] / (pms[i] * 1e-3) / 1e9
                 breakdown[k]["hbm_frac"] = breakdown[k]["achieved_GBps"] / pk["hbm"]
-        i = KIND_NAMES.index("gemm")
-        if pln[i]:
-            breakdown["gemm"]["achieved_TFLOPs"] = pfl[i] / (pms[i] * 1e-3) / 1e12
-            breakdown["gemm"]["tensor_frac"] = breakdown["gemm"]["achieved_TFLOPs"] / pk["tf_sustained"]
+        for k in ("gemm", "logit_sample"):
+            i = KIND_NAMES.index(k)
+            if i < nk and pln[i]:
+                breakdown[k]["achieved_TFLOPs"] = pfl[i] / (pms[i] * 1e-3) / 1e12
+                breakdown[k]["tensor_frac"] = breakdown[k]["achieved_TFLOPs"] / pk["tf_sustained"]
+        # all tcgen05 launches together (the plain GEMMs and the 16 fused logit + sampling launches,
+        # which are bound by the ALU work of their epilogue): r1's "gemm" class
+        ig, il = KIND_NAMES.index("gemm"), KIND_NAMES.index("logit_sample")
+        if roof is not None and il < nk and pln[ig] and pln[il]:
+            tf_all = (pfl[ig] + pfl[il]) / ((pms[ig] + pms[il]) * 1e-3) / 1e12
+            roof["all_tensor_core_launches"] = dict(
+                launches_per_step=(pln[ig] + pln[il]) / psteps, ms_per_step=(pms[ig] + pms[il]) / psteps,
+                achieved=tf_all, frac=tf_all / pk["tf_sustained"])
         del resident
 
     # ---------------- the other BASELINE.json configurations (side lines, rank 0) ----------------

@@ -56,6 +56,7 @@ enum ProfKind : int {
   PROF_REDUCE,
   PROF_PACK,
   PROF_ADAM,
+  PROF_LOGIT_SAMPLE,   // the logit GEMM with the sampler in its epilogue: a tcgen05 contraction bound by ALU issue
   PROF_NKINDS
 };
 // counts the launch; when the timeline is enabled also records an event on `stream` so that the

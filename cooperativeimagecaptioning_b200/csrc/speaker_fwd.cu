@@ -535,7 +535,7 @@ static int logit_sample_step(const coopcap_speaker* c, int t, const bf16* out16_
   }
   if (rc) return rc;
   // dense contraction; algorithmic bytes of the fused sampler: the fp16 logits written once
-  prof_mark(PROF_GEMM, s, 2.0 * double(B) * V1 * R, 2.0 * (double(B) * R + double(V1) * R) + 2.0 * double(B) * V1);
+  prof_mark(PROF_LOGIT_SAMPLE, s, 2.0 * double(B) * V1 * R, 2.0 * (double(B) * R + double(V1) * R) + 2.0 * double(B) * V1);
   const int nrec = LS_RECS_PER_TILE * ((V1 + LS_BN - 1) / LS_BN);
   CC_CHECK_CUDA(launch_pdl(
       sample_finish_kernel, dim3(B), dim3(FIN_THREADS), 0, s, static_cast<const float*>(c->ls_part), nrec,

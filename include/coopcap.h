@@ -667,7 +667,8 @@ uint64_t coopcap_cider_hash(uint64_t key);
  * launch; the library's launches on one stream run back to back, so the gap between consecutive
  * events is that launch's duration); coopcap_prof_report sums per kernel class (index = ProfKind in
  * csrc/common.cuh: 0 misc, 1 gemm, 2 att_fwd, 3 att_bwd, 4 att_deferred, 5 lstm, 6 sample,
- * 7 st_bwd, 8 logp_bwd, 9 gru, 10 hinge, 11 reduce, 12 pack, 13 adam) the elapsed ms, the
+ * 7 st_bwd, 8 logp_bwd, 9 gru, 10 hinge, 11 reduce, 12 pack, 13 adam, 14 logit_sample = the logit
+ * GEMM with the sampler in its epilogue) the elapsed ms, the
  * algorithmic FLOPs / bytes the launches declared, and the launch count, then clears the timeline. */
 long long coopcap_launch_count(void);
 int coopcap_prof_kinds(void);

@@ -15,9 +15,10 @@ from collections import OrderedDict
 
 CLASSES = [
     ("adam", r"clamp_adam"),
-    # the fused logit GEMM + sampler and the fused cell steps are tcgen05 contractions: bench.py's
-    # timeline counts them in the gemm class too (prof_mark(PROF_GEMM, ...) at their launch sites)
-    ("gemm", r"gemm_tc_kernel|gemm_simt|logit_sample_kernel|cell_step_kernel"), ("att_fwd", r"attention_fwd"),
+    # same classes as bench.py's timeline (prof_mark(...) at the launch sites): the fused logit GEMM +
+    # sampler is its own class, the opt-in fused cell steps count as GEMMs
+    ("logit_sample", r"logit_sample_kernel"),
+    ("gemm", r"gemm_tc_kernel|gemm_simt|cell_step_kernel"), ("att_fwd", r"attention_fwd"),
     ("att_bwd", r"attention_bwd"), ("att_deferred", r"attention_deferred"), ("lstm", r"lstm_"),
     ("sample", r"sample_kernel|ps_vec|ps_mask|ban_prev"), ("st_bwd", r"st_bwd"), ("logp_bwd", r"logp_bwd"),
     ("gru", r"gru_"), ("hinge", r"hinge|l2norm|pool_kernel"),
