@@ -98,3 +98,46 @@ def test_shared_embedding_steps_like_two_torch_adams(reward):
     # the shared embedding really moved (it was orphaned before the fix)
     fresh = _Agents(True).cuda()
     assert float((mine.vse["embed"].weight - fresh.vse["embed"].weight).abs().max()) > 1e-3
+
+
+def test_learning_rate_schedule_of_train_py_drives_the_optimizers():
+    """train.py:50-76 `update_learning_rate`: the decayed rate is written into
+    `optimizer.param_groups[*]['lr']` of every optimizer of the nested dict (misc/utils.py:60-62
+    `set_lr`) between steps.  FlatAdam must take its step size from there, like torch's Adam."""
+    from cooperativeimagecaptioning_b200 import optimizer as OPT
+    opt = argparse.Namespace(is_alternating=1, alternating_turn=["speaker", "listener"],
+                             retrieval_reward="gumbel", start_from=None, share_embed=0,
+                             learning_rate=5e-3, weight_decay=0.0, grad_clip=0.1, phase=None,
+                             learning_rate_decay_start=0, learning_rate_decay_every=1,
+                             learning_rate_decay_rate=0.5)
+    mine, ref = _Agents(False).cuda(), _Agents(False).cuda()
+    ref.load_state_dict(mine.state_dict())
+    od = OPT.load_optimizer(mine, opt)
+    r_spk = torch.optim.Adam(list(ref.caption_generator.parameters()), lr=5e-3)
+    r_lis = torch.optim.Adam(list(ref.vse.parameters()), lr=5e-3)
+    gen = torch.Generator().manual_seed(5)
+    for epoch in range(1, 5):
+        # the reference's loop body, verbatim in structure (gumbel case: every optimizer under 'speaker')
+        frac = (epoch - opt.learning_rate_decay_start) // opt.learning_rate_decay_every
+        opt.current_lr = opt.learning_rate * opt.learning_rate_decay_rate ** frac
+        for agent_in in od["speaker"].keys():
+            OPT.set_lr(od["speaker"][agent_in], opt.current_lr)
+        for o in (r_spk, r_lis):
+            for group in o.param_groups:
+                group["lr"] = opt.current_lr
+        ids = torch.randint(0, 37, (12,), generator=gen).cuda()
+        optimizer = od["speaker"]
+        OPT.zeroing_optimizer(opt, od, optimizer)
+        mine(ids).backward()
+        OPT.update_optimizer(od, optimizer, opt)
+        for o in (r_spk, r_lis):
+            o.zero_grad()
+        ref(ids).backward()
+        for o in (r_spk, r_lis):
+            for p in o.param_groups[0]["params"]:
+                if p.grad is not None:
+                    p.grad.clamp_(-0.1, 0.1)
+            o.step()
+        for (n, a), (_, b) in zip(mine.named_parameters(), ref.named_parameters()):
+            assert _rel(a.data, b.data) <= 2e-6, (epoch, n)
+    assert abs(opt.current_lr - 5e-3 * 0.5 ** 4) < 1e-12
