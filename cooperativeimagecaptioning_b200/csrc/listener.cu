@@ -24,6 +24,8 @@ int wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, 
 // emb16[s, b, :] = bf16(W_emb[tok[s, b], :])                           (VSEFCModel.py:102-106)
 __global__ void gather_embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ w_emb,
                                     int E, bf16* __restrict__ emb16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t row = blockIdx.x;
   const float4* src = reinterpret_cast<const float4*>(w_emb + tok[row] * E);
   uint2* dst = reinterpret_cast<uint2*>(emb16 + row * E);
@@ -87,6 +89,8 @@ __global__ void gru_fwd_kernel(const float* __restrict__ gi, const float* __rest
 // y = x / (||x||_2 + 1e-7), one CTA (256 threads) per row          (VSEFCModel.py:12-17)
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int M,
                                   int passthrough, int use_abs) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   const float* xr = x + int64_t(blockIdx.x) * M;
   float* yr = y + int64_t(blockIdx.x) * M;
@@ -102,6 +106,8 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict
 __global__ void l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                   float* __restrict__ dx, bf16* __restrict__ dx16, int M,
                                   int passthrough, int use_abs) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   const float* xr = x + int64_t(blockIdx.x) * M;
   const float* dr = dy + int64_t(blockIdx.x) * M;
@@ -129,6 +135,8 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ x, const float* __re
 //   cost_im[j] = relu(margin + max_{i != j} S_ij - S_jj)   (image retrieval, column max)
 __global__ void hinge_rows_kernel(const float* __restrict__ S, int B, float margin,
                                   float* __restrict__ cost_s, int* __restrict__ arg_s) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sv[8];
   __shared__ int si[8];
   const int i = blockIdx.x;
@@ -159,6 +167,8 @@ __global__ void hinge_rows_kernel(const float* __restrict__ S, int B, float marg
 
 __global__ void hinge_cols_kernel(const float* __restrict__ S, int B, float margin,
                                   float* __restrict__ cost_im, int* __restrict__ arg_im) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sv[8][33];
   __shared__ int si[8][33];
   const int j = blockIdx.x * 32 + threadIdx.x;
@@ -287,6 +297,8 @@ __global__ void pool_kernel(const float* __restrict__ h32, const int* __restrict
 __global__ void hinge_finish_kernel(const float* __restrict__ cost_s, const float* __restrict__ cost_im,
                                     int B, int only, float* __restrict__ loss_rows,
                                     float* __restrict__ loss) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   float acc = 0.f;
   for (int i = threadIdx.x; i < B; i += 256) {
@@ -308,6 +320,8 @@ __global__ void hinge_bwd_kernel(const float* __restrict__ im, const float* __re
                                  const int* __restrict__ arg_s, const int* __restrict__ arg_im,
                                  const float* __restrict__ g_loss, const float* __restrict__ g_rows,
                                  int only, int M, float* __restrict__ d_im, float* __restrict__ d_cap) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x;
   const float g = g_loss ? g_loss[0] : g_rows[i];
   const bool do_s = (only != 1) && cost_s[i] > 0.f && g != 0.f;
@@ -406,6 +420,8 @@ __global__ void gru_bwd_kernel(float* __restrict__ dh, const float* __restrict__
 __global__ void embed_scatter_kernel(const int64_t* __restrict__ tok, const int* __restrict__ len,
                                      const bf16* __restrict__ demb16, int B, int E,
                                      float* __restrict__ g_w_emb) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t row = blockIdx.x;
   const int s = int(row / B), b = int(row % B);
   if (s >= len[b]) return;
@@ -449,11 +465,11 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
     e.alpha = 1.f; e.bias = c->b_img; e.C = c->img_pre; e.ldc = M;
     if ((rc = gemm_run(0, 0, 0, c->fc16, F, c->w_img16, F, B, M, F, 1, 0, e, s))) return rc;
   }
-  l2norm_fwd_kernel<<<B, 256, 0, s>>>(c->img_pre, c->im, M, c->no_imgnorm, c->use_abs);
+  CC_CHECK_CUDA(launch_pdl(l2norm_fwd_kernel, dim3(B), dim3(256), size_t(0), s, c->img_pre, c->im, M, c->no_imgnorm, c->use_abs));
   CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   // caption branch                                                    (VSEFCModel.py:83-140)
   if (!c->emb_given) {
-    gather_embed_kernel<<<S * B, 128, 0, s>>>(c->tok, c->w_emb, E, reinterpret_cast<bf16*>(c->emb16));
+    CC_CHECK_CUDA(launch_pdl(gather_embed_kernel, dim3(S * B), dim3(128), size_t(0), s, c->tok, c->w_emb, E, reinterpret_cast<bf16*>(c->emb16)));
     CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
   }
   {
@@ -491,7 +507,7 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
     CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
     pooled = c->cap_pre;
   }
-  l2norm_fwd_kernel<<<B, 256, 0, s>>>(pooled, c->cap, M, 0, c->use_abs);
+  CC_CHECK_CUDA(launch_pdl(l2norm_fwd_kernel, dim3(B), dim3(256), size_t(0), s, pooled, c->cap, M, 0, c->use_abs));
   CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   // scores (tf32 operands: the hinge compares score differences against a 0.2 margin)
   {
@@ -505,14 +521,14 @@ int listener_fwd(const coopcap_listener* c, cudaStream_t s) {
     hinge_sum_cols_kernel<<<(B + 31) / 32, dim3(32, 8), 0, s>>>(c->scores, B, c->margin, c->cost_im);
     CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   } else {
-    hinge_rows_kernel<<<B, 256, 0, s>>>(c->scores, B, c->margin, c->cost_s, c->arg_s);
+    CC_CHECK_CUDA(launch_pdl(hinge_rows_kernel, dim3(B), dim3(256), size_t(0), s, c->scores, B, c->margin, c->cost_s, c->arg_s));
     CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
-    hinge_cols_kernel<<<(B + 31) / 32, dim3(32, 8), 0, s>>>(c->scores, B, c->margin, c->cost_im,
-                                                             c->arg_im);
+    CC_CHECK_CUDA(launch_pdl(hinge_cols_kernel, dim3((B + 31) / 32), dim3(32, 8), size_t(0), s, c->scores, B, c->margin, c->cost_im,
+                                                             c->arg_im));
     CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   }
-  hinge_finish_kernel<<<1, 256, 0, s>>>(c->cost_s, c->cost_im, B, c->only_one_retrieval,
-                                        c->loss_rows, c->loss);
+  CC_CHECK_CUDA(launch_pdl(hinge_finish_kernel, dim3(1), dim3(256), size_t(0), s, c->cost_s, c->cost_im, B, c->only_one_retrieval,
+                                        c->loss_rows, c->loss));
   CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   return CC_OK;
 }
@@ -547,26 +563,26 @@ int listener_bwd(const coopcap_listener* c, const coopcap_listener_grads* g, cud
   } else {
     CC_CHECK_CUDA(cudaMemsetAsync(g->d_im, 0, sizeof(float) * B * M, s));
     CC_CHECK_CUDA(cudaMemsetAsync(g->d_cap, 0, sizeof(float) * B * M, s));
-    hinge_bwd_kernel<<<B, 256, 0, s>>>(c->im, c->cap, c->cost_s, c->cost_im, c->arg_s, c->arg_im,
+    CC_CHECK_CUDA(launch_pdl(hinge_bwd_kernel, dim3(B), dim3(256), size_t(0), s, c->im, c->cap, c->cost_s, c->cost_im, c->arg_s, c->arg_im,
                                        g->g_loss, g->g_rows, c->only_one_retrieval, M, g->d_im,
-                                       g->d_cap);
+                                       g->d_cap));
     CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
   }
   if (g->need_param_grads) {
-    l2norm_bwd_kernel<<<B, 256, 0, s>>>(c->img_pre, g->d_im, nullptr,
+    CC_CHECK_CUDA(launch_pdl(l2norm_bwd_kernel, dim3(B), dim3(256), size_t(0), s, c->img_pre, g->d_im, nullptr,
                                         reinterpret_cast<bf16*>(g->d_img_pre16), M, c->no_imgnorm,
-                                        c->use_abs);
+                                        c->use_abs));
     CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
     if ((rc = wgrad(g->d_img_pre16, M, c->fc16, F, M, F, B, g->g_w_img, F, s))) return rc;
     if ((rc = colsum_bf16(g->d_img_pre16, B, M, M, g->g_b_img, s))) return rc;
   }
   if (c->pool_type == 0) {
-    l2norm_bwd_kernel<<<B, 256, 0, s>>>(c->h32 + int64_t(S) * B * M, g->d_cap, g->dh, nullptr, M, 0,
-                                        c->use_abs);
+    CC_CHECK_CUDA(launch_pdl(l2norm_bwd_kernel, dim3(B), dim3(256), size_t(0), s, c->h32 + int64_t(S) * B * M, g->d_cap, g->dh, nullptr, M, 0,
+                                        c->use_abs));
   } else {
     // the pooled state feeds every valid step (mean) / its arg-max step (max): gru_bwd_kernel adds it
     CC_REQUIRE(g->d_pool != nullptr, "listener_bwd: pool mean / max need d_pool");
-    l2norm_bwd_kernel<<<B, 256, 0, s>>>(c->cap_pre, g->d_cap, g->d_pool, nullptr, M, 0, c->use_abs);
+    CC_CHECK_CUDA(launch_pdl(l2norm_bwd_kernel, dim3(B), dim3(256), size_t(0), s, c->cap_pre, g->d_cap, g->d_pool, nullptr, M, 0, c->use_abs));
     CC_CHECK_CUDA(cudaMemsetAsync(g->dh, 0, sizeof(float) * B * M, s));
   }
   CC_LAUNCH_CHECK_K(PROF_HINGE, s, 0.0, 0.0);
@@ -601,9 +617,9 @@ int listener_bwd(const coopcap_listener* c, const coopcap_listener_grads* g, cud
     if ((rc = colsum_bf16(d_gi16, K, 3 * M, 3 * M, g->g_b_ih, s))) return rc;
     if ((rc = colsum_bf16(d_gh16, K, 3 * M, 3 * M, g->g_b_hh, s))) return rc;
     if (!c->emb_given) {   // dense captions: coopcap_caption_embed_dense_bwd forms this gradient
-      embed_scatter_kernel<<<S * B, 128, 0, s>>>(c->tok, c->len,
+      CC_CHECK_CUDA(launch_pdl(embed_scatter_kernel, dim3(S * B), dim3(128), size_t(0), s, c->tok, c->len,
                                                  reinterpret_cast<const bf16*>(g->demb16), B, E,
-                                                 g->g_w_emb);
+                                                 g->g_w_emb));
       CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
     }
   }

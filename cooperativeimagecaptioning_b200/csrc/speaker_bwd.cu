@@ -21,6 +21,8 @@ size_t attention_smem_bytes(int A, int R, int L);
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ src, int64_t rows, int cols, int64_t ld,
                               float* __restrict__ out, int64_t rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sm[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int64_t r0 = int64_t(blockIdx.y) * rows_per_block;
@@ -47,6 +49,8 @@ __global__ void colsum_kernel(const T* __restrict__ src, int64_t rows, int cols,
 __global__ void __launch_bounds__(256)
 colsum_bf16x8_kernel(const bf16* __restrict__ src, int64_t rows, int cols, int64_t ld,
                      float* __restrict__ out, int64_t rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sm[8][32][9];
   const int c0 = (blockIdx.x * 32 + threadIdx.x) * 8;
   const int64_t r0 = int64_t(blockIdx.y) * rows_per_block;
@@ -98,8 +102,8 @@ static int colsum_impl(const T* src, int64_t rows, int cols, int64_t ld, float* 
       if (row_blocks > (rows + 63) / 64) row_blocks = (rows + 63) / 64;
       if (row_blocks < 1) row_blocks = 1;
       const int64_t rpb = (rows + row_blocks - 1) / row_blocks;
-      colsum_bf16x8_kernel<<<dim3(col_blocks, (unsigned)row_blocks), dim3(32, 8), 0, s>>>(
-          reinterpret_cast<const bf16*>(src), rows, cols, ld, out, rpb);
+      CC_CHECK_CUDA(launch_pdl(colsum_bf16x8_kernel, dim3(col_blocks, (unsigned)row_blocks), dim3(32, 8), size_t(0), s, 
+          reinterpret_cast<const bf16*>(src), rows, cols, ld, out, rpb));
       CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
       return CC_OK;
     }
@@ -109,8 +113,8 @@ static int colsum_impl(const T* src, int64_t rows, int cols, int64_t ld, float* 
   if (row_blocks > (rows + 63) / 64) row_blocks = (rows + 63) / 64;
   if (row_blocks < 1) row_blocks = 1;
   const int64_t rpb = (rows + row_blocks - 1) / row_blocks;
-  colsum_kernel<T><<<dim3(col_blocks, (unsigned)row_blocks), dim3(32, 8), 0, s>>>(src, rows, cols,
-                                                                                  ld, out, rpb);
+  CC_CHECK_CUDA(launch_pdl(colsum_kernel<T>, dim3(col_blocks, (unsigned)row_blocks), dim3(32, 8), size_t(0), s, src, rows, cols,
+                                                                                  ld, out, rpb));
   CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
   return CC_OK;
 }
@@ -526,6 +530,8 @@ attention_deferred_bwd_kernel(const bf16* __restrict__ p_att16, const int* __res
 // d_pre16 = bf16(d_att_e * scale * [att_e > 0])   (relu and dropout share the "output > 0" mask)
 __global__ void mask_pre_kernel(const float* __restrict__ d_att_e, const bf16* __restrict__ att_e16,
                                 int64_t n4, float scale, bf16* __restrict__ d_pre16) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4;
        i += int64_t(gridDim.x) * blockDim.x) {
     const float4 d = *reinterpret_cast<const float4*>(d_att_e + 4 * i);
@@ -541,6 +547,8 @@ __global__ void mask_pre_kernel(const float* __restrict__ d_att_e, const bf16* _
 __global__ void embed_grad_kernel(const int64_t* __restrict__ tok_fed, const float* __restrict__ d_xh,
                                   const bf16* __restrict__ xh16, int E, int XH, float scale,
                                   float* __restrict__ g_embed) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t row = blockIdx.x;
   float* dst = g_embed + tok_fed[row] * E;
   const float* dx = d_xh + row * XH;
@@ -799,9 +807,9 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
     if (n > 1 &&
         (rc = wgrad(c->soft16, V1, ps_dpre16 + int64_t(B) * E, E, V1, E, int(rows - B), g->g_embed, E, s)))
       return rc;
-    embed_grad_kernel<<<(unsigned)B, 128, 0, s>>>(c->tok_fed, g->d_xh, xh16, E, XH, scale, g->g_embed);
+    CC_CHECK_CUDA(launch_pdl(embed_grad_kernel, dim3((unsigned)B), dim3(128), size_t(0), s, c->tok_fed, g->d_xh, xh16, E, XH, scale, g->g_embed));
   } else {
-    embed_grad_kernel<<<(unsigned)rows, 128, 0, s>>>(c->tok_fed, g->d_xh, xh16, E, XH, scale, g->g_embed);
+    CC_CHECK_CUDA(launch_pdl(embed_grad_kernel, dim3((unsigned)rows), dim3(128), size_t(0), s, c->tok_fed, g->d_xh, xh16, E, XH, scale, g->g_embed));
   }
   CC_LAUNCH_CHECK_K(PROF_REDUCE, s, 0.0, 0.0);
   // region tensors: deferred accumulation over the steps, then the prologue layers
@@ -814,10 +822,10 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
       const size_t smem = attention_deferred2_smem<512, ST>(c->L, n);
       CC_REQUIRE(smem <= 227 * 1024, "deferred attention backward needs %zu B of shared memory", smem);
       if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_deferred2_kernel<512, ST>), int(smem)))) return rc;
-      attention_deferred2_kernel<512, ST><<<B, ATT_THREADS, smem, s>>>(
+      CC_CHECK_CUDA(launch_pdl(attention_deferred2_kernel<512, ST>, dim3(B), dim3(ATT_THREADS), size_t(smem), s, 
           reinterpret_cast<const bf16*>(c->p_att16), c->att_off, c->L, c->s_all, NS, 5 * R,
           int64_t(B) * NS, c->w_alpha, g->d_att_res, c->att_w, g->de, NL, n, B, g->d_att_e,
-          reinterpret_cast<bf16*>(g->d_p_att16), galpha_part, gbias_part, c->att_order);
+          reinterpret_cast<bf16*>(g->d_p_att16), galpha_part, gbias_part, c->att_order));
     } else {
       const int Lp = (c->L + 3) & ~3;
       const int groups = ATT_THREADS / (A / 8);
@@ -844,9 +852,9 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
     const int64_t n4 = int64_t(NL) * R / 4;
     int64_t blocks = (n4 + 255) / 256;
     if (blocks > int64_t(num_sms()) * 16) blocks = int64_t(num_sms()) * 16;
-    mask_pre_kernel<<<(unsigned)blocks, 256, 0, s>>>(g->d_att_e,
+    CC_CHECK_CUDA(launch_pdl(mask_pre_kernel, dim3((unsigned)blocks), dim3(256), size_t(0), s, g->d_att_e,
                                                      reinterpret_cast<const bf16*>(c->att_e16), n4,
-                                                     scale, reinterpret_cast<bf16*>(g->d_pre16));
+                                                     scale, reinterpret_cast<bf16*>(g->d_pre16)));
     CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
     if ((rc = wgrad(g->d_p_att16, A, c->att_e16, R, A, R, NL, g->g_w_ctx2att, R, s))) return rc;
     if ((rc = wgrad(g->d_pre16, R, c->att16, c->D, R, c->D, NL, g->g_w_att_embed, c->D, s))) return rc;
@@ -860,6 +868,8 @@ __global__ void clamp_adam_kernel(float* __restrict__ p, const float* __restrict
                                   float* __restrict__ m, float* __restrict__ v, int64_t n,
                                   float grad_scale, float clip, float step_size, float b1c, float b2,
                                   float b2c, float eps, float wd, float bc2_sqrt) {
+  pdl_launch_dependents();
+  pdl_wait();
   // b1c = 1 - beta1, b2c = 1 - beta2, rounded from double like torch's scalar arguments
   const int64_t n4 = n / 4;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4;
@@ -952,10 +962,10 @@ int coopcap_clamp_adam(float* param, const float* grad, float* exp_avg, float* e
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks > int64_t(num_sms()) * 8) blocks = int64_t(num_sms()) * 8;
   if (blocks < 1) blocks = 1;
-  clamp_adam_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  CC_CHECK_CUDA(launch_pdl(clamp_adam_kernel, dim3((unsigned)blocks), dim3(256), size_t(0), reinterpret_cast<cudaStream_t>(stream), 
       param, grad, exp_avg, exp_avg_sq, n, float(grad_scale), float(clip), float(lr / bc1),
       float(1.0 - beta1), float(beta2), float(1.0 - beta2), float(eps), float(weight_decay),
-      float(sqrt(bc2)));
+      float(sqrt(bc2))));
   CC_LAUNCH_CHECK_K(PROF_ADAM, reinterpret_cast<cudaStream_t>(stream), 0.0, 28.0 * double(n));
   return CC_OK;
 }

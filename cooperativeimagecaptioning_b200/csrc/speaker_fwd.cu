@@ -22,6 +22,8 @@ using bf16 = __nv_bfloat16;
 // fp32 [rows, cols] -> bf16 block of a wider matrix (ld_dst), 4 elements per thread
 __global__ void cast_block_kernel(const float* __restrict__ src, int64_t rows, int cols,
                                   bf16* __restrict__ dst, int64_t ld_dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t n4 = rows * (cols / 4);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4;
        i += int64_t(gridDim.x) * blockDim.x) {
@@ -44,7 +46,7 @@ int cast_block(const float* src, int64_t rows, int cols, void* dst, int64_t ld_d
   const int64_t n4 = rows * (cols / 4);
   int64_t want = (n4 + 255) / 256, cap_blocks = int64_t(num_sms()) * 16;
   int grid = int(want < cap_blocks ? want : cap_blocks);
-  cast_block_kernel<<<grid, 256, 0, s>>>(src, rows, cols, reinterpret_cast<bf16*>(dst), ld_dst);
+  CC_CHECK_CUDA(launch_pdl(cast_block_kernel, dim3(grid), dim3(256), size_t(0), s, src, rows, cols, reinterpret_cast<bf16*>(dst), ld_dst));
   CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
   return CC_OK;
 }
@@ -70,6 +72,8 @@ struct CastJobs {
   int n;
 };
 __global__ void __launch_bounds__(256) cast_multi_kernel(const CastJobs J) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = J.first[J.n];
   for (int64_t g = int64_t(blockIdx.x) * 256 + threadIdx.x; g < total; g += int64_t(gridDim.x) * 256) {
     int k = 0;
@@ -104,7 +108,7 @@ struct CastBatch {
     static const int per_sm = [] { const char* e = getenv("COOPCAP_CAST_CTAS_PER_SM"); return e ? atoi(e) : 16; }();
     const int64_t cap = int64_t(num_sms()) * per_sm;
     if (grid > cap) grid = cap;
-    cast_multi_kernel<<<unsigned(grid), 256, 0, s>>>(J);
+    CC_CHECK_CUDA(launch_pdl(cast_multi_kernel, dim3(unsigned(grid)), dim3(256), size_t(0), s, J));
     CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 0.0);
     return CC_OK;
   }
@@ -152,6 +156,8 @@ template <int PACK_ROWS>
 __global__ void __launch_bounds__(PACK_THREADS)
 pack_att_kernel(const float* __restrict__ att, const int* __restrict__ off, int B, int L, int D,
                 int NL, bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int d4 = D / 4;                      // float4 per row
   const int n_items = (NL + PACK_ROWS - 1) / PACK_ROWS;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -203,6 +209,8 @@ __global__ void start_step_kernel(const float* __restrict__ embed, int64_t start
                                   const uint8_t* __restrict__ keep_embed, uint64_t seed,
                                   float drop_p, bf16* __restrict__ xh0, float* __restrict__ c0,
                                   int64_t* __restrict__ tok_fed0) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int64_t start = start_rows ? start_rows[b] : start_scalar;
   bf16* row = xh0 + int64_t(b) * (E + R);
@@ -427,6 +435,8 @@ ps_mask_kernel(const uint8_t* __restrict__ unf, int V1, bf16* __restrict__ soft1
 // cap_len[b] = min(k_b + 2, n + 1)                    (AlternatingJointModel.py:353-355)
 __global__ void caption_summary_kernel(const int64_t* __restrict__ tok_out, int B, int n_steps,
                                        int* __restrict__ n_out, int* __restrict__ cap_len) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ int s_max;
   if (threadIdx.x == 0) s_max = 0;
   __syncthreads();
@@ -593,8 +603,8 @@ int speaker_prologue_fwd(const coopcap_speaker* c, cudaStream_t s) {
   if (rc) return rc;
   if (!c->att_prepacked) {
     CC_REQUIRE(c->att_feats != nullptr, "speaker: att_feats is null and att16 is not pre-packed");
-    pack_att_kernel<1><<<c->NL, PACK_THREADS, 0, s>>>(c->att_feats, c->att_off, c->B, c->L, c->D, c->NL,
-                                          reinterpret_cast<bf16*>(c->att16));
+    CC_CHECK_CUDA(launch_pdl(pack_att_kernel<1>, dim3(c->NL), dim3(PACK_THREADS), size_t(0), s, c->att_feats, c->att_off, c->B, c->L, c->D, c->NL,
+                                          reinterpret_cast<bf16*>(c->att16)));
     CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 6.0 * c->NL * c->D);
   }
   EpiStoreParams ep = {};
@@ -626,8 +636,8 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
   bf16* xh16 = reinterpret_cast<bf16*>(c->xh16);
   bf16* att_res16 = reinterpret_cast<bf16*>(c->att_res16);
   bf16* out16 = reinterpret_cast<bf16*>(c->out16);
-  start_step_kernel<<<B, 128, 0, s>>>(c->embed, c->start_token, c->start_tokens, B, E, R, c->keep_embed, c->seed,
-                                      c->drop_p, xh16, c->c_all, c->tok_fed);
+  CC_CHECK_CUDA(launch_pdl(start_step_kernel, dim3(B), dim3(128), size_t(0), s, c->embed, c->start_token, c->start_tokens, B, E, R, c->keep_embed, c->seed,
+                                      c->drop_p, xh16, c->c_all, c->tok_fed));
   CC_LAUNCH_CHECK_K(PROF_SAMPLE, s, 0.0, 0.0);
   for (int t = 0; t < c->n_steps; ++t) {
     float* s_t = c->s_all + int64_t(t) * B * NS;
@@ -689,7 +699,7 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     }
   }
   if (c->n_out && c->cap_len) {
-    caption_summary_kernel<<<1, 1024, 0, s>>>(c->tok_out, B, c->n_steps, c->n_out, c->cap_len);
+    CC_CHECK_CUDA(launch_pdl(caption_summary_kernel, dim3(1), dim3(1024), size_t(0), s, c->tok_out, B, c->n_steps, c->n_out, c->cap_len));
     CC_LAUNCH_CHECK_K(PROF_MISC, s, 0.0, 0.0);
   }
   return CC_OK;
@@ -750,7 +760,7 @@ int coopcap_pack_att_from_host(const float* att_feats_pinned, const int* att_off
   if (ctas > items) ctas = items;
   const float* src = reinterpret_cast<const float*>(dptr);
   bf16* dst = reinterpret_cast<bf16*>(att16);
-  if (rows_per_item == 1) pack_att_kernel<1><<<ctas, PACK_THREADS, 0, s>>>(src, att_off, B, L, D, NL, dst);
+  if (rows_per_item == 1) CC_CHECK_CUDA(launch_pdl(pack_att_kernel<1>, dim3(ctas), dim3(PACK_THREADS), size_t(0), s, src, att_off, B, L, D, NL, dst));
   else if (rows_per_item == 2) pack_att_kernel<2><<<ctas, PACK_THREADS, 0, s>>>(src, att_off, B, L, D, NL, dst);
   else pack_att_kernel<4><<<ctas, PACK_THREADS, 0, s>>>(src, att_off, B, L, D, NL, dst);
   CC_LAUNCH_CHECK_K(PROF_PACK, s, 0.0, 4.0 * NL * D);
