@@ -76,7 +76,7 @@ attention_fwd4_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bflo
                       const int* __restrict__ off, int Lfix, const int* __restrict__ order,
                       const float* __restrict__ s_row0, int64_t lds, int att_h_col,
                       const float* __restrict__ w_alpha, __nv_bfloat16* __restrict__ att_res16,
-                      float* att_w, int B) {
+                      float* att_w, int B, float* __restrict__ att_res32) {
   static_assert(AR == 512, "lane -> 2 x 8 columns mapping; one region row = 1 KB");
   constexpr int EPL = AR / 32;
   constexpr int ROWB = AR * 2;                    // bytes of one region row
@@ -210,6 +210,11 @@ attention_fwd4_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bflo
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (f1 * part[c0 + j] + f2 * other[c0 + j]) * inv;
       *reinterpret_cast<uint4*>(att_res16 + int64_t(b) * AR + c0) = float8_to_bf16x8(o);
+      if (att_res32) {      // fp32 copy for the single-pass backward (softmax-backward mean, see bwd5)
+        float* d = att_res32 + int64_t(b) * AR + c0;
+        *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
     }
     for (int l = lane; l < n; l += 32) wrow[l] = __expf(wrow[l] - M) * inv;
     // the partner must be done with this warp's partials before the next row's copies land on them
@@ -361,6 +366,160 @@ attention_bwd4_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bflo
       issue(ng + c + ATT4_STAGES);
     }
     it += 2 * ng;
+    cp_async_wait<0>();
+    float* part = reinterpret_cast<float*>(ring);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float* d = part + h * 256 + lane * 8;
+      *reinterpret_cast<float4*>(d) = make_float4(acc[h * 8], acc[h * 8 + 1], acc[h * 8 + 2], acc[h * 8 + 3]);
+      *reinterpret_cast<float4*>(d + 4) =
+          make_float4(acc[h * 8 + 4], acc[h * 8 + 5], acc[h * 8 + 6], acc[h * 8 + 7]);
+    }
+    pair_barrier(map.pair);
+    {
+      const float* other = reinterpret_cast<const float*>(smem4 + partner * (ATT4_STAGES * ATT4_STAGE_BYTES));
+      const int c0 = half * 256 + lane * 8;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (part[c0 + j] + other[c0 + j]) * __ldg(w_alpha + c0 + j);
+      *reinterpret_cast<uint4*>(dscat + int64_t(b) * lds + att_h_col + c0) = float8_to_bf16x8(o);
+    }
+    if (rank + gridDim.x * ATT4_ROWS < B) pair_barrier(map.pair);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// v5 backward: ONE pass.  The softmax backward needs dot = sum_l w_l dw_l with dw_l = <d_att_res,
+// att_e_l>, which is why v4 walks att_e first and p_att second.  But
+//     sum_l w_l <d_att_res, att_e_l> = <d_att_res, sum_l w_l att_e_l> = <d_att_res, att_res>,
+// and att_res is what the forward pass produced (kept in fp32 for this purpose): the mean is known
+// before the first region arrives, so (att_e, p_att) stream through together exactly like in the
+// forward kernel -- ring items [p0 p1 e0 e1], no barrier between the two halves of a row until
+// their d_att_h partials meet.  Same arithmetic otherwise:
+//     de_l = w_l (dw_l - dot) ;  d_att_h[j] = alpha_j sum_l de_l (1 - tanh^2(p_att[l,j] + att_h[j]))
+// ------------------------------------------------------------------------------------------
+template <int AR>
+__global__ void __launch_bounds__(ATT4_THREADS, 1)
+attention_bwd5_kernel(const __nv_bfloat16* __restrict__ p_att16, const __nv_bfloat16* __restrict__ att_e16,
+                      const int* __restrict__ off, int Lfix, const int* __restrict__ order,
+                      const float* __restrict__ s_row0, int64_t lds, int att_h_col,
+                      const float* __restrict__ w_alpha, const float* __restrict__ d_att_res,
+                      const float* __restrict__ att_res32, const float* __restrict__ att_w,
+                      float* de_out, __nv_bfloat16* __restrict__ dscat, int B) {
+  static_assert(AR == 512, "lane -> 2 x 8 columns mapping; one region row = 1 KB");
+  constexpr int EPL = AR / 32;
+  constexpr int ROWB = AR * 2;
+  extern __shared__ __align__(128) uint8_t smem4[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Att4Map map(warp);
+  const int half = map.half;
+  const int partner = 15 - warp;
+  uint8_t* ring = smem4 + warp * (ATT4_STAGES * ATT4_STAGE_BYTES);
+  pdl_launch_dependents();
+  pdl_wait();
+  uint32_t it = 0;
+  for (int rank = blockIdx.x + gridDim.x * map.pair; rank < B; rank += gridDim.x * ATT4_ROWS) {
+    const int b = order ? order[rank] : rank;
+    const int r0 = off ? off[b] : b * Lfix;
+    const int Lb = off ? off[b + 1] - r0 : Lfix;
+    const int n0 = (Lb + 1) >> 1;
+    const int a0 = half ? n0 : 0;                 // this warp: regions [a0, a0 + n)
+    const int n = half ? Lb - n0 : n0;
+    const int npair = (n + 1) >> 1;
+    const __nv_bfloat16* pg = p_att16 + int64_t(r0 + a0) * AR;
+    const __nv_bfloat16* eg = att_e16 + int64_t(r0 + a0) * AR;
+    auto issue = [&](int i) {
+      if (i < npair) {
+        uint8_t* dst = ring + ((it + i) % ATT4_STAGES) * ATT4_STAGE_BYTES;
+        const int pieces = min(2, n - 2 * i) * (ROWB / 512);
+        const uint8_t* ps = reinterpret_cast<const uint8_t*>(pg + int64_t(2 * i) * AR) + lane * 16;
+        const uint8_t* es = reinterpret_cast<const uint8_t*>(eg + int64_t(2 * i) * AR) + lane * 16;
+#pragma unroll
+        for (int k = 0; k < 2 * (ROWB / 512); ++k)
+          if (k < pieces) {
+            cp_async16(dst + k * 512 + lane * 16, ps + k * 512);
+            cp_async16(dst + 2 * ROWB + k * 512 + lane * 16, es + k * 512);
+          }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < ATT4_STAGES; ++i) issue(i);
+    // per-row vectors: d_att_res, att_h; dot = <d_att_res, att_res> (every warp covers all columns)
+    float dr[EPL], ah[EPL], acc[EPL];
+    float dot = 0.f;
+    {
+      const float* att_h = s_row0 + int64_t(b) * lds + att_h_col;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = h * 256 + lane * 8;
+        const float4 x = *reinterpret_cast<const float4*>(d_att_res + int64_t(b) * AR + c0);
+        const float4 y = *reinterpret_cast<const float4*>(d_att_res + int64_t(b) * AR + c0 + 4);
+        const float4 rx = *reinterpret_cast<const float4*>(att_res32 + int64_t(b) * AR + c0);
+        const float4 ry = *reinterpret_cast<const float4*>(att_res32 + int64_t(b) * AR + c0 + 4);
+        const float4 hx = *reinterpret_cast<const float4*>(att_h + c0);
+        const float4 hy = *reinterpret_cast<const float4*>(att_h + c0 + 4);
+        dr[h * 8 + 0] = x.x; dr[h * 8 + 1] = x.y; dr[h * 8 + 2] = x.z; dr[h * 8 + 3] = x.w;
+        dr[h * 8 + 4] = y.x; dr[h * 8 + 5] = y.y; dr[h * 8 + 6] = y.z; dr[h * 8 + 7] = y.w;
+        ah[h * 8 + 0] = hx.x; ah[h * 8 + 1] = hx.y; ah[h * 8 + 2] = hx.z; ah[h * 8 + 3] = hx.w;
+        ah[h * 8 + 4] = hy.x; ah[h * 8 + 5] = hy.y; ah[h * 8 + 6] = hy.z; ah[h * 8 + 7] = hy.w;
+        dot += x.x * rx.x + x.y * rx.y + x.z * rx.z + x.w * rx.w + y.x * ry.x + y.y * ry.y + y.z * ry.z +
+               y.w * ry.w;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) acc[j] = 0.f;
+    const float* wrow = att_w + r0 + a0;
+    float* drow = de_out + r0 + a0;
+    for (int i = 0; i < npair; ++i) {
+      const int st = (it + i) % ATT4_STAGES;
+      cp_async_wait<ATT4_STAGES - 1>();
+      __syncwarp();
+      const bool two = 2 * i + 1 < n;
+      const uint8_t* ps = ring + st * ATT4_STAGE_BYTES;
+      const uint8_t* es = ps + 2 * ROWB;
+      const int o1 = two ? ROWB : 0;              // a single-region stage re-reads region 0 (de = 0)
+      const float w0 = wrow[2 * i], w1 = two ? wrow[2 * i + 1] : 0.f;
+      float dw0 = 0.f, dw1 = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float f0[8], f1[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(es + (h * 256 + lane * 8) * 2), f0);
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(es + o1 + (h * 256 + lane * 8) * 2), f1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dw0 += dr[h * 8 + j] * f0[j];
+          dw1 += dr[h * 8 + j] * f1[j];
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dw0 += __shfl_xor_sync(0xffffffffu, dw0, o);
+        dw1 += __shfl_xor_sync(0xffffffffu, dw1, o);
+      }
+      const float de0 = w0 * (dw0 - dot), de1 = two ? w1 * (dw1 - dot) : 0.f;
+      if (lane == 0) {
+        drow[2 * i] = de0;
+        if (two) drow[2 * i + 1] = de1;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float f0[8], f1[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(ps + (h * 256 + lane * 8) * 2), f0);
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(ps + o1 + (h * 256 + lane * 8) * 2), f1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t0 = tanh_fast(f0[j] + ah[h * 8 + j]);
+          const float t1 = tanh_fast(f1[j] + ah[h * 8 + j]);
+          acc[h * 8 + j] += de0 * (1.f - t0 * t0) + de1 * (1.f - t1 * t1);
+        }
+      }
+      __syncwarp();                               // every lane is done with this stage
+      issue(i + ATT4_STAGES);
+    }
+    it += npair;
     cp_async_wait<0>();
     float* part = reinterpret_cast<float*>(ring);
 #pragma unroll

@@ -20,7 +20,7 @@ namespace coopcap {
 using bf16 = __nv_bfloat16;
 
 int attention_fwd_launch(const coopcap_speaker* c, const float* s_t, bf16* att_res16_t, float* att_w_t,
-                         cudaStream_t s);
+                         cudaStream_t s, float* att_res32_t);
 int lstm_fwd_launch(const coopcap_speaker* c, const float* s_t, const float* u_t, const float* c_prev,
                     float* c_next, bf16* h_out16, int64_t ld_h, bf16* out16_t, const uint8_t* keep,
                     uint64_t site, float drop_p, int rows, cudaStream_t s);
@@ -266,7 +266,7 @@ int speaker_beam_fwd(const coopcap_speaker* c, const coopcap_beam* bm, cudaStrea
     if ((rc = gemm_run(0, 0, 0, xh_cur, XH, c->w_cat16, XH, rows, NS, XH, 1, 0, e1, s))) return rc;
     for (int q = 0; q < bs; ++q)                   // slot q: the n_img images, the context's regions
       if ((rc = attention_fwd_launch(c, bm->s_t + int64_t(q) * n_img * NS, att_res16 + int64_t(q) * n_img * R,
-                                     bm->att_w + int64_t(q) * c->NL, s)))
+                                     bm->att_w + int64_t(q) * c->NL, s, nullptr)))
         return rc;
     EpiStoreParams e2 = {};
     e2.alpha = 1.f; e2.bias = c->b_a2c; e2.C = bm->u_t; e2.ldc = 2 * R;

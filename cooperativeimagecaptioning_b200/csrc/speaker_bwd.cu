@@ -754,7 +754,18 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
       e.alpha = 1.f; e.C = dres_t; e.ldc = R;
       if ((rc = gemm_run(0, 0, 1, ds_t + 3 * R, NS, c->w_a2c16, R, B, R, 2 * R, 1, 0, e, s))) return rc;
     }
-    if (A == 512 && R == 512) {
+    static const bool att_one_pass = [] { const char* e = getenv("COOPCAP_ATT_BWD_TWO_PASS"); return !(e && e[0] == '1'); }();
+    if (A == 512 && R == 512 && c->att_res32 && att_one_pass) {
+      // single pass over (att_e, p_att): the softmax backward's mean comes from the saved fp32 att_res
+      if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_bwd5_kernel<512>), ATT4_SMEM))) return rc;
+      CC_CHECK_CUDA(launch_pdl(attention_bwd5_kernel<512>, dim3(std::min(num_sms(), B)),
+                               dim3(ATT4_THREADS), size_t(ATT4_SMEM), s,
+                               reinterpret_cast<const bf16*>(c->p_att16),
+                               reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L,
+                               c->att_order, s_t, int64_t(NS), 5 * R, c->w_alpha, dres_t,
+                               c->att_res32 + int64_t(t) * B * R, c->att_w + int64_t(t) * NL,
+                               g->de + int64_t(t) * NL, ds_t, B));
+    } else if (A == 512 && R == 512) {
       if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_bwd4_kernel<512>), ATT4_SMEM))) return rc;
       CC_CHECK_CUDA(launch_pdl(attention_bwd4_kernel<512>, dim3(std::min(num_sms(), B)),
                                dim3(ATT4_THREADS), size_t(ATT4_SMEM), s,

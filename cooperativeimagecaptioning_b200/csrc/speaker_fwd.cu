@@ -565,7 +565,7 @@ static int logit_sample_step(const coopcap_speaker* c, int t, const bf16* out16_
 // 5R of every row.  Shared by the decode loop and the beam search (csrc/beam.cu), which calls it once
 // per beam slot with that slot's rows.
 int attention_fwd_launch(const coopcap_speaker* c, const float* s_t, bf16* att_res16_t, float* att_w_t,
-                         cudaStream_t s) {
+                         cudaStream_t s, float* att_res32_t) {
   const int B = c->B, R = c->R, A = c->A, NS = 5 * R + A;
   int rc;
   if (A == 512 && R == 512) {
@@ -573,7 +573,7 @@ int attention_fwd_launch(const coopcap_speaker* c, const float* s_t, bf16* att_r
     CC_CHECK_CUDA(launch_pdl(attention_fwd4_kernel<512>, dim3(std::min(num_sms(), B)), dim3(ATT4_THREADS),
                              size_t(ATT4_SMEM), s, reinterpret_cast<const bf16*>(c->p_att16),
                              reinterpret_cast<const bf16*>(c->att_e16), c->att_off, c->L, c->att_order, s_t,
-                             int64_t(NS), 5 * R, c->w_alpha, att_res16_t, att_w_t, B));
+                             int64_t(NS), 5 * R, c->w_alpha, att_res16_t, att_w_t, B, att_res32_t));
   } else {
     const size_t att_smem = attention_smem_bytes(A, R, c->L);
     if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_fwd_kernel), int(att_smem)))) return rc;
@@ -647,7 +647,8 @@ int speaker_decode_fwd(const coopcap_speaker* c, cudaStream_t s) {
     e1.alpha = 1.f; e1.bias = c->b_cat; e1.C = s_t; e1.ldc = NS;
     rc = gemm_run(0, 0, 0, xh16 + int64_t(t) * B * XH, XH, c->w_cat16, XH, B, NS, XH, 1, 0, e1, s);
     if (rc) return rc;
-    if ((rc = attention_fwd_launch(c, s_t, att_res16 + int64_t(t) * B * R, c->att_w + int64_t(t) * c->NL, s)))
+    if ((rc = attention_fwd_launch(c, s_t, att_res16 + int64_t(t) * B * R, c->att_w + int64_t(t) * c->NL, s,
+                                   c->att_res32 ? c->att_res32 + int64_t(t) * B * R : nullptr)))
       return rc;
     if (cell_step_ok<LstmCell>(R, R)) {
       // a2c GEMM with the maxout-LSTM update as its epilogue (csrc/cell_step.cuh)

@@ -268,6 +268,8 @@ def speaker_forward(P: Dict[str, torch.Tensor], packed: dict, att_feats: torch.T
         xh16=torch.empty(cap + 1, B, XH, **bf),
         s_all=torch.empty(cap, B, NS, **f32), u_all=torch.empty(cap, B, 2 * d.R, **f32),
         c_all=torch.empty(cap + 1, B, d.R, **f32), att_res16=torch.empty(cap, B, d.R, **bf),
+        # fp32 attention output: lets the per-step attention backward run as one pass (attention.cuh v5)
+        att_res32=torch.empty(cap, B, d.R, **f32),
         out16=torch.empty(cap, B, d.R, **bf),
         # logits are kept in fp16 for the backward pass only; the sampler runs on the fp32
         # accumulators inside the logit GEMM (csrc/logit_sample.cuh)

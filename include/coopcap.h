@@ -266,6 +266,10 @@ typedef struct coopcap_speaker {
    * longer be rebuilt, so coopcap_logp_backward refuses such a context: callers that differentiate
    * the sampled ids' log-probabilities (the CIDEr term) leave this 0. */
   int store_perturbed;
+  /* fp32 copy of the attention output, [cap, B, R], or NULL.  When present (and A == R == 512) the
+   * per-step attention backward is a single pass over (att_e, p_att): the softmax backward's mean
+   * sum_l w_l <d_att_res, att_e_l> equals <d_att_res, att_res> (csrc/attention.cuh, v5). */
+  float* att_res32;
 } coopcap_speaker;
 
 /* att16, att_e16, p_att16 from att_feats (AttModel.py:110-114 / :315-319). */
