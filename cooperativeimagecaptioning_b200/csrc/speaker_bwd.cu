@@ -234,6 +234,65 @@ st_bwd_kernel(const __half* __restrict__ z, const GT* __restrict__ g, int64_t ld
   }
 }
 
+// The benchmarked case of st_bwd_kernel -- perturbed fp16 logits z + G kept by the forward pass, bf16
+// upstream gradient from the factored listener path -- with the row held in REGISTERS: every thread
+// owns up to ST_REG_IT groups of 8 consecutive columns, issues all its 16-byte loads of z and g
+// up front, forms y and <y, g>, and writes dz from the same registers.  One read of each input, one
+// write, no shared-memory copy of y, no second pass over g.  V1 <= 8 * 256 * ST_REG_IT.
+constexpr int ST_REG_IT = 5;
+__global__ void __launch_bounds__(256)
+st_bwd_pert_kernel(const __half* __restrict__ z, const bf16* __restrict__ g, int V1, float inv_tau,
+                   const float* __restrict__ ymax, const float* __restrict__ ysum,
+                   const uint8_t* __restrict__ unf, bf16* __restrict__ dz) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8];
+  const int64_t row = blockIdx.x;
+  const int nv8 = V1 >> 3;
+  uint4* dr = reinterpret_cast<uint4*>(dz + row * V1);
+  if (!unf[row]) {
+    for (int v8 = threadIdx.x; v8 < nv8; v8 += 256) dr[v8] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const uint4* zr = reinterpret_cast<const uint4*>(z + row * V1);
+  const uint4* gr = reinterpret_cast<const uint4*>(g + row * V1);
+  uint4 zq[ST_REG_IT], gq[ST_REG_IT];
+#pragma unroll
+  for (int k = 0; k < ST_REG_IT; ++k) {
+    const int v8 = threadIdx.x + k * 256;
+    if (v8 < nv8) { zq[k] = zr[v8]; gq[k] = gr[v8]; }
+  }
+  const float m = ymax[row], inv_s = 1.f / ysum[row];
+  float y[ST_REG_IT][8];
+  float dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < ST_REG_IT; ++k) {
+    const int v8 = threadIdx.x + k * 256;
+    if (v8 < nv8) {
+      float x8[8], g8[8];
+      f16x8_to_float(zq[k], x8);
+      bf16x8_to_float(gq[k], g8);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        y[k][q] = ex2_ftz((x8[q] * inv_tau - m) * 1.4426950408889634f) * inv_s;
+        dot += y[k][q] * g8[q];
+      }
+    }
+  }
+  dot = block_sum_256(dot, red);
+#pragma unroll
+  for (int k = 0; k < ST_REG_IT; ++k) {
+    const int v8 = threadIdx.x + k * 256;
+    if (v8 < nv8) {
+      float g8[8], o[8];
+      bf16x8_to_float(gq[k], g8);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = inv_tau * y[k][q] * (g8[q] - dot);
+      dr[v8] = float8_to_bf16x8(o);
+    }
+  }
+}
+
 // d(loss)/d(v . embed) of the partial-sampling next input x = dropout(relu(v . embed)): the ReLU
 // and dropout decisions are both recovered from the saved x (x > 0)
 __global__ void ps_dpre_kernel(const float* __restrict__ d_xh, const bf16* __restrict__ xh16, int E,
@@ -615,6 +674,13 @@ int st_backward(const coopcap_speaker* c, const void* demb16, const void* w_emb1
       rc = gemm_run(0, 0, 0, reinterpret_cast<const bf16*>(demb16) + int64_t(t0) * B * E, E, w_emb16,
                     E, int(rows), V1, E, 1, 0, e, s);
       if (rc) return rc;
+      if (pert && V1 % 8 == 0 && V1 <= 8 * 256 * ST_REG_IT) {
+        CC_CHECK_CUDA(launch_pdl(st_bwd_pert_kernel, dim3((unsigned)rows), dim3(256), size_t(0), s, z_t,
+                                 static_cast<const bf16*>(reinterpret_cast<bf16*>(g_ws)), V1, c->inv_tau,
+                                 static_cast<const float*>(c->y_max + int64_t(t0) * B),
+                                 static_cast<const float*>(c->y_sum + int64_t(t0) * B),
+                                 static_cast<const uint8_t*>(c->unfinished + int64_t(t0) * B), dz_t));
+      } else
       CC_CHECK_CUDA(launch_pdl(
           pert ? st_bwd_kernel<bf16, true> : st_bwd_kernel<bf16, false>, dim3((unsigned)rows), dim3(256), smem, s, z_t,
           static_cast<const bf16*>(reinterpret_cast<bf16*>(g_ws)), int64_t(V1), V1, c->mode, c->inv_tau, n_t,
