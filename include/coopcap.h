@@ -113,6 +113,7 @@ int coopcap_cast_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_s
  *   u_all      fp32 [cap, B, 2R]        per step: a2c(att_res) (+bias)
  *   c_all      fp32 [cap+1, B, R]       cell state, c_all[0] = 0
  *   att_res16  bf16 [cap, B, R]         attention output per step
+ *   att_res32  fp32 [cap, B, R]         the same in fp32 (optional; single-pass attention backward)
  *   att_w      fp32 [cap, NL]           attention weights per step (packed like the regions)
  *   out16      bf16 [cap, B, R]         dropout(h_t) (operand of the logit GEMM)
  *   z16_all    fp16 [cap, B, V1]        vocabulary logits per step.  The sampler runs on the fp32
