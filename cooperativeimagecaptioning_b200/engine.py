@@ -82,7 +82,7 @@ def _arena_alloc(dev: torch.device, shape, dtype=torch.bfloat16) -> torch.Tensor
     if a is None:
         a = _arena[ix] = dict(buf=torch.empty(_ARENA_BYTES, dtype=torch.uint8, device=dev), used=0,
                               windows={})
-    nbytes = math.prod(shape) * torch.empty((), dtype=dtype).element_size()
+    nbytes = math.prod(shape) * dtype.itemsize
     start = (a["used"] + 255) // 256 * 256
     if start + nbytes > _ARENA_BYTES:
         return torch.empty(shape, dtype=dtype, device=dev)

@@ -1,5 +1,6 @@
 """Developer tool (GPU box, torchrun): cost of the gradient exchange in the data-parallel step.
-Variants: early slices on a side stream (product), one late all-reduce, no exchange at all."""
+Variants: one all-reduce after backward (the product's default), slices exchanged early on a side
+stream (COOPCAP_EARLY_REDUCE=1), no exchange at all."""
 import os
 import sys
 
@@ -61,10 +62,11 @@ def timed(tag, n=30):
         print(f"{tag}: {float(t):.3f} ms/step", flush=True)
 
 
-timed("early slices (product)")
+OPT._EARLY_REDUCE = True
+timed("early slices (COOPCAP_EARLY_REDUCE=1)")
 real_async = OPT.FlatAdam.reduce_async
 OPT.FlatAdam.reduce_async = lambda self, params: False
-timed("one late all-reduce")
+timed("one late all-reduce (default)")
 real_ar = dist.all_reduce
 OPT.dist = None
 import torch.distributed as D2
@@ -72,5 +74,5 @@ D2.all_reduce = lambda *a, **k: None
 timed("no exchange")
 D2.all_reduce = real_ar
 OPT.FlatAdam.reduce_async = real_async
-timed("early slices (product), again")
+timed("early slices, again")
 dist.destroy_process_group()
