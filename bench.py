@@ -858,7 +858,7 @@ def main():
                         speaker="att2in2 rnn512", listener="vsefc gru1024", gumbel_temp=1.0,
                         dropout=0.5, optimizer="clamp(0.1)+Adam, both agents",
                         parallelism=f"dp{world}",
-                        l2="inputs (839 MB att feats + 622 MB logits per step) exceed the 126 MB L2",
+                        l2="inputs (839 MB att feats, 311 MB of fp16 logits per step) exceed the 126 MB L2",
                         accumulate="fp32 accumulation, bf16 tensor-core operands, fp32 master weights"),
             e2e=e2e, e2e_host_features=e2e_host_features,
             gpu_launches=int(launches),
