@@ -529,6 +529,12 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st0 = torch.cuda.memory_stats()
     import gc
+    # like timeit: no cyclic-GC pass inside the timed region.  The region starts on an EMPTY launch
+    # queue (the barrier above synchronises), so a generation-2 collection during the first step --
+    # a few ms with torch's object graph -- starves the device (seen once: 5.46 instead of 5.33 ms/step
+    # over 20 steps); in steady state the queue is ~1000 launches deep and hides it
+    gc.collect()
+    gc.disable()
     gc_before = gc.get_count()
     e0.record()
     h0 = time.perf_counter()
@@ -540,6 +546,7 @@ def main():
         loss = train_step(resident[i % 2])
         gaps.append((time.perf_counter() - g0) * 1e3)
     e1.record()
+    gc.enable()
     host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / args.steps   # CPU time to queue one step
     st1 = torch.cuda.memory_stats()
     loop_debug = dict(host_ms_per_step=[round(g, 2) for g in gaps],
@@ -697,9 +704,12 @@ def main():
         barrier()
         a0 = torch.cuda.memory_stats()["num_device_alloc"]
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gc.collect()
+        gc.disable()
         t0.record()
         e2e_loop(args.steps, True)
         t1.record()
+        gc.enable()
         allocs = torch.cuda.memory_stats()["num_device_alloc"] - a0
         moved = store.last_bytes if store is not None else \
             (packer.last_bytes if packer is not None else upload_batch.last_bytes)
