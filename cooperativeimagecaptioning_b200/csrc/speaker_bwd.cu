@@ -346,7 +346,8 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ d_out, const bf16* __r
                                 const float* __restrict__ dc_in, float* __restrict__ dc_out,
                                 const float* __restrict__ s, int64_t lds, const float* __restrict__ u,
                                 const float* __restrict__ c_prev, const float* __restrict__ c_cur,
-                                bf16* __restrict__ dscat, float drop_p, int B, int R) {
+                                bf16* __restrict__ dscat, float drop_p, int B, int R,
+                                float* __restrict__ zero_row0, int zero_cols) {
   pdl_launch_dependents();
   pdl_wait();
   // 4 hidden units per thread: 16-byte loads, 8-byte bf16 stores
@@ -354,6 +355,12 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ d_out, const bf16* __r
   const int per_row = R / 4;
   if (idx4 >= B * per_row) return;
   const int b = idx4 / per_row, j = (idx4 % per_row) * 4;
+  if (zero_row0) {
+    // this step's slice of d[x|h]: the split-K dgrad GEMM that follows reduce-ADDs into it (was one
+    // 67 MB memset in front of the loop); zero_cols floats per row, spread over the row's threads
+    float4* zr = reinterpret_cast<float4*>(zero_row0 + int64_t(b) * zero_cols);
+    for (int q = idx4 % per_row; q < zero_cols / 4; q += per_row) zr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const int64_t idx = int64_t(b) * R + j;
   auto ld4 = [](const float* p, float (&o)[4]) {
     const float4 v = *reinterpret_cast<const float4*>(p);
@@ -761,8 +768,7 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
   // BPTT.  d[x|h] = dscat . w_cat has only 8 x 8 output tiles for K = 5R+A: it runs split along K
   // with TMA reduce-add into a zeroed buffer so that the whole machine works on it.
   const int dxh_split = (int64_t(B) * XH <= int64_t(128) * 128 * 74 && NS >= 2048) ? 2 : 1;
-  if (dxh_split > 1)
-    CC_CHECK_CUDA(cudaMemsetAsync(g->d_xh, 0, sizeof(float) * size_t(n) * B * XH, s));
+  // (the slices of d_xh are zeroed step by step inside lstm_bwd_kernel)
   for (int t = n - 1; t >= 0; --t) {
     const float* s_t = c->s_all + int64_t(t) * B * NS;
     bf16* ds_t = dscat16 + int64_t(t) * B * NS;
@@ -810,7 +816,8 @@ int speaker_decode_bwd(const coopcap_speaker* c, const coopcap_speaker_grads* g,
           lstm_bwd_kernel, dim3((nthr + 255) / 256), dim3(256), 0, s, g->d_out + int64_t(t) * B * R,
           out16 + int64_t(t) * B * R, dh_next, int64_t(XH), dc_in, dc_out, s_t, int64_t(NS),
           c->u_all + int64_t(t) * B * 2 * R, c->c_all + int64_t(t) * B * R,
-          c->c_all + int64_t(t + 1) * B * R, ds_t, c->drop_p, B, R));
+          c->c_all + int64_t(t + 1) * B * R, ds_t, c->drop_p, B, R,
+          (dxh_split > 1 && XH % 4 == 0) ? g->d_xh + int64_t(t) * B * XH : static_cast<float*>(nullptr), XH));
       CC_LAUNCH_CHECK_K(PROF_LSTM, s, 0.0, 0.0);
     }
     // d_att_res = d_u . W_a2c      ([B,2R] x [2R,R])
