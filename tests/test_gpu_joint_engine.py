@@ -11,7 +11,7 @@ from gpu_util import REAL, branch_replay, check_near_ties, cuda_params, pack_kee
 pytestmark = pytest.mark.gpu
 
 BF16_TOL = 2e-2   # north star: 2e-2 relative (bf16 operands, fp32 accumulation)
-NEAR_TIE = 5e-2   # maxout / ReLU decisions may differ only below 5% of the median margin
+NEAR_TIE = 2e-2   # maxout / ReLU decisions may differ only below 2% of the median margin
 
 
 def _grad_err(g, ref):
